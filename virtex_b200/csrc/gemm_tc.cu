@@ -1,0 +1,547 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a -- the one tensor-core kernel behind every GEMM-shaped op of the
+// VirTex bicaptioning step (1x1 convs, implicit 3x3 convs, im2col'd strided convs, all nn.Linear fwd/dgrad/wgrad,
+// vocabulary projection).  See include/virtex_b200.h (VtxGemm) for the contract.
+//
+// Structure (persistent, warp specialised, one CTA per SM, 256 threads):
+//   warp 0 : TMA producer   (one elected lane)  global -> 128B-swizzled smem ring, 4 stages of (A 16 KB, B <= 32 KB)
+//   warp 1 : MMA issuer     (one elected lane)  tcgen05.mma.cta_group::1.kind::f16, M=128, N=tile_n, K=16 per issue
+//   warp 2 : TMEM allocator (512 columns = 2 accumulator stages of up to 256 fp32 columns)
+//   warps 4-7 : epilogue    tcgen05.ld -> registers -> stats / bias / residual / activation -> global
+// Three mbarrier pipelines: smem full/empty (TMA <-> MMA), tmem full/empty (MMA <-> epilogue), and a static
+// round-robin tile schedule shared by the three roles.
+//
+// Operand "major-ness" is a runtime property (instruction-descriptor bits + smem descriptor strides), so the same
+// kernel serves fprop (A,B K-major), dgrad (B MN-major) and wgrad (A,B MN-major) without transposing activations.
+// conv_mode 1/2 replace the 2D TMA loads by 4D NHWC box loads whose out-of-bounds elements are zero-filled by the
+// TMA unit: that *is* the im2col of a 3x3/stride-1/pad-1 convolution, with no extra HBM traffic.
+#include "ptx.cuh"
+#include "vtx_common.cuh"
+#include "../../include/virtex_b200.h"
+
+namespace vtx {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;
+constexpr int kStages = 4;
+constexpr int kABytes = kBM * kBK * 2;        // 16384
+constexpr int kBBytesMax = 256 * kBK * 2;     // 32768
+constexpr int kStageBytes = kABytes + kBBytesMax;
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int kThreads = 256;
+
+struct GemmKParams {
+  int M, N, K;
+  int bn;
+  int a_mn, b_mn;
+  int m_tiles, n_tiles, k_splits;
+  int kb_total, kb_per_split;
+  int mode;
+  int cH, cW, cN, cpb;
+  int lbw, lbh, lbn;
+  int tiles_w, tiles_h;
+  int out_f32, atomic, act;
+  float alpha;
+  void* D;
+  long long ldd;
+  const float* bias;
+  const __nv_bfloat16* residual;
+  long long ldr;
+  float* stats;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+// Per-warp transpose-reduce: every lane holds v[0..31] (one row, 32 columns); on return lane l holds, in v[0],
+// the sum over the warp's 32 rows of column l.
+__device__ __forceinline__ float warp_colsum32(float* v, int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool hi = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      float send = hi ? v[i] : v[i + s];
+      float keep = hi ? v[i + s] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* full_bar = bars;                 // [kStages]
+  uint64_t* empty_bar = bars + kStages;      // [kStages]
+  uint64_t* tfull_bar = bars + 2 * kStages;  // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.m_tiles * p.n_tiles * p.k_splits;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const uint32_t b_bytes = (uint32_t)p.bn * kBK * 2;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int ks = t / (p.m_tiles * p.n_tiles);
+        const int rem = t - ks * (p.m_tiles * p.n_tiles);
+        const int mt = rem / p.n_tiles;
+        const int nt = rem - mt * p.n_tiles;
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        int w0 = 0, h0 = 0, n0 = 0;
+        if (p.mode == 1) {
+          const int tw = mt % p.tiles_w;
+          const int th = (mt / p.tiles_w) % p.tiles_h;
+          const int tn = mt / (p.tiles_w * p.tiles_h);
+          w0 = tw << p.lbw; h0 = th << p.lbh; n0 = tn << p.lbn;
+        }
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sA = smem + stage * kStageBytes;
+          uint8_t* sB = sA + kABytes;
+          mbar_arrive_expect_tx(&full_bar[stage], kABytes + b_bytes);
+          if (p.mode == 0) {
+            if (!p.a_mn) {
+              tma_load_2d(sA, &tmA, &full_bar[stage], kb * kBK, mt * kBM);
+            } else {
+              tma_load_2d(sA, &tmA, &full_bar[stage], mt * kBM, kb * kBK);
+              tma_load_2d(sA + 8192, &tmA, &full_bar[stage], mt * kBM + 64, kb * kBK);
+            }
+            if (!p.b_mn) {
+              tma_load_2d(sB, &tmB, &full_bar[stage], kb * kBK, nt * p.bn);
+            } else {
+              for (int j = 0; j < (p.bn >> 6); ++j)
+                tma_load_2d(sB + j * 8192, &tmB, &full_bar[stage], nt * p.bn + 64 * j, kb * kBK);
+            }
+          } else if (p.mode == 1) {
+            const int tap = kb / p.cpb;
+            const int cb = kb - tap * p.cpb;
+            const int kh = tap / 3, kw = tap - kh * 3;
+            tma_load_4d(sA, &tmA, &full_bar[stage], cb * 64, w0 + kw - 1, h0 + kh - 1, n0);
+            tma_load_2d(sB, &tmB, &full_bar[stage], kb * kBK, nt * p.bn);
+          } else {
+            // wgrad: reduction block kb is a spatial box of 64 output positions
+            const int tw = kb % p.tiles_w;
+            const int th = (kb / p.tiles_w) % p.tiles_h;
+            const int tn = kb / (p.tiles_w * p.tiles_h);
+            const int bw0 = tw << p.lbw, bh0 = th << p.lbh, bn0 = tn << p.lbn;
+            tma_load_4d(sA, &tmA, &full_bar[stage], mt * kBM, bw0, bh0, bn0);
+            tma_load_4d(sA + 8192, &tmA, &full_bar[stage], mt * kBM + 64, bw0, bh0, bn0);
+            for (int j = 0; j < (p.bn >> 6); ++j) {
+              const int atom = nt * (p.bn >> 6) + j;
+              const int tap = atom / p.cpb;
+              const int cb = atom - tap * p.cpb;
+              const int kh = tap / 3, kw = tap - kh * 3;
+              // atoms past the 9 taps are loaded fully out of bounds (zero fill) to keep the tx count fixed
+              const int nn = tap < 9 ? bn0 : p.cN + 1;
+              tma_load_4d(sB + j * 8192, &tmB, &full_bar[stage], cb * 64, bw0 + kw - 1, bh0 + kh - 1, nn);
+            }
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(p.bn, p.a_mn, p.b_mn);
+      const uint32_t a_step = p.a_mn ? 2048u : 32u;
+      const uint32_t b_step = p.b_mn ? 2048u : 32u;
+      const uint32_t a_lbo = p.a_mn ? 8192u : 16u;
+      const uint32_t b_lbo = p.b_mn ? 8192u : 16u;
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+        const int ks = t / (p.m_tiles * p.n_tiles);
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        const int as = it & 1;
+        mbar_wait(&tempty_bar[as], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)as * 256u;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sA = smem_u32(smem + stage * kStageBytes);
+          const uint32_t sB = sA + kABytes;
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            const uint64_t ad = make_smem_desc(sA + k * a_step, a_lbo, 1024);
+            const uint64_t bd = make_smem_desc(sB + k * b_step, b_lbo, 1024);
+            umma_bf16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[as]);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ===================================================== epilogue
+    const int ew = warp & 3;  // TMEM lanes [32*ew, 32*ew+32)
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const int rem = t % (p.m_tiles * p.n_tiles);
+      const int mt = rem / p.n_tiles;
+      const int nt = rem - mt * p.n_tiles;
+      const int as = it & 1;
+      mbar_wait(&tfull_bar[as], (it >> 1) & 1);
+      tc_fence_after();
+
+      const int r_in_tile = ew * 32 + lane;
+      long long grow;  // global output row, or -1 if masked
+      if (p.mode == 1) {
+        const int tw = mt % p.tiles_w;
+        const int th = (mt / p.tiles_w) % p.tiles_h;
+        const int tn = mt / (p.tiles_w * p.tiles_h);
+        const int dw = r_in_tile & ((1 << p.lbw) - 1);
+        const int dh = (r_in_tile >> p.lbw) & ((1 << p.lbh) - 1);
+        const int dn = r_in_tile >> (p.lbw + p.lbh);
+        const int w = (tw << p.lbw) + dw, h = (th << p.lbh) + dh, n = (tn << p.lbn) + dn;
+        grow = (w < p.cW && h < p.cH && n < p.cN) ? ((long long)(n * p.cH + h) * p.cW + w) : -1;
+      } else {
+        const int r = mt * kBM + r_in_tile;
+        grow = r < p.M ? r : -1;
+      }
+      const int n_base = nt * p.bn;
+      const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)as * 256u;
+
+      for (int c0 = 0; c0 < p.bn; c0 += 32) {
+        if (n_base + c0 >= p.N) break;
+        float v[32];
+        tmem_ld32(t_row + c0, v);
+        tmem_ld_wait();
+        const int col0 = n_base + c0;
+        if (p.stats != nullptr) {
+          float s[32], q[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float x = grow >= 0 ? v[i] : 0.f;
+            s[i] = x;
+            q[i] = x * x;
+          }
+          const float cs = warp_colsum32(s, lane);
+          const float cq = warp_colsum32(q, lane);
+          if (col0 + lane < p.N) {
+            atomicAdd(p.stats + col0 + lane, cs);
+            atomicAdd(p.stats + p.N + col0 + lane, cq);
+          }
+        }
+        if (grow >= 0) {
+          const bool full = (col0 + 32 <= p.N);
+          if (p.alpha != 1.0f) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] *= p.alpha;
+          }
+          if (p.bias != nullptr) {
+            if (full) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                const float4 b = *reinterpret_cast<const float4*>(p.bias + col0 + i);
+                v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (col0 + i < p.N) v[i] += p.bias[col0 + i];
+            }
+          }
+          if (p.residual != nullptr) {
+            const __nv_bfloat16* rp = p.residual + grow * p.ldr + col0;
+            if (full) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 8) {
+                const uint4 u = *reinterpret_cast<const uint4*>(rp + i);
+                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 f = __bfloat1622float2(h2[j]);
+                  v[i + 2 * j] += f.x;
+                  v[i + 2 * j + 1] += f.y;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (col0 + i < p.N) v[i] += __bfloat162float(rp[i]);
+            }
+          }
+          if (p.act == 1) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+          } else if (p.act == 2) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+          }
+          if (p.out_f32) {
+            float* op = reinterpret_cast<float*>(p.D) + grow * p.ldd + col0;
+            if (p.atomic) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (col0 + i < p.N) atomicAdd(op + i, v[i]);
+            } else if (full) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4)
+                *reinterpret_cast<float4*>(op + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (col0 + i < p.N) op[i] = v[i];
+            }
+          } else {
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.D) + grow * p.ldd + col0;
+            if (full) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 8) {
+                uint4 u;
+                __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) h2[j] = __floats2bfloat162_rn(v[i + 2 * j], v[i + 2 * j + 1]);
+                *reinterpret_cast<uint4*>(op + i) = u;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (col0 + i < p.N) op[i] = __float2bfloat16_rn(v[i]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// bf16 tensor map of rank 2 or 4; dims[0] is the contiguous dimension; strides in elements for dims 1..rank-1.
+static int make_tmap(CUtensorMap* tm, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+                     const uint32_t* box) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return set_error(VTX_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[5];
+  cuuint32_t bx[5];
+  cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+  }
+  for (int i = 0; i < rank - 1; ++i) gstr[i] = strides_elems[i] * 2;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return set_error(VTX_EINVAL, "TMA base pointer not 16B aligned");
+  for (int i = 0; i < rank - 1; ++i)
+    if (gstr[i] % 16 != 0) return set_error(VTX_EINVAL, "TMA stride not a multiple of 16 bytes");
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), gdim, gstr, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(VTX_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return VTX_OK;
+}
+
+static int ilog2(int x) {
+  int l = 0;
+  while ((1 << l) < x) ++l;
+  return l;
+}
+
+// choose a power-of-two (w,h,n) box with w*h*n == positions that tiles an H x W image with the least waste
+static void choose_box(int H, int W, int positions, int* bw, int* bh, int* bn) {
+  int best_w = 1, best_h = 1;
+  double best_eff = -1;
+  for (int w = 1; w <= positions; w <<= 1)
+    for (int h = 1; w * h <= positions; h <<= 1) {
+      if (w > 2 * W || h > 2 * H) continue;
+      const int tw = (W + w - 1) / w, th = (H + h - 1) / h;
+      const double eff = (double)(W * H) / ((double)tw * w * th * h);
+      // prefer higher efficiency, then larger contiguous w, then larger h
+      const double score = eff * 1000.0 + w * 0.01 + h * 0.0001;
+      if (score > best_eff) { best_eff = score; best_w = w; best_h = h; }
+    }
+  *bw = best_w; *bh = best_h; *bn = positions / (best_w * best_h);
+}
+
+}  // namespace vtx
+
+using namespace vtx;
+
+extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!g || !g->A || !g->B || !g->D) return set_error(VTX_EINVAL, "vtx_gemm: null pointer");
+  if (g->M <= 0 || g->N <= 0 || g->K <= 0) return set_error(VTX_EINVAL, "vtx_gemm: empty problem");
+  if (g->atomic && !g->out_f32) return set_error(VTX_EINVAL, "vtx_gemm: atomic accumulate needs fp32 output");
+  const int split_k = g->split_k > 1 ? g->split_k : 1;
+  if (split_k > 1 && !g->atomic) return set_error(VTX_EINVAL, "vtx_gemm: split_k > 1 needs atomic = 1");
+  if (g->ldd % (g->out_f32 ? 4 : 8) != 0) return set_error(VTX_EINVAL, "vtx_gemm: ldd must keep rows 16B aligned");
+
+  GemmKParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = g->M; p.N = g->N; p.K = g->K;
+  p.a_mn = g->a_mn; p.b_mn = g->b_mn;
+  p.mode = g->conv_mode;
+  if (p.mode == 1) { p.a_mn = 0; p.b_mn = 0; }
+  if (p.mode == 2) { p.a_mn = 1; p.b_mn = 1; }
+  // ---- tile_n
+  int bn = g->tile_n;
+  if (bn == 0) {
+    const int gran = p.b_mn ? 64 : 16;
+    if (g->N >= 256) bn = 256;
+    else bn = ((g->N + gran - 1) / gran) * gran;
+    // prefer 128-wide tiles when that fills the machine noticeably better
+    if (bn == 256) {
+      const long mt = (g->M + kBM - 1) / kBM;
+      const long t256 = mt * ((g->N + 255) / 256) * split_k;
+      if (t256 < 148 && g->N % 256 != 0 && g->N <= 2048) bn = 128;
+      if (t256 < 100) bn = 128;
+    }
+  }
+  if (bn < 16 || bn > 256 || bn % 16 != 0 || (p.b_mn && bn % 64 != 0))
+    return set_error(VTX_EINVAL, "vtx_gemm: bad tile_n %d", bn);
+  p.bn = bn;
+  p.n_tiles = (g->N + bn - 1) / bn;
+  p.out_f32 = g->out_f32; p.atomic = g->atomic; p.act = g->act;
+  p.alpha = g->alpha == 0.f ? 1.0f : g->alpha;
+  p.D = g->D; p.ldd = g->ldd;
+  p.bias = g->bias;
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(g->residual);
+  p.ldr = g->ldr;
+  p.stats = g->stats;
+
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (p.mode == 0) {
+    p.m_tiles = (g->M + kBM - 1) / kBM;
+    p.kb_total = (g->K + kBK - 1) / kBK;
+    {
+      uint64_t dims[2], str[1];
+      uint32_t box[2];
+      if (!p.a_mn) { dims[0] = g->K; dims[1] = g->M; box[0] = 64; box[1] = 128; }
+      else { dims[0] = g->M; dims[1] = g->K; box[0] = 64; box[1] = 64; }
+      str[0] = g->lda;
+      if ((rc = make_tmap(&tmA, g->A, 2, dims, str, box)) != VTX_OK) return rc;
+    }
+    {
+      uint64_t dims[2], str[1];
+      uint32_t box[2];
+      if (!p.b_mn) { dims[0] = g->K; dims[1] = g->N; box[0] = 64; box[1] = (uint32_t)bn; }
+      else { dims[0] = g->N; dims[1] = g->K; box[0] = 64; box[1] = 64; }
+      str[0] = g->ldb;
+      if ((rc = make_tmap(&tmB, g->B, 2, dims, str, box)) != VTX_OK) return rc;
+    }
+  } else {
+    const int C = g->conv_c, H = g->conv_h, W = g->conv_w, NI = g->conv_n;
+    if (C <= 0 || C % 64 != 0) return set_error(VTX_EINVAL, "vtx_gemm: implicit conv needs channels %% 64 == 0");
+    p.cH = H; p.cW = W; p.cN = NI; p.cpb = C / 64;
+    int bw, bh, bnn;
+    choose_box(H, W, p.mode == 1 ? 128 : 64, &bw, &bh, &bnn);
+    p.lbw = ilog2(bw); p.lbh = ilog2(bh); p.lbn = ilog2(bnn);
+    p.tiles_w = (W + bw - 1) / bw;
+    p.tiles_h = (H + bh - 1) / bh;
+    const int tiles_n = (NI + bnn - 1) / bnn;
+    if (p.mode == 1) {
+      // A: activation [NI,H,W,C]; M = NI*H*W (tiled as boxes); K = 9*C; B: weights [N, 9*C] K-major
+      if (g->M != NI * H * W || g->K != 9 * C) return set_error(VTX_EINVAL, "vtx_gemm: conv fprop shape mismatch");
+      p.m_tiles = p.tiles_w * p.tiles_h * tiles_n;
+      p.kb_total = 9 * p.cpb;
+      uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)NI};
+      uint64_t str[3] = {(uint64_t)C, (uint64_t)W * C, (uint64_t)H * W * C};
+      uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bh, (uint32_t)bnn};
+      if ((rc = make_tmap(&tmA, g->A, 4, dims, str, box)) != VTX_OK) return rc;
+      uint64_t bd[2] = {(uint64_t)g->K, (uint64_t)g->N};
+      uint64_t bs[1] = {(uint64_t)g->ldb};
+      uint32_t bb[2] = {64, (uint32_t)bn};
+      if ((rc = make_tmap(&tmB, g->B, 2, bd, bs, bb)) != VTX_OK) return rc;
+    } else {
+      // wgrad: D[M = Cout, N = 9*C] += sum over positions dy[pos, Cout] * x_shift[pos, C]
+      //   A = dy [NI,H,W,Cout] (lda = Cout), B = x [NI,H,W,C]
+      if (g->N != 9 * C) return set_error(VTX_EINVAL, "vtx_gemm: conv wgrad shape mismatch");
+      const int Cout = g->M;
+      if (Cout % 64 != 0) return set_error(VTX_EINVAL, "vtx_gemm: conv wgrad needs Cout %% 64 == 0");
+      p.m_tiles = (Cout + kBM - 1) / kBM;
+      p.kb_total = p.tiles_w * p.tiles_h * tiles_n;
+      uint64_t ad[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)NI};
+      uint64_t as[3] = {(uint64_t)Cout, (uint64_t)W * Cout, (uint64_t)H * W * Cout};
+      uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bh, (uint32_t)bnn};
+      if ((rc = make_tmap(&tmA, g->A, 4, ad, as, box)) != VTX_OK) return rc;
+      uint64_t bd[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)NI};
+      uint64_t bs[3] = {(uint64_t)C, (uint64_t)W * C, (uint64_t)H * W * C};
+      if ((rc = make_tmap(&tmB, g->B, 4, bd, bs, box)) != VTX_OK) return rc;
+    }
+  }
+  p.k_splits = split_k;
+  if (p.k_splits > p.kb_total) p.k_splits = p.kb_total;
+  p.kb_per_split = (p.kb_total + p.k_splits - 1) / p.k_splits;
+  p.k_splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return set_error(VTX_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const long total = (long)p.m_tiles * p.n_tiles * p.k_splits;
+  const int sms = vtx_num_sms();
+  const int grid = (int)(total < sms ? total : sms);
+  gemm_tc_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(VTX_ECUDA, "gemm_tc_kernel launch: %s", cudaGetErrorString(e));
+  return VTX_OK;
+}
