@@ -1,0 +1,102 @@
+"""The CPU oracle (oracle/virtex_oracle.py) against fixtures produced by the UNMODIFIED reference
+(oracle/make_golden.py, run in the build container).  This is what pins the oracle."""
+import os
+
+import pytest
+import torch
+
+from oracle import virtex_oracle as O
+
+CASES = ["r50_l1_h1024_post_b2", "r50_l2_h256_pre_b3_ragged", "r50_l1_h128_post_b4_ragged"]
+
+
+def _load(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, name + ".pt"), weights_only=False)
+
+
+def _setup(g):
+    spec = O.Spec(**g["spec"])
+    state = O.synth_state(spec, g["seed"])
+    batch = O.synth_batch(max_len=spec.max_len, vocab=spec.vocab, **g["batch"])
+    return spec, state, batch
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_train_forward_backward_f64(golden_dir, name):
+    """float64 oracle == float64 reference to round-off: loss, both components, every gradient, BN buffers."""
+    g = _load(golden_dir, name)
+    spec, state, batch = _setup(g)
+    out, grads, bufs = O.loss_and_grads(state, batch, spec, dtype=torch.float64)
+    ref = g["f64"]
+    assert abs(out["loss"].item() - ref["loss"].item()) < 1e-9
+    assert abs(out["loss_components"]["captioning_forward"].item() - ref["loss_forward"].item()) < 1e-9
+    assert abs(out["loss_components"]["captioning_backward"].item() - ref["loss_backward"].item()) < 1e-9
+    names = ref["grads"]["names"]
+    assert sorted(grads) == names
+    norm = torch.tensor([grads[n].norm().item() for n in names], dtype=torch.float64)
+    ssum = torch.tensor([grads[n].sum().item() for n in names], dtype=torch.float64)
+    assert torch.allclose(norm, ref["grads"]["norm"], rtol=1e-7, atol=1e-12)
+    assert ((ssum - ref["grads"]["sum"]).abs() <= 1e-6 * ref["grads"]["sum"].abs() + 1e-9 * (1 + norm)).all()
+    for k, probe in ref["grad_probe"].items():
+        assert torch.allclose(grads[k].flatten()[:64], probe, rtol=1e-7, atol=1e-12), k
+    assert torch.allclose(bufs["visual.cnn.layer4.2.bn3.running_mean"], ref["bn_running_mean_layer4"], rtol=1e-9)
+    assert torch.allclose(bufs["visual.cnn.bn1.running_var"], ref["bn_running_var_stem"], rtol=1e-9)
+    assert int(bufs["visual.cnn.bn1.num_batches_tracked"]) == int(ref["num_batches_tracked"]) == 1
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_train_loss_f32(golden_dir, name):
+    """float32 oracle vs float32 and float64 reference: loss to 1e-6 relative."""
+    g = _load(golden_dir, name)
+    spec, state, batch = _setup(g)
+    with torch.no_grad():
+        out = O.model_forward(state, batch, spec, training=True)
+    for tag in ("f32", "f64"):
+        assert abs(out["loss"].item() - g[tag]["loss"].item()) < 2e-6 * g[tag]["loss"].item()
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_eval_logits_and_argmax(golden_dir, name):
+    g = _load(golden_dir, name)
+    spec, state, batch = _setup(g)
+    st64 = O.cast_state(state, torch.float64)
+    b64 = dict(batch)
+    b64["image"] = batch["image"].double()
+    with torch.no_grad():
+        out = O.model_forward(st64, b64, spec, training=False, return_logits=True)
+    ref = g["f64"]
+    assert abs(out["loss"].item() - ref["eval_loss"].item()) < 1e-9
+    assert torch.equal(out["predictions"], ref["eval_predictions"])  # argmax ids bit-exact
+    assert torch.allclose(out["logits"][:, :, :48], ref["eval_logits_slice"], rtol=1e-8, atol=1e-10)
+    assert torch.allclose(out["logits"].max(-1).values, ref["eval_logits_max"], rtol=1e-8, atol=1e-10)
+    assert torch.allclose(out["visual_features"][:, :32], ref["eval_visual_slice"], rtol=1e-8, atol=1e-10)
+    # float32 oracle: same argmax as the float32 reference
+    with torch.no_grad():
+        out32 = O.model_forward(state, batch, spec, training=False)
+    assert torch.equal(out32["predictions"], g["f32"]["eval_predictions"])
+
+
+def test_trainer_trajectory(golden_dir):
+    """6 reference optimiser steps (SGD+momentum+wd per-parameter groups, clip 10, Lookahead k=5, warm-up LR)."""
+    g = _load(golden_dir, "trainer_r50_l1_h128_6steps")
+    spec = O.Spec(**g["spec"])
+    tr = O.OracleTrainer(O.synth_state(spec, g["seed"]), spec, O.OptimCfg(**g["optim"]))
+    for it in range(6):
+        out = tr.step(O.synth_batch(2, seed=10 + it))
+        assert abs(out["loss"].item() - g["losses"][it].item()) < 5e-4 * g["losses"][it].item(), it
+        assert abs(out["grad_norm"].item() - g["grad_norms"][it].item()) < 5e-2 * g["grad_norms"][it].item(), it
+    for k, ref_norm in g["final_param_norms"].items():
+        assert abs(tr.state[k].double().norm().item() - ref_norm) <= 1e-2 * ref_norm + 1e-6, k
+    for k, probe in g["final_probe"].items():
+        assert torch.allclose(tr.state[k].flatten()[:64], probe, rtol=5e-2, atol=1e-2), k
+
+
+def test_state_dict_key_set():
+    """Unique-tensor inventory expands to the reference's 370-key state_dict."""
+    spec = O.Spec()
+    state = O.synth_state(spec, 0)
+    sd = O.to_reference_state_dict(state, spec)
+    assert len(sd) == 370
+    nparams = sum(v.numel() for k, v in state.items() if not O.is_buffer(k))
+    assert nparams == 69_482_320
+    assert sum(1 for k in state if not O.is_buffer(k)) == 202
