@@ -100,7 +100,7 @@ def run_trainer_case():
     from virtex.factories import LRSchedulerFactory, OptimizerFactory, PretrainingModelFactory
 
     over = ["MODEL.TEXTUAL.NAME", "transdec_postnorm::L1_H128_A2_F256", "MODEL.TEXTUAL.DROPOUT", 0.0,
-            "OPTIM.WARMUP_STEPS", 3, "OPTIM.NUM_ITERATIONS", 20, "OPTIM.BATCH_SIZE", 2]
+            "OPTIM.WARMUP_STEPS", 3, "OPTIM.NUM_ITERATIONS", 20, "OPTIM.BATCH_SIZE", 2, "OPTIM.CNN_LR", 0.005]
     cfg = Config(os.path.join(ref_shim.REFERENCE_ROOT, "configs", "_base_bicaptioning_R_50_L1_H1024.yaml"), over)
     spec = O.Spec(hidden=128, layers=1, heads=2, ffn=256)
     state = O.synth_state(spec, 3)
@@ -130,7 +130,7 @@ def run_trainer_case():
                                  "textual.transformer.layers.0.linear1.weight")},
                 "final_bn_running_var_stem": bufs["visual.cnn.bn1.running_var"].clone(),
                 "spec": dict(hidden=128, layers=1, heads=2, ffn=256), "seed": 3,
-                "optim": dict(warmup_steps=3, num_iterations=20)},
+                "optim": dict(warmup_steps=3, num_iterations=20, cnn_lr=0.005)},
                os.path.join(GOLDEN_DIR, "trainer_r50_l1_h128_6steps.pt"))
 
 
@@ -141,9 +141,12 @@ def main():
     ref_shim.install()
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.manual_seed(0)
+    only = sys.argv[1:]
     for name, (spec_kw, batch_kw, seed) in CASES.items():
-        run_case(name, spec_kw, batch_kw, seed)
-    run_trainer_case()
+        if not only or name in only:
+            run_case(name, spec_kw, batch_kw, seed)
+    if not only or "trainer" in only:
+        run_trainer_case()
 
 
 if __name__ == "__main__":
