@@ -70,6 +70,91 @@ typedef struct VtxGemm {
 
 int vtx_gemm(const VtxGemm* g, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Backbone auxiliaries (NHWC bf16 activations).  Replace cuDNN BatchNorm / ATen elementwise + pooling kernels called by
+ * torchvision/models/resnet.py:143-163,268-276 and the im2col side of strided convolutions.
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* 7x7/stride 2/pad 3 stem: image fp32 NCHW -> cols bf16 [N*Ho*Wo, ldc], k = (kh*7+kw)*3 + c, zero padded to ldc */
+int vtx_stem_im2col(const float* img, void* cols, int N, int H, int W, int ldc, void* stream);
+/* 3x3 / pad 1 / given stride: x [N,H,W,C] -> cols [N*Ho*Wo, 9*C] (k = tap*C + c) and its adjoint */
+int vtx_im2col3x3(const void* x, void* cols, int N, int H, int W, int C, int stride, void* stream);
+int vtx_col2im3x3(const void* dcols, void* dx, int N, int H, int W, int C, int stride, void* stream);
+/* strided 1x1 (downsample) gather and its adjoint (dx += scatter(dxs)) */
+int vtx_subsample(const void* x, void* xs, int N, int H, int W, int C, int stride, void* stream);
+int vtx_upsample_add(const void* dxs, void* dx, int N, int H, int W, int C, int stride, void* stream);
+/* stats [2,C] (sum, sumsq from the GEMM epilogue) -> bnp [4,C] = mean, invstd, scale, shift; updates running stats */
+int vtx_bn_finalize(const float* stats, float count, const float* gamma, const float* beta, float* running_mean,
+                    float* running_var, int64_t* num_batches_tracked, float momentum, float eps, int training,
+                    float* bnp, int C, void* stream);
+/* out = act(y*scale + shift [+ res | + res*scale_r + shift_r]) */
+int vtx_bn_act(const void* y, const float* bnp, const void* res, const float* bnp_res, void* out, int64_t M, int C,
+               int relu, void* stream);
+int vtx_bn_relu_maxpool(const void* y, const float* bnp, void* out, uint8_t* idx, int N, int H, int W, int C,
+                        void* stream);
+int vtx_maxpool_bwd(const void* dpool, const uint8_t* idx, void* da, int N, int H, int W, int C, void* stream);
+/* BN backward in three steps: per-channel sums of dz and dz*xhat (dz = dA*[a>0]); coefficients + dgamma/dbeta;
+   dy = scale*(dz - mean(dz) - xhat*mean(dz*xhat)).  A second BN sharing dz (downsample branch) rides along. */
+int vtx_bn_bwd_reduce(const void* dA, const void* a, const void* y, const float* bnp, const void* y2,
+                      const float* bnp2, float* sums, float* sums2, int64_t M, int C, void* stream);
+int vtx_bn_bwd_finalize(const float* sums, const float* bnp, float count, float* coef, float* dgamma, float* dbeta,
+                        int C, void* stream);
+int vtx_bn_bwd_apply(const void* dA, const void* a, const void* y, const float* bnp, const float* coef, void* dy,
+                     const void* y2, const float* bnp2, const float* coef2, void* dy2, void* dz_out, int64_t M, int C,
+                     void* stream);
+/* conv weight layouts: fp32 OIHW <-> bf16 [O, (kh,kw,I)] GEMM operand; flipped/transposed dgrad operand */
+int vtx_conv_w_pack(const float* w, void* out, int O, int I, int KH, int KW, int ldk, void* stream);
+int vtx_conv_w_pack_dgrad(const float* w, void* out, int O, int I, void* stream);
+int vtx_conv_w_unpack_add(const float* dwp, float* grad, int O, int I, int KH, int KW, int ldk, void* stream);
+int vtx_cast_bf16(const float* in, void* out, int64_t n, void* stream);
+int vtx_nhwc_to_nchw_f32(const void* in, float* out, int N, int HW, int C, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Textual-head auxiliaries.  `seed` is a DEVICE pointer to the 64-bit dropout seed of the current step (so a captured
+ * CUDA graph can be replayed with fresh masks); `site` distinguishes dropout call sites; p = 0 disables dropout.
+ * Replace nn.Embedding/LayerNorm/Dropout (virtex/modules/embedding.py:58-73), F.scaled_dot_product_attention with
+ * the merged float mask (torch/nn/functional.py:6608-6682), GELU, nn.CrossEntropyLoss (virtex/models/captioning.py:69).
+ * ------------------------------------------------------------------------------------------------------------------ */
+int vtx_embed_fwd(const int64_t* tokens, const float* words, const float* positions, const float* gamma,
+                  const float* beta, float* z, float* stats, float* out, void* out_bf, int M, int T, int H, int pad,
+                  float eps, float p, const uint64_t* seed, uint32_t site, void* stream);
+int vtx_embed_bwd(const float* dy_a, const void* dy_b, const int64_t* tokens, const float* z, const float* stats,
+                  const float* gamma, float* d_words, float* d_pos, float* d_gamma, float* d_beta, int M, int T, int H,
+                  int pad, float p, const uint64_t* seed, uint32_t site, void* stream);
+/* z = res + dropout(branch); out = LN(z) (ln=1) or z (ln=0) */
+int vtx_add_ln_fwd(const float* res, const void* branch, const float* gamma, const float* beta, float* z, float* stats,
+                   float* out, void* out_bf, int M, int H, float eps, float p, const uint64_t* seed, uint32_t site,
+                   int ln, void* stream);
+int vtx_ln_bwd(const float* dy_a, const void* dy_b, const float* z, const float* stats, const float* gamma,
+               const float* d_skip, float* d_res, void* d_branch, float* d_gamma, float* d_beta, int M, int H, float p,
+               const uint64_t* seed, uint32_t site, int ln, void* stream);
+/* attention core, head_dim 64, Tq <= 32, Tk <= 64; causal=1: key j visible to query i iff j <= i and j < lengths[b] */
+int vtx_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,
+                 int64_t ldo, float* lse, int B, int heads, int Tq, int Tk, const int64_t* lengths, int causal,
+                 float p, const uint64_t* seed, uint32_t site, void* stream);
+int vtx_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* dout,
+                 int64_t ldo, const float* lse, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
+                 int B, int heads, int Tq, int Tk, const int64_t* lengths, int causal, float p, const uint64_t* seed,
+                 uint32_t site, void* stream);
+int vtx_gelu_dropout_fwd(const void* u, void* h, int64_t n, float p, const uint64_t* seed, uint32_t site, void* stream);
+int vtx_gelu_dropout_bwd(const void* dh, const void* u, void* du, int64_t n, float p, const uint64_t* seed,
+                         uint32_t site, void* stream);
+int vtx_count_valid(const int64_t* tokens, int B, int T, int pad, float* count, void* stream);
+/* logits bf16 [B*T, ldl]; loss += mean NLL over valid targets; write_grad: logits := dlogits in place */
+int vtx_cross_entropy(void* logits, int64_t ldl, const int64_t* tokens, int B, int T, int V, int pad,
+                      const float* count, float* loss, int write_grad, void* stream);
+int vtx_colsum(const void* X, int64_t ld, int M, int N, float* out, void* stream);
+int vtx_argmax_rows(const float* X, int64_t ld, int M, int N, int64_t* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Fused optimiser tail over flat fp32 arenas (scripts/pretrain_virtex.py:157-162; virtex/factories.py:529-545;
+ * virtex/optim/lookahead.py:82-102).  segs: device array of {int64 begin, int64 end, float lr, float wd}.
+ * ctl[0] = gradient scale (clip / world size), ctl[1] = gradient norm; hyper = {lr multiplier, first step, lookahead}.
+ * ------------------------------------------------------------------------------------------------------------------ */
+int vtx_sumsq(const float* x, int64_t n, float* out, void* stream);
+int vtx_clip_coef(const float* sumsq, int world_size, float max_norm, float* ctl, void* stream);
+int vtx_sgd_step(float* p, const float* g, float* mom, float* slow, void* p_bf, const void* segs, int nseg,
+                 const float* ctl, const float* hyper, float momentum, float la_alpha, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,654 @@
+// Memory-bound kernels of the ResNet backbone (NHWC bf16 activations, fp32 statistics).
+// They surround the tcgen05 GEMM (gemm_tc.cu): train-mode BatchNorm finalize/apply/backward, ReLU, residual add,
+// stem im2col + fused BN/ReLU/max-pool, strided-conv gathers, and conv-weight layout transforms.
+// Reference semantics: torchvision/models/resnet.py:143-163 (Bottleneck), :268-276 (stem), nn.BatchNorm2d train mode
+// (SURVEY.md Appendix C.2): biased variance for normalisation, unbiased for running_var, momentum 0.1, eps 1e-5.
+// All kernels are HBM-bound: 16-byte vector accesses along the contiguous channel dimension, grid-stride loops
+// sized to a multiple of the SM count.
+#include "vtx_common.cuh"
+#include "../../include/virtex_b200.h"
+
+namespace vtx {
+
+static inline int grid_for(long long work_items, int threads, int per_sm = 8) {
+  long long blocks = (work_items + threads - 1) / threads;
+  long long cap = (long long)vtx_num_sms() * per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+// ---------------------------------------------------------------------------------------------- stem im2col
+// image fp32 NCHW [N,3,H,W] -> cols bf16 [N*Ho*Wo, ldc], k = (kh*7 + kw)*3 + c for the 7x7/stride 2/pad 3 stem,
+// columns [147, ldc) zero.
+__global__ void stem_im2col_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ cols, int N, int H, int W,
+                                   int Ho, int Wo, int ldc) {
+  const long long total = (long long)N * Ho * Wo * (ldc / 8);
+  const int groups = ldc / 8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    const long long pos = i / groups;
+    const int wo = (int)(pos % Wo);
+    const int ho = (int)((pos / Wo) % Ho);
+    const int n = (int)(pos / ((long long)Wo * Ho));
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = g * 8 + j;
+      float x = 0.f;
+      if (k < 147) {
+        const int c = k % 3;
+        const int t = k / 3;
+        const int kw = t % 7, kh = t / 7;
+        const int h = ho * 2 - 3 + kh, w = wo * 2 - 3 + kw;
+        if (h >= 0 && h < H && w >= 0 && w < W) x = __ldg(img + (((long long)n * 3 + c) * H + h) * W + w);
+      }
+      v[j] = x;
+    }
+    *reinterpret_cast<bf16x8*>(cols + pos * ldc + g * 8) = pack8(v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- generic 3x3 im2col
+// x bf16 NHWC [N,H,W,C] -> cols [N*Ho*Wo, 9*C], k = (kh*3+kw)*C + c, pad 1, given stride.
+__global__ void im2col3x3_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ cols, int N, int H,
+                                 int W, int C, int Ho, int Wo, int stride) {
+  const int cg = C / 8;
+  const long long total = (long long)N * Ho * Wo * 9 * cg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    long long r = i / cg;
+    const int tap = (int)(r % 9);
+    const long long pos = r / 9;
+    const int wo = (int)(pos % Wo);
+    const int ho = (int)((pos / Wo) % Ho);
+    const int n = (int)(pos / ((long long)Wo * Ho));
+    const int kh = tap / 3, kw = tap % 3;
+    const int h = ho * stride - 1 + kh, w = wo * stride - 1 + kw;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (h >= 0 && h < H && w >= 0 && w < W)
+      v = *reinterpret_cast<const uint4*>(x + (((long long)n * H + h) * W + w) * C + g * 8);
+    *reinterpret_cast<uint4*>(cols + pos * (9LL * C) + (long long)tap * C + g * 8) = v;
+  }
+}
+
+// dcols [N*Ho*Wo, 9*C] -> dx [N,H,W,C]  (gather form: every input pixel sums the taps that touched it)
+__global__ void col2im3x3_kernel(const __nv_bfloat16* __restrict__ dcols, __nv_bfloat16* __restrict__ dx, int N, int H,
+                                 int W, int C, int Ho, int Wo, int stride) {
+  const int cg = C / 8;
+  const long long total = (long long)N * H * W * cg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    const long long pix = i / cg;
+    const int w = (int)(pix % W);
+    const int h = (int)((pix / W) % H);
+    const int n = (int)(pix / ((long long)W * H));
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int hn = h + 1 - kh;
+      if (hn < 0 || hn % stride != 0) continue;
+      const int ho = hn / stride;
+      if (ho >= Ho) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int wn = w + 1 - kw;
+        if (wn < 0 || wn % stride != 0) continue;
+        const int wo = wn / stride;
+        if (wo >= Wo) continue;
+        const long long pos = ((long long)n * Ho + ho) * Wo + wo;
+        const bf16x8 u = *reinterpret_cast<const bf16x8*>(dcols + pos * (9LL * C) + (long long)(kh * 3 + kw) * C + g * 8);
+        float f[8];
+        unpack8(u, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += f[j];
+      }
+    }
+    *reinterpret_cast<bf16x8*>(dx + pix * C + g * 8) = pack8(acc);
+  }
+}
+
+// xs[n,ho,wo,:] = x[n,ho*s,wo*s,:]
+__global__ void subsample_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ xs, int N, int H,
+                                 int W, int C, int Ho, int Wo, int stride) {
+  const int cg = C / 8;
+  const long long total = (long long)N * Ho * Wo * cg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    const long long pos = i / cg;
+    const int wo = (int)(pos % Wo);
+    const int ho = (int)((pos / Wo) % Ho);
+    const int n = (int)(pos / ((long long)Wo * Ho));
+    *reinterpret_cast<uint4*>(xs + pos * C + g * 8) =
+        *reinterpret_cast<const uint4*>(x + (((long long)n * H + ho * stride) * W + wo * stride) * C + g * 8);
+  }
+}
+
+// dx[n,ho*s,wo*s,:] += dxs[n,ho,wo,:]
+__global__ void upsample_add_kernel(const __nv_bfloat16* __restrict__ dxs, __nv_bfloat16* __restrict__ dx, int N, int H,
+                                    int W, int C, int Ho, int Wo, int stride) {
+  const int cg = C / 8;
+  const long long total = (long long)N * Ho * Wo * cg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    const long long pos = i / cg;
+    const int wo = (int)(pos % Wo);
+    const int ho = (int)((pos / Wo) % Ho);
+    const int n = (int)(pos / ((long long)Wo * Ho));
+    __nv_bfloat16* p = dx + (((long long)n * H + ho * stride) * W + wo * stride) * C + g * 8;
+    float a[8], b[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(p), a);
+    unpack8(*reinterpret_cast<const bf16x8*>(dxs + pos * C + g * 8), b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] += b[j];
+    *reinterpret_cast<bf16x8*>(p) = pack8(a);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- BatchNorm forward
+// stats [2,C] (sum, sumsq over `count` samples)  ->  bnp [4,C] = mean, invstd, scale = gamma*invstd, shift
+// training: also running_mean/var (momentum, unbiased var) and num_batches_tracked.  eval: statistics come from
+// the running buffers instead (stats may be null).
+__global__ void bn_finalize_kernel(const float* __restrict__ stats, float count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ rmean, float* __restrict__ rvar,
+                                   long long* __restrict__ nbt, float momentum, float eps, int training,
+                                   float* __restrict__ bnp, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && training && nbt != nullptr) *nbt += 1;
+  if (c >= C) return;
+  float mean, var;
+  if (training) {
+    mean = stats[c] / count;
+    var = fmaxf(stats[C + c] / count - mean * mean, 0.f);
+    rmean[c] = (1.f - momentum) * rmean[c] + momentum * mean;
+    rvar[c] = (1.f - momentum) * rvar[c] + momentum * var * (count / fmaxf(count - 1.f, 1.f));
+  } else {
+    mean = rmean[c];
+    var = rvar[c];
+  }
+  const float invstd = rsqrtf(var + eps);
+  const float sc = gamma[c] * invstd;
+  bnp[c] = mean;
+  bnp[C + c] = invstd;
+  bnp[2 * C + c] = sc;
+  bnp[3 * C + c] = beta[c] - mean * sc;
+}
+
+// a = act( y*scale + shift  [+ res  |  + res*scale2 + shift2] )
+__global__ void bn_act_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ bnp,
+                              const __nv_bfloat16* __restrict__ res, const float* __restrict__ bnp_res,
+                              __nv_bfloat16* __restrict__ out, long long M, int C, int relu) {
+  const int cg = C / 8;
+  const long long total = M * cg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    const int c0 = g * 8;
+    float v[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(y + i * 8), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = v[j] * __ldg(bnp + 2 * C + c0 + j) + __ldg(bnp + 3 * C + c0 + j);
+    if (res != nullptr) {
+      float r[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(res + i * 8), r);
+      if (bnp_res != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = r[j] * __ldg(bnp_res + 2 * C + c0 + j) + __ldg(bnp_res + 3 * C + c0 + j);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += r[j];
+    }
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    *reinterpret_cast<bf16x8*>(out + i * 8) = pack8(v);
+  }
+}
+
+// stem: pooled[n,ph,pw,:] = max over the 3x3/stride 2/pad 1 window of relu(y*scale+shift); idx = window slot of the max
+__global__ void bn_relu_maxpool_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ bnp,
+                                       __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ idx, int N, int H, int W,
+                                       int C, int Ho, int Wo) {
+  const int cg = C / 8;
+  const long long total = (long long)N * Ho * Wo * cg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    const int c0 = g * 8;
+    const long long pos = i / cg;
+    const int pw = (int)(pos % Wo);
+    const int ph = (int)((pos / Wo) % Ho);
+    const int n = (int)(pos / ((long long)Wo * Ho));
+    float sc[8], sh[8], best[8];
+    int bi[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sc[j] = __ldg(bnp + 2 * C + c0 + j);
+      sh[j] = __ldg(bnp + 3 * C + c0 + j);
+      best[j] = -INFINITY;
+      bi[j] = 0;
+    }
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int h = ph * 2 - 1 + kh;
+      if (h < 0 || h >= H) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int w = pw * 2 - 1 + kw;
+        if (w < 0 || w >= W) continue;
+        float v[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(y + (((long long)n * H + h) * W + w) * C + c0), v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          // the reference rounds the BN output and the ReLU output to bf16 before pooling
+          const float a = bf2f(f2bf(fmaxf(v[j] * sc[j] + sh[j], 0.f)));
+          if (a > best[j]) { best[j] = a; bi[j] = kh * 3 + kw; }
+        }
+      }
+    }
+    *reinterpret_cast<bf16x8*>(out + pos * C + c0) = pack8(best);
+    uint8_t b[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) b[j] = (uint8_t)bi[j];
+    *reinterpret_cast<uint2*>(idx + pos * C + c0) = *reinterpret_cast<uint2*>(b);
+  }
+}
+
+// da[n,h,w,:] = sum over pooled windows (ph,pw) whose argmax slot points at (h,w) of dpool[n,ph,pw,:]
+__global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dpool, const uint8_t* __restrict__ idx,
+                                   __nv_bfloat16* __restrict__ da, int N, int H, int W, int C, int Ho, int Wo) {
+  const int cg = C / 8;
+  const long long total = (long long)N * H * W * cg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    const int c0 = g * 8;
+    const long long pix = i / cg;
+    const int w = (int)(pix % W);
+    const int h = (int)((pix / W) % H);
+    const int n = (int)(pix / ((long long)W * H));
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int hn = h + 1 - kh;
+      if (hn < 0 || (hn & 1)) continue;
+      const int ph = hn >> 1;
+      if (ph >= Ho) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int wn = w + 1 - kw;
+        if (wn < 0 || (wn & 1)) continue;
+        const int pw = wn >> 1;
+        if (pw >= Wo) continue;
+        const long long pos = ((long long)n * Ho + ph) * Wo + pw;
+        const uint2 raw = *reinterpret_cast<const uint2*>(idx + pos * C + c0);
+        const uint8_t* b = reinterpret_cast<const uint8_t*>(&raw);
+        float d[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(dpool + pos * C + c0), d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (b[j] == kh * 3 + kw) acc[j] += d[j];
+      }
+    }
+    *reinterpret_cast<bf16x8*>(da + pix * C + c0) = pack8(acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- BatchNorm backward
+// sums[0,c] = sum_m dz, sums[1,c] = sum_m dz * xhat, with dz = dA * [a > 0] (a == null: no ReLU) and
+// xhat = (y - mean) * invstd.  Optionally the same for a second BN (y2, bnp2) sharing dz (downsample branch).
+template <int kTwo>
+__global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloat16* __restrict__ a,
+                                     const __nv_bfloat16* __restrict__ y, const float* __restrict__ bnp,
+                                     const __nv_bfloat16* __restrict__ y2, const float* __restrict__ bnp2,
+                                     float* __restrict__ sums, float* __restrict__ sums2, long long M, int C) {
+  extern __shared__ float red[];  // [rows_par][C][2 or 4]
+  const int cg = C / 8;
+  const int rows_par = blockDim.x / cg;  // rows handled in parallel by one CTA
+  const int g = threadIdx.x % cg;
+  const int rr = threadIdx.x / cg;
+  const int c0 = g * 8;
+  float s1[8], s2[8], t1[8], t2[8];
+  float mean[8], istd[8], mean2[8], istd2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    s1[j] = s2[j] = t1[j] = t2[j] = 0.f;
+    mean[j] = __ldg(bnp + c0 + j);
+    istd[j] = __ldg(bnp + C + c0 + j);
+    if (kTwo) {
+      mean2[j] = __ldg(bnp2 + c0 + j);
+      istd2[j] = __ldg(bnp2 + C + c0 + j);
+    }
+  }
+  if (rr < rows_par) {
+    for (long long m = (long long)blockIdx.x * rows_par + rr; m < M; m += (long long)gridDim.x * rows_par) {
+      const long long off = m * C + c0;
+      float d[8], yy[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(dA + off), d);
+      if (a != nullptr) {
+        float aa[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(a + off), aa);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] = aa[j] > 0.f ? d[j] : 0.f;
+      }
+      unpack8(*reinterpret_cast<const bf16x8*>(y + off), yy);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s1[j] += d[j];
+        s2[j] += d[j] * (yy[j] - mean[j]) * istd[j];
+      }
+      if (kTwo) {
+        unpack8(*reinterpret_cast<const bf16x8*>(y2 + off), yy);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          t1[j] += d[j];
+          t2[j] += d[j] * (yy[j] - mean2[j]) * istd2[j];
+        }
+      }
+    }
+  }
+  // cross-row reduction through shared memory, then one atomic per channel per CTA
+  const int per = kTwo ? 4 : 2;
+  if (rr < rows_par) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float* p = red + ((long long)rr * C + c0 + j) * per;
+      p[0] = s1[j];
+      p[1] = s2[j];
+      if (kTwo) { p[2] = t1[j]; p[3] = t2[j]; }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int r = 0; r < rows_par; ++r) {
+      const float* p = red + ((long long)r * C + c) * per;
+      acc[0] += p[0];
+      acc[1] += p[1];
+      if (kTwo) { acc[2] += p[2]; acc[3] += p[3]; }
+    }
+    atomicAdd(sums + c, acc[0]);
+    atomicAdd(sums + C + c, acc[1]);
+    if (kTwo) {
+      atomicAdd(sums2 + c, acc[2]);
+      atomicAdd(sums2 + C + c, acc[3]);
+    }
+  }
+}
+
+// sums [2,C] -> coef [3,C] = (scale, sum_dz/count, sum_dz_xhat/count);  dgamma += sum_dz_xhat, dbeta += sum_dz
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ sums, const float* __restrict__ bnp, float count,
+                                       float* __restrict__ coef, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                       int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float s1 = sums[c], s2 = sums[C + c];
+  coef[c] = bnp[2 * C + c];
+  coef[C + c] = s1 / count;
+  coef[2 * C + c] = s2 / count;
+  if (dgamma != nullptr) dgamma[c] += s2;
+  if (dbeta != nullptr) dbeta[c] += s1;
+}
+
+// dy = scale * (dz - m1 - xhat * m2);  optional second BN sharing dz;  optional dz output (identity shortcut grad)
+template <int kTwo>
+__global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloat16* __restrict__ a,
+                                    const __nv_bfloat16* __restrict__ y, const float* __restrict__ bnp,
+                                    const float* __restrict__ coef, __nv_bfloat16* __restrict__ dy,
+                                    const __nv_bfloat16* __restrict__ y2, const float* __restrict__ bnp2,
+                                    const float* __restrict__ coef2, __nv_bfloat16* __restrict__ dy2,
+                                    __nv_bfloat16* __restrict__ dz_out, long long M, int C) {
+  const int cg = C / 8;
+  const long long total = M * cg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % cg) * 8;
+    float d[8], yy[8], o[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(dA + i * 8), d);
+    if (a != nullptr) {
+      float aa[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(a + i * 8), aa);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d[j] = aa[j] > 0.f ? d[j] : 0.f;
+    }
+    unpack8(*reinterpret_cast<const bf16x8*>(y + i * 8), yy);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c0 + j;
+      const float xhat = (yy[j] - __ldg(bnp + c)) * __ldg(bnp + C + c);
+      o[j] = __ldg(coef + c) * (d[j] - __ldg(coef + C + c) - xhat * __ldg(coef + 2 * C + c));
+    }
+    *reinterpret_cast<bf16x8*>(dy + i * 8) = pack8(o);
+    if (kTwo) {
+      unpack8(*reinterpret_cast<const bf16x8*>(y2 + i * 8), yy);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = c0 + j;
+        const float xhat = (yy[j] - __ldg(bnp2 + c)) * __ldg(bnp2 + C + c);
+        o[j] = __ldg(coef2 + c) * (d[j] - __ldg(coef2 + C + c) - xhat * __ldg(coef2 + 2 * C + c));
+      }
+      *reinterpret_cast<bf16x8*>(dy2 + i * 8) = pack8(o);
+    }
+    if (dz_out != nullptr) *reinterpret_cast<bf16x8*>(dz_out + i * 8) = pack8(d);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- weight layouts
+// fp32 OIHW [O,I,KH,KW] -> bf16 [O, ldk] with k = (kh*KW + kw)*I + i   (columns >= KH*KW*I zero)
+__global__ void conv_w_pack_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int O, int I, int KH,
+                                   int KW, int ldk) {
+  const long long total = (long long)O * ldk;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(t % ldk);
+    const int o = (int)(t / ldk);
+    float v = 0.f;
+    if (k < KH * KW * I) {
+      const int i = k % I;
+      const int tap = k / I;
+      v = w[((long long)o * I + i) * KH * KW + tap];
+    }
+    out[t] = f2bf(v);
+  }
+}
+// fp32 OIHW [O,I,3,3] -> bf16 [I, 9*O] with k = ((2-kh)*3 + (2-kw))*O + o   (flipped + transposed: dgrad weights)
+__global__ void conv_w_pack_dgrad_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int O, int I) {
+  const long long total = (long long)I * 9 * O;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int o = (int)(t % O);
+    const int tapf = (int)((t / O) % 9);
+    const int i = (int)(t / (9LL * O));
+    const int tap = 8 - tapf;  // (2-kh)*3 + (2-kw)
+    out[t] = f2bf(w[((long long)o * I + i) * 9 + tap]);
+  }
+}
+// grad OIHW += dwp [O, ldk] (k = tap*I + i)
+__global__ void conv_w_unpack_add_kernel(const float* __restrict__ dwp, float* __restrict__ grad, int O, int I, int KH,
+                                         int KW, int ldk) {
+  const long long total = (long long)O * I * KH * KW;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int tap = (int)(t % (KH * KW));
+    const int i = (int)((t / (KH * KW)) % I);
+    const int o = (int)(t / ((long long)KH * KW * I));
+    grad[t] += dwp[(long long)o * ldk + (long long)tap * I + i];
+  }
+}
+__global__ void cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
+  const long long n4 = n / 4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(in)[i];
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&a);
+    u.y = *reinterpret_cast<uint32_t*>(&b);
+    reinterpret_cast<uint2*>(out)[i] = u;
+  }
+  for (long long i = n4 * 4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = f2bf(in[i]);
+}
+// NHWC bf16 [N,H,W,C] -> NCHW fp32 (the reference-shaped `visual_features` handed back to callers)
+__global__ void nhwc_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, int N, int HW,
+                                        int C) {
+  const long long total = (long long)N * HW * C;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(t % HW);
+    const int c = (int)((t / HW) % C);
+    const int n = (int)(t / ((long long)HW * C));
+    out[t] = bf2f(in[((long long)n * HW + p) * C + c]);
+  }
+}
+
+}  // namespace vtx
+
+using namespace vtx;
+#define STREAM reinterpret_cast<cudaStream_t>(stream)
+#define REQ(cond, msg) \
+  if (!(cond)) return set_error(VTX_EINVAL, "%s: %s", __func__, msg)
+
+extern "C" int vtx_stem_im2col(const float* img, void* cols, int N, int H, int W, int ldc, void* stream) {
+  REQ(img && cols && ldc >= 152 && ldc % 8 == 0, "bad arguments");
+  const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
+  const long long total = (long long)N * Ho * Wo * (ldc / 8);
+  stem_im2col_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>(img, (__nv_bfloat16*)cols, N, H, W, Ho, Wo, ldc);
+  return check_launch("stem_im2col");
+}
+extern "C" int vtx_im2col3x3(const void* x, void* cols, int N, int H, int W, int C, int stride, void* stream) {
+  REQ(x && cols && C % 8 == 0 && stride >= 1, "bad arguments");
+  const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  const long long total = (long long)N * Ho * Wo * 9 * (C / 8);
+  im2col3x3_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)cols, N, H, W, C,
+                                                             Ho, Wo, stride);
+  return check_launch("im2col3x3");
+}
+extern "C" int vtx_col2im3x3(const void* dcols, void* dx, int N, int H, int W, int C, int stride, void* stream) {
+  REQ(dcols && dx && C % 8 == 0 && stride >= 1, "bad arguments");
+  const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  const long long total = (long long)N * H * W * (C / 8);
+  col2im3x3_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>((const __nv_bfloat16*)dcols, (__nv_bfloat16*)dx, N, H, W,
+                                                             C, Ho, Wo, stride);
+  return check_launch("col2im3x3");
+}
+extern "C" int vtx_subsample(const void* x, void* xs, int N, int H, int W, int C, int stride, void* stream) {
+  REQ(x && xs && C % 8 == 0, "bad arguments");
+  const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  const long long total = (long long)N * Ho * Wo * (C / 8);
+  subsample_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)xs, N, H, W, C,
+                                                             Ho, Wo, stride);
+  return check_launch("subsample");
+}
+extern "C" int vtx_upsample_add(const void* dxs, void* dx, int N, int H, int W, int C, int stride, void* stream) {
+  REQ(dxs && dx && C % 8 == 0, "bad arguments");
+  const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  const long long total = (long long)N * Ho * Wo * (C / 8);
+  upsample_add_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>((const __nv_bfloat16*)dxs, (__nv_bfloat16*)dx, N, H, W,
+                                                                C, Ho, Wo, stride);
+  return check_launch("upsample_add");
+}
+extern "C" int vtx_bn_finalize(const float* stats, float count, const float* gamma, const float* beta, float* rmean,
+                               float* rvar, int64_t* nbt, float momentum, float eps, int training, float* bnp, int C,
+                               void* stream) {
+  REQ(gamma && beta && rmean && rvar && bnp && (stats || !training), "bad arguments");
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, STREAM>>>(stats, count, gamma, beta, rmean, rvar, (long long*)nbt,
+                                                          momentum, eps, training, bnp, C);
+  return check_launch("bn_finalize");
+}
+extern "C" int vtx_bn_act(const void* y, const float* bnp, const void* res, const float* bnp_res, void* out,
+                          int64_t M, int C, int relu, void* stream) {
+  REQ(y && bnp && out && C % 8 == 0, "bad arguments");
+  bn_act_kernel<<<grid_for(M * (C / 8), 256), 256, 0, STREAM>>>((const __nv_bfloat16*)y, bnp,
+                                                                (const __nv_bfloat16*)res, bnp_res,
+                                                                (__nv_bfloat16*)out, M, C, relu);
+  return check_launch("bn_act");
+}
+extern "C" int vtx_bn_relu_maxpool(const void* y, const float* bnp, void* out, uint8_t* idx, int N, int H, int W, int C,
+                                   void* stream) {
+  REQ(y && bnp && out && idx && C % 8 == 0, "bad arguments");
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const long long total = (long long)N * Ho * Wo * (C / 8);
+  bn_relu_maxpool_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>((const __nv_bfloat16*)y, bnp, (__nv_bfloat16*)out,
+                                                                   idx, N, H, W, C, Ho, Wo);
+  return check_launch("bn_relu_maxpool");
+}
+extern "C" int vtx_maxpool_bwd(const void* dpool, const uint8_t* idx, void* da, int N, int H, int W, int C,
+                               void* stream) {
+  REQ(dpool && idx && da && C % 8 == 0, "bad arguments");
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const long long total = (long long)N * H * W * (C / 8);
+  maxpool_bwd_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>((const __nv_bfloat16*)dpool, idx, (__nv_bfloat16*)da, N,
+                                                               H, W, C, Ho, Wo);
+  return check_launch("maxpool_bwd");
+}
+extern "C" int vtx_bn_bwd_reduce(const void* dA, const void* a, const void* y, const float* bnp, const void* y2,
+                                 const float* bnp2, float* sums, float* sums2, int64_t M, int C, void* stream) {
+  REQ(dA && y && bnp && sums && C % 8 == 0 && C / 8 <= 256, "bad arguments");
+  const int threads = 256;
+  const int rows_par = threads / (C / 8);
+  const bool two = (y2 != nullptr);
+  const size_t smem = (size_t)rows_par * C * (two ? 4 : 2) * sizeof(float);
+  long long blocks = (M + rows_par - 1) / rows_par;
+  const long long cap = (long long)vtx_num_sms() * 4;
+  if (blocks > cap) blocks = cap;
+  if (two) {
+    REQ(bnp2 && sums2, "second BN needs bnp2/sums2");
+    bn_bwd_reduce_kernel<1><<<(int)blocks, threads, smem, STREAM>>>((const __nv_bfloat16*)dA, (const __nv_bfloat16*)a,
+                                                                    (const __nv_bfloat16*)y, bnp,
+                                                                    (const __nv_bfloat16*)y2, bnp2, sums, sums2, M, C);
+  } else {
+    bn_bwd_reduce_kernel<0><<<(int)blocks, threads, smem, STREAM>>>((const __nv_bfloat16*)dA, (const __nv_bfloat16*)a,
+                                                                    (const __nv_bfloat16*)y, bnp, nullptr, nullptr,
+                                                                    sums, nullptr, M, C);
+  }
+  return check_launch("bn_bwd_reduce");
+}
+extern "C" int vtx_bn_bwd_finalize(const float* sums, const float* bnp, float count, float* coef, float* dgamma,
+                                   float* dbeta, int C, void* stream) {
+  REQ(sums && bnp && coef, "bad arguments");
+  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, STREAM>>>(sums, bnp, count, coef, dgamma, dbeta, C);
+  return check_launch("bn_bwd_finalize");
+}
+extern "C" int vtx_bn_bwd_apply(const void* dA, const void* a, const void* y, const float* bnp, const float* coef,
+                                void* dy, const void* y2, const float* bnp2, const float* coef2, void* dy2,
+                                void* dz_out, int64_t M, int C, void* stream) {
+  REQ(dA && y && bnp && coef && dy && C % 8 == 0, "bad arguments");
+  const int grid = grid_for(M * (C / 8), 256);
+  if (y2 != nullptr) {
+    REQ(bnp2 && coef2 && dy2, "second BN needs bnp2/coef2/dy2");
+    bn_bwd_apply_kernel<1><<<grid, 256, 0, STREAM>>>((const __nv_bfloat16*)dA, (const __nv_bfloat16*)a,
+                                                     (const __nv_bfloat16*)y, bnp, coef, (__nv_bfloat16*)dy,
+                                                     (const __nv_bfloat16*)y2, bnp2, coef2, (__nv_bfloat16*)dy2,
+                                                     (__nv_bfloat16*)dz_out, M, C);
+  } else {
+    bn_bwd_apply_kernel<0><<<grid, 256, 0, STREAM>>>((const __nv_bfloat16*)dA, (const __nv_bfloat16*)a,
+                                                     (const __nv_bfloat16*)y, bnp, coef, (__nv_bfloat16*)dy, nullptr,
+                                                     nullptr, nullptr, nullptr, (__nv_bfloat16*)dz_out, M, C);
+  }
+  return check_launch("bn_bwd_apply");
+}
+extern "C" int vtx_conv_w_pack(const float* w, void* out, int O, int I, int KH, int KW, int ldk, void* stream) {
+  REQ(w && out && ldk >= KH * KW * I, "bad arguments");
+  conv_w_pack_kernel<<<grid_for((long long)O * ldk, 256), 256, 0, STREAM>>>(w, (__nv_bfloat16*)out, O, I, KH, KW, ldk);
+  return check_launch("conv_w_pack");
+}
+extern "C" int vtx_conv_w_pack_dgrad(const float* w, void* out, int O, int I, void* stream) {
+  REQ(w && out, "bad arguments");
+  conv_w_pack_dgrad_kernel<<<grid_for((long long)O * I * 9, 256), 256, 0, STREAM>>>(w, (__nv_bfloat16*)out, O, I);
+  return check_launch("conv_w_pack_dgrad");
+}
+extern "C" int vtx_conv_w_unpack_add(const float* dwp, float* grad, int O, int I, int KH, int KW, int ldk,
+                                     void* stream) {
+  REQ(dwp && grad && ldk >= KH * KW * I, "bad arguments");
+  conv_w_unpack_add_kernel<<<grid_for((long long)O * I * KH * KW, 256), 256, 0, STREAM>>>(dwp, grad, O, I, KH, KW, ldk);
+  return check_launch("conv_w_unpack_add");
+}
+extern "C" int vtx_cast_bf16(const float* in, void* out, int64_t n, void* stream) {
+  REQ(in && out && n >= 0, "bad arguments");
+  if (n == 0) return VTX_OK;
+  cast_bf16_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, STREAM>>>(in, (__nv_bfloat16*)out, n);
+  return check_launch("cast_bf16");
+}
+extern "C" int vtx_nhwc_to_nchw_f32(const void* in, float* out, int N, int HW, int C, void* stream) {
+  REQ(in && out, "bad arguments");
+  nhwc_to_nchw_f32_kernel<<<grid_for((long long)N * HW * C, 256), 256, 0, STREAM>>>((const __nv_bfloat16*)in, out, N,
+                                                                                   HW, C);
+  return check_launch("nhwc_to_nchw_f32");
+}
