@@ -1,0 +1,69 @@
+"""CPU-side checks: module tree / state_dict compatibility, C-ABI library loads and exports every declared symbol."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from oracle import virtex_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _build(spec):
+    from virtex_b200.models import VirTexModel
+    from virtex_b200.modules import TorchvisionVisualBackbone, TransformerDecoderTextualHead
+    visual = TorchvisionVisualBackbone(spec.backbone, visual_feature_size=spec.visual_feature_size)
+    textual = TransformerDecoderTextualHead(
+        visual_feature_size=spec.visual_feature_size, vocab_size=spec.vocab, hidden_size=spec.hidden,
+        num_layers=spec.layers, attention_heads=spec.heads, feedforward_size=spec.ffn, dropout=0.1,
+        norm_first=spec.norm_first, max_caption_length=spec.max_len, padding_idx=spec.pad)
+    return VirTexModel(visual, textual)
+
+
+def test_state_dict_matches_reference_key_set():
+    spec = O.Spec()
+    model = _build(spec)
+    ref_sd = O.to_reference_state_dict(O.synth_state(spec, 0), spec)
+    sd = model.state_dict()
+    assert set(sd) == set(ref_sd)
+    assert len(sd) == 370
+    for k, v in ref_sd.items():
+        assert tuple(sd[k].shape) == tuple(v.shape), k
+    assert sum(p.numel() for p in model.parameters()) == 69_482_320
+    assert len(list(model.parameters())) == 202
+    model.load_state_dict(ref_sd, strict=True)
+
+
+def test_weight_sharing_and_init():
+    spec = O.Spec(hidden=128, layers=2, heads=2, ffn=256)
+    m = _build(spec)
+    assert m.backward_textual.embedding is m.textual.embedding
+    assert m.backward_textual.visual_projection is m.textual.visual_projection
+    assert m.backward_textual.output is m.textual.output
+    assert m.textual.output.weight is m.textual.embedding.words.weight
+    assert m.backward_textual.transformer is not m.textual.transformer
+    assert torch.all(m.textual.embedding.words.weight[0] == 0)
+    # zero_init_residual
+    assert torch.all(m.visual.cnn.layer1[0].bn3.weight == 0)
+    assert abs(m.textual.transformer.layers[0].linear1.weight.std().item() - 0.02) < 2e-3
+
+
+def test_no_cpu_fallback():
+    spec = O.Spec(hidden=128, layers=1, heads=2, ffn=256)
+    m = _build(spec)
+    batch = O.synth_batch(2, 0)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m(batch)
+
+
+def test_library_exports_every_declared_symbol():
+    from virtex_b200 import lib as L, ops
+    header = open(os.path.join(ROOT, "include", "virtex_b200.h")).read()
+    declared = set(re.findall(r"\b(vtx_[a-z0-9_]+)\s*\(", header))
+    so = ctypes.CDLL(L.LIB_PATH)
+    for name in declared:
+        assert hasattr(so, name), f"{name} declared in include/virtex_b200.h but not exported"
+    assert declared == set(ops.exported_symbols())
+    assert so.vtx_version() >= 100

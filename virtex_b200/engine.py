@@ -1,0 +1,702 @@
+"""Execution engine of the bicaptioning step: schedules the C-ABI kernels over pre-allocated HBM buffers.
+
+This replaces, for the hot path, what autograd + cuDNN + cuBLASLt + ATen do for the reference
+(`virtex/models/captioning.py:99-143` forward; its autograd backward).  One `Engine` owns
+
+  * a flat fp32 parameter arena (the modules' nn.Parameters are re-pointed to views of it), a flat fp32 gradient arena
+    of identical layout (what the data-parallel all-reduce and the fused optimiser consume), and a flat bf16 mirror of
+    the parameters (the GEMM B operands) plus packed bf16 layouts for the 3x3 / 7x7 convolution weights;
+  * every activation / workspace buffer, allocated once per (batch, caption length) shape -- no allocation, no host
+    synchronisation and no Python-side tensor math inside a step, so a whole step can be captured in a CUDA graph.
+
+Data layout in HBM: backbone activations NHWC bf16 (a conv output is a row-major [N*H*W, C] matrix: 1x1 convs are
+GEMMs as-is, 3x3/stride-1 convs are implicit GEMMs through 4-D TMA boxes), BN statistics / affine parameters fp32,
+decoder residual stream fp32 with bf16 shadows feeding the GEMMs, logits bf16 (fp32 only for eval argmax).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+from torch import nn
+
+from . import ops
+from .ops import call, gemm, _p, _stream
+
+BF16, F32 = torch.bfloat16, torch.float32
+_ALIGN = 64  # arena alignment in elements (256 B for fp32, 128 B for bf16: TMA base pointers need 16 B)
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+class Arena:
+    """Flat fp32 parameter / gradient storage with a bf16 mirror; parameters become views into it."""
+
+    def __init__(self, named_params: List[Tuple[str, nn.Parameter]], device):
+        self.device = device
+        self.names: List[str] = []
+        self.offsets: Dict[str, int] = {}
+        self.numels: Dict[str, int] = {}
+        self.shapes: Dict[str, torch.Size] = {}
+        off = 0
+        seen = {}
+        for name, p in named_params:
+            if id(p) in seen:
+                continue
+            seen[id(p)] = name
+            self.names.append(name)
+            self.offsets[name] = off
+            self.numels[name] = p.numel()
+            self.shapes[name] = p.shape
+            off = _round_up(off + p.numel(), _ALIGN)
+        self.total = off
+        self.params = torch.zeros(off, dtype=F32, device=device)
+        self.grads = torch.zeros(off, dtype=F32, device=device)
+        self.mirror = torch.zeros(off, dtype=BF16, device=device)
+        self._param_objs = {seen[id(p)]: p for _, p in named_params}
+        with torch.no_grad():
+            for name in self.names:
+                p = self._param_objs[name]
+                v = self.view(self.params, name)
+                v.copy_(p.data.to(device=device, dtype=F32))
+                p.data = v
+                p.grad = None
+
+    def view(self, flat, name):
+        o = self.offsets[name]
+        return flat[o:o + self.numels[name]].view(self.shapes[name])
+
+    def p(self, name):
+        return self.view(self.params, name)
+
+    def g(self, name):
+        return self.view(self.grads, name)
+
+    def w(self, name):
+        return self.view(self.mirror, name)
+
+    def intact(self):
+        """True while every parameter still aliases the arena (a `.to()` / `.half()` on the module breaks it)."""
+        base, end = self.params.data_ptr(), self.params.data_ptr() + self.total * 4
+        for name in (self.names[0], self.names[-1]):
+            ptr = self._param_objs[name].data_ptr()
+            if not (base <= ptr < end):
+                return False
+        return True
+
+    def refresh_mirror(self):
+        call("vtx_cast_bf16", self.params.data_ptr(), self.mirror.data_ptr(), self.total, _stream())
+
+
+class _Workspace:
+    """Named device buffers that only ever grow: after the first step of a given shape nothing is allocated."""
+
+    def __init__(self, device):
+        self.device = device
+        self.flat: Dict[str, torch.Tensor] = {}
+
+    def get(self, name, shape, dtype):
+        shape = tuple(int(s) for s in shape)
+        n = 1
+        for s in shape:
+            n *= s
+        t = self.flat.get(name)
+        if t is None or t.dtype != dtype or t.numel() < n:
+            t = torch.empty(max(n, 1), dtype=dtype, device=self.device)
+            self.flat[name] = t
+        return t[:n].view(shape)
+
+    def nbytes(self):
+        return sum(t.numel() * t.element_size() for t in self.flat.values())
+
+
+class Engine:
+    """Forward/backward of (backbone) + (forward head) + (backward head) on one GPU.  Any part may be absent."""
+
+    def __init__(self, visual=None, textual=None, backward_textual=None, prefix_map=None):
+        self.visual, self.textual, self.backward_textual = visual, textual, backward_textual
+        named: List[Tuple[str, nn.Parameter]] = []
+        if visual is not None:
+            named += [("visual." + n, p) for n, p in visual.named_parameters()]
+        if textual is not None:
+            named += [("textual." + n, p) for n, p in textual.named_parameters()]
+        if backward_textual is not None:
+            named += [("backward_textual." + n, p) for n, p in backward_textual.named_parameters()]
+        dev = None
+        for _, p in named:
+            dev = p.device
+            break
+        if dev is None or dev.type != "cuda":
+            raise RuntimeError("virtex_b200 has no CPU path: move the model to a CUDA device first (model.cuda())")
+        self.device = dev
+        self.arena = Arena(named, dev)
+        self.ws = _Workspace(dev)
+        self.buffers: Dict[str, torch.Tensor] = {}
+        if visual is not None:
+            self.buffers.update({"visual." + n: b for n, b in visual.named_buffers()})
+        head = textual if textual is not None else backward_textual
+        self.pad = head.padding_idx if head is not None else 0
+        self.seed = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.loss = torch.zeros(2, dtype=F32, device=dev)       # per-direction mean NLL
+        self.count = torch.zeros(2, dtype=F32, device=dev)      # per-direction number of valid targets
+        self._packed: Dict[str, torch.Tensor] = {}
+        self._tape = None
+        self._weights_fresh = False
+        self._build_backbone_plan()
+
+    # ------------------------------------------------------------------------------------------------ parameters
+    def P(self, name):
+        return self.arena.p(name)
+
+    def W(self, name):
+        return self.arena.w(name)
+
+    def G(self, name):
+        return self.arena.g(name)
+
+    def mark_weights_dirty(self):
+        self._weights_fresh = False
+
+    def _build_backbone_plan(self):
+        self.blocks = []
+        if self.visual is None:
+            return
+        cnn = self.visual.cnn
+        for li in range(1, 5):
+            layer = getattr(cnn, f"layer{li}")
+            for bi, blk in enumerate(layer):
+                self.blocks.append((f"visual.cnn.layer{li}.{bi}", blk))
+
+    def prepare_weights(self, mirror=True):
+        """bf16 mirror of all parameters + packed GEMM layouts of the k>1 convolution weights."""
+        if mirror:
+            self.arena.refresh_mirror()
+        if self.visual is not None:
+            s = _stream()
+            w = self.P("visual.cnn.conv1.weight")
+            pk = self._pack_buf("visual.cnn.conv1.weight", (64, 160))
+            call("vtx_conv_w_pack", w.data_ptr(), pk.data_ptr(), 64, 3, 7, 7, 160, s)
+            for name, blk in self.blocks:
+                w = self.P(name + ".conv2.weight")
+                planes = w.shape[0]
+                pk = self._pack_buf(name + ".conv2.weight", (planes, 9 * planes))
+                call("vtx_conv_w_pack", w.data_ptr(), pk.data_ptr(), planes, planes, 3, 3, 9 * planes, s)
+                if blk.stride == 1:
+                    pd = self._pack_buf(name + ".conv2.weight#dgrad", (planes, 9 * planes))
+                    call("vtx_conv_w_pack_dgrad", w.data_ptr(), pd.data_ptr(), planes, planes, s)
+        self._weights_fresh = True
+
+    def _pack_buf(self, key, shape):
+        t = self._packed.get(key)
+        if t is None:
+            t = torch.empty(shape, dtype=BF16, device=self.device)
+            self._packed[key] = t
+        return t
+
+    # ------------------------------------------------------------------------------------------------ backbone fwd
+    def _bn_fwd(self, y, bn_name, M, C, training, stats):
+        bnp = self.ws.get("bnp:" + bn_name, (4, C), F32)
+        nbt = self.buffers[bn_name + ".num_batches_tracked"]
+        call("vtx_bn_finalize", _p(stats), float(M), self.P(bn_name + ".weight").data_ptr(),
+             self.P(bn_name + ".bias").data_ptr(), self.buffers[bn_name + ".running_mean"].data_ptr(),
+             self.buffers[bn_name + ".running_var"].data_ptr(), nbt.data_ptr(), 0.1, 1e-5, int(training),
+             bnp.data_ptr(), C, _stream())
+        return bnp
+
+    def _stats_slab(self, training):
+        """One zeroed fp32 slab per step holding every BN's [2,C] sum/sumsq (fwd) and [2,C] dz sums (bwd)."""
+        total = 2 * 64 * 2
+        for name, blk in self.blocks:
+            planes = blk.conv1.weight.shape[0]
+            total += 2 * 2 * (planes + planes + 4 * planes + (4 * planes if blk.downsample is not None else 0))
+        slab = self.ws.get("bn_slab", (total,), F32)
+        slab.zero_()
+        self._slab, self._slab_off = slab, 0
+        return slab
+
+    def _slab_take(self, n):
+        t = self._slab[self._slab_off:self._slab_off + n]
+        self._slab_off += n
+        return t
+
+    def backbone_forward(self, image: torch.Tensor, training: bool):
+        """image fp32 NCHW [B,3,H,W] -> NHWC bf16 feature matrix [B*h*w, 2048]; fills the tape used by backward."""
+        if not self._weights_fresh:
+            self.prepare_weights()
+        if self.visual is not None and getattr(self.visual, "frozen", False):
+            training = False
+        B, _, H, W = image.shape
+        s = _stream()
+        ws = self.ws
+        self._stats_slab(training)
+        tape = {"B": B, "blocks": [], "training": training}
+        # ---- stem: im2col -> GEMM(+stats) -> BN finalize -> BN+ReLU+maxpool
+        Ho, Wo = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
+        M0 = B * Ho * Wo
+        cols = ws.get("stem.cols", (M0, 160), BF16)
+        call("vtx_stem_im2col", image.data_ptr(), cols.data_ptr(), B, H, W, 160, s)
+        y0 = ws.get("stem.y", (M0, 64), BF16)
+        st = self._slab_take(128) if training else None
+        gemm(cols, self._packed["visual.cnn.conv1.weight"], y0, M0, 64, 160, stats=st)
+        bnp0 = self._bn_fwd(y0, "visual.cnn.bn1", M0, 64, training, st)
+        Hp, Wp = (Ho - 1) // 2 + 1, (Wo - 1) // 2 + 1
+        x = ws.get("stem.pool", (B * Hp * Wp, 64), BF16)
+        idx = ws.get("stem.idx", (B * Hp * Wp, 64), torch.uint8)
+        call("vtx_bn_relu_maxpool", y0.data_ptr(), bnp0.data_ptr(), x.data_ptr(), idx.data_ptr(), B, Ho, Wo, 64, s)
+        tape["stem"] = dict(cols=cols, y=y0, bnp=bnp0, idx=idx, Ho=Ho, Wo=Wo, Hp=Hp, Wp=Wp, M=M0)
+        Hc, Wc, Cin = Hp, Wp, 64
+        # ---- bottleneck blocks
+        for name, blk in self.blocks:
+            planes = blk.conv1.weight.shape[0]
+            stride = blk.stride
+            Hn, Wn = (Hc - 1) // stride + 1, (Wc - 1) // stride + 1
+            Min, Mout = B * Hc * Wc, B * Hn * Wn
+            rec = dict(name=name, x=x, Hin=Hc, Win=Wc, Hout=Hn, Wout=Wn, Cin=Cin, planes=planes, stride=stride,
+                       Min=Min, Mout=Mout, has_ds=blk.downsample is not None)
+            # conv1 1x1
+            y1 = ws.get(name + ".y1", (Min, planes), BF16)
+            st1 = self._slab_take(2 * planes) if training else None
+            gemm(x, self.W(name + ".conv1.weight").view(planes, Cin), y1, Min, planes, Cin, stats=st1)
+            bnp1 = self._bn_fwd(y1, name + ".bn1", Min, planes, training, st1)
+            a1 = ws.get(name + ".a1", (Min, planes), BF16)
+            call("vtx_bn_act", y1.data_ptr(), bnp1.data_ptr(), 0, 0, a1.data_ptr(), Min, planes, 1, s)
+            # conv2 3x3 (stride)
+            y2 = ws.get(name + ".y2", (Mout, planes), BF16)
+            st2 = self._slab_take(2 * planes) if training else None
+            w2 = self._packed[name + ".conv2.weight"]
+            if stride == 1 and planes % 64 == 0:
+                gemm(a1, w2, y2, Mout, planes, 9 * planes, lda=planes, stats=st2, conv=(B, Hc, Wc, planes), conv_mode=1)
+                rec["cols2"] = None
+            else:
+                cols2 = ws.get(name + ".cols2", (Mout, 9 * planes), BF16)
+                call("vtx_im2col3x3", a1.data_ptr(), cols2.data_ptr(), B, Hc, Wc, planes, stride, s)
+                gemm(cols2, w2, y2, Mout, planes, 9 * planes, stats=st2)
+                rec["cols2"] = cols2
+            bnp2 = self._bn_fwd(y2, name + ".bn2", Mout, planes, training, st2)
+            a2 = ws.get(name + ".a2", (Mout, planes), BF16)
+            call("vtx_bn_act", y2.data_ptr(), bnp2.data_ptr(), 0, 0, a2.data_ptr(), Mout, planes, 1, s)
+            # conv3 1x1
+            C4 = 4 * planes
+            y3 = ws.get(name + ".y3", (Mout, C4), BF16)
+            st3 = self._slab_take(2 * C4) if training else None
+            gemm(a2, self.W(name + ".conv3.weight").view(C4, planes), y3, Mout, C4, planes, stats=st3)
+            bnp3 = self._bn_fwd(y3, name + ".bn3", Mout, C4, training, st3)
+            out = ws.get(name + ".out", (Mout, C4), BF16)
+            if blk.downsample is not None:
+                if stride == 1:
+                    xs = x
+                else:
+                    xs = ws.get(name + ".xs", (Mout, Cin), BF16)
+                    call("vtx_subsample", x.data_ptr(), xs.data_ptr(), B, Hc, Wc, Cin, stride, s)
+                yd = ws.get(name + ".yd", (Mout, C4), BF16)
+                std = self._slab_take(2 * C4) if training else None
+                gemm(xs, self.W(name + ".downsample.0.weight").view(C4, Cin), yd, Mout, C4, Cin, stats=std)
+                bnpd = self._bn_fwd(yd, name + ".downsample.1", Mout, C4, training, std)
+                call("vtx_bn_act", y3.data_ptr(), bnp3.data_ptr(), yd.data_ptr(), bnpd.data_ptr(), out.data_ptr(),
+                     Mout, C4, 1, s)
+                rec.update(xs=xs, yd=yd, bnpd=bnpd)
+            else:
+                call("vtx_bn_act", y3.data_ptr(), bnp3.data_ptr(), x.data_ptr(), 0, out.data_ptr(), Mout, C4, 1, s)
+            rec.update(y1=y1, bnp1=bnp1, a1=a1, y2=y2, bnp2=bnp2, a2=a2, y3=y3, bnp3=bnp3, out=out)
+            tape["blocks"].append(rec)
+            x, Hc, Wc, Cin = out, Hn, Wn, C4
+        tape["feat"] = x
+        tape["hw"] = (Hc, Wc)
+        tape["C"] = Cin
+        self._tape = tape
+        return x, Hc, Wc
+
+    # ------------------------------------------------------------------------------------------------ backbone bwd
+    def _wgrad(self, dY, X, dW, n_out, k_in, m_rows):
+        """dW[n_out, k_in] (fp32, += ) = dY[m_rows, n_out]^T . X[m_rows, k_in]   (both operands MN-major, split-K)."""
+        tiles = ((n_out + 127) // 128) * ((k_in + 255) // 256)
+        sk = ops.split_k_for(tiles, (m_rows + 63) // 64)
+        gemm(dY, X, dW, n_out, k_in, m_rows, a_mn=1, b_mn=1, atomic=True, split_k=sk, ldd=k_in, out_f32=True)
+
+    def _bn_bwd(self, dA, a, y, bnp, bn_name, M, C, dy, two=None, dz_out=None):
+        """dA -> dy through (ReLU mask from `a`) + train-mode BN; two = (y2, bnp2, bn2_name, dy2) shares dz."""
+        s = _stream()
+        sums = self._slab_take(2 * C)
+        coef = self.ws.get("coef:" + bn_name, (3, C), F32)
+        if two is None:
+            call("vtx_bn_bwd_reduce", dA.data_ptr(), _p(a), y.data_ptr(), bnp.data_ptr(), 0, 0, sums.data_ptr(), 0,
+                 M, C, s)
+            call("vtx_bn_bwd_finalize", sums.data_ptr(), bnp.data_ptr(), float(M), coef.data_ptr(),
+                 self.G(bn_name + ".weight").data_ptr(), self.G(bn_name + ".bias").data_ptr(), C, s)
+            call("vtx_bn_bwd_apply", dA.data_ptr(), _p(a), y.data_ptr(), bnp.data_ptr(), coef.data_ptr(),
+                 dy.data_ptr(), 0, 0, 0, 0, _p(dz_out), M, C, s)
+        else:
+            y2, bnp2, bn2_name, dy2 = two
+            sums2 = self._slab_take(2 * C)
+            coef2 = self.ws.get("coef:" + bn2_name, (3, C), F32)
+            call("vtx_bn_bwd_reduce", dA.data_ptr(), _p(a), y.data_ptr(), bnp.data_ptr(), y2.data_ptr(),
+                 bnp2.data_ptr(), sums.data_ptr(), sums2.data_ptr(), M, C, s)
+            call("vtx_bn_bwd_finalize", sums.data_ptr(), bnp.data_ptr(), float(M), coef.data_ptr(),
+                 self.G(bn_name + ".weight").data_ptr(), self.G(bn_name + ".bias").data_ptr(), C, s)
+            call("vtx_bn_bwd_finalize", sums2.data_ptr(), bnp2.data_ptr(), float(M), coef2.data_ptr(),
+                 self.G(bn2_name + ".weight").data_ptr(), self.G(bn2_name + ".bias").data_ptr(), C, s)
+            call("vtx_bn_bwd_apply", dA.data_ptr(), _p(a), y.data_ptr(), bnp.data_ptr(), coef.data_ptr(),
+                 dy.data_ptr(), y2.data_ptr(), bnp2.data_ptr(), coef2.data_ptr(), dy2.data_ptr(), _p(dz_out), M, C, s)
+
+    def backbone_backward(self, dfeat: torch.Tensor):
+        """dfeat bf16 [B*h*w, C]: gradient w.r.t. the backbone output.  Accumulates into the gradient arena."""
+        tape = self._tape
+        if not tape["training"]:
+            return  # frozen backbone
+        B = tape["B"]
+        s = _stream()
+        ws = self.ws
+        dOut = dfeat
+        scratch_i = 0
+        for rec in reversed(tape["blocks"]):
+            name, planes, Cin, stride = rec["name"], rec["planes"], rec["Cin"], rec["stride"]
+            Min, Mout, C4 = rec["Min"], rec["Mout"], 4 * rec["planes"]
+            Hc, Wc, Hn, Wn = rec["Hin"], rec["Win"], rec["Hout"], rec["Wout"]
+            # ---- block output: ReLU mask + bn3 (+ downsample BN) backward
+            dy3 = ws.get("bwd.dy3", (Mout, C4), BF16)
+            if rec["has_ds"]:
+                dyd = ws.get("bwd.dyd", (Mout, C4), BF16)
+                self._bn_bwd(dOut, rec["out"], rec["y3"], rec["bnp3"], name + ".bn3", Mout, C4, dy3,
+                             two=(rec["yd"], rec["bnpd"], name + ".downsample.1", dyd))
+                dz = None
+            else:
+                dz = ws.get("bwd.dz", (Mout, C4), BF16)
+                self._bn_bwd(dOut, rec["out"], rec["y3"], rec["bnp3"], name + ".bn3", Mout, C4, dy3, dz_out=dz)
+            # ---- conv3 (1x1): wgrad + dgrad
+            self._wgrad(dy3, rec["a2"], self.G(name + ".conv3.weight"), C4, planes, Mout)
+            da2 = ws.get("bwd.da2", (Mout, planes), BF16)
+            gemm(dy3, self.W(name + ".conv3.weight").view(C4, planes), da2, Mout, planes, C4, b_mn=1)
+            # ---- bn2 + ReLU backward
+            dy2 = ws.get("bwd.dy2", (Mout, planes), BF16)
+            self._bn_bwd(da2, rec["a2"], rec["y2"], rec["bnp2"], name + ".bn2", Mout, planes, dy2)
+            # ---- conv2 (3x3): wgrad + dgrad
+            dwp = ws.get("bwd.dwp", (planes, 9 * planes), F32)
+            dwp.zero_()
+            da1 = ws.get("bwd.da1", (Min, planes), BF16)
+            if rec["cols2"] is None:
+                tiles = ((planes + 127) // 128) * ((9 * planes + 255) // 256)
+                sk = ops.split_k_for(tiles, (Mout + 63) // 64)
+                gemm(dy2, rec["a1"], dwp, planes, 9 * planes, Mout, atomic=True, split_k=sk, lda=planes, ldb=planes,
+                     conv=(B, Hc, Wc, planes), conv_mode=2, out_f32=True)
+                gemm(dy2, self._packed[name + ".conv2.weight#dgrad"], da1, Min, planes, 9 * planes, lda=planes,
+                     conv=(B, Hc, Wc, planes), conv_mode=1)
+            else:
+                self._wgrad(dy2, rec["cols2"], dwp, planes, 9 * planes, Mout)
+                dcols = ws.get("bwd.dcols", (Mout, 9 * planes), BF16)
+                gemm(dy2, self._packed[name + ".conv2.weight"], dcols, Mout, 9 * planes, planes, b_mn=1)
+                call("vtx_col2im3x3", dcols.data_ptr(), da1.data_ptr(), B, Hc, Wc, planes, stride, s)
+            call("vtx_conv_w_unpack_add", dwp.data_ptr(), self.G(name + ".conv2.weight").data_ptr(), planes, planes, 3,
+                 3, 9 * planes, s)
+            # ---- bn1 + ReLU backward
+            dy1 = ws.get("bwd.dy1", (Min, planes), BF16)
+            self._bn_bwd(da1, rec["a1"], rec["y1"], rec["bnp1"], name + ".bn1", Min, planes, dy1)
+            # ---- conv1 (1x1): wgrad + dgrad (+ shortcut gradient)
+            self._wgrad(dy1, rec["x"], self.G(name + ".conv1.weight"), planes, Cin, Min)
+            dx = ws.get(f"bwd.dx{scratch_i & 1}", (Min, Cin), BF16)
+            scratch_i += 1
+            w1 = self.W(name + ".conv1.weight").view(planes, Cin)
+            if rec["has_ds"]:
+                wd = self.W(name + ".downsample.0.weight").view(C4, Cin)
+                self._wgrad(dyd, rec["xs"], self.G(name + ".downsample.0.weight"), C4, Cin, Mout)
+                gemm(dy1, w1, dx, Min, Cin, planes, b_mn=1)
+                if stride == 1:
+                    gemm(dyd, wd, dx, Min, Cin, C4, b_mn=1, residual=dx)
+                else:
+                    dxs = ws.get("bwd.dxs", (Mout, Cin), BF16)
+                    gemm(dyd, wd, dxs, Mout, Cin, C4, b_mn=1)
+                    call("vtx_upsample_add", dxs.data_ptr(), dx.data_ptr(), B, Hc, Wc, Cin, stride, s)
+            else:
+                gemm(dy1, w1, dx, Min, Cin, planes, b_mn=1, residual=dz)
+            dOut = dx
+        # ---- stem: maxpool bwd -> ReLU/BN bwd -> wgrad
+        st = tape["stem"]
+        M0 = st["M"]
+        da0 = ws.get("bwd.da0", (M0, 64), BF16)
+        call("vtx_maxpool_bwd", dOut.data_ptr(), st["idx"].data_ptr(), da0.data_ptr(), B, st["Ho"], st["Wo"], 64, s)
+        # ReLU mask of the stem comes from the BN output sign: recompute a = relu(bn(y)) into a scratch buffer
+        a0 = ws.get("bwd.a0", (M0, 64), BF16)
+        call("vtx_bn_act", st["y"].data_ptr(), st["bnp"].data_ptr(), 0, 0, a0.data_ptr(), M0, 64, 1, s)
+        dy0 = ws.get("bwd.dy0", (M0, 64), BF16)
+        self._bn_bwd(da0, a0, st["y"], st["bnp"], "visual.cnn.bn1", M0, 64, dy0)
+        dwp0 = ws.get("bwd.dwp0", (64, 160), F32)
+        dwp0.zero_()
+        self._wgrad(dy0, st["cols"], dwp0, 64, 160, M0)
+        call("vtx_conv_w_unpack_add", dwp0.data_ptr(), self.G("visual.cnn.conv1.weight").data_ptr(), 64, 3, 7, 7, 160, s)
+
+    # ------------------------------------------------------------------------------------------------ head
+    def _head_modules(self, direction):
+        return self.textual if direction == "textual" else self.backward_textual
+
+    def visual_projection_forward(self, feat, S):
+        """mem[S,H] = feat[S,Cv] . Wvp^T + b   (computed once, shared by both directions)."""
+        H = self.textual.hidden_size
+        mem = self.ws.get("head.mem", (S, H), BF16)
+        gemm(feat, self.W("textual.visual_projection.weight"), mem, S, H, feat.shape[1],
+             bias=self.P("textual.visual_projection.bias"))
+        return mem
+
+    def head_forward(self, direction, mem, tokens, lengths, training, want_logits_f32=False):
+        """tokens int64 [B,T] -> bf16 logits [B*T, V] (and the tape for backward)."""
+        mod = self._head_modules(direction)
+        if mod.norm_first:
+            raise NotImplementedError("transdec_prenorm forward is scheduled but not implemented in this round")
+        B, T = tokens.shape
+        M, H, Fd, V, A = B * T, mod.hidden_size, mod.feedforward_size, mod.vocab_size, mod.attention_heads
+        S = mem.shape[0]
+        Sk = S // B
+        p = float(mod.dropout) if training else 0.0
+        d = direction
+        di = 0 if d == "textual" else 1
+        s = _stream()
+        ws = self.ws
+        seed = self.seed.data_ptr()
+        site = di * 1000
+        rec = dict(direction=d, B=B, T=T, M=M, S=S, Sk=Sk, p=p, layers=[], tokens=tokens, lengths=lengths, mem=mem)
+        emb = "textual.embedding."
+        z0 = ws.get(d + ".z0", (M, H), F32)
+        st0 = ws.get(d + ".st0", (M, 2), F32)
+        x = ws.get(d + ".x0", (M, H), F32)
+        xb = ws.get(d + ".x0b", (M, H), BF16)
+        call("vtx_embed_fwd", tokens.data_ptr(), self.P(emb + "words.weight").data_ptr(),
+             self.P(emb + "positions.weight").data_ptr(), self.P(emb + "layer_norm.weight").data_ptr(),
+             self.P(emb + "layer_norm.bias").data_ptr(), z0.data_ptr(), st0.data_ptr(), x.data_ptr(), xb.data_ptr(),
+             M, T, H, self.pad, 1e-8, p, seed, site, s)
+        rec.update(z0=z0, st0=st0)
+        for l in range(mod.num_layers):
+            q = f"{d}.transformer.layers.{l}."
+            k = f"{d}.L{l}."
+            sb = site + 10 * (l + 1)
+            lr = dict(q=q, x_in=x, x_inb=xb)
+            # self-attention block
+            qkv = ws.get(k + "qkv", (M, 3 * H), BF16)
+            gemm(xb, self.W(q + "self_attn.in_proj_weight"), qkv, M, 3 * H, H, bias=self.P(q + "self_attn.in_proj_bias"))
+            o_s = ws.get(k + "o_s", (M, H), BF16)
+            lse_s = ws.get(k + "lse_s", (B * A * 32,), F32)
+            e = qkv.element_size()
+            call("vtx_attn_fwd", qkv.data_ptr(), 3 * H, qkv.data_ptr() + H * e, 3 * H, qkv.data_ptr() + 2 * H * e,
+                 3 * H, o_s.data_ptr(), H, lse_s.data_ptr(), B, A, T, T, lengths.data_ptr(), 1, p, seed, sb + 0, s)
+            pr = ws.get(k + "proj", (M, H), BF16)
+            gemm(o_s, self.W(q + "self_attn.out_proj.weight"), pr, M, H, H, bias=self.P(q + "self_attn.out_proj.bias"))
+            z1, st1 = ws.get(k + "z1", (M, H), F32), ws.get(k + "st1", (M, 2), F32)
+            x1, x1b = ws.get(k + "x1", (M, H), F32), ws.get(k + "x1b", (M, H), BF16)
+            call("vtx_add_ln_fwd", x.data_ptr(), pr.data_ptr(), self.P(q + "norm1.weight").data_ptr(),
+                 self.P(q + "norm1.bias").data_ptr(), z1.data_ptr(), st1.data_ptr(), x1.data_ptr(), x1b.data_ptr(), M,
+                 H, 1e-5, p, seed, sb + 1, 1, s)
+            # cross-attention block
+            wc, bc = self.W(q + "multihead_attn.in_proj_weight"), self.P(q + "multihead_attn.in_proj_bias")
+            qc = ws.get(k + "qc", (M, H), BF16)
+            gemm(x1b, wc[:H], qc, M, H, H, bias=bc[:H])
+            kv = ws.get(k + "kv", (S, 2 * H), BF16)
+            gemm(mem, wc[H:], kv, S, 2 * H, H, bias=bc[H:])
+            o_c = ws.get(k + "o_c", (M, H), BF16)
+            lse_c = ws.get(k + "lse_c", (B * A * 32,), F32)
+            call("vtx_attn_fwd", qc.data_ptr(), H, kv.data_ptr(), 2 * H, kv.data_ptr() + H * e, 2 * H, o_c.data_ptr(),
+                 H, lse_c.data_ptr(), B, A, T, Sk, 0, 0, p, seed, sb + 2, s)
+            gemm(o_c, self.W(q + "multihead_attn.out_proj.weight"), pr, M, H, H,
+                 bias=self.P(q + "multihead_attn.out_proj.bias"))
+            z2, st2 = ws.get(k + "z2", (M, H), F32), ws.get(k + "st2", (M, 2), F32)
+            x2, x2b = ws.get(k + "x2", (M, H), F32), ws.get(k + "x2b", (M, H), BF16)
+            call("vtx_add_ln_fwd", x1.data_ptr(), pr.data_ptr(), self.P(q + "norm2.weight").data_ptr(),
+                 self.P(q + "norm2.bias").data_ptr(), z2.data_ptr(), st2.data_ptr(), x2.data_ptr(), x2b.data_ptr(), M,
+                 H, 1e-5, p, seed, sb + 3, 1, s)
+            # feed-forward block
+            u = ws.get(k + "u", (M, Fd), BF16)
+            gemm(x2b, self.W(q + "linear1.weight"), u, M, Fd, H, bias=self.P(q + "linear1.bias"))
+            h = ws.get(k + "h", (M, Fd), BF16)
+            call("vtx_gelu_dropout_fwd", u.data_ptr(), h.data_ptr(), M * Fd, p, seed, sb + 4, s)
+            gemm(h, self.W(q + "linear2.weight"), pr, M, H, Fd, bias=self.P(q + "linear2.bias"))
+            z3, st3 = ws.get(k + "z3", (M, H), F32), ws.get(k + "st3", (M, 2), F32)
+            x3, x3b = ws.get(k + "x3", (M, H), F32), ws.get(k + "x3b", (M, H), BF16)
+            call("vtx_add_ln_fwd", x2.data_ptr(), pr.data_ptr(), self.P(q + "norm3.weight").data_ptr(),
+                 self.P(q + "norm3.bias").data_ptr(), z3.data_ptr(), st3.data_ptr(), x3.data_ptr(), x3b.data_ptr(), M,
+                 H, 1e-5, p, seed, sb + 5, 1, s)
+            lr.update(qkv=qkv, o_s=o_s, lse_s=lse_s, z1=z1, st1=st1, x1b=x1b, qc=qc, kv=kv, o_c=o_c, lse_c=lse_c,
+                      z2=z2, st2=st2, x2b=x2b, u=u, h=h, z3=z3, st3=st3, sb=sb)
+            rec["layers"].append(lr)
+            x, xb = x3, x3b
+        rec["x_out_b"] = xb
+        # tied output projection
+        wv = self.W("textual.embedding.words.weight")
+        bo = self.P("textual.output.bias")
+        if want_logits_f32:
+            lf = ws.get(d + ".logits_f32", (M, V), F32)
+            gemm(xb, wv, lf, M, V, H, bias=bo)
+            rec["logits_f32"] = lf
+        logits = ws.get(d + ".logits", (M, V), BF16)
+        gemm(xb, wv, logits, M, V, H, bias=bo)
+        rec["logits"] = logits
+        return rec
+
+    def head_loss(self, rec, write_grad):
+        di = 0 if rec["direction"] == "textual" else 1
+        s = _stream()
+        V = rec["logits"].shape[1]
+        call("vtx_count_valid", rec["tokens"].data_ptr(), rec["B"], rec["T"], self.pad, self.count[di:].data_ptr(), s)
+        call("vtx_cross_entropy", rec["logits"].data_ptr(), V, rec["tokens"].data_ptr(), rec["B"], rec["T"], V,
+             self.pad, self.count[di:].data_ptr(), self.loss[di:].data_ptr(), int(write_grad), s)
+
+    def _linear_bwd(self, dY, X, wname, bname, dX, M, n_out, k_in, w_rows=None, residual=None):
+        """Backward of Y = X W^T + b for W [n_out, k_in] (optionally the row slice `w_rows` of a packed weight)."""
+        W, dW, db = self.W(wname), self.G(wname), self.G(bname)
+        if w_rows is not None:
+            W, dW, db = W[w_rows], dW[w_rows], db[w_rows]
+        call("vtx_colsum", dY.data_ptr(), dY.stride(0), M, n_out, db.data_ptr(), _stream())
+        self._wgrad(dY, X, dW, n_out, k_in, M)
+        if dX is not None:
+            gemm(dY, W, dX, M, k_in, n_out, b_mn=1, residual=residual)
+
+    def head_backward(self, rec, dmem, dmem_started):
+        """Backward of one direction from the dlogits already written in place of rec['logits'].
+        Accumulates parameter gradients; adds this direction's contribution to dmem [S,H]."""
+        d = rec["direction"]
+        mod = self._head_modules(d)
+        B, T, M, S, Sk, p = rec["B"], rec["T"], rec["M"], rec["S"], rec["Sk"], rec["p"]
+        H, Fd, V, A = mod.hidden_size, mod.feedforward_size, mod.vocab_size, mod.attention_heads
+        s = _stream()
+        ws = self.ws
+        seed = self.seed.data_ptr()
+        dlog = rec["logits"]
+        # tied output projection: d_bias, d_words (vocab-projection part), dx
+        call("vtx_colsum", dlog.data_ptr(), V, M, V, self.G("textual.output.bias").data_ptr(), s)
+        self._wgrad(dlog, rec["x_out_b"], self.G("textual.embedding.words.weight"), V, H, M)
+        dxb = ws.get("hb.dxb", (M, H), BF16)
+        gemm(dlog, self.W("textual.embedding.words.weight"), dxb, M, H, V, b_mn=1)
+        dres_a = ws.get("hb.dres_a", (M, H), F32)
+        dres_b = ws.get("hb.dres_b", (M, H), F32)
+        dbr = ws.get("hb.dbr", (M, H), BF16)
+        dy_a, dy_b = None, dxb
+        e = 2
+        for l in reversed(range(mod.num_layers)):
+            lr = rec["layers"][l]
+            q, sb = lr["q"], lr["sb"]
+            # LN3 / FFN
+            call("vtx_ln_bwd", _p(dy_a), _p(dy_b), lr["z3"].data_ptr(), lr["st3"].data_ptr(),
+                 self.P(q + "norm3.weight").data_ptr(), 0, dres_a.data_ptr(), dbr.data_ptr(),
+                 self.G(q + "norm3.weight").data_ptr(), self.G(q + "norm3.bias").data_ptr(), M, H, p, seed, sb + 5, 1, s)
+            dh = ws.get("hb.dh", (M, Fd), BF16)
+            self._linear_bwd(dbr, lr["h"], q + "linear2.weight", q + "linear2.bias", dh, M, H, Fd)
+            call("vtx_gelu_dropout_bwd", dh.data_ptr(), lr["u"].data_ptr(), dh.data_ptr(), M * Fd, p, seed, sb + 4, s)
+            self._linear_bwd(dh, lr["x2b"], q + "linear1.weight", q + "linear1.bias", dxb, M, Fd, H)
+            # LN2 / cross attention
+            call("vtx_ln_bwd", dres_a.data_ptr(), dxb.data_ptr(), lr["z2"].data_ptr(), lr["st2"].data_ptr(),
+                 self.P(q + "norm2.weight").data_ptr(), 0, dres_b.data_ptr(), dbr.data_ptr(),
+                 self.G(q + "norm2.weight").data_ptr(), self.G(q + "norm2.bias").data_ptr(), M, H, p, seed, sb + 3, 1, s)
+            do = ws.get("hb.do", (M, H), BF16)
+            self._linear_bwd(dbr, lr["o_c"], q + "multihead_attn.out_proj.weight", q + "multihead_attn.out_proj.bias",
+                             do, M, H, H)
+            dqc = ws.get("hb.dqc", (M, H), BF16)
+            dkv = ws.get("hb.dkv", (S, 2 * H), BF16)
+            kv = lr["kv"]
+            call("vtx_attn_bwd", lr["qc"].data_ptr(), H, kv.data_ptr(), 2 * H, kv.data_ptr() + H * e, 2 * H,
+                 do.data_ptr(), H, lr["lse_c"].data_ptr(), dqc.data_ptr(), H, dkv.data_ptr(), 2 * H,
+                 dkv.data_ptr() + H * e, 2 * H, B, A, T, Sk, 0, 0, p, seed, sb + 2, s)
+            wn, bn = q + "multihead_attn.in_proj_weight", q + "multihead_attn.in_proj_bias"
+            self._linear_bwd(dqc, lr["x1b"], wn, bn, dxb, M, H, H, w_rows=slice(0, H))
+            self._linear_bwd(dkv, rec["mem"], wn, bn, dmem, S, 2 * H, H, w_rows=slice(H, 3 * H),
+                             residual=dmem if dmem_started else None)
+            dmem_started = True
+            # LN1 / self attention
+            call("vtx_ln_bwd", dres_b.data_ptr(), dxb.data_ptr(), lr["z1"].data_ptr(), lr["st1"].data_ptr(),
+                 self.P(q + "norm1.weight").data_ptr(), 0, dres_a.data_ptr(), dbr.data_ptr(),
+                 self.G(q + "norm1.weight").data_ptr(), self.G(q + "norm1.bias").data_ptr(), M, H, p, seed, sb + 1, 1, s)
+            self._linear_bwd(dbr, lr["o_s"], q + "self_attn.out_proj.weight", q + "self_attn.out_proj.bias", do, M, H, H)
+            dqkv = ws.get("hb.dqkv", (M, 3 * H), BF16)
+            qkv = lr["qkv"]
+            call("vtx_attn_bwd", qkv.data_ptr(), 3 * H, qkv.data_ptr() + H * e, 3 * H, qkv.data_ptr() + 2 * H * e,
+                 3 * H, do.data_ptr(), H, lr["lse_s"].data_ptr(), dqkv.data_ptr(), 3 * H, dqkv.data_ptr() + H * e,
+                 3 * H, dqkv.data_ptr() + 2 * H * e, 3 * H, B, A, T, T, rec["lengths"].data_ptr(), 1, p, seed, sb + 0, s)
+            self._linear_bwd(dqkv, lr["x_inb"], q + "self_attn.in_proj_weight", q + "self_attn.in_proj_bias", dxb, M,
+                             3 * H, H)
+            dy_a, dy_b = dres_a, dxb
+        emb = "textual.embedding."
+        di = 0 if d == "textual" else 1
+        call("vtx_embed_bwd", _p(dy_a), _p(dy_b), rec["tokens"].data_ptr(), rec["z0"].data_ptr(),
+             rec["st0"].data_ptr(), self.P(emb + "layer_norm.weight").data_ptr(),
+             self.G(emb + "words.weight").data_ptr(), self.G(emb + "positions.weight").data_ptr(),
+             self.G(emb + "layer_norm.weight").data_ptr(), self.G(emb + "layer_norm.bias").data_ptr(), M, T, H,
+             self.pad, p, seed, di * 1000, s)
+        return dmem_started
+
+    # ------------------------------------------------------------------------------------------------ full model
+    def forward(self, image, tokens, noitpac, lengths, training=True, with_grad=True):
+        """Loss of the bicaptioning model.  Leaves dlogits in the logits buffers when `with_grad`."""
+        if not self.arena.intact():
+            raise RuntimeError("model parameters were moved after the engine adopted them; rebuild the engine")
+        self.loss.zero_()
+        self.count.zero_()
+        feat, h, w = self.backbone_forward(image, training)
+        B = image.shape[0]
+        S = B * h * w
+        mem = self.visual_projection_forward(feat, S)
+        recs = [self.head_forward("textual", mem, tokens, lengths, training, want_logits_f32=not training)]
+        self.head_loss(recs[0], with_grad)
+        if self.backward_textual is not None:
+            recs.append(self.head_forward("backward_textual", mem, noitpac, lengths, training))
+            self.head_loss(recs[1], with_grad)
+        self._recs, self._mem, self._feat = recs, mem, feat
+        return self.loss
+
+    def backward(self, zero_grads=True):
+        """Gradients of (loss_fwd + loss_bwd) w.r.t. every parameter into the flat gradient arena."""
+        if zero_grads:
+            self.arena.grads.zero_()
+        feat, mem = self._feat, self._mem
+        S, H = mem.shape
+        dmem = self.ws.get("hb.dmem", (S, H), BF16)
+        started = False
+        for rec in reversed(self._recs):
+            started = self.head_backward(rec, dmem, started)
+        Cv = feat.shape[1]
+        dfeat = self.ws.get("hb.dfeat", (S, Cv), BF16)
+        frozen = getattr(self.visual, "frozen", False)
+        self._linear_bwd(dmem, feat, "textual.visual_projection.weight", "textual.visual_projection.bias",
+                         None if frozen else dfeat, S, H, Cv)
+        if not frozen:
+            self.backbone_backward(dfeat)
+
+    def predictions(self):
+        """argmax over the fp32 forward-direction logits of the last eval-mode forward -> int64 [B,T]."""
+        rec = self._recs[0]
+        lf = rec["logits_f32"]
+        out = self.ws.get("pred", (rec["M"],), torch.int64)
+        call("vtx_argmax_rows", lf.data_ptr(), lf.stride(0), rec["M"], lf.shape[1], out.data_ptr(), _stream())
+        return out.view(rec["B"], rec["T"])
+
+
+# ---------------------------------------------------------------------------------------------------- module-level API
+def _module_engine(mod, **kw):
+    eng = getattr(mod, "_vtx_engine", None)
+    if eng is None or not eng.arena.intact():
+        eng = Engine(**kw)
+        object.__setattr__(mod, "_vtx_engine", eng)
+    return eng
+
+
+@torch.no_grad()
+def backbone_features(backbone, image: torch.Tensor) -> torch.Tensor:
+    """`TorchvisionVisualBackbone.forward`: (B,3,H,W) fp32 -> (B,C,H/32,W/32) fp32, NCHW-shaped like the reference.
+    Module-level calls are inference-style (no autograd); training goes through the model-level engine."""
+    eng = _module_engine(backbone, visual=backbone)
+    eng.mark_weights_dirty()
+    feat, h, w = eng.backbone_forward(image.contiguous().float(), training=backbone.cnn.training)
+    B, C = image.shape[0], feat.shape[1]
+    out = torch.empty(B, C, h, w, dtype=F32, device=image.device)
+    call("vtx_nhwc_to_nchw_f32", feat.data_ptr(), out.data_ptr(), B, h * w, C, _stream())
+    return out
+
+
+@torch.no_grad()
+def head_logits(head, visual_features, caption_tokens, caption_lengths) -> torch.Tensor:
+    """`TransformerDecoderTextualHead.forward`: (B,C,h,w), (B,T), (B,) -> fp32 logits (B,T,V)."""
+    eng = _module_engine(head, textual=head)
+    eng.mark_weights_dirty()
+    eng.prepare_weights()
+    B, C, h, w = visual_features.shape
+    feat = visual_features.permute(0, 2, 3, 1).reshape(B * h * w, C).to(BF16).contiguous()
+    mem = eng.visual_projection_forward(feat, B * h * w)
+    rec = eng.head_forward("textual", mem, caption_tokens.contiguous(), caption_lengths.contiguous(),
+                           training=head.training, want_logits_f32=True)
+    return rec["logits_f32"].view(B, caption_tokens.shape[1], -1).clone()

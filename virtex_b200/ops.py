@@ -1,0 +1,119 @@
+"""Python-side launchers of the C-ABI kernels: torch tensors in, raw pointers out.
+
+Every function launches on torch's current CUDA stream, never allocates and never synchronises.  There is no
+fallback: a missing library or a non-CUDA tensor raises.
+"""
+import ctypes
+from ctypes import c_float, c_int, c_int32, c_int64, c_uint32, c_void_p
+
+import torch
+
+from . import lib as L
+
+P, I, I64, F, U32 = c_void_p, c_int, c_int64, c_float, c_uint32
+
+_PROTOS = {
+    "vtx_gemm": [P, P],
+    "vtx_stem_im2col": [P, P, I, I, I, I, P],
+    "vtx_im2col3x3": [P, P, I, I, I, I, I, P],
+    "vtx_col2im3x3": [P, P, I, I, I, I, I, P],
+    "vtx_subsample": [P, P, I, I, I, I, I, P],
+    "vtx_upsample_add": [P, P, I, I, I, I, I, P],
+    "vtx_bn_finalize": [P, F, P, P, P, P, P, F, F, I, P, I, P],
+    "vtx_bn_act": [P, P, P, P, P, I64, I, I, P],
+    "vtx_bn_relu_maxpool": [P, P, P, P, I, I, I, I, P],
+    "vtx_maxpool_bwd": [P, P, P, I, I, I, I, P],
+    "vtx_bn_bwd_reduce": [P, P, P, P, P, P, P, P, I64, I, P],
+    "vtx_bn_bwd_finalize": [P, P, F, P, P, P, I, P],
+    "vtx_bn_bwd_apply": [P, P, P, P, P, P, P, P, P, P, P, I64, I, P],
+    "vtx_conv_w_pack": [P, P, I, I, I, I, I, P],
+    "vtx_conv_w_pack_dgrad": [P, P, I, I, P],
+    "vtx_conv_w_unpack_add": [P, P, I, I, I, I, I, P],
+    "vtx_cast_bf16": [P, P, I64, P],
+    "vtx_nhwc_to_nchw_f32": [P, P, I, I, I, P],
+    "vtx_embed_fwd": [P, P, P, P, P, P, P, P, P, I, I, I, I, F, F, P, U32, P],
+    "vtx_embed_bwd": [P, P, P, P, P, P, P, P, P, P, I, I, I, I, F, P, U32, P],
+    "vtx_add_ln_fwd": [P, P, P, P, P, P, P, P, I, I, F, F, P, U32, I, P],
+    "vtx_ln_bwd": [P, P, P, P, P, P, P, P, P, P, I, I, F, P, U32, I, P],
+    "vtx_attn_fwd": [P, I64, P, I64, P, I64, P, I64, P, I, I, I, I, P, I, F, P, U32, P],
+    "vtx_attn_bwd": [P, I64, P, I64, P, I64, P, I64, P, P, I64, P, I64, P, I64, I, I, I, I, P, I, F, P, U32, P],
+    "vtx_gelu_dropout_fwd": [P, P, I64, F, P, U32, P],
+    "vtx_gelu_dropout_bwd": [P, P, P, I64, F, P, U32, P],
+    "vtx_count_valid": [P, I, I, I, P, P],
+    "vtx_cross_entropy": [P, I64, P, I, I, I, I, P, P, I, P],
+    "vtx_colsum": [P, I64, I, I, P, P],
+    "vtx_argmax_rows": [P, I64, I, I, P, P],
+    "vtx_sumsq": [P, I64, P, P],
+    "vtx_clip_coef": [P, I, F, P, P],
+    "vtx_sgd_step": [P, P, P, P, P, P, I, P, P, F, F, P],
+}
+
+_fn = {}
+
+
+def _get(name):
+    f = _fn.get(name)
+    if f is None:
+        f = getattr(L.load(), name)
+        f.argtypes = _PROTOS[name]
+        f.restype = c_int
+        _fn[name] = f
+    return f
+
+
+def exported_symbols():
+    """All C-ABI entry points this module binds (used by the CPU test that checks the library exports them)."""
+    return sorted(_PROTOS) + ["vtx_last_error", "vtx_version", "vtx_num_sms"]
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def call(name, *args):
+    rc = _get(name)(*args)
+    if rc != 0:
+        L.check(rc, name)
+
+
+def num_sms():
+    return L.load().vtx_num_sms()
+
+
+# --------------------------------------------------------------------------------------------------------------- GEMM
+_gemm_struct = L.VtxGemm()
+
+
+def gemm(A, B, D, M, N, K, *, lda=None, ldb=None, ldd=None, a_mn=0, b_mn=0, bias=None, act=0, residual=None,
+         ldr=0, stats=None, atomic=False, split_k=1, tile_n=0, conv=None, conv_mode=0, out_f32=None):
+    """D[M,N] = epilogue(A . B^T) through the tcgen05 kernel; see include/virtex_b200.h (VtxGemm)."""
+    g = _gemm_struct
+    g.A, g.B, g.D = A.data_ptr(), B.data_ptr(), D.data_ptr()
+    g.bias, g.residual, g.stats = _p(bias), _p(residual), _p(stats)
+    g.lda = A.stride(0) if lda is None else lda
+    g.ldb = B.stride(0) if ldb is None else ldb
+    g.ldd = D.stride(0) if ldd is None else ldd
+    g.ldr = (residual.stride(0) if residual is not None else 0) if not ldr else ldr
+    g.M, g.N, g.K = M, N, K
+    g.a_mn, g.b_mn = a_mn, b_mn
+    g.out_f32 = int(D.dtype == torch.float32) if out_f32 is None else int(out_f32)
+    g.atomic, g.act, g.split_k, g.tile_n = int(atomic), act, split_k, tile_n
+    g.alpha = 1.0
+    if conv is not None:
+        g.conv_n, g.conv_h, g.conv_w, g.conv_c = conv
+    else:
+        g.conv_n = g.conv_h = g.conv_w = g.conv_c = 0
+    g.conv_mode = conv_mode
+    call("vtx_gemm", ctypes.addressof(g), _stream())
+
+
+def split_k_for(m_tiles_x_n_tiles, k_blocks, sms=None):
+    """Split-K factor that fills the machine for reduction-heavy (wgrad) GEMMs."""
+    sms = sms or num_sms()
+    if m_tiles_x_n_tiles >= sms:
+        return 1
+    return max(1, min(k_blocks, (2 * sms + m_tiles_x_n_tiles - 1) // m_tiles_x_n_tiles))
