@@ -158,12 +158,16 @@ def from_reference_state_dict(sd: Dict[str, torch.Tensor], spec: Spec) -> Dict[s
     return OrderedDict((k, sd[k]) for k in unique_shapes(spec))
 
 
-def synth_state(spec: Spec, seed: int = 0, randomize_bn: bool = True) -> "OrderedDict[str, torch.Tensor]":
+def synth_state(spec: Spec, seed: int = 0, randomize_bn: bool = True,
+                bn3_gain: float = 1.0) -> "OrderedDict[str, torch.Tensor]":
     """Deterministic synthetic weights, reproducible anywhere from (spec, seed) alone.
 
     Scales follow the reference initialisers (Kaiming fan_out convs, N(0, 0.02) head weights) but BN affine
     parameters and running statistics are randomised when `randomize_bn` so that every gradient is exercised
-    (fresh `zero_init_residual` makes 112 of 202 gradients identically zero; SURVEY section 8c gotcha (i))."""
+    (fresh `zero_init_residual` makes 112 of 202 gradients identically zero; SURVEY section 8c gotcha (i)).
+    `bn3_gain` scales the last BN gamma of every bottleneck: with gain 1 a random 16-block residual stack amplifies any
+    perturbation ~1.25x per block (bf16 rounding -> 50% feature error at layer4), which is a property of that random
+    network, not of an implementation; bf16-vs-fp32 parity tests therefore use a residual branch gain of ~0.25."""
     g = torch.Generator().manual_seed(seed)
     out: "OrderedDict[str, torch.Tensor]" = OrderedDict()
     for name, shape in unique_shapes(spec).items():
@@ -180,6 +184,8 @@ def synth_state(spec: Spec, seed: int = 0, randomize_bn: bool = True) -> "Ordere
             t = torch.rand(shape, generator=g) + 0.5 if randomize_bn else torch.ones(shape)
             if not randomize_bn and ".bn3." in name:
                 t = torch.zeros(shape)
+            elif ".bn3." in name:
+                t = t * bn3_gain
         elif "visual.cnn" in name:  # BN beta
             t = torch.randn(shape, generator=g) * 0.1 if randomize_bn else torch.zeros(shape)
         elif re.search(r"(norm\d?|layer_norm)\.weight$", name):
@@ -240,20 +246,31 @@ def _batch_norm(x, P, prefix, training, new_buffers, eps=1e-5, momentum=0.1):
     return xhat * w[None, :, None, None] + b[None, :, None, None]
 
 
-def backbone_forward(P, image, spec: Spec, training=True, new_buffers=None):
-    """(B,3,H,W) -> (B,2048,H/32,W/32).  torchvision ResNet children conv1..layer4."""
+def backbone_forward(P, image, spec: Spec, training=True, new_buffers=None, record=None):
+    """(B,3,H,W) -> (B,2048,H/32,W/32).  torchvision ResNet children conv1..layer4.
+    `record` (dict) optionally receives intermediate activations keyed by layer name (debug / per-layer parity)."""
     p = "visual.cnn."
     x = F.conv2d(image, P[p + "conv1.weight"], stride=2, padding=3)
+    if record is not None:
+        record["stem.y"] = x
     x = torch.relu(_batch_norm(x, P, p + "bn1", training, new_buffers))
     x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
+    if record is not None:
+        record["stem.pool"] = x
     for li, nblocks in enumerate(spec.blocks, start=1):
         for bi in range(nblocks):
             stride = 2 if (bi == 0 and li > 1) else 1
             q = f"{p}layer{li}.{bi}."
             identity = x
             out = F.conv2d(x, P[q + "conv1.weight"])
+            if record is not None:
+                record[q + "y1"] = out
             out = torch.relu(_batch_norm(out, P, q + "bn1", training, new_buffers))
+            if record is not None:
+                record[q + "a1"] = out
             out = F.conv2d(out, P[q + "conv2.weight"], stride=stride, padding=1)
+            if record is not None:
+                record[q + "y2"] = out
             out = torch.relu(_batch_norm(out, P, q + "bn2", training, new_buffers))
             out = F.conv2d(out, P[q + "conv3.weight"])
             out = _batch_norm(out, P, q + "bn3", training, new_buffers)
@@ -261,6 +278,8 @@ def backbone_forward(P, image, spec: Spec, training=True, new_buffers=None):
                 identity = F.conv2d(x, P[q + "downsample.0.weight"], stride=stride)
                 identity = _batch_norm(identity, P, q + "downsample.1", training, new_buffers)
             x = torch.relu(out + identity)
+            if record is not None:
+                record[q + "out"] = x
     return x
 
 
