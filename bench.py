@@ -1,0 +1,293 @@
+#!/usr/bin/env python
+"""Benchmark of the bicaptioning pretraining step (BASELINE.json metric: image-caption pairs/sec, R50-L1-H1024).
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference algorithm on the host cores (oracle port)
+
+A "step" is one full optimisation step (forward + backward + gradient all-reduce + clip + SGD/Lookahead) on a synthetic
+batch of 256 pairs per GPU (weak scaling), random-init weights of the named architecture, dropout 0.1 as configured.
+Rank 0 prints ONE JSON line.  `value` = device-resident inputs, CUDA-event timed, max over ranks; `e2e` = the same
+step through `Trainer.step` fed from pinned HOST buffers (H2D copy of every batch and D2H read of every loss inside
+the timed region).  `roofline` is for the dominant kernel (the tcgen05 GEMM, which runs every conv and linear layer).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "image-caption pairs/sec bicaptioning R50-L1-H1024"
+GFLOP_PER_PAIR = 35.17  # fwd+bwd conv+matmul work per pair, vis-proj de-duplicated
+
+
+def synth_host_batch(B, T=30, vocab=10000, seed=0, pin=True):
+    g = torch.Generator().manual_seed(seed)
+    image = torch.randn(B, 3, 224, 224, generator=g)
+    tokens = torch.randint(4, vocab, (B, T), generator=g)
+    tokens[:, 0], tokens[:, -1] = 1, 2
+    batch = {"image": image, "caption_tokens": tokens, "noitpac_tokens": tokens.flip(1).contiguous(),
+             "caption_lengths": torch.full((B,), T, dtype=torch.int64)}
+    if pin:
+        batch = {k: v.pin_memory() for k, v in batch.items()}
+    return batch
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return p.get("bf16_tflops_sustained", 1412.4), p.get("hbm_gbs", 6590.9), "measured (MEASURED_PEAKS.json, sustained)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------------- CPU / reference
+def run_cpu_reference(steps, warmup, batch, threads=None):
+    """The reference algorithm (oracle port, fp32, CPU autograd) timed on the host cores: full optimisation steps."""
+    from oracle import virtex_oracle as O
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    spec = O.Spec()
+    tr = O.OracleTrainer(O.synth_state(spec, 0, randomize_bn=False), spec)
+    hb = synth_host_batch(batch, pin=False)
+    hb["image_id"] = torch.arange(batch)
+    for _ in range(warmup):
+        tr.step(hb)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        tr.step(hb)
+    dt = time.perf_counter() - t0
+    return steps * batch / dt, dt / steps, threads
+
+
+def main_reference(args, rank, world):
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 3))
+    warm = 1
+    B = args.cpu_batch
+    v, sec, threads = run_cpu_reference(steps, warm, B)
+    line = {"impl": "reference", "metric": METRIC, "value": round(v, 3), "unit": "pairs/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": round(sec * 1e3, 2), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "bicaptioning R50_L1_H1024 full optimisation step, reference algorithm on host cores",
+                       "global_batch": B},
+            "cpu_baseline": {"value": round(v, 3), "unit": "pairs/s", "cores": threads, "kind": "port",
+                             "sample": f"{steps} full steps at batch {B} after {warm} warm-up (oracle port of the reference, fp32)"},
+            "e2e": {"value": round(v, 3), "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------- ours
+def main_ours(args, rank, world, local):
+    import torch.distributed as dist
+    from virtex_b200 import ops
+    from virtex_b200.config import Config
+    from virtex_b200.factories import PretrainingModelFactory
+    from virtex_b200.trainer import Trainer
+
+    dev = torch.device("cuda", local)
+    B = args.batch_per_gpu
+    cfg = Config(args.config, ["OPTIM.BATCH_SIZE", B * world] + args.config_override)
+    torch.manual_seed(cfg.RANDOM_SEED)
+    model = PretrainingModelFactory.from_config(cfg).to(dev)
+    model.train()
+    trainer = Trainer(model, cfg)
+    T = cfg.DATA.MAX_CAPTION_LENGTH
+    host = [synth_host_batch(B, T, cfg.DATA.VOCAB_SIZE, seed=rank * 100 + i) for i in range(2)]
+    dev_batch = {k: v.to(dev) for k, v in host[0].items()}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return t.item()
+        return ms
+
+    # ---- warm-up (allocates every workspace buffer), then the device-resident timed region
+    for _ in range(max(args.warmup, 3)):
+        trainer.step(dev_batch)
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    launches0 = ops.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        loss = trainer.step(dev_batch)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = ops.launch_count - launches0
+    clk = clocks.stop() if rank == 0 else None
+    loss_val = float(loss.sum().item())
+    value = args.steps * B * world / (ms / 1e3)
+
+    # ---- end to end: pinned host batches -> H2D (prefetched on a copy stream) -> step -> D2H loss read, every step
+    copy_stream = torch.cuda.Stream(device=dev)
+    slots = [{k: torch.empty_like(v, device=dev) for k, v in host[0].items()} for _ in range(2)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    loss_host = torch.zeros(2, 2).pin_memory()
+    h2d = sum(v.numel() * v.element_size() for v in host[0].values())
+
+    def upload(i):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[i % 2])
+            for k, v in host[i % 2].items():
+                slots[i % 2][k].copy_(v, non_blocking=True)
+            ready[i % 2].record(copy_stream)
+
+    def e2e_run(n):
+        for e in consumed:
+            e.record()
+        upload(0)
+        seen = []
+        for i in range(n):
+            if i + 1 < n:
+                upload(i + 1)
+            torch.cuda.current_stream().wait_event(ready[i % 2])
+            l = trainer.step(slots[i % 2])
+            consumed[i % 2].record()
+            loss_host[i % 2].copy_(l, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record()
+            if seen:  # read the previous step's loss on the host (one step of slack keeps the launch queue full)
+                ev, slot = seen.pop()
+                ev.synchronize()
+                _ = float(loss_host[slot].sum())
+            seen.append((done, i % 2))
+        ev, slot = seen.pop()
+        ev.synchronize()
+        return float(loss_host[slot].sum())
+
+    e2e_run(2)
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    e2e_run(args.steps)
+    t1.record()
+    barrier()
+    ms_e2e = max_over_ranks(t0.elapsed_time(t1))
+    e2e_value = args.steps * B * world / (ms_e2e / 1e3)
+
+    # ---- roofline of the dominant kernel: CUDA events around every tcgen05 GEMM launch of 2 further steps
+    roof = None
+    if rank == 0:
+        ops.start_gemm_profile()
+        e0.record()
+        for _ in range(2):
+            trainer.step(dev_batch)
+        e1.record()
+        prof = ops.stop_gemm_profile()
+        prof_ms = e0.elapsed_time(e1) / 2
+        peak_tf, peak_bw, peak_src = measured_peaks()
+        g_ms = sum(p[0] for p in prof) / 2
+        g_fl = sum(p[1] for p in prof) / 2
+        roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 GEMM: all convs + linears)",
+                "achieved": round(g_fl / (g_ms * 1e-3) / 1e12, 1), "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": round(g_fl / (g_ms * 1e-3) / 1e12 / peak_tf, 4), "traffic": None, "peak_source": peak_src,
+                "launches_per_step": len(prof) // 2, "gemm_ms_per_step": round(g_ms, 3),
+                "gemm_share_of_step": round(g_ms / prof_ms, 3),
+                "algorithmic_gflop_per_step": round(g_fl / 1e9, 1)}
+    barrier()
+
+    if rank == 0:
+        cpu_v, cpu_sec, cpu_threads = run_cpu_reference(2, 1, args.cpu_batch) if not args.skip_cpu else (None, None, 0)
+        line = {"metric": METRIC, "value": round(value, 1), "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": f"bicaptioning R50_L1_H1024 full optimisation step, batch {B} per GPU",
+                           "config_file": args.config, "global_batch": B * world, "seq_len": T,
+                           "parallelism": f"dp{world}", "dropout": cfg.MODEL.TEXTUAL.DROPOUT,
+                           "l2_policy": "per-step working set (>= 150 MB of inputs, GBs of activations) exceeds the 126 MB L2"},
+                "loss": round(loss_val, 4), "clocks": clk,
+                "e2e": {"value": round(e2e_value, 1), "unit": "pairs/s", "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": 8, "ms_per_step": round(ms_e2e / args.steps, 3),
+                        "api": "virtex_b200.trainer.Trainer.step on pinned host batches"},
+                "gpu_launches": launches, "roofline": roof,
+                "model_tflops": round(value * GFLOP_PER_PAIR / 1e3, 1),
+                "cpu_baseline": None if cpu_v is None else {
+                    "value": round(cpu_v, 3), "unit": "pairs/s", "cores": cpu_threads, "kind": "port",
+                    "sample": f"2 full steps at batch {args.cpu_batch} after 1 warm-up (oracle port of the reference, fp32)"}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch-per-gpu", type=int, default=256)
+    ap.add_argument("--cpu-batch", type=int, default=32)
+    ap.add_argument("--config", default="_base_bicaptioning_R_50_L1_H1024.yaml")
+    ap.add_argument("--config-override", nargs="*", default=[])
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if args.impl == "reference":
+        main_reference(args, rank, world)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU path (use --impl reference for the CPU baseline)")
+    from virtex_b200.distributed import init_from_env
+    rank, world, local = init_from_env()
+    main_ours(args, rank, world, local)
+
+
+if __name__ == "__main__":
+    main()

@@ -341,8 +341,9 @@ class Engine:
             call("vtx_bn_bwd_apply", dA.data_ptr(), _p(a), y.data_ptr(), bnp.data_ptr(), coef.data_ptr(),
                  dy.data_ptr(), y2.data_ptr(), bnp2.data_ptr(), coef2.data_ptr(), dy2.data_ptr(), _p(dz_out), M, C, s)
 
-    def backbone_backward(self, dfeat: torch.Tensor):
-        """dfeat bf16 [B*h*w, C]: gradient w.r.t. the backbone output.  Accumulates into the gradient arena."""
+    def backbone_backward(self, dfeat: torch.Tensor, bucket_cb=None):
+        """dfeat bf16 [B*h*w, C]: gradient w.r.t. the backbone output.  Accumulates into the gradient arena.
+        `bucket_cb(tag)` is called when every gradient of 'layer4' / 'layer3' / 'layer2' has been enqueued."""
         tape = self._tape
         if not tape["training"]:
             return  # frozen backbone
@@ -351,8 +352,13 @@ class Engine:
         ws = self.ws
         dOut = dfeat
         scratch_i = 0
+        prev_layer = None
         for rec in reversed(tape["blocks"]):
             name, planes, Cin, stride = rec["name"], rec["planes"], rec["Cin"], rec["stride"]
+            layer = name.split(".")[2]
+            if bucket_cb is not None and prev_layer is not None and layer != prev_layer:
+                bucket_cb(prev_layer)
+            prev_layer = layer
             Min, Mout, C4 = rec["Min"], rec["Mout"], 4 * rec["planes"]
             Hc, Wc, Hn, Wn = rec["Hin"], rec["Win"], rec["Hout"], rec["Wout"]
             # ---- block output: ReLU mask + bn3 (+ downsample BN) backward
@@ -639,8 +645,10 @@ class Engine:
         self._recs, self._mem, self._feat = recs, mem, feat
         return self.loss
 
-    def backward(self, zero_grads=True):
-        """Gradients of (loss_fwd + loss_bwd) w.r.t. every parameter into the flat gradient arena."""
+    def backward(self, zero_grads=True, bucket_cb=None):
+        """Gradients of (loss_fwd + loss_bwd) w.r.t. every parameter into the flat gradient arena.
+        `bucket_cb(tag)`, tag in {'head','layer4','layer3','layer2','rest'}, fires as gradient ranges complete (in
+        backward order) so a data-parallel all-reduce can overlap the remaining backward."""
         if zero_grads:
             self.arena.grads.zero_()
         feat, mem = self._feat, self._mem
@@ -654,8 +662,12 @@ class Engine:
         frozen = getattr(self.visual, "frozen", False)
         self._linear_bwd(dmem, feat, "textual.visual_projection.weight", "textual.visual_projection.bias",
                          None if frozen else dfeat, S, H, Cv)
+        if bucket_cb is not None:
+            bucket_cb("head")
         if not frozen:
-            self.backbone_backward(dfeat)
+            self.backbone_backward(dfeat, bucket_cb)
+        if bucket_cb is not None:
+            bucket_cb("rest")
 
     def predictions(self):
         """argmax over the fp32 forward-direction logits of the last eval-mode forward -> int64 [B,T]."""

@@ -74,10 +74,30 @@ def _p(t):
     return 0 if t is None else t.data_ptr()
 
 
+launch_count = 0          # number of kernels of this library launched so far (every entry point launches exactly one)
+_gemm_profile = None      # when a list: (start_event, stop_event, flops, M, N, K, conv_mode, a_mn, b_mn) per GEMM launch
+
+
 def call(name, *args):
+    global launch_count
     rc = _get(name)(*args)
     if rc != 0:
         L.check(rc, name)
+    launch_count += 1
+
+
+def start_gemm_profile():
+    global _gemm_profile
+    _gemm_profile = []
+
+
+def stop_gemm_profile():
+    """Returns [(milliseconds, flops, M, N, K, conv_mode, a_mn, b_mn)] for every GEMM launched since start."""
+    global _gemm_profile
+    torch.cuda.synchronize()
+    out = [(a.elapsed_time(b),) + rest for (a, b, *rest) in _gemm_profile]
+    _gemm_profile = None
+    return out
 
 
 def num_sms():
@@ -108,7 +128,14 @@ def gemm(A, B, D, M, N, K, *, lda=None, ldb=None, ldd=None, a_mn=0, b_mn=0, bias
     else:
         g.conv_n = g.conv_h = g.conv_w = g.conv_c = 0
     g.conv_mode = conv_mode
-    call("vtx_gemm", ctypes.addressof(g), _stream())
+    if _gemm_profile is None:
+        call("vtx_gemm", ctypes.addressof(g), _stream())
+    else:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        call("vtx_gemm", ctypes.addressof(g), _stream())
+        e1.record()
+        _gemm_profile.append((e0, e1, 2.0 * M * N * K, M, N, K, conv_mode, a_mn, b_mn))
 
 
 def split_k_for(m_tiles_x_n_tiles, k_blocks, sms=None):
