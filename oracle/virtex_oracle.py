@@ -228,12 +228,32 @@ def synth_batch(batch_size: int, seed: int = 0, max_len: int = 30, vocab: int = 
 
 
 # ------------------------------------------------------------------------------------------------------- forward math
-def _batch_norm(x, P, prefix, training, new_buffers, eps=1e-5, momentum=0.1):
+class _RoundBF16(torch.autograd.Function):
+    """Round-to-bf16 in forward AND on the gradient in backward: marks where the bf16-autocast reference (and the
+    CUDA path) materialise a bf16 tensor.  Used only by the `emulate_bf16` variants below."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.bfloat16().to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.bfloat16().to(g.dtype)
+
+
+def _rb(x):
+    return _RoundBF16.apply(x)
+
+
+def _batch_norm(x, P, prefix, training, new_buffers, eps=1e-5, momentum=0.1, emulate_bf16=False):
     w, b = P[prefix + ".weight"], P[prefix + ".bias"]
+    x_stat = x  # statistics come from the fp32 conv accumulators; the normalised tensor is the bf16-rounded one
+    if emulate_bf16:
+        x = _rb(x)
     if training:
         n = x.numel() // x.shape[1]
-        mean = x.mean(dim=(0, 2, 3))
-        var_b = ((x - mean[None, :, None, None]) ** 2).mean(dim=(0, 2, 3))  # biased
+        mean = x_stat.mean(dim=(0, 2, 3))
+        var_b = ((x_stat - mean[None, :, None, None]) ** 2).mean(dim=(0, 2, 3))  # biased
         if new_buffers is not None:
             with torch.no_grad():
                 new_buffers[prefix + ".running_mean"] = (1 - momentum) * P[prefix + ".running_mean"] + momentum * mean
@@ -246,14 +266,16 @@ def _batch_norm(x, P, prefix, training, new_buffers, eps=1e-5, momentum=0.1):
     return xhat * w[None, :, None, None] + b[None, :, None, None]
 
 
-def backbone_forward(P, image, spec: Spec, training=True, new_buffers=None, record=None):
+def backbone_forward(P, image, spec: Spec, training=True, new_buffers=None, record=None, emulate_bf16=False):
     """(B,3,H,W) -> (B,2048,H/32,W/32).  torchvision ResNet children conv1..layer4.
     `record` (dict) optionally receives intermediate activations keyed by layer name (debug / per-layer parity)."""
     p = "visual.cnn."
-    x = F.conv2d(image, P[p + "conv1.weight"], stride=2, padding=3)
+    rb = _rb if emulate_bf16 else (lambda t: t)
+    bn = lambda t, name: _batch_norm(t, P, name, training, new_buffers, emulate_bf16=emulate_bf16)
+    x = F.conv2d(rb(image), rb(P[p + "conv1.weight"]), stride=2, padding=3)
     if record is not None:
         record["stem.y"] = x
-    x = torch.relu(_batch_norm(x, P, p + "bn1", training, new_buffers))
+    x = rb(torch.relu(bn(x, p + "bn1")))
     x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
     if record is not None:
         record["stem.pool"] = x
@@ -262,22 +284,22 @@ def backbone_forward(P, image, spec: Spec, training=True, new_buffers=None, reco
             stride = 2 if (bi == 0 and li > 1) else 1
             q = f"{p}layer{li}.{bi}."
             identity = x
-            out = F.conv2d(x, P[q + "conv1.weight"])
+            out = F.conv2d(x, rb(P[q + "conv1.weight"]))
             if record is not None:
                 record[q + "y1"] = out
-            out = torch.relu(_batch_norm(out, P, q + "bn1", training, new_buffers))
+            out = rb(torch.relu(bn(out, q + "bn1")))
             if record is not None:
                 record[q + "a1"] = out
-            out = F.conv2d(out, P[q + "conv2.weight"], stride=stride, padding=1)
+            out = F.conv2d(out, rb(P[q + "conv2.weight"]), stride=stride, padding=1)
             if record is not None:
                 record[q + "y2"] = out
-            out = torch.relu(_batch_norm(out, P, q + "bn2", training, new_buffers))
-            out = F.conv2d(out, P[q + "conv3.weight"])
-            out = _batch_norm(out, P, q + "bn3", training, new_buffers)
+            out = rb(torch.relu(bn(out, q + "bn2")))
+            out = F.conv2d(out, rb(P[q + "conv3.weight"]))
+            out = bn(out, q + "bn3")
             if q + "downsample.0.weight" in P:
-                identity = F.conv2d(x, P[q + "downsample.0.weight"], stride=stride)
-                identity = _batch_norm(identity, P, q + "downsample.1", training, new_buffers)
-            x = torch.relu(out + identity)
+                identity = F.conv2d(x, rb(P[q + "downsample.0.weight"]), stride=stride)
+                identity = bn(identity, q + "downsample.1")
+            x = rb(torch.relu(out + identity))
             if record is not None:
                 record[q + "out"] = x
     return x

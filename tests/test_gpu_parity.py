@@ -143,7 +143,10 @@ def test_attention_and_ce_kernels():
 
 # ---------------------------------------------------------------------------------------------------------- backbone
 def test_backbone_forward_backward_vs_oracle():
-    """Backbone alone with a random (well-conditioned) upstream gradient."""
+    """Backbone alone with a random (well-conditioned) upstream gradient, against the oracle run with the bf16
+    rounding placement of the autocast reference (`emulate_bf16`): a random BN/ReLU stack turns every bf16 rounding
+    of the forward pass into ReLU-mask flips, so only a comparator with the SAME placement can check backward tightly.
+    The fp32 oracle is compared too, with the loose bound that bf16 itself imposes."""
     _need_cuda()
     spec = O.Spec(hidden=128, layers=1, heads=2, ffn=256)
     state = O.synth_state(spec, 5, bn3_gain=0.25)
@@ -153,15 +156,15 @@ def test_backbone_forward_backward_vs_oracle():
     eng = model.engine
     model.train()
     feat, h, w = eng.backbone_forward(batch["image"].cuda(), training=True)
-    # oracle
     P = {k: (v.clone().requires_grad_(True) if not O.is_buffer(k) else v.clone()) for k, v in state.items()}
     nb = {}
-    ref = O.backbone_forward(P, batch["image"], spec, training=True, new_buffers=nb)
+    ref = O.backbone_forward(P, batch["image"], spec, training=True, new_buffers=nb, emulate_bf16=True)
     ref_nhwc = ref.permute(0, 2, 3, 1).reshape(B * h * w, -1)
-    # 53 bf16 conv layers (each output and each BN/ReLU result rounded to bf16, as under autocast) against fp32
-    assert rel(feat, ref_nhwc) < 8e-2, rel(feat, ref_nhwc)
+    with torch.no_grad():
+        ref32 = O.backbone_forward(state, batch["image"], spec, training=True)
+    f_emul, f_32 = rel(feat, ref_nhwc), rel(feat, ref32.permute(0, 2, 3, 1).reshape(B * h * w, -1))
     g = torch.Generator().manual_seed(0)
-    dfeat = torch.randn(ref_nhwc.shape, generator=g) * 0.01
+    dfeat = (torch.randn(ref_nhwc.shape, generator=g) * 0.01).bfloat16().float()
     ref_nhwc.backward(dfeat)
     eng.arena.grads.zero_()
     eng.backbone_backward(dfeat.cuda().bfloat16().contiguous())
@@ -177,12 +180,13 @@ def test_backbone_forward_backward_vs_oracle():
     import os
     os.makedirs("gpurun_out", exist_ok=True)
     with open("gpurun_out/backbone_parity.txt", "w") as f:
-        f.write(f"feat rel {rel(feat, ref_nhwc):.4f} median grad rel {med:.4f}\n")
+        f.write(f"feat rel vs bf16-placement oracle {f_emul:.5f} vs fp32 oracle {f_32:.5f}; median grad rel {med:.4f}\n")
         for c, r, n in worst:
             f.write(f"{n} cos {c:.5f} rel {r:.4f}\n")
-    assert worst[0][0] > 0.95, worst[:5]
-    assert med < 1e-1, (med, worst[:5])
-    # running statistics
+    assert f_emul < 1e-2, f_emul
+    assert f_32 < 8e-2, f_32
+    assert worst[0][0] > 0.99, worst[:5]
+    assert med < 5e-2, (med, worst[:5])
     for k in ("visual.cnn.bn1.running_var", "visual.cnn.layer4.2.bn3.running_mean", "visual.cnn.layer2.0.downsample.1.running_var"):
         assert rel(eng.buffers[k], nb[k]) < 2e-2, k
     assert int(eng.buffers["visual.cnn.bn1.num_batches_tracked"]) == 1

@@ -95,7 +95,7 @@ def stop_gemm_profile():
     """Returns [(milliseconds, flops, M, N, K, conv_mode, a_mn, b_mn)] for every GEMM launched since start."""
     global _gemm_profile
     torch.cuda.synchronize()
-    out = [(a.elapsed_time(b),) + rest for (a, b, *rest) in _gemm_profile]
+    out = [(a.elapsed_time(b),) + tuple(rest) for (a, b, *rest) in _gemm_profile]
     _gemm_profile = None
     return out
 

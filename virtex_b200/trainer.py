@@ -22,6 +22,36 @@ from .ops import _stream, call
 from .optim import lr_multiplier_fn
 
 _CHUNK = 65536
+BUCKET_ORDER = ("head", "layer4", "layer3", "layer2", "rest")  # completion order of gradient ranges in backward
+
+
+def bucket_ranges(names, offsets, numels) -> Dict[str, Optional[tuple]]:
+    """Contiguous [begin, end) element ranges of the flat gradient arena per all-reduce bucket (pure host logic)."""
+
+    def rng(pred):
+        sel = [n for n in names if pred(n)]
+        if not sel:
+            return None
+        return offsets[sel[0]], offsets[sel[-1]] + numels[sel[-1]]
+
+    out = {"head": rng(lambda n: not n.startswith("visual."))}
+    for l in ("layer4", "layer3", "layer2"):
+        out[l] = rng(lambda n, l=l: n.startswith(f"visual.cnn.{l}."))
+    out["rest"] = rng(lambda n: n.startswith("visual.cnn.") and (".layer1." in n or ".layer" not in n))
+    return out
+
+
+def optimizer_segments(names, offsets, numels, hparams, chunk=_CHUNK):
+    """[(begin, end, lr, wd)] chunks of <= `chunk` elements; hparams(name) -> (lr, wd) or None for frozen tensors."""
+    segs = []
+    for name in names:
+        hp = hparams(name)
+        if hp is None:
+            continue
+        b, e = offsets[name], offsets[name] + numels[name]
+        for c in range(b, e, chunk):
+            segs.append((c, min(e, c + chunk), hp[0], hp[1]))
+    return segs
 
 
 class Trainer:
@@ -43,14 +73,9 @@ class Trainer:
         self.la_k = int(O.LOOKAHEAD.STEPS)
         self.lr_fn = lr_multiplier_fn(O.LR_DECAY_NAME, O.NUM_ITERATIONS, O.WARMUP_STEPS, O.LR_STEPS, O.LR_GAMMA)
         # ---- per-parameter (lr, wd) by NAME, split into <= 64 Ki-element chunks for load balance
-        segs = []
-        for name in arena.names:
-            lr, wd = param_group_hparams(config, name)
-            if not arena._param_objs[name].requires_grad:
-                continue
-            b, e = arena.offsets[name], arena.offsets[name] + arena.numels[name]
-            for c in range(b, e, _CHUNK):
-                segs.append((c, min(e, c + _CHUNK), lr, wd))
+        segs = optimizer_segments(
+            arena.names, arena.offsets, arena.numels,
+            lambda n: param_group_hparams(config, n) if arena._param_objs[n].requires_grad else None)
         blob = b"".join(struct.pack("<qqff", *s) for s in segs)
         self.nseg = len(segs)
         self.segs = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(dev)
@@ -76,18 +101,7 @@ class Trainer:
     # ------------------------------------------------------------------------------------------------- DP buckets
     def _bucket_ranges(self) -> Dict[str, tuple]:
         a = self.arena
-
-        def rng(pred):
-            names = [n for n in a.names if pred(n)]
-            if not names:
-                return None
-            return a.offsets[names[0]], a.offsets[names[-1]] + a.numels[names[-1]]
-
-        out = {"head": rng(lambda n: not n.startswith("visual."))}
-        for l in ("layer4", "layer3", "layer2"):
-            out[l] = rng(lambda n, l=l: n.startswith(f"visual.cnn.{l}."))
-        out["rest"] = rng(lambda n: n.startswith("visual.cnn.") and (".layer1." in n or ".layer" not in n))
-        return out
+        return bucket_ranges(a.names, a.offsets, a.numels)
 
     def _on_bucket(self, tag):
         r = self._ranges.get(tag)
