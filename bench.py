@@ -85,10 +85,23 @@ def measured_peaks():
 
 
 # ------------------------------------------------------------------------------------------------------- CPU / reference
+def usable_cores():
+    """Host cores this process may really use: min(affinity mask, cgroup CPU quota)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()
+        if quota != "max":
+            n = min(n, max(1, int(quota) // int(period)))
+    except (OSError, ValueError):
+        pass
+    return n
+
+
 def run_cpu_reference(steps, warmup, batch, threads=None):
     """The reference algorithm (oracle port, fp32, CPU autograd) timed on the host cores: full optimisation steps."""
     from oracle import virtex_oracle as O
-    threads = threads or os.cpu_count()
+    threads = threads or usable_cores()
     torch.set_num_threads(threads)
     spec = O.Spec()
     tr = O.OracleTrainer(O.synth_state(spec, 0, randomize_bn=False), spec)
