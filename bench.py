@@ -244,6 +244,11 @@ def main_ours(args, rank, world, local):
         e1.record()
         prof = ops.stop_gemm_profile()
         prof_ms = e0.elapsed_time(e1) / 2
+        if args.dump_gemm_profile:
+            os.makedirs(os.path.dirname(os.path.abspath(args.dump_gemm_profile)), exist_ok=True)
+            with open(args.dump_gemm_profile, "w") as f:
+                json.dump([dict(ms=p[0], flops=p[1], M=p[2], N=p[3], K=p[4], conv_mode=p[5], a_mn=p[6], b_mn=p[7])
+                           for p in prof[len(prof) // 2:]], f)
         peak_tf, peak_bw, peak_src = measured_peaks()
         g_ms = sum(p[0] for p in prof) / 2
         g_fl = sum(p[1] for p in prof) / 2
@@ -289,6 +294,7 @@ def main():
     ap.add_argument("--config", default="_base_bicaptioning_R_50_L1_H1024.yaml")
     ap.add_argument("--config-override", nargs="*", default=[])
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--dump-gemm-profile", default="")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

@@ -10,7 +10,7 @@
 
 namespace vtx {
 
-static inline int grid_for(long long work_items, int threads, int per_sm = 8) {
+static inline int grid_for(long long work_items, int threads, int per_sm = 16) {
   long long blocks = (work_items + threads - 1) / threads;
   long long cap = (long long)vtx_num_sms() * per_sm;
   if (blocks > cap) blocks = cap;
@@ -182,22 +182,28 @@ __global__ void bn_act_kernel(const __nv_bfloat16* __restrict__ y, const float* 
                               __nv_bfloat16* __restrict__ out, long long M, int C, int relu) {
   const int cg = C / 8;
   const long long total = M * cg;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(i % cg);
-    const int c0 = g * 8;
+  // blockDim.x (256) is a multiple of cg, so a thread's 8-channel group never changes across the grid-stride loop:
+  // per-channel parameters live in registers.
+  const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int c0 = (int)(i0 % cg) * 8;
+  float sc[8], sh[8], sc2[8], sh2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = bnp[2 * C + c0 + j];
+    sh[j] = bnp[3 * C + c0 + j];
+    sc2[j] = bnp_res ? bnp_res[2 * C + c0 + j] : 1.f;
+    sh2[j] = bnp_res ? bnp_res[3 * C + c0 + j] : 0.f;
+  }
+  for (long long i = i0; i < total; i += (long long)gridDim.x * blockDim.x) {
     float v[8];
     unpack8(*reinterpret_cast<const bf16x8*>(y + i * 8), v);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = v[j] * __ldg(bnp + 2 * C + c0 + j) + __ldg(bnp + 3 * C + c0 + j);
+    for (int j = 0; j < 8; ++j) v[j] = v[j] * sc[j] + sh[j];
     if (res != nullptr) {
       float r[8];
       unpack8(*reinterpret_cast<const bf16x8*>(res + i * 8), r);
-      if (bnp_res != nullptr) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = r[j] * __ldg(bnp_res + 2 * C + c0 + j) + __ldg(bnp_res + 3 * C + c0 + j);
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] += r[j];
+      for (int j = 0; j < 8; ++j) v[j] += r[j] * sc2[j] + sh2[j];
     }
     if (relu) {
 #pragma unroll
@@ -402,8 +408,25 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dA, const 
                                     __nv_bfloat16* __restrict__ dz_out, long long M, int C) {
   const int cg = C / 8;
   const long long total = M * cg;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c0 = (int)(i % cg) * 8;
+  const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int c0 = (int)(i0 % cg) * 8;  // loop invariant (blockDim.x % cg == 0)
+  // dy = k0*dz + k1*y + k2 with k0 = scale, k1 = -scale*m2*invstd, k2 = scale*(m2*invstd*mean - m1)
+  float k0[8], k1[8], k2[8], q0[8], q1[8], q2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = c0 + j;
+    const float mean = bnp[c], istd = bnp[C + c], scl = coef[c], m1 = coef[C + c], m2 = coef[2 * C + c];
+    k0[j] = scl;
+    k1[j] = -scl * m2 * istd;
+    k2[j] = scl * (m2 * istd * mean - m1);
+    if (kTwo) {
+      const float mean_b = bnp2[c], istd_b = bnp2[C + c], scl_b = coef2[c], m1b = coef2[C + c], m2b = coef2[2 * C + c];
+      q0[j] = scl_b;
+      q1[j] = -scl_b * m2b * istd_b;
+      q2[j] = scl_b * (m2b * istd_b * mean_b - m1b);
+    }
+  }
+  for (long long i = i0; i < total; i += (long long)gridDim.x * blockDim.x) {
     float d[8], yy[8], o[8];
     unpack8(*reinterpret_cast<const bf16x8*>(dA + i * 8), d);
     if (a != nullptr) {
@@ -414,20 +437,12 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dA, const 
     }
     unpack8(*reinterpret_cast<const bf16x8*>(y + i * 8), yy);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = c0 + j;
-      const float xhat = (yy[j] - __ldg(bnp + c)) * __ldg(bnp + C + c);
-      o[j] = __ldg(coef + c) * (d[j] - __ldg(coef + C + c) - xhat * __ldg(coef + 2 * C + c));
-    }
+    for (int j = 0; j < 8; ++j) o[j] = k0[j] * d[j] + k1[j] * yy[j] + k2[j];
     *reinterpret_cast<bf16x8*>(dy + i * 8) = pack8(o);
     if (kTwo) {
       unpack8(*reinterpret_cast<const bf16x8*>(y2 + i * 8), yy);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int c = c0 + j;
-        const float xhat = (yy[j] - __ldg(bnp2 + c)) * __ldg(bnp2 + C + c);
-        o[j] = __ldg(coef2 + c) * (d[j] - __ldg(coef2 + C + c) - xhat * __ldg(coef2 + 2 * C + c));
-      }
+      for (int j = 0; j < 8; ++j) o[j] = q0[j] * d[j] + q1[j] * yy[j] + q2[j];
       *reinterpret_cast<bf16x8*>(dy2 + i * 8) = pack8(o);
     }
     if (dz_out != nullptr) *reinterpret_cast<bf16x8*>(dz_out + i * 8) = pack8(d);

@@ -194,13 +194,14 @@ __global__ void ln_bwd_kernel(const float* __restrict__ dy_a, const __nv_bfloat1
                               float* __restrict__ d_gamma, float* __restrict__ d_beta, int M, int H, float p,
                               const uint64_t* seed_ptr, uint32_t site, int ln) {
   const uint64_t seed = seed_ptr ? *seed_ptr : 0ull;
-  extern __shared__ float acc[];
-  if (ln) {
-    for (int i = threadIdx.x; i < 2 * H; i += blockDim.x) acc[i] = 0.f;
-    __syncthreads();
-  }
+  extern __shared__ float acc[];  // [warps][2][H] per-warp partial dgamma / dbeta (no atomics in the row loop)
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
+  float* my = acc + (size_t)warp * 2 * H;
+  if (ln) {
+    for (int i = lane; i < 2 * H; i += 32) my[i] = 0.f;
+    __syncwarp();
+  }
   const float inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
   for (int row = blockIdx.x * kWarpsPerBlock + warp; row < M; row += gridDim.x * kWarpsPerBlock) {
     const long long base = (long long)row * H;
@@ -208,36 +209,82 @@ __global__ void ln_bwd_kernel(const float* __restrict__ dy_a, const __nv_bfloat1
     if (ln) {
       mean = stats[2 * row];
       rstd = stats[2 * row + 1];
-      for (int i = lane; i < H; i += 32) {
-        float g = dy_a ? dy_a[base + i] : 0.f;
-        if (dy_b) g += bf2f(dy_b[base + i]);
-        const float xh = (z[base + i] - mean) * rstd;
-        atomicAdd(&acc[i], g * xh);
-        atomicAdd(&acc[H + i], g);
-        const float dxh = g * gamma[i];
-        s1 += dxh;
-        s2 += dxh * xh;
+      for (int i = lane * 4; i < H; i += 128) {
+        float g[4] = {0.f, 0.f, 0.f, 0.f};
+        if (dy_a) {
+          const float4 t = *reinterpret_cast<const float4*>(dy_a + base + i);
+          g[0] = t.x; g[1] = t.y; g[2] = t.z; g[3] = t.w;
+        }
+        if (dy_b) {
+          const uint2 u = *reinterpret_cast<const uint2*>(dy_b + base + i);
+          const float2 b0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+          const float2 b1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+          g[0] += b0.x; g[1] += b0.y; g[2] += b1.x; g[3] += b1.y;
+        }
+        const float4 zz = *reinterpret_cast<const float4*>(z + base + i);
+        const float4 gm = *reinterpret_cast<const float4*>(gamma + i);
+        const float xh[4] = {(zz.x - mean) * rstd, (zz.y - mean) * rstd, (zz.z - mean) * rstd, (zz.w - mean) * rstd};
+        const float gw[4] = {gm.x, gm.y, gm.z, gm.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          my[i + j] += g[j] * xh[j];
+          my[H + i + j] += g[j];
+          const float dxh = g[j] * gw[j];
+          s1 += dxh;
+          s2 += dxh * xh[j];
+        }
       }
       s1 = warp_sum(s1) / H;
       s2 = warp_sum(s2) / H;
     }
-    for (int i = lane; i < H; i += 32) {
-      float g = dy_a ? dy_a[base + i] : 0.f;
-      if (dy_b) g += bf2f(dy_b[base + i]);
-      float dz = g;
-      if (ln) {
-        const float xh = (z[base + i] - mean) * rstd;
-        dz = rstd * (g * gamma[i] - s1 - xh * s2);
+    for (int i = lane * 4; i < H; i += 128) {
+      float g[4] = {0.f, 0.f, 0.f, 0.f};
+      if (dy_a) {
+        const float4 t = *reinterpret_cast<const float4*>(dy_a + base + i);
+        g[0] = t.x; g[1] = t.y; g[2] = t.z; g[3] = t.w;
       }
-      if (d_branch) d_branch[base + i] = f2bf(dz * dropout_scale(p, inv_keep, seed, site, (uint64_t)base + i));
-      if (d_res) d_res[base + i] = dz + (d_skip ? d_skip[base + i] : 0.f);
+      if (dy_b) {
+        const uint2 u = *reinterpret_cast<const uint2*>(dy_b + base + i);
+        const float2 b0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+        const float2 b1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+        g[0] += b0.x; g[1] += b0.y; g[2] += b1.x; g[3] += b1.y;
+      }
+      float dz[4] = {g[0], g[1], g[2], g[3]};
+      if (ln) {
+        const float4 zz = *reinterpret_cast<const float4*>(z + base + i);
+        const float4 gm = *reinterpret_cast<const float4*>(gamma + i);
+        dz[0] = rstd * (g[0] * gm.x - s1 - (zz.x - mean) * rstd * s2);
+        dz[1] = rstd * (g[1] * gm.y - s1 - (zz.y - mean) * rstd * s2);
+        dz[2] = rstd * (g[2] * gm.z - s1 - (zz.z - mean) * rstd * s2);
+        dz[3] = rstd * (g[3] * gm.w - s1 - (zz.w - mean) * rstd * s2);
+      }
+      if (d_branch) {
+        float t[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) t[j] = dz[j] * dropout_scale(p, inv_keep, seed, site, (uint64_t)base + i + j);
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(t[0], t[1]), h1 = __floats2bfloat162_rn(t[2], t[3]);
+        uint2 u;
+        u.x = *reinterpret_cast<uint32_t*>(&h0);
+        u.y = *reinterpret_cast<uint32_t*>(&h1);
+        *reinterpret_cast<uint2*>(d_branch + base + i) = u;
+      }
+      if (d_res) {
+        float4 o = make_float4(dz[0], dz[1], dz[2], dz[3]);
+        if (d_skip) {
+          const float4 k = *reinterpret_cast<const float4*>(d_skip + base + i);
+          o.x += k.x; o.y += k.y; o.z += k.z; o.w += k.w;
+        }
+        *reinterpret_cast<float4*>(d_res + base + i) = o;
+      }
     }
   }
   if (ln) {
     __syncthreads();
-    for (int i = threadIdx.x; i < H; i += blockDim.x) {
-      atomicAdd(d_gamma + i, acc[i]);
-      atomicAdd(d_beta + i, acc[H + i]);
+    for (int i = threadIdx.x; i < 2 * H; i += blockDim.x) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < kWarpsPerBlock; ++w) t += acc[(size_t)w * 2 * H + i];
+      atomicAdd((i < H ? d_gamma + i : d_beta + (i - H)), t);
     }
   }
 }
@@ -663,7 +710,13 @@ extern "C" int vtx_ln_bwd(const float* dy_a, const void* dy_b, const float* z, c
   int blocks = (M + kWarpsPerBlock - 1) / kWarpsPerBlock;
   const int cap = vtx_num_sms() * 2;
   if (blocks > cap) blocks = cap;
-  ln_bwd_kernel<<<blocks, 32 * kWarpsPerBlock, ln ? 2 * H * sizeof(float) : 0, STREAM>>>(
+  const size_t ln_smem = ln ? (size_t)kWarpsPerBlock * 2 * H * sizeof(float) : 0;
+  static size_t ln_attr = 0;
+  if (ln_smem > 48 * 1024 && ln_smem > ln_attr) {
+    cudaFuncSetAttribute(ln_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ln_smem);
+    ln_attr = ln_smem;
+  }
+  ln_bwd_kernel<<<blocks, 32 * kWarpsPerBlock, ln_smem, STREAM>>>(
       dy_a, (const __nv_bfloat16*)dy_b, z, stats, gamma, d_skip, d_res, (__nv_bfloat16*)d_branch, d_gamma, d_beta, M, H,
       p, seed_ptr, site, ln);
   return check_launch("ln_bwd");
