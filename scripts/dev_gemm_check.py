@@ -74,10 +74,17 @@ report("bias+gelu", rel(D, torch.nn.functional.gelu(ref + bias)))
 D = gemm(A, B, M, N, K, residual=res, act=1)
 report("residual+relu", rel(D, torch.relu(ref + res.float())))
 stats = torch.zeros(2, N, device=dev)
-D = gemm(A, B, M, N, K, stats=stats, out_f32=True)
+D = gemm(A, B, M, N, K, out_f32=True)
 report("f32 out", rel(D, ref), 1e-5)
-report("stats sum", rel(stats[0], ref.sum(0)), 1e-4)
-report("stats sumsq", rel(stats[1], (ref * ref).sum(0)), 1e-4)
+D = gemm(A, B, M, N, K, stats=stats)
+rb = D.float()
+report("stats sum", rel(stats[0], rb.sum(0)), 1e-4)
+report("stats sumsq", rel(stats[1], (rb * rb).sum(0)), 1e-4)
+for bn_ in (64, 128, 256):
+    D = gemm(A, B, M, N, K, bias=bias, tile_n=bn_)
+    report(f"tile_n {bn_}", rel(D, ref + bias))
+D = gemm(A[:, :96].contiguous(), B[:, :96].contiguous(), M, 200, 96, bias=bias[:200])
+report("N tail 200, K 96", rel(D, (A[:, :96].float() @ B[:200, :96].float().t()) + bias[:200]))
 
 # ---- 3. dgrad: B MN-major ([K, N] storage):  dX[M,Kout] = dY[M,Nred] @ W[Nred,Kout]
 M, Nred, Kout = 640, 320, 448

@@ -2,11 +2,16 @@
 // VirTex bicaptioning step (1x1 convs, implicit 3x3 convs, im2col'd strided convs, all nn.Linear fwd/dgrad/wgrad,
 // vocabulary projection).  See include/virtex_b200.h (VtxGemm) for the contract.
 //
-// Structure (persistent, warp specialised, one CTA per SM, 256 threads):
-//   warp 0 : TMA producer   (one elected lane)  global -> 128B-swizzled smem ring, 4 stages of (A 16 KB, B <= 32 KB)
+// Structure (persistent, warp specialised, one CTA per SM, 384 threads):
+//   warp 0 : TMA producer   (one elected lane)  global -> 128B-swizzled smem ring of (A 16 KB, B = tile_n*128 B) stages;
+//                           the ring depth is whatever fits next to the output staging tile (3..8 stages)
 //   warp 1 : MMA issuer     (one elected lane)  tcgen05.mma.cta_group::1.kind::f16, M=128, N=tile_n, K=16 per issue
 //   warp 2 : TMEM allocator (512 columns = 2 accumulator stages of up to 256 fp32 columns)
-//   warps 4-7 : epilogue    tcgen05.ld -> registers -> stats / bias / residual / activation -> global
+//   warps 4-11 : epilogue   phase 1: tcgen05.ld (double buffered) -> bias / residual / activation in fp32 -> bf16 tile
+//                           in padded smem; TMEM is released to the MMA warp here.  phase 2: per-column BN statistics
+//                           read conflict-free from the staged tile, and whole output rows written as coalesced
+//                           16-byte-per-lane stores.  (fp32 / split-K outputs skip staging: vector stores or
+//                           red.global.add.v4.f32 straight from registers.)
 // Three mbarrier pipelines: smem full/empty (TMA <-> MMA), tmem full/empty (MMA <-> epilogue), and a static
 // round-robin tile schedule shared by the three roles.
 //
@@ -22,12 +27,12 @@ namespace vtx {
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;
-constexpr int kStages = 4;
+constexpr int kMaxStages = 8;
 constexpr int kABytes = kBM * kBK * 2;        // 16384
-constexpr int kBBytesMax = 256 * kBK * 2;     // 32768
-constexpr int kStageBytes = kABytes + kBBytesMax;
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int kThreads = 256;
+constexpr int kSmemTotal = 232448;            // 227 KB: the per-CTA maximum on sm_100
+constexpr int kCtrlBytes = 1024;              // barriers + TMEM slot, placed right after the 1024-aligned base
+constexpr int kThreads = 384;
+constexpr int kEpiThreads = 256;
 
 struct GemmKParams {
   int M, N, K;
@@ -40,6 +45,7 @@ struct GemmKParams {
   int lbw, lbh, lbn;
   int tiles_w, tiles_h;
   int out_f32, atomic, act;
+  int stages, stage_bytes, cstage_stride;  // smem ring depth / bytes per stage / staging row stride in bytes (0: none)
   float alpha;
   void* D;
   long long ldd;
@@ -67,33 +73,111 @@ __device__ __forceinline__ float warp_colsum32(float* v, int lane) {
   return v[0];
 }
 
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// fp32 epilogue math on one 32-column chunk of one accumulator row
+__device__ __forceinline__ void epi_math(float* v, const GemmKParams& p, long long grow, int col0, bool full) {
+  if (p.alpha != 1.0f) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] *= p.alpha;
+  }
+  if (p.bias != nullptr) {
+    if (full) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 b = *reinterpret_cast<const float4*>(p.bias + col0 + i);
+        v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < p.N) v[i] += p.bias[col0 + i];
+    }
+  }
+  if (p.residual != nullptr && grow >= 0) {
+    const __nv_bfloat16* rp = p.residual + grow * p.ldr + col0;
+    if (full) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        const uint4 u = *reinterpret_cast<const uint4*>(rp + i);
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __bfloat1622float2(h2[j]);
+          v[i + 2 * j] += f.x;
+          v[i + 2 * j + 1] += f.y;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < p.N) v[i] += __bfloat162float(rp[i]);
+    }
+  }
+  if (p.act == 1) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+  } else if (p.act == 2) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+  }
+}
+
+// registers -> global for fp32 outputs (plain or atomic accumulate)
+__device__ __forceinline__ void epi_store_f32(const float* v, const GemmKParams& p, long long grow, int col0, bool full) {
+  float* op = reinterpret_cast<float*>(p.D) + grow * p.ldd + col0;
+  if (p.atomic) {
+    if (full) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) red_add_v4(op + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < p.N) atomicAdd(op + i, v[i]);
+    }
+  } else if (full) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(op + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (col0 + i < p.N) op[i] = v[i];
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmKParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
-  uint64_t* full_bar = bars;                 // [kStages]
-  uint64_t* empty_bar = bars + kStages;      // [kStages]
-  uint64_t* tfull_bar = bars + 2 * kStages;  // [2]
-  uint64_t* tempty_bar = tfull_bar + 2;      // [2]
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base);
+  uint64_t* full_bar = bars;                     // [kMaxStages]
+  uint64_t* empty_bar = bars + kMaxStages;       // [kMaxStages]
+  uint64_t* tfull_bar = bars + 2 * kMaxStages;   // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;          // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint8_t* smem = base + kCtrlBytes;                       // stage ring (1024-aligned)
+  uint8_t* cstage = smem + p.stages * p.stage_bytes;       // bf16 output staging tile [128][cstage_stride]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.m_tiles * p.n_tiles * p.k_splits;
+  const int nstages = p.stages;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < kStages; ++i) {
+    for (int i = 0; i < nstages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 128);
+      mbar_init(&tempty_bar[i], kEpiThreads);
     }
     fence_mbar_init();
   }
@@ -129,7 +213,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sA = smem + stage * kStageBytes;
+          uint8_t* sA = smem + stage * p.stage_bytes;
           uint8_t* sB = sA + kABytes;
           mbar_arrive_expect_tx(&full_bar[stage], kABytes + b_bytes);
           if (p.mode == 0) {
@@ -169,7 +253,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               tma_load_4d(sB + j * 8192, &tmB, &full_bar[stage], cb * 64, bw0 + kw - 1, bh0 + kh - 1, nn);
             }
           }
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -196,7 +280,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sA = smem_u32(smem + stage * kStageBytes);
+          const uint32_t sA = smem_u32(smem + stage * p.stage_bytes);
           const uint32_t sB = sA + kABytes;
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
@@ -205,145 +289,137 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             umma_bf16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tfull_bar[as]);
       }
     }
     __syncwarp();
   } else if (warp >= 4) {
-    // ===================================================== epilogue
-    const int ew = warp & 3;  // TMEM lanes [32*ew, 32*ew+32)
+    // ===================================================== epilogue (8 warps)
+    const int ew = warp & 3;          // TMEM lane quadrant: lanes [32*ew, 32*ew+32)
+    const int hf = (warp - 4) >> 2;   // chunk parity handled by this warp (chunks of 32 columns)
+    const int et = threadIdx.x - 128; // 0..255 within the epilogue group
+    const bool staged = p.cstage_stride != 0;
+    const int nchunks = (p.bn + 31) >> 5;
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const int rem = t % (p.m_tiles * p.n_tiles);
       const int mt = rem / p.n_tiles;
       const int nt = rem - mt * p.n_tiles;
       const int as = it & 1;
+      const int n_base = nt * p.bn;
+      int tw = 0, th = 0, tn = 0;
+      if (p.mode == 1) {
+        tw = mt % p.tiles_w;
+        th = (mt / p.tiles_w) % p.tiles_h;
+        tn = mt / (p.tiles_w * p.tiles_h);
+      }
+      auto global_row = [&](int r_in_tile) -> long long {
+        if (p.mode == 1) {
+          const int dw = r_in_tile & ((1 << p.lbw) - 1);
+          const int dh = (r_in_tile >> p.lbw) & ((1 << p.lbh) - 1);
+          const int dn = r_in_tile >> (p.lbw + p.lbh);
+          const int w = (tw << p.lbw) + dw, h = (th << p.lbh) + dh, n = (tn << p.lbn) + dn;
+          return (w < p.cW && h < p.cH && n < p.cN) ? ((long long)(n * p.cH + h) * p.cW + w) : -1;
+        }
+        const int r = mt * kBM + r_in_tile;
+        return r < p.M ? (long long)r : -1;
+      };
       mbar_wait(&tfull_bar[as], (it >> 1) & 1);
       tc_fence_after();
 
+      // ---------------- phase 1: TMEM -> registers -> fp32 epilogue math -> staged bf16 (or fp32 global)
       const int r_in_tile = ew * 32 + lane;
-      long long grow;  // global output row, or -1 if masked
-      if (p.mode == 1) {
-        const int tw = mt % p.tiles_w;
-        const int th = (mt / p.tiles_w) % p.tiles_h;
-        const int tn = mt / (p.tiles_w * p.tiles_h);
-        const int dw = r_in_tile & ((1 << p.lbw) - 1);
-        const int dh = (r_in_tile >> p.lbw) & ((1 << p.lbh) - 1);
-        const int dn = r_in_tile >> (p.lbw + p.lbh);
-        const int w = (tw << p.lbw) + dw, h = (th << p.lbh) + dh, n = (tn << p.lbn) + dn;
-        grow = (w < p.cW && h < p.cH && n < p.cN) ? ((long long)(n * p.cH + h) * p.cW + w) : -1;
-      } else {
-        const int r = mt * kBM + r_in_tile;
-        grow = r < p.M ? r : -1;
-      }
-      const int n_base = nt * p.bn;
+      const long long grow = global_row(r_in_tile);
       const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)as * 256u;
-
-      for (int c0 = 0; c0 < p.bn; c0 += 32) {
-        if (n_base + c0 >= p.N) break;
-        float v[32];
-        tmem_ld32(t_row + c0, v);
+      float va[32], vb[32];
+      int j = hf;
+      if (j < nchunks && n_base + 32 * j < p.N) tmem_ld32(t_row + 32 * j, va);
+      for (; j < nchunks; j += 4) {
+        const int c0 = 32 * j, c1 = 32 * (j + 2);
+        const bool have0 = n_base + c0 < p.N;
+        const bool have1 = (j + 2 < nchunks) && (n_base + c1 < p.N);
+        if (!have0) break;
         tmem_ld_wait();
-        const int col0 = n_base + c0;
-        if (p.stats != nullptr) {
-          float s[32], q[32];
+        if (have1) tmem_ld32(t_row + c1, vb);
+        {
+          const int col0 = n_base + c0;
+          const bool full = col0 + 32 <= p.N;
+          epi_math(va, p, grow, col0, full);
+          if (staged) {
+            uint8_t* sp = cstage + (size_t)r_in_tile * p.cstage_stride + c0 * 2;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float x = grow >= 0 ? v[i] : 0.f;
-            s[i] = x;
-            q[i] = x * x;
-          }
-          const float cs = warp_colsum32(s, lane);
-          const float cq = warp_colsum32(q, lane);
-          if (col0 + lane < p.N) {
-            atomicAdd(p.stats + col0 + lane, cs);
-            atomicAdd(p.stats + p.N + col0 + lane, cq);
+            for (int i = 0; i < 32; i += 8) *reinterpret_cast<bf16x8*>(sp + i * 2) = pack8(va + i);
+          } else if (grow >= 0) {
+            epi_store_f32(va, p, grow, col0, full);
           }
         }
-        if (grow >= 0) {
-          const bool full = (col0 + 32 <= p.N);
-          if (p.alpha != 1.0f) {
+        if (!have1) break;
+        tmem_ld_wait();
+        const int c2 = 32 * (j + 4);
+        if (j + 4 < nchunks && n_base + c2 < p.N) tmem_ld32(t_row + c2, va);
+        {
+          const int col0 = n_base + c1;
+          const bool full = col0 + 32 <= p.N;
+          epi_math(vb, p, grow, col0, full);
+          if (staged) {
+            uint8_t* sp = cstage + (size_t)r_in_tile * p.cstage_stride + c1 * 2;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] *= p.alpha;
-          }
-          if (p.bias != nullptr) {
-            if (full) {
-#pragma unroll
-              for (int i = 0; i < 32; i += 4) {
-                const float4 b = *reinterpret_cast<const float4*>(p.bias + col0 + i);
-                v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (col0 + i < p.N) v[i] += p.bias[col0 + i];
-            }
-          }
-          if (p.residual != nullptr) {
-            const __nv_bfloat16* rp = p.residual + grow * p.ldr + col0;
-            if (full) {
-#pragma unroll
-              for (int i = 0; i < 32; i += 8) {
-                const uint4 u = *reinterpret_cast<const uint4*>(rp + i);
-                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float2 f = __bfloat1622float2(h2[j]);
-                  v[i + 2 * j] += f.x;
-                  v[i + 2 * j + 1] += f.y;
-                }
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (col0 + i < p.N) v[i] += __bfloat162float(rp[i]);
-            }
-          }
-          if (p.act == 1) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-          } else if (p.act == 2) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
-          }
-          if (p.out_f32) {
-            float* op = reinterpret_cast<float*>(p.D) + grow * p.ldd + col0;
-            if (p.atomic) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (col0 + i < p.N) atomicAdd(op + i, v[i]);
-            } else if (full) {
-#pragma unroll
-              for (int i = 0; i < 32; i += 4)
-                *reinterpret_cast<float4*>(op + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (col0 + i < p.N) op[i] = v[i];
-            }
-          } else {
-            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.D) + grow * p.ldd + col0;
-            if (full) {
-#pragma unroll
-              for (int i = 0; i < 32; i += 8) {
-                uint4 u;
-                __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) h2[j] = __floats2bfloat162_rn(v[i + 2 * j], v[i + 2 * j + 1]);
-                *reinterpret_cast<uint4*>(op + i) = u;
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (col0 + i < p.N) op[i] = __float2bfloat16_rn(v[i]);
-            }
+            for (int i = 0; i < 32; i += 8) *reinterpret_cast<bf16x8*>(sp + i * 2) = pack8(vb + i);
+          } else if (grow >= 0) {
+            epi_store_f32(vb, p, grow, col0, full);
           }
         }
       }
+      tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(&tempty_bar[as]);
+      mbar_arrive(&tempty_bar[as]);  // accumulator stage is free for the MMA warp
+
+      if (staged) {
+        epi_bar();
+        // ---------------- phase 2a: per-column sum / sum of squares of the staged (bf16-rounded) tile
+        if (p.stats != nullptr) {
+          const int col = et;  // one column per thread
+          if (col < p.bn && n_base + col < p.N) {
+            float s1 = 0.f, s2 = 0.f;
+            const uint8_t* cp = cstage + col * 2;
+            const int rows = (p.mode == 1) ? kBM : min(kBM, p.M - mt * kBM);
+            // rows outside the problem are exact zeros (TMA zero fill; stats forbids bias/residual), no masking needed
+            for (int r = 0; r < rows; ++r) {
+              const float x = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(cp + (size_t)r * p.cstage_stride));
+              s1 += x;
+              s2 += x * x;
+            }
+            atomicAdd(p.stats + n_base + col, s1);
+            atomicAdd(p.stats + p.N + n_base + col, s2);
+          }
+        }
+        // ---------------- phase 2b: coalesced row stores (16 B per lane, whole rows per warp)
+        {
+          const int cpr = p.bn >> 3;  // 16-byte chunks per row
+          const int ewarp = warp - 4;
+          const int items = 16 * cpr;  // this warp's 16 rows
+          __nv_bfloat16* D = reinterpret_cast<__nv_bfloat16*>(p.D);
+          for (int idx = lane; idx < items; idx += 32) {
+            const int r = ewarp * 16 + idx / cpr;
+            const int ch = idx - (idx / cpr) * cpr;
+            const long long gr = global_row(r);
+            const int col0 = n_base + ch * 8;
+            if (gr < 0 || col0 >= p.N) continue;
+            const uint4 v = *reinterpret_cast<const uint4*>(cstage + (size_t)r * p.cstage_stride + ch * 16);
+            __nv_bfloat16* op = D + gr * p.ldd + col0;
+            if (col0 + 8 <= p.N) {
+              *reinterpret_cast<uint4*>(op) = v;
+            } else {
+              const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&v);
+              for (int i = 0; i < 8; ++i)
+                if (col0 + i < p.N) op[i] = e[i];
+            }
+          }
+        }
+        epi_bar();  // staging tile free for the next tile's phase 1
+      }
     }
   }
 
@@ -430,6 +506,8 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
   if (g->atomic && !g->out_f32) return set_error(VTX_EINVAL, "vtx_gemm: atomic accumulate needs fp32 output");
   const int split_k = g->split_k > 1 ? g->split_k : 1;
   if (split_k > 1 && !g->atomic) return set_error(VTX_EINVAL, "vtx_gemm: split_k > 1 needs atomic = 1");
+  if (g->stats && (g->out_f32 || g->bias || g->residual || g->act || (g->alpha != 0.f && g->alpha != 1.f)))
+    return set_error(VTX_EINVAL, "vtx_gemm: stats needs a plain bf16 output (no bias/residual/activation/alpha)");
   if (g->ldd % (g->out_f32 ? 4 : 8) != 0) return set_error(VTX_EINVAL, "vtx_gemm: ldd must keep rows 16B aligned");
 
   GemmKParams p;
@@ -531,16 +609,26 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
   p.kb_per_split = (p.kb_total + p.k_splits - 1) / p.k_splits;
   p.k_splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
 
+  // ---- shared-memory carve-up: [1 KB control][stages x (A 16 KB + B bn*128 B)][bf16 staging tile 128 x (bn*2+16) B]
+  p.stage_bytes = kABytes + bn * kBK * 2;
+  p.cstage_stride = p.out_f32 ? 0 : bn * 2 + 16;
+  {
+    const int avail = kSmemTotal - 1024 /*alignment slack*/ - kCtrlBytes - kBM * p.cstage_stride;
+    int st = avail / p.stage_bytes;
+    if (st > kMaxStages) st = kMaxStages;
+    if (st < 2) return set_error(VTX_EUNSUPPORTED, "vtx_gemm: not enough shared memory for a 2-stage pipeline");
+    p.stages = st;
+  }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
     if (e != cudaSuccess) return set_error(VTX_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
   const long total = (long)p.m_tiles * p.n_tiles * p.k_splits;
   const int sms = vtx_num_sms();
   const int grid = (int)(total < sms ? total : sms);
-  gemm_tc_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, p);
+  gemm_tc_kernel<<<grid, kThreads, kSmemTotal, stream>>>(tmA, tmB, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(VTX_ECUDA, "gemm_tc_kernel launch: %s", cudaGetErrorString(e));
   return VTX_OK;

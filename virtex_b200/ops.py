@@ -143,4 +143,5 @@ def split_k_for(m_tiles_x_n_tiles, k_blocks, sms=None):
     sms = sms or num_sms()
     if m_tiles_x_n_tiles >= sms:
         return 1
-    return max(1, min(k_blocks, (2 * sms + m_tiles_x_n_tiles - 1) // m_tiles_x_n_tiles))
+    # about one wave of tiles: every extra split multiplies the fp32 atomic traffic of the epilogue
+    return max(1, min(max(1, k_blocks // 4), sms // m_tiles_x_n_tiles))
