@@ -1,0 +1,33 @@
+"""A few representative GEMM launches for `ncu --set full` captures (run under gpurun)."""
+import sys
+import torch
+sys.path.insert(0, ".")
+from virtex_b200 import ops
+
+dev = "cuda"
+torch.manual_seed(0)
+
+
+def bf(*s):
+    return (torch.randn(*s, device=dev) * 0.5).bfloat16()
+
+
+cases = sys.argv[1:] or ["l1conv3", "ffn1", "l1dgrad"]
+for _ in range(2):
+    if "l1conv3" in cases:  # layer1 1x1 conv 64->256 fprop with BN statistics: HBM bound
+        M, N, K = 802816, 256, 64
+        A, B, D = bf(M, K), bf(N, K), torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        st = torch.zeros(2, N, device=dev)
+        ops.gemm(A, B, D, M, N, K, stats=st)
+    if "l1dgrad" in cases:  # layer1 conv1 dgrad + residual
+        M, N, K = 802816, 256, 64
+        A, B, D = bf(M, K), bf(K, N), torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        R = bf(M, N)
+        ops.gemm(A, B, D, M, N, K, b_mn=1, residual=R)
+    if "ffn1" in cases:  # FFN linear1 with bias: tensor bound
+        M, N, K = 7680, 4096, 1024
+        A, B, D = bf(M, K), bf(N, K), torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        bias = torch.randn(N, device=dev)
+        ops.gemm(A, B, D, M, N, K, bias=bias)
+    torch.cuda.synchronize()
+print("done")

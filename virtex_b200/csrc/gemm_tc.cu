@@ -79,7 +79,8 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // fp32 epilogue math on one 32-column chunk of one accumulator row
-__device__ __forceinline__ void epi_math(float* v, const GemmKParams& p, long long grow, int col0, bool full) {
+__device__ __forceinline__ void epi_math(float* v, const GemmKParams& p, long long grow, int col0, bool full,
+                                         bool defer_residual) {
   if (p.alpha != 1.0f) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] *= p.alpha;
@@ -97,6 +98,7 @@ __device__ __forceinline__ void epi_math(float* v, const GemmKParams& p, long lo
         if (col0 + i < p.N) v[i] += p.bias[col0 + i];
     }
   }
+  if (defer_residual) return;  // staged path: residual (+ activation) are applied on coalesced rows in phase 2
   if (p.residual != nullptr && grow >= 0) {
     const __nv_bfloat16* rp = p.residual + grow * p.ldr + col0;
     if (full) {
@@ -301,7 +303,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int hf = (warp - 4) >> 2;   // chunk parity handled by this warp (chunks of 32 columns)
     const int et = threadIdx.x - 128; // 0..255 within the epilogue group
     const bool staged = p.cstage_stride != 0;
+    const bool defer_res = staged && p.residual != nullptr;
     const int nchunks = (p.bn + 31) >> 5;
+    // BN statistics: thread (scg, srg) owns 8 columns x 16 rows of every staged tile and keeps running partial sums in
+    // registers across all tiles of this CTA that share the same column block; they are reduced through shared
+    // memory and flushed with one atomic per column only when the column block changes (or at the end).
+    const int scg = et & 31, srg = et >> 5;
+    float st_s[8], st_q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) st_s[i] = st_q[i] = 0.f;
+    int st_nt = -1;
+    auto flush_stats = [&]() {
+      // staging tile is free here (callers guarantee a preceding epi_bar)
+      float* scr = reinterpret_cast<float*>(cstage);
+      if (scg * 8 < p.bn) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          scr[(srg * p.bn + scg * 8 + i) * 2] = st_s[i];
+          scr[(srg * p.bn + scg * 8 + i) * 2 + 1] = st_q[i];
+          st_s[i] = st_q[i] = 0.f;
+        }
+      }
+      epi_bar();
+      if (et < p.bn && st_nt * p.bn + et < p.N) {
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          a += scr[(g * p.bn + et) * 2];
+          b += scr[(g * p.bn + et) * 2 + 1];
+        }
+        atomicAdd(p.stats + st_nt * p.bn + et, a);
+        atomicAdd(p.stats + p.N + st_nt * p.bn + et, b);
+      }
+      epi_bar();
+    };
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const int rem = t % (p.m_tiles * p.n_tiles);
@@ -326,6 +361,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int r = mt * kBM + r_in_tile;
         return r < p.M ? (long long)r : -1;
       };
+      if (p.stats != nullptr && st_nt != nt) {
+        if (st_nt >= 0) flush_stats();
+        st_nt = nt;
+      }
       mbar_wait(&tfull_bar[as], (it >> 1) & 1);
       tc_fence_after();
 
@@ -346,7 +385,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         {
           const int col0 = n_base + c0;
           const bool full = col0 + 32 <= p.N;
-          epi_math(va, p, grow, col0, full);
+          epi_math(va, p, grow, col0, full, defer_res);
           if (staged) {
             uint8_t* sp = cstage + (size_t)r_in_tile * p.cstage_stride + c0 * 2;
 #pragma unroll
@@ -362,7 +401,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         {
           const int col0 = n_base + c1;
           const bool full = col0 + 32 <= p.N;
-          epi_math(vb, p, grow, col0, full);
+          epi_math(vb, p, grow, col0, full, defer_res);
           if (staged) {
             uint8_t* sp = cstage + (size_t)r_in_tile * p.cstage_stride + c1 * 2;
 #pragma unroll
@@ -378,49 +417,71 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
       if (staged) {
         epi_bar();
-        // ---------------- phase 2a: per-column sum / sum of squares of the staged (bf16-rounded) tile
-        if (p.stats != nullptr) {
-          const int col = et;  // one column per thread
-          if (col < p.bn && n_base + col < p.N) {
-            float s1 = 0.f, s2 = 0.f;
-            const uint8_t* cp = cstage + col * 2;
-            const int rows = (p.mode == 1) ? kBM : min(kBM, p.M - mt * kBM);
-            // rows outside the problem are exact zeros (TMA zero fill; stats forbids bias/residual), no masking needed
-            for (int r = 0; r < rows; ++r) {
-              const float x = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(cp + (size_t)r * p.cstage_stride));
-              s1 += x;
-              s2 += x * x;
+        // ---------------- phase 2a: BN statistics of the staged (bf16-rounded) tile, accumulated in registers.
+        // Rows outside the problem are exact zeros (TMA zero fill; stats forbids bias/residual): no masking needed.
+        if (p.stats != nullptr && scg * 8 < p.bn) {
+          const uint8_t* cp = cstage + (size_t)(srg * 16) * p.cstage_stride + scg * 16;
+#pragma unroll 4
+          for (int r = 0; r < 16; ++r) {
+            float f[8];
+            unpack8(*reinterpret_cast<const bf16x8*>(cp + (size_t)r * p.cstage_stride), f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              st_s[i] += f[i];
+              st_q[i] += f[i] * f[i];
             }
-            atomicAdd(p.stats + n_base + col, s1);
-            atomicAdd(p.stats + p.N + n_base + col, s2);
           }
         }
-        // ---------------- phase 2b: coalesced row stores (16 B per lane, whole rows per warp)
+        // ---------------- phase 2b: coalesced row stores (16 B per lane, whole rows per warp) (+ deferred residual)
         {
           const int cpr = p.bn >> 3;  // 16-byte chunks per row
+          const int lcpr = 31 - __clz(cpr);
+          const bool pow2 = (cpr & (cpr - 1)) == 0;
           const int ewarp = warp - 4;
           const int items = 16 * cpr;  // this warp's 16 rows
           __nv_bfloat16* D = reinterpret_cast<__nv_bfloat16*>(p.D);
           for (int idx = lane; idx < items; idx += 32) {
-            const int r = ewarp * 16 + idx / cpr;
-            const int ch = idx - (idx / cpr) * cpr;
-            const long long gr = global_row(r);
+            const int rr = pow2 ? (idx >> lcpr) : (idx / cpr);
+            const int ch = idx - rr * cpr;
+            const int r = ewarp * 16 + rr;
+            const long long gr = (p.mode == 1) ? global_row(r) : ((mt * kBM + r < p.M) ? (long long)(mt * kBM + r) : -1);
             const int col0 = n_base + ch * 8;
             if (gr < 0 || col0 >= p.N) continue;
-            const uint4 v = *reinterpret_cast<const uint4*>(cstage + (size_t)r * p.cstage_stride + ch * 16);
+            uint4 v = *reinterpret_cast<const uint4*>(cstage + (size_t)r * p.cstage_stride + ch * 16);
             __nv_bfloat16* op = D + gr * p.ldd + col0;
             if (col0 + 8 <= p.N) {
+              if (defer_res) {
+                float a[8], b[8];
+                unpack8(*reinterpret_cast<const bf16x8*>(&v), a);
+                unpack8(*reinterpret_cast<const bf16x8*>(p.residual + gr * p.ldr + col0), b);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  a[i] += b[i];
+                  if (p.act == 1) a[i] = fmaxf(a[i], 0.f);
+                  else if (p.act == 2) a[i] = gelu_erf(a[i]);
+                }
+                *reinterpret_cast<bf16x8*>(&v) = pack8(a);
+              }
               *reinterpret_cast<uint4*>(op) = v;
             } else {
               const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&v);
               for (int i = 0; i < 8; ++i)
-                if (col0 + i < p.N) op[i] = e[i];
+                if (col0 + i < p.N) {
+                  float a = __bfloat162float(e[i]);
+                  if (defer_res) {
+                    a += __bfloat162float(p.residual[gr * p.ldr + col0 + i]);
+                    if (p.act == 1) a = fmaxf(a, 0.f);
+                    else if (p.act == 2) a = gelu_erf(a);
+                  }
+                  op[i] = __float2bfloat16_rn(a);
+                }
             }
           }
         }
         epi_bar();  // staging tile free for the next tile's phase 1
       }
     }
+    if (p.stats != nullptr && st_nt >= 0) flush_stats();
   }
 
   tc_fence_before();
@@ -611,7 +672,7 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
 
   // ---- shared-memory carve-up: [1 KB control][stages x (A 16 KB + B bn*128 B)][bf16 staging tile 128 x (bn*2+16) B]
   p.stage_bytes = kABytes + bn * kBK * 2;
-  p.cstage_stride = p.out_f32 ? 0 : bn * 2 + 16;
+  p.cstage_stride = p.out_f32 ? 0 : ((bn + 31) / 32) * 64 + 16;  // whole 32-column chunks + 16 B pad
   {
     const int avail = kSmemTotal - 1024 /*alignment slack*/ - kCtrlBytes - kBM * p.cstage_stride;
     int st = avail / p.stage_bytes;
