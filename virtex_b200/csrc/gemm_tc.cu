@@ -7,11 +7,13 @@
 //                           the ring depth is whatever fits next to the output staging tile (3..8 stages)
 //   warp 1 : MMA issuer     (one elected lane)  tcgen05.mma.cta_group::1.kind::f16, M=128, N=tile_n, K=16 per issue
 //   warp 2 : TMEM allocator (512 columns = 2 accumulator stages of up to 256 fp32 columns)
-//   warps 4-11 : epilogue   phase 1: tcgen05.ld (double buffered) -> bias / residual / activation in fp32 -> bf16 tile
-//                           in padded smem; TMEM is released to the MMA warp here.  phase 2: per-column BN statistics
-//                           read conflict-free from the staged tile, and whole output rows written as coalesced
-//                           16-byte-per-lane stores.  (fp32 / split-K outputs skip staging: vector stores or
-//                           red.global.add.v4.f32 straight from registers.)
+//   warps 4-11 : epilogue   tcgen05.ld (double buffered) -> bias / residual / activation in fp32 -> bf16 tile in
+//                           128B-swizzled smem (TMEM is released to the MMA warp here) -> one elected thread issues
+//                           TMA stores (cp.async.bulk.tensor, out-of-bounds rows/columns clipped by the hardware);
+//                           per-column BN statistics are read from the staged tile and accumulated in registers across
+//                           the CTA's tiles.  Two staging buffers when the K loop is short (HBM-bound convs) so the
+//                           store of tile i overlaps the epilogue of tile i+1.  (fp32 / split-K outputs skip staging:
+//                           vector stores or red.global.add.v4.f32 straight from registers.)
 // Three mbarrier pipelines: smem full/empty (TMA <-> MMA), tmem full/empty (MMA <-> epilogue), and a static
 // round-robin tile schedule shared by the three roles.
 //
@@ -19,6 +21,7 @@
 // kernel serves fprop (A,B K-major), dgrad (B MN-major) and wgrad (A,B MN-major) without transposing activations.
 // conv_mode 1/2 replace the 2D TMA loads by 4D NHWC box loads whose out-of-bounds elements are zero-filled by the
 // TMA unit: that *is* the im2col of a 3x3/stride-1/pad-1 convolution, with no extra HBM traffic.
+#include <stdlib.h>
 #include "ptx.cuh"
 #include "vtx_common.cuh"
 #include "../../include/virtex_b200.h"
@@ -45,7 +48,9 @@ struct GemmKParams {
   int lbw, lbh, lbn;
   int tiles_w, tiles_h;
   int out_f32, atomic, act;
-  int stages, stage_bytes, cstage_stride;  // smem ring depth / bytes per stage / staging row stride in bytes (0: none)
+  int dbg;  // developer knobs (VTX_GEMM_DBG): selectively disable epilogue parts for attribution experiments
+  int stages, stage_bytes;   // smem ring depth / bytes per stage
+  int cbytes, nbuf;          // bytes of one bf16 staging buffer (0: no staging) / number of staging buffers
   float alpha;
   void* D;
   long long ldd;
@@ -79,8 +84,7 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // fp32 epilogue math on one 32-column chunk of one accumulator row
-__device__ __forceinline__ void epi_math(float* v, const GemmKParams& p, long long grow, int col0, bool full,
-                                         bool defer_residual) {
+__device__ __forceinline__ void epi_math(float* v, const GemmKParams& p, long long grow, int col0, bool full) {
   if (p.alpha != 1.0f) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] *= p.alpha;
@@ -98,7 +102,6 @@ __device__ __forceinline__ void epi_math(float* v, const GemmKParams& p, long lo
         if (col0 + i < p.N) v[i] += p.bias[col0 + i];
     }
   }
-  if (defer_residual) return;  // staged path: residual (+ activation) are applied on coalesced rows in phase 2
   if (p.residual != nullptr && grow >= 0) {
     const __nv_bfloat16* rp = p.residual + grow * p.ldr + col0;
     if (full) {
@@ -151,7 +154,8 @@ __device__ __forceinline__ void epi_store_f32(const float* v, const GemmKParams&
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmKParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmD, const GemmKParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(base);
@@ -161,7 +165,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tempty_bar = tfull_bar + 2;          // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   uint8_t* smem = base + kCtrlBytes;                       // stage ring (1024-aligned)
-  uint8_t* cstage = smem + p.stages * p.stage_bytes;       // bf16 output staging tile [128][cstage_stride]
+  uint8_t* cstage0 = smem + p.stages * p.stage_bytes;      // bf16 staging: nbuf x [bn/64 slabs][128 rows][128 B], SW128
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -171,6 +175,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.cbytes) tma_prefetch_desc(&tmD);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < nstages; ++i) {
@@ -198,6 +203,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================================================== TMA producer
     if (lane == 0) {
       int stage = 0;
+      int fills = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int ks = t / (p.m_tiles * p.n_tiles);
@@ -217,7 +223,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sA = smem + stage * p.stage_bytes;
           uint8_t* sB = sA + kABytes;
-          mbar_arrive_expect_tx(&full_bar[stage], kABytes + b_bytes);
+          // dbg&16 (experiment; valid only for n_tiles == 1 && kb_total == 1): B is identical for every tile, so each
+          // stage buffer is filled once and never reloaded
+          const bool skip_b = (p.dbg & 16) && fills >= nstages;
+          ++fills;
+          mbar_arrive_expect_tx(&full_bar[stage], kABytes + (skip_b ? 0u : b_bytes));
           if (p.mode == 0) {
             if (!p.a_mn) {
               tma_load_2d(sA, &tmA, &full_bar[stage], kb * kBK, mt * kBM);
@@ -225,7 +235,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               tma_load_2d(sA, &tmA, &full_bar[stage], mt * kBM, kb * kBK);
               tma_load_2d(sA + 8192, &tmA, &full_bar[stage], mt * kBM + 64, kb * kBK);
             }
-            if (!p.b_mn) {
+            if (skip_b) {
+            } else if (!p.b_mn) {
               tma_load_2d(sB, &tmB, &full_bar[stage], kb * kBK, nt * p.bn);
             } else {
               for (int j = 0; j < (p.bn >> 6); ++j)
@@ -302,8 +313,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int ew = warp & 3;          // TMEM lane quadrant: lanes [32*ew, 32*ew+32)
     const int hf = (warp - 4) >> 2;   // chunk parity handled by this warp (chunks of 32 columns)
     const int et = threadIdx.x - 128; // 0..255 within the epilogue group
-    const bool staged = p.cstage_stride != 0;
-    const bool defer_res = staged && p.residual != nullptr;
+    const bool staged = p.cbytes != 0;
     const int nchunks = (p.bn + 31) >> 5;
     // BN statistics: thread (scg, srg) owns 8 columns x 16 rows of every staged tile and keeps running partial sums in
     // registers across all tiles of this CTA that share the same column block; they are reduced through shared
@@ -313,9 +323,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
     for (int i = 0; i < 8; ++i) st_s[i] = st_q[i] = 0.f;
     int st_nt = -1;
-    auto flush_stats = [&]() {
-      // staging tile is free here (callers guarantee a preceding epi_bar)
-      float* scr = reinterpret_cast<float*>(cstage);
+    auto flush_stats = [&](uint8_t* scratch) {
+      // `scratch` is a staging buffer no TMA store is reading and nobody is writing (callers guarantee it)
+      float* scr = reinterpret_cast<float*>(scratch);
       if (scg * 8 < p.bn) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -350,28 +360,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         th = (mt / p.tiles_w) % p.tiles_h;
         tn = mt / (p.tiles_w * p.tiles_h);
       }
-      auto global_row = [&](int r_in_tile) -> long long {
+      uint8_t* cbuf = cstage0 + (size_t)(p.nbuf > 1 ? (it & 1) : 0) * p.cbytes;
+      if (staged) {
+        // the TMA store that last read this staging buffer must have finished reading it
+        if (et == 0) {
+          if (p.nbuf > 1) tma_store_wait_read<1>();
+          else tma_store_wait_read<0>();
+        }
+        epi_bar();
+        if (p.stats != nullptr && st_nt != nt) {
+          if (st_nt >= 0) flush_stats(cbuf);
+          st_nt = nt;
+        }
+      }
+      mbar_wait(&tfull_bar[as], (it >> 1) & 1);
+      tc_fence_after();
+
+      // ---------------- phase 1: TMEM -> registers -> fp32 epilogue math -> swizzled bf16 staging (or fp32 global)
+      const int r_in_tile = ew * 32 + lane;
+      long long grow = -1;
+      if (!staged || p.residual != nullptr) {
         if (p.mode == 1) {
           const int dw = r_in_tile & ((1 << p.lbw) - 1);
           const int dh = (r_in_tile >> p.lbw) & ((1 << p.lbh) - 1);
           const int dn = r_in_tile >> (p.lbw + p.lbh);
           const int w = (tw << p.lbw) + dw, h = (th << p.lbh) + dh, n = (tn << p.lbn) + dn;
-          return (w < p.cW && h < p.cH && n < p.cN) ? ((long long)(n * p.cH + h) * p.cW + w) : -1;
+          grow = (w < p.cW && h < p.cH && n < p.cN) ? ((long long)(n * p.cH + h) * p.cW + w) : -1;
+        } else {
+          const int r = mt * kBM + r_in_tile;
+          grow = r < p.M ? (long long)r : -1;
         }
-        const int r = mt * kBM + r_in_tile;
-        return r < p.M ? (long long)r : -1;
-      };
-      if (p.stats != nullptr && st_nt != nt) {
-        if (st_nt >= 0) flush_stats();
-        st_nt = nt;
       }
-      mbar_wait(&tfull_bar[as], (it >> 1) & 1);
-      tc_fence_after();
-
-      // ---------------- phase 1: TMEM -> registers -> fp32 epilogue math -> staged bf16 (or fp32 global)
-      const int r_in_tile = ew * 32 + lane;
-      const long long grow = global_row(r_in_tile);
       const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)as * 256u;
+      uint8_t* srow = cbuf + r_in_tile * 128;
+      const int sw = r_in_tile & 7;
       float va[32], vb[32];
       int j = hf;
       if (j < nchunks && n_base + 32 * j < p.N) tmem_ld32(t_row + 32 * j, va);
@@ -385,11 +407,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         {
           const int col0 = n_base + c0;
           const bool full = col0 + 32 <= p.N;
-          epi_math(va, p, grow, col0, full, defer_res);
+          epi_math(va, p, grow, col0, full);
           if (staged) {
-            uint8_t* sp = cstage + (size_t)r_in_tile * p.cstage_stride + c0 * 2;
+            uint8_t* sp = srow + (j >> 1) * 16384;
+            const int cb = (j & 1) * 4;
 #pragma unroll
-            for (int i = 0; i < 32; i += 8) *reinterpret_cast<bf16x8*>(sp + i * 2) = pack8(va + i);
+            for (int i = 0; i < 4; ++i) *reinterpret_cast<bf16x8*>(sp + (((cb + i) ^ sw) << 4)) = pack8(va + 8 * i);
           } else if (grow >= 0) {
             epi_store_f32(va, p, grow, col0, full);
           }
@@ -401,11 +424,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         {
           const int col0 = n_base + c1;
           const bool full = col0 + 32 <= p.N;
-          epi_math(vb, p, grow, col0, full, defer_res);
+          epi_math(vb, p, grow, col0, full);
           if (staged) {
-            uint8_t* sp = cstage + (size_t)r_in_tile * p.cstage_stride + c1 * 2;
+            uint8_t* sp = srow + ((j + 2) >> 1) * 16384;
+            const int cb = ((j + 2) & 1) * 4;
 #pragma unroll
-            for (int i = 0; i < 32; i += 8) *reinterpret_cast<bf16x8*>(sp + i * 2) = pack8(vb + i);
+            for (int i = 0; i < 4; ++i) *reinterpret_cast<bf16x8*>(sp + (((cb + i) ^ sw) << 4)) = pack8(vb + 8 * i);
           } else if (grow >= 0) {
             epi_store_f32(vb, p, grow, col0, full);
           }
@@ -416,15 +440,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_arrive(&tempty_bar[as]);  // accumulator stage is free for the MMA warp
 
       if (staged) {
+        fence_proxy_async();  // make this thread's staging writes visible to the TMA (async proxy)
         epi_bar();
-        // ---------------- phase 2a: BN statistics of the staged (bf16-rounded) tile, accumulated in registers.
+        // ---------------- TMA store of the staged tile: one 64-column slab per instruction
+        if (et == 0) {
+          const int slabs = (min(p.bn, p.N - n_base) + 63) >> 6;
+          for (int sl = 0; sl < slabs; ++sl) {
+            if (p.mode == 1)
+              tma_store_4d(&tmD, cbuf + sl * 16384, n_base + sl * 64, tw << p.lbw, th << p.lbh, tn << p.lbn);
+            else
+              tma_store_2d(&tmD, cbuf + sl * 16384, n_base + sl * 64, mt * kBM);
+          }
+          tma_store_commit();
+        }
+        // ---------------- BN statistics of the staged (bf16-rounded) tile, accumulated in registers.
         // Rows outside the problem are exact zeros (TMA zero fill; stats forbids bias/residual): no masking needed.
         if (p.stats != nullptr && scg * 8 < p.bn) {
-          const uint8_t* cp = cstage + (size_t)(srg * 16) * p.cstage_stride + scg * 16;
+          const uint8_t* cp = cbuf + (scg >> 3) * 16384 + (srg * 16) * 128;
+          const int c8 = scg & 7;
 #pragma unroll 4
           for (int r = 0; r < 16; ++r) {
             float f[8];
-            unpack8(*reinterpret_cast<const bf16x8*>(cp + (size_t)r * p.cstage_stride), f);
+            unpack8(*reinterpret_cast<const bf16x8*>(cp + r * 128 + ((c8 ^ (r & 7)) << 4)), f);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               st_s[i] += f[i];
@@ -432,56 +469,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         }
-        // ---------------- phase 2b: coalesced row stores (16 B per lane, whole rows per warp) (+ deferred residual)
-        {
-          const int cpr = p.bn >> 3;  // 16-byte chunks per row
-          const int lcpr = 31 - __clz(cpr);
-          const bool pow2 = (cpr & (cpr - 1)) == 0;
-          const int ewarp = warp - 4;
-          const int items = 16 * cpr;  // this warp's 16 rows
-          __nv_bfloat16* D = reinterpret_cast<__nv_bfloat16*>(p.D);
-          for (int idx = lane; idx < items; idx += 32) {
-            const int rr = pow2 ? (idx >> lcpr) : (idx / cpr);
-            const int ch = idx - rr * cpr;
-            const int r = ewarp * 16 + rr;
-            const long long gr = (p.mode == 1) ? global_row(r) : ((mt * kBM + r < p.M) ? (long long)(mt * kBM + r) : -1);
-            const int col0 = n_base + ch * 8;
-            if (gr < 0 || col0 >= p.N) continue;
-            uint4 v = *reinterpret_cast<const uint4*>(cstage + (size_t)r * p.cstage_stride + ch * 16);
-            __nv_bfloat16* op = D + gr * p.ldd + col0;
-            if (col0 + 8 <= p.N) {
-              if (defer_res) {
-                float a[8], b[8];
-                unpack8(*reinterpret_cast<const bf16x8*>(&v), a);
-                unpack8(*reinterpret_cast<const bf16x8*>(p.residual + gr * p.ldr + col0), b);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  a[i] += b[i];
-                  if (p.act == 1) a[i] = fmaxf(a[i], 0.f);
-                  else if (p.act == 2) a[i] = gelu_erf(a[i]);
-                }
-                *reinterpret_cast<bf16x8*>(&v) = pack8(a);
-              }
-              *reinterpret_cast<uint4*>(op) = v;
-            } else {
-              const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&v);
-              for (int i = 0; i < 8; ++i)
-                if (col0 + i < p.N) {
-                  float a = __bfloat162float(e[i]);
-                  if (defer_res) {
-                    a += __bfloat162float(p.residual[gr * p.ldr + col0 + i]);
-                    if (p.act == 1) a = fmaxf(a, 0.f);
-                    else if (p.act == 2) a = gelu_erf(a);
-                  }
-                  op[i] = __float2bfloat16_rn(a);
-                }
-            }
-          }
-        }
-        epi_bar();  // staging tile free for the next tile's phase 1
       }
     }
-    if (p.stats != nullptr && st_nt >= 0) flush_stats();
+    if (staged) {
+      if (et == 0) tma_store_wait_read<0>();
+      epi_bar();
+      if (p.stats != nullptr && st_nt >= 0) flush_stats(cstage0);
+    }
   }
 
   tc_fence_before();
@@ -671,14 +665,41 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
   p.k_splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
 
   // ---- shared-memory carve-up: [1 KB control][stages x (A 16 KB + B bn*128 B)][bf16 staging tile 128 x (bn*2+16) B]
-  p.stage_bytes = kABytes + bn * kBK * 2;
-  p.cstage_stride = p.out_f32 ? 0 : ((bn + 31) / 32) * 64 + 16;  // whole 32-column chunks + 16 B pad
   {
-    const int avail = kSmemTotal - 1024 /*alignment slack*/ - kCtrlBytes - kBM * p.cstage_stride;
+    const char* e = getenv("VTX_GEMM_DBG");
+    p.dbg = e ? atoi(e) : 0;
+  }
+  p.stage_bytes = kABytes + bn * kBK * 2;
+  p.cbytes = p.out_f32 ? 0 : ((bn + 63) / 64) * 16384;
+  {
+    // two staging buffers when a tile's K loop is too short to hide the output store behind it
+    const int kb_tile = p.kb_per_split;
+    p.nbuf = (p.cbytes && kb_tile <= 4) ? 2 : 1;
+    int avail = kSmemTotal - 1024 /*alignment slack*/ - kCtrlBytes - p.nbuf * p.cbytes;
     int st = avail / p.stage_bytes;
+    if (st < 2 && p.nbuf == 2) {
+      p.nbuf = 1;
+      avail = kSmemTotal - 1024 - kCtrlBytes - p.cbytes;
+      st = avail / p.stage_bytes;
+    }
     if (st > kMaxStages) st = kMaxStages;
     if (st < 2) return set_error(VTX_EUNSUPPORTED, "vtx_gemm: not enough shared memory for a 2-stage pipeline");
     p.stages = st;
+  }
+  CUtensorMap tmD;
+  memset(&tmD, 0, sizeof(tmD));
+  if (p.cbytes) {
+    if (p.mode == 1) {
+      uint64_t dd[4] = {(uint64_t)g->N, (uint64_t)g->conv_w, (uint64_t)g->conv_h, (uint64_t)g->conv_n};
+      uint64_t ds[3] = {(uint64_t)g->ldd, (uint64_t)g->conv_w * g->ldd, (uint64_t)g->conv_h * g->conv_w * g->ldd};
+      uint32_t db[4] = {64, 1u << p.lbw, 1u << p.lbh, 1u << p.lbn};
+      if ((rc = make_tmap(&tmD, g->D, 4, dd, ds, db)) != VTX_OK) return rc;
+    } else {
+      uint64_t dd[2] = {(uint64_t)g->N, (uint64_t)g->M};
+      uint64_t ds[1] = {(uint64_t)g->ldd};
+      uint32_t db[2] = {64, 128};
+      if ((rc = make_tmap(&tmD, g->D, 2, dd, ds, db)) != VTX_OK) return rc;
+    }
   }
   static bool attr_set = false;
   if (!attr_set) {
@@ -689,7 +710,7 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
   const long total = (long)p.m_tiles * p.n_tiles * p.k_splits;
   const int sms = vtx_num_sms();
   const int grid = (int)(total < sms ? total : sms);
-  gemm_tc_kernel<<<grid, kThreads, kSmemTotal, stream>>>(tmA, tmB, p);
+  gemm_tc_kernel<<<grid, kThreads, kSmemTotal, stream>>>(tmA, tmB, tmD, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(VTX_ECUDA, "gemm_tc_kernel launch: %s", cudaGetErrorString(e));
   return VTX_OK;
