@@ -1,5 +1,6 @@
 """Data-parallel plumbing: one process per GPU over NCCL/NVLink (mirrors virtex/utils/distributed.py:82-160, with
 torchrun-style environment rendezvous instead of mp.spawn + tcp://)."""
+import datetime
 import os
 
 import torch
@@ -14,11 +15,12 @@ def init_from_env(backend: str = None):
     if world > 1 and not dist.is_initialized():
         if backend is None:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
+        timeout = datetime.timedelta(seconds=int(os.environ.get("VTX_DIST_TIMEOUT_S", "180")))
         if backend == "nccl":
             torch.cuda.set_device(local)
-            dist.init_process_group(backend, device_id=torch.device("cuda", local))
+            dist.init_process_group(backend, device_id=torch.device("cuda", local), timeout=timeout)
         else:
-            dist.init_process_group(backend)
+            dist.init_process_group(backend, timeout=timeout)
     elif torch.cuda.is_available():
         torch.cuda.set_device(local)
     return rank, world, local
