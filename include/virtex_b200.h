@@ -93,14 +93,16 @@ int vtx_bn_relu_maxpool(const void* y, const float* bnp, void* out, uint8_t* idx
                         void* stream);
 int vtx_maxpool_bwd(const void* dpool, const uint8_t* idx, void* da, int N, int H, int W, int C, void* stream);
 /* BN backward in three steps: per-channel sums of dz and dz*xhat (dz = dA*[a>0]); coefficients + dgamma/dbeta;
-   dy = scale*(dz - mean(dz) - xhat*mean(dz*xhat)).  A second BN sharing dz (downsample branch) rides along. */
+   dy = scale*(dz - mean(dz) - xhat*mean(dz*xhat)).  A second BN sharing dz (downsample branch) rides along.
+   a == NULL && mask_from_y: the ReLU mask is recomputed as [y*scale + shift > 0] instead of being read. */
 int vtx_bn_bwd_reduce(const void* dA, const void* a, const void* y, const float* bnp, const void* y2,
-                      const float* bnp2, float* sums, float* sums2, int64_t M, int C, void* stream);
+                      const float* bnp2, float* sums, float* sums2, int64_t M, int C, int mask_from_y,
+                      void* stream);
 int vtx_bn_bwd_finalize(const float* sums, const float* bnp, float count, float* coef, float* dgamma, float* dbeta,
                         int C, void* stream);
 int vtx_bn_bwd_apply(const void* dA, const void* a, const void* y, const float* bnp, const float* coef, void* dy,
                      const void* y2, const float* bnp2, const float* coef2, void* dy2, void* dz_out, int64_t M, int C,
-                     void* stream);
+                     int mask_from_y, void* stream);
 /* conv weight layouts: fp32 OIHW <-> bf16 [O, (kh,kw,I)] GEMM operand; flipped/transposed dgrad operand */
 int vtx_conv_w_pack(const float* w, void* out, int O, int I, int KH, int KW, int ldk, void* stream);
 int vtx_conv_w_pack_dgrad(const float* w, void* out, int O, int I, void* stream);

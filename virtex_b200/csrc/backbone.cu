@@ -309,7 +309,8 @@ template <int kTwo>
 __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloat16* __restrict__ a,
                                      const __nv_bfloat16* __restrict__ y, const float* __restrict__ bnp,
                                      const __nv_bfloat16* __restrict__ y2, const float* __restrict__ bnp2,
-                                     float* __restrict__ sums, float* __restrict__ sums2, long long M, int C) {
+                                     float* __restrict__ sums, float* __restrict__ sums2, long long M, int C,
+                                     int mask_from_y) {
   extern __shared__ float red[];  // [rows_par][C][2 or 4]
   const int cg = C / 8;
   const int rows_par = blockDim.x / cg;  // rows handled in parallel by one CTA
@@ -317,12 +318,14 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dA, const
   const int rr = threadIdx.x / cg;
   const int c0 = g * 8;
   float s1[8], s2[8], t1[8], t2[8];
-  float mean[8], istd[8], mean2[8], istd2[8];
+  float mean[8], istd[8], mean2[8], istd2[8], msc[8], msh[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     s1[j] = s2[j] = t1[j] = t2[j] = 0.f;
     mean[j] = __ldg(bnp + c0 + j);
     istd[j] = __ldg(bnp + C + c0 + j);
+    msc[j] = __ldg(bnp + 2 * C + c0 + j);
+    msh[j] = __ldg(bnp + 3 * C + c0 + j);
     if (kTwo) {
       mean2[j] = __ldg(bnp2 + c0 + j);
       istd2[j] = __ldg(bnp2 + C + c0 + j);
@@ -333,13 +336,16 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dA, const
       const long long off = m * C + c0;
       float d[8], yy[8];
       unpack8(*reinterpret_cast<const bf16x8*>(dA + off), d);
+      unpack8(*reinterpret_cast<const bf16x8*>(y + off), yy);
       if (a != nullptr) {
         float aa[8];
         unpack8(*reinterpret_cast<const bf16x8*>(a + off), aa);
 #pragma unroll
         for (int j = 0; j < 8; ++j) d[j] = aa[j] > 0.f ? d[j] : 0.f;
+      } else if (mask_from_y) {  // ReLU mask recomputed from the BN output sign: a = relu(y*scale + shift)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] = (yy[j] * msc[j] + msh[j] > 0.f) ? d[j] : 0.f;
       }
-      unpack8(*reinterpret_cast<const bf16x8*>(y + off), yy);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         s1[j] += d[j];
@@ -405,11 +411,17 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dA, const 
                                     const float* __restrict__ coef, __nv_bfloat16* __restrict__ dy,
                                     const __nv_bfloat16* __restrict__ y2, const float* __restrict__ bnp2,
                                     const float* __restrict__ coef2, __nv_bfloat16* __restrict__ dy2,
-                                    __nv_bfloat16* __restrict__ dz_out, long long M, int C) {
+                                    __nv_bfloat16* __restrict__ dz_out, long long M, int C, int mask_from_y) {
   const int cg = C / 8;
   const long long total = M * cg;
   const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const int c0 = (int)(i0 % cg) * 8;  // loop invariant (blockDim.x % cg == 0)
+  float msc[8], msh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    msc[j] = bnp[2 * C + c0 + j];
+    msh[j] = bnp[3 * C + c0 + j];
+  }
   // dy = k0*dz + k1*y + k2 with k0 = scale, k1 = -scale*m2*invstd, k2 = scale*(m2*invstd*mean - m1)
   float k0[8], k1[8], k2[8], q0[8], q1[8], q2[8];
 #pragma unroll
@@ -429,13 +441,16 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dA, const 
   for (long long i = i0; i < total; i += (long long)gridDim.x * blockDim.x) {
     float d[8], yy[8], o[8];
     unpack8(*reinterpret_cast<const bf16x8*>(dA + i * 8), d);
+    unpack8(*reinterpret_cast<const bf16x8*>(y + i * 8), yy);
     if (a != nullptr) {
       float aa[8];
       unpack8(*reinterpret_cast<const bf16x8*>(a + i * 8), aa);
 #pragma unroll
       for (int j = 0; j < 8; ++j) d[j] = aa[j] > 0.f ? d[j] : 0.f;
+    } else if (mask_from_y) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d[j] = (yy[j] * msc[j] + msh[j] > 0.f) ? d[j] : 0.f;
     }
-    unpack8(*reinterpret_cast<const bf16x8*>(y + i * 8), yy);
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = k0[j] * d[j] + k1[j] * yy[j] + k2[j];
     *reinterpret_cast<bf16x8*>(dy + i * 8) = pack8(o);
@@ -594,7 +609,8 @@ extern "C" int vtx_maxpool_bwd(const void* dpool, const uint8_t* idx, void* da, 
   return check_launch("maxpool_bwd");
 }
 extern "C" int vtx_bn_bwd_reduce(const void* dA, const void* a, const void* y, const float* bnp, const void* y2,
-                                 const float* bnp2, float* sums, float* sums2, int64_t M, int C, void* stream) {
+                                 const float* bnp2, float* sums, float* sums2, int64_t M, int C, int mask_from_y,
+                                 void* stream) {
   REQ(dA && y && bnp && sums && C % 8 == 0 && C / 8 <= 256, "bad arguments");
   const int threads = 256;
   const int rows_par = threads / (C / 8);
@@ -607,11 +623,12 @@ extern "C" int vtx_bn_bwd_reduce(const void* dA, const void* a, const void* y, c
     REQ(bnp2 && sums2, "second BN needs bnp2/sums2");
     bn_bwd_reduce_kernel<1><<<(int)blocks, threads, smem, STREAM>>>((const __nv_bfloat16*)dA, (const __nv_bfloat16*)a,
                                                                     (const __nv_bfloat16*)y, bnp,
-                                                                    (const __nv_bfloat16*)y2, bnp2, sums, sums2, M, C);
+                                                                    (const __nv_bfloat16*)y2, bnp2, sums, sums2, M, C,
+                                                                    mask_from_y);
   } else {
     bn_bwd_reduce_kernel<0><<<(int)blocks, threads, smem, STREAM>>>((const __nv_bfloat16*)dA, (const __nv_bfloat16*)a,
                                                                     (const __nv_bfloat16*)y, bnp, nullptr, nullptr,
-                                                                    sums, nullptr, M, C);
+                                                                    sums, nullptr, M, C, mask_from_y);
   }
   return check_launch("bn_bwd_reduce");
 }
@@ -623,7 +640,7 @@ extern "C" int vtx_bn_bwd_finalize(const float* sums, const float* bnp, float co
 }
 extern "C" int vtx_bn_bwd_apply(const void* dA, const void* a, const void* y, const float* bnp, const float* coef,
                                 void* dy, const void* y2, const float* bnp2, const float* coef2, void* dy2,
-                                void* dz_out, int64_t M, int C, void* stream) {
+                                void* dz_out, int64_t M, int C, int mask_from_y, void* stream) {
   REQ(dA && y && bnp && coef && dy && C % 8 == 0, "bad arguments");
   const int grid = grid_for(M * (C / 8), 256);
   if (y2 != nullptr) {
@@ -631,11 +648,11 @@ extern "C" int vtx_bn_bwd_apply(const void* dA, const void* a, const void* y, co
     bn_bwd_apply_kernel<1><<<grid, 256, 0, STREAM>>>((const __nv_bfloat16*)dA, (const __nv_bfloat16*)a,
                                                      (const __nv_bfloat16*)y, bnp, coef, (__nv_bfloat16*)dy,
                                                      (const __nv_bfloat16*)y2, bnp2, coef2, (__nv_bfloat16*)dy2,
-                                                     (__nv_bfloat16*)dz_out, M, C);
+                                                     (__nv_bfloat16*)dz_out, M, C, mask_from_y);
   } else {
     bn_bwd_apply_kernel<0><<<grid, 256, 0, STREAM>>>((const __nv_bfloat16*)dA, (const __nv_bfloat16*)a,
                                                      (const __nv_bfloat16*)y, bnp, coef, (__nv_bfloat16*)dy, nullptr,
-                                                     nullptr, nullptr, nullptr, (__nv_bfloat16*)dz_out, M, C);
+                                                     nullptr, nullptr, nullptr, (__nv_bfloat16*)dz_out, M, C, mask_from_y);
   }
   return check_launch("bn_bwd_apply");
 }

@@ -672,16 +672,21 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
   p.stage_bytes = kABytes + bn * kBK * 2;
   p.cbytes = p.out_f32 ? 0 : ((bn + 63) / 64) * 16384;
   {
-    // two staging buffers when a tile's K loop is too short to hide the output store behind it
+    // two staging buffers (the TMA store of tile i overlaps the epilogue of tile i+1) whenever the operand ring still
+    // gets >= 4 stages, or holds a whole tile's K loop
     const int kb_tile = p.kb_per_split;
-    p.nbuf = (p.cbytes && kb_tile <= 4) ? 2 : 1;
-    int avail = kSmemTotal - 1024 /*alignment slack*/ - kCtrlBytes - p.nbuf * p.cbytes;
-    int st = avail / p.stage_bytes;
-    if (st < 2 && p.nbuf == 2) {
-      p.nbuf = 1;
-      avail = kSmemTotal - 1024 - kCtrlBytes - p.cbytes;
-      st = avail / p.stage_bytes;
+    const int budget = kSmemTotal - 1024 /*alignment slack*/ - kCtrlBytes;
+    int st = 0;
+    p.nbuf = 1;
+    if (p.cbytes) {
+      const int st2 = (budget - 2 * p.cbytes) / p.stage_bytes;
+      if (st2 >= 4 || st2 >= kb_tile + 1) { p.nbuf = 2; st = st2; }
     }
+    {
+      const char* e = getenv("VTX_GEMM_NBUF");
+      if (e && p.cbytes) { p.nbuf = atoi(e) == 2 ? 2 : 1; st = 0; }
+    }
+    if (st == 0) st = (budget - p.nbuf * p.cbytes) / p.stage_bytes;
     if (st > kMaxStages) st = kMaxStages;
     if (st < 2) return set_error(VTX_EUNSUPPORTED, "vtx_gemm: not enough shared memory for a 2-stage pipeline");
     p.stages = st;

@@ -290,11 +290,14 @@ __global__ void ln_bwd_kernel(const float* __restrict__ dy_a, const __nv_bfloat1
 }
 
 // ------------------------------------------------------------------------------------------------ attention
-// One warp per (batch b, head h); head_dim = 64; Tq <= 32 queries (lane = query), Tk <= 64 keys.
-// causal != 0: key j allowed for query i iff j <= i and j < lengths[b]  (self-attention of the captioning head)
-// causal == 0: all Tk keys allowed (cross-attention over the visual grid).
+// One warp per (batch b, head h); head_dim = 64; Tq <= 32 queries, Tk <= 64 keys.  The five small matrix products
+// (S = Q K^T, O = P V; backward: dP = dO V^T, dQ = dS K, dK = dS^T Q, dV = P^T dO) run on mma.sync.m16n8k16 bf16
+// tiles with fp32 accumulation -- the tiles are 30x30 / 30x49, far below a tcgen05 instruction shape, and the kernel
+// is bound by its q/k/v/o bytes, not by math.  Operands are staged once in shared memory (row stride 72 halves:
+// conflict-free ldmatrix); the causal + key-padding mask comes from caption_lengths and is never materialised.
+// causal != 0: key j allowed for query i iff j <= i and j < lengths[b]; causal == 0: all Tk keys (cross-attention).
 constexpr int kD = 64;
-constexpr int kPS = 65;  // padded row stride (floats) of per-query smem rows -> conflict free for lane = row access
+constexpr int kLd = 72;  // smem row stride in bf16 elements (144 B)
 
 struct AttnArgs {
   const __nv_bfloat16 *q, *k, *v;
@@ -307,186 +310,353 @@ struct AttnArgs {
   uint32_t site;
 };
 
-__device__ __forceinline__ void load_rows_f32(float* dst, int dst_stride, const __nv_bfloat16* src, long long ld,
-                                              int rows, int lane) {
-  // rows x 64 bf16 -> fp32 smem; each lane moves 8 elements (16 B) per step
-  for (int e = lane; e < rows * 8; e += 32) {
+__device__ __forceinline__ void mma16816(float* c, const uint32_t* a, const uint32_t* b) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t* r, const __nv_bfloat16* p) {
+  const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t* r, const __nv_bfloat16* p) {
+  const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t* r, const __nv_bfloat16* p) {
+  const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x2_t(uint32_t* r, const __nv_bfloat16* p) {
+  const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(a));
+}
+__device__ __forceinline__ uint32_t pack_bf2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// A fragment (m16 x k16) of a row-major [m][k] smem tile at (m0, k0)
+__device__ __forceinline__ void frag_a(uint32_t* a, const __nv_bfloat16* t, int m0, int k0, int lane) {
+  ldsm_x4(a, t + (m0 + (lane & 7) + ((lane >> 3) & 1) * 8) * kLd + k0 + (lane >> 4) * 8);
+}
+// A fragment of the TRANSPOSE of a row-major [k][m] smem tile: A[m][k] = X[k][m]
+__device__ __forceinline__ void frag_a_t(uint32_t* a, const __nv_bfloat16* x, int m0, int k0, int lane) {
+  ldsm_x4_t(a, x + (k0 + (lane & 7) + (lane >> 4) * 8) * kLd + m0 + ((lane >> 3) & 1) * 8);
+}
+// B fragment (k16 x n8) where the smem tile is [n][k] row-major (k contiguous)
+__device__ __forceinline__ void frag_b(uint32_t* b, const __nv_bfloat16* t, int n0, int k0, int lane) {
+  ldsm_x2(b, t + (n0 + (lane & 7)) * kLd + k0 + ((lane >> 3) & 1) * 8);
+}
+// B fragment where the smem tile is [k][n] row-major (n contiguous)
+__device__ __forceinline__ void frag_b_t(uint32_t* b, const __nv_bfloat16* t, int k0, int n0, int lane) {
+  ldsm_x2_t(b, t + (k0 + (lane & 7) + ((lane >> 3) & 1) * 8) * kLd + n0);
+}
+
+// rows x 64 bf16 global -> smem [rows_pad][kLd], zero filling rows >= rows
+__device__ __forceinline__ void stage_rows(__nv_bfloat16* dst, const __nv_bfloat16* src, long long ld, int rows,
+                                           int rows_pad, int lane) {
+  for (int e = lane; e < rows_pad * 8; e += 32) {
     const int r = e >> 3, c = (e & 7) * 8;
-    float f[8];
-    unpack8(*reinterpret_cast<const bf16x8*>(src + (long long)r * ld + c), f);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) dst[r * dst_stride + c + j] = f[j];
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (r < rows) v = *reinterpret_cast<const uint4*>(src + (long long)r * ld + c);
+    *reinterpret_cast<uint4*>(dst + r * kLd + c) = v;
   }
 }
 
-__global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnArgs a, __nv_bfloat16* __restrict__ out, long long ldo,
-                                                        float* __restrict__ lse) {
-  const uint64_t seed = a.seed_ptr ? *a.seed_ptr : 0ull;
-  extern __shared__ float sm[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int unit = blockIdx.x * kWarpsPerBlock + warp;
-  if (unit >= a.B * a.heads) return;
-  const int b = unit / a.heads, h = unit % a.heads;
-  float* sK = sm + (size_t)warp * (2 * 64 * kD + 32 * kPS);
-  float* sV = sK + 64 * kD;
-  float* sS = sV + 64 * kD;  // [32][kPS]
-  load_rows_f32(sK, kD, a.k + (long long)b * a.Tk * a.ldk + h * kD, a.ldk, a.Tk, lane);
-  load_rows_f32(sV, kD, a.v + (long long)b * a.Tk * a.ldv + h * kD, a.ldv, a.Tk, lane);
-  __syncwarp();
-  const int i = lane;
-  const bool active = i < a.Tq;
-  const int len = a.causal ? (int)a.lengths[b] : a.Tk;
-  float q[kD];
-  if (active) {
-    const __nv_bfloat16* qp = a.q + ((long long)b * a.Tq + i) * a.ldq + h * kD;
-#pragma unroll
-    for (int c = 0; c < kD; c += 8) unpack8(*reinterpret_cast<const bf16x8*>(qp + c), q + c);
-  } else {
-#pragma unroll
-    for (int c = 0; c < kD; ++c) q[c] = 0.f;
-  }
-  float mx = -INFINITY;
-  for (int j = 0; j < a.Tk; ++j) {
-    float s = 0.f;
-#pragma unroll
-    for (int c = 0; c < kD; c += 4) {
-      const float4 kk = *reinterpret_cast<const float4*>(sK + j * kD + c);
-      s += q[c] * kk.x + q[c + 1] * kk.y + q[c + 2] * kk.z + q[c + 3] * kk.w;
-    }
-    s *= a.scale;
-    const bool ok = a.causal ? (j <= i && j < len) : true;
-    s = ok ? s : -INFINITY;
-    sS[i * kPS + j] = s;
-    mx = fmaxf(mx, s);
-  }
-  float o[kD];
-#pragma unroll
-  for (int c = 0; c < kD; ++c) o[c] = 0.f;
-  float l = 0.f;
-  const float inv_keep = a.p > 0.f ? 1.f / (1.f - a.p) : 1.f;
-  for (int j = 0; j < a.Tk; ++j) {
-    const float s = sS[i * kPS + j];
-    float pr = (s == -INFINITY) ? 0.f : __expf(s - mx);
-    l += pr;
-    pr *= dropout_scale(a.p, inv_keep, seed, a.site, ((uint64_t)unit * 32 + i) * 64 + j);
-#pragma unroll
-    for (int c = 0; c < kD; c += 4) {
-      const float4 vv = *reinterpret_cast<const float4*>(sV + j * kD + c);
-      o[c] += pr * vv.x; o[c + 1] += pr * vv.y; o[c + 2] += pr * vv.z; o[c + 3] += pr * vv.w;
-    }
-  }
-  if (active) {
-    const float inv = 1.f / l;
-    __nv_bfloat16* op = out + ((long long)b * a.Tq + i) * ldo + h * kD;
-#pragma unroll
-    for (int c = 0; c < kD; c += 8) {
-      float t[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) t[j] = o[c + j] * inv;
-      *reinterpret_cast<bf16x8*>(op + c) = pack8(t);
-    }
-    if (lse) lse[(long long)unit * 32 + i] = mx + __logf(l);
-  }
-}
+constexpr int kAttnFwdWarps = 4;
+constexpr int kAttnFwdSmemPerWarp = (32 + 64 + 64) * kLd * 2;  // Q, K, V
 
-// backward: dq [.., ldq-like layout given by ldgq], dk, dv
-__global__ void __launch_bounds__(64) attn_bwd_kernel(const AttnArgs a, const __nv_bfloat16* __restrict__ dout,
-                                                       long long ldo, const float* __restrict__ lse,
-                                                       __nv_bfloat16* __restrict__ dq, long long lddq,
-                                                       __nv_bfloat16* __restrict__ dk, long long lddk,
-                                                       __nv_bfloat16* __restrict__ dv, long long lddv) {
+__global__ void __launch_bounds__(32 * kAttnFwdWarps) attn_fwd_kernel(const AttnArgs a, __nv_bfloat16* __restrict__ out,
+                                                                        long long ldo, float* __restrict__ lse) {
   const uint64_t seed = a.seed_ptr ? *a.seed_ptr : 0ull;
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) uint8_t sm_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int unit = blockIdx.x * 2 + warp;
+  const int unit = blockIdx.x * kAttnFwdWarps + warp;
   if (unit >= a.B * a.heads) return;
   const int b = unit / a.heads, h = unit % a.heads;
-  constexpr int per_warp = 2 * 64 * kD + 4 * 32 * kPS;
-  float* sK = sm + (size_t)warp * per_warp;
-  float* sV = sK + 64 * kD;
-  float* sQ = sV + 64 * kD;   // [32][kPS]
-  float* sdO = sQ + 32 * kPS;  // [32][kPS]
-  float* sP = sdO + 32 * kPS;  // [32][kPS]  dropped probabilities Pd
-  float* sdS = sP + 32 * kPS;  // [32][kPS]
-  load_rows_f32(sK, kD, a.k + (long long)b * a.Tk * a.ldk + h * kD, a.ldk, a.Tk, lane);
-  load_rows_f32(sV, kD, a.v + (long long)b * a.Tk * a.ldv + h * kD, a.ldv, a.Tk, lane);
-  load_rows_f32(sQ, kPS, a.q + (long long)b * a.Tq * a.ldq + h * kD, a.ldq, a.Tq, lane);
-  load_rows_f32(sdO, kPS, dout + (long long)b * a.Tq * ldo + h * kD, ldo, a.Tq, lane);
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(sm_raw + (size_t)warp * kAttnFwdSmemPerWarp);
+  __nv_bfloat16* sK = sQ + 32 * kLd;
+  __nv_bfloat16* sV = sK + 64 * kLd;
+  const int Tk16 = (a.Tk + 15) & ~15;
+  stage_rows(sQ, a.q + (long long)b * a.Tq * a.ldq + h * kD, a.ldq, a.Tq, 32, lane);
+  stage_rows(sK, a.k + (long long)b * a.Tk * a.ldk + h * kD, a.ldk, a.Tk, Tk16, lane);
+  stage_rows(sV, a.v + (long long)b * a.Tk * a.ldv + h * kD, a.ldv, a.Tk, Tk16, lane);
   __syncwarp();
-  const int i = lane;
-  const bool active = i < a.Tq;
+  const int g = lane >> 2, tq = lane & 3;
   const int len = a.causal ? (int)a.lengths[b] : a.Tk;
-  const float inv_keep = a.p > 0.f ? 1.f / (1.f - a.p) : 1.f;
-  // ---- phase A (lane = query): P, dP, D_i, dS, dq
-  const float L = active ? lse[(long long)unit * 32 + i] : 0.f;
-  float Di = 0.f;
-  for (int j = 0; j < a.Tk; ++j) {
-    float s = 0.f, dp = 0.f;
-    if (active) {
-#pragma unroll 16
-      for (int c = 0; c < kD; ++c) {
-        s += sQ[i * kPS + c] * sK[j * kD + c];
-        dp += sdO[i * kPS + c] * sV[j * kD + c];
+  const int nkt = Tk16 >> 3;  // 8-key tiles
+  float s[2][8][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s[mt][nt][e] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    uint32_t af[2][4];
+    frag_a(af[0], sQ, 0, ks * 16, lane);
+    frag_a(af[1], sQ, 16, ks * 16, lane);
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      if (nt < nkt) {
+        uint32_t bf[2];
+        frag_b(bf, sK, nt * 8, ks * 16, lane);
+        mma16816(s[0][nt], af[0], bf);
+        mma16816(s[1][nt], af[1], bf);
       }
     }
-    s *= a.scale;
-    const bool ok = active && (a.causal ? (j <= i && j < len) : true);
-    const float pr = ok ? __expf(s - L) : 0.f;
-    const float mk = dropout_scale(a.p, inv_keep, seed, a.site, ((uint64_t)unit * 32 + i) * 64 + j);
-    const float dpr = dp * mk;  // dP = dPd * mask
-    Di += pr * dpr;
-    sP[i * kPS + j] = pr * mk;   // Pd
-    sdS[i * kPS + j] = dpr;      // dP for now (turned into dS by the second pass)
   }
-  float dqv[kD];
+  // masked softmax over keys; rows live in quads (4 lanes x 2 elements x 8 key tiles)
+  const float inv_keep = a.p > 0.f ? 1.f / (1.f - a.p) : 1.f;
+  float rsum[2][2];
 #pragma unroll
-  for (int c = 0; c < kD; ++c) dqv[c] = 0.f;
-  for (int j = 0; j < a.Tk; ++j) {
-    // recompute s -> P (cheap: 64 FMAs) to form dS exactly, including dropped entries
-    float s = 0.f;
-    if (active) {
-#pragma unroll 16
-      for (int c = 0; c < kD; ++c) s += sQ[i * kPS + c] * sK[j * kD + c];
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const int i = mt * 16 + g + hh * 8;
+      float mx = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = nt * 8 + 2 * tq + e;
+          const bool ok = (j < a.Tk) && (a.causal ? (j <= i && j < len) : true);
+          const float v = ok ? s[mt][nt][hh * 2 + e] * a.scale : -INFINITY;
+          s[mt][nt][hh * 2 + e] = v;
+          mx = fmaxf(mx, v);
+        }
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      float sum = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = nt * 8 + 2 * tq + e;
+          const float v = s[mt][nt][hh * 2 + e];
+          float pr = (v == -INFINITY) ? 0.f : __expf(v - mx);
+          sum += pr;
+          pr *= dropout_scale(a.p, inv_keep, seed, a.site, ((uint64_t)unit * 32 + i) * 64 + j);
+          s[mt][nt][hh * 2 + e] = pr;
+        }
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      rsum[mt][hh] = sum;
+      if (tq == 0 && i < a.Tq && lse) lse[(long long)unit * 32 + i] = mx + __logf(sum);
     }
-    s *= a.scale;
-    const bool ok = active && (a.causal ? (j <= i && j < len) : true);
-    const float pr = ok ? __expf(s - L) : 0.f;
-    const float ds = pr * (sdS[i * kPS + j] - Di) * a.scale;
-    sdS[i * kPS + j] = ds;
+  // O = P V
+  float o[2][8][4];
 #pragma unroll
-    for (int c = 0; c < kD; c += 4) {
-      const float4 kk = *reinterpret_cast<const float4*>(sK + j * kD + c);
-      dqv[c] += ds * kk.x; dqv[c + 1] += ds * kk.y; dqv[c + 2] += ds * kk.z; dqv[c + 3] += ds * kk.w;
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[mt][nt][e] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    if (ks * 16 < Tk16) {
+      uint32_t pf[2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        pf[mt][0] = pack_bf2(s[mt][2 * ks][0], s[mt][2 * ks][1]);
+        pf[mt][1] = pack_bf2(s[mt][2 * ks][2], s[mt][2 * ks][3]);
+        pf[mt][2] = pack_bf2(s[mt][2 * ks + 1][0], s[mt][2 * ks + 1][1]);
+        pf[mt][3] = pack_bf2(s[mt][2 * ks + 1][2], s[mt][2 * ks + 1][3]);
+      }
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        uint32_t bf[2];
+        frag_b_t(bf, sV, ks * 16, nt * 8, lane);
+        mma16816(o[0][nt], pf[0], bf);
+        mma16816(o[1][nt], pf[1], bf);
+      }
     }
   }
-  if (active) {
-    __nv_bfloat16* p = dq + ((long long)b * a.Tq + i) * lddq + h * kD;
 #pragma unroll
-    for (int c = 0; c < kD; c += 8) *reinterpret_cast<bf16x8*>(p + c) = pack8(dqv + c);
-  }
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const int i = mt * 16 + g + hh * 8;
+      if (i >= a.Tq) continue;
+      const float inv = 1.f / rsum[mt][hh];
+      __nv_bfloat16* op = out + ((long long)b * a.Tq + i) * ldo + h * kD + 2 * tq;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+        *reinterpret_cast<uint32_t*>(op + nt * 8) = pack_bf2(o[mt][nt][hh * 2] * inv, o[mt][nt][hh * 2 + 1] * inv);
+    }
+}
+
+constexpr int kAttnBwdWarps = 3;
+constexpr int kAttnBwdSmemPerWarp = (32 + 32 + 64 + 64 + 32 + 32) * kLd * 2;  // Q, dO, K, V, Pd, dS
+
+__global__ void __launch_bounds__(32 * kAttnBwdWarps) attn_bwd_kernel(const AttnArgs a, const __nv_bfloat16* __restrict__ dout,
+                                                                        long long ldo, const float* __restrict__ lse,
+                                                                        __nv_bfloat16* __restrict__ dq, long long lddq,
+                                                                        __nv_bfloat16* __restrict__ dk, long long lddk,
+                                                                        __nv_bfloat16* __restrict__ dv, long long lddv) {
+  const uint64_t seed = a.seed_ptr ? *a.seed_ptr : 0ull;
+  extern __shared__ __align__(16) uint8_t sm_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int unit = blockIdx.x * kAttnBwdWarps + warp;
+  if (unit >= a.B * a.heads) return;
+  const int b = unit / a.heads, h = unit % a.heads;
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(sm_raw + (size_t)warp * kAttnBwdSmemPerWarp);
+  __nv_bfloat16* sdO = sQ + 32 * kLd;
+  __nv_bfloat16* sK = sdO + 32 * kLd;
+  __nv_bfloat16* sV = sK + 64 * kLd;
+  __nv_bfloat16* sP = sV + 64 * kLd;   // dropped probabilities Pd [query][key]
+  __nv_bfloat16* sdS = sP + 32 * kLd;  // dS [query][key]
+  const int Tk16 = (a.Tk + 15) & ~15;
+  stage_rows(sQ, a.q + (long long)b * a.Tq * a.ldq + h * kD, a.ldq, a.Tq, 32, lane);
+  stage_rows(sdO, dout + (long long)b * a.Tq * ldo + h * kD, ldo, a.Tq, 32, lane);
+  stage_rows(sK, a.k + (long long)b * a.Tk * a.ldk + h * kD, a.ldk, a.Tk, Tk16, lane);
+  stage_rows(sV, a.v + (long long)b * a.Tk * a.ldv + h * kD, a.ldv, a.Tk, Tk16, lane);
   __syncwarp();
-  // ---- phase B (lane = key): dV_j = sum_i Pd_ij dO_i ; dK_j = sum_i dS_ij Q_i
-  for (int j0 = 0; j0 < a.Tk; j0 += 32) {
-    const int j = j0 + lane;
-    float dvv[kD], dkv[kD];
+  const int g = lane >> 2, tq = lane & 3;
+  const int len = a.causal ? (int)a.lengths[b] : a.Tk;
+  const int nkt = Tk16 >> 3;
+  const float inv_keep = a.p > 0.f ? 1.f / (1.f - a.p) : 1.f;
+  // ---- S = Q K^T and dPd = dO V^T
+  float s[2][8][4], dp[2][8][4];
 #pragma unroll
-    for (int c = 0; c < kD; ++c) dvv[c] = dkv[c] = 0.f;
-    if (j < a.Tk) {
-      for (int ii = 0; ii < a.Tq; ++ii) {
-        const float pd = sP[ii * kPS + j];
-        const float ds = sdS[ii * kPS + j];
+  for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int c = 0; c < kD; ++c) {
-          dvv[c] += pd * sdO[ii * kPS + c];
-          dkv[c] += ds * sQ[ii * kPS + c];
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s[mt][nt][e] = dp[mt][nt][e] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    uint32_t aq[2][4], ao[2][4];
+    frag_a(aq[0], sQ, 0, ks * 16, lane);
+    frag_a(aq[1], sQ, 16, ks * 16, lane);
+    frag_a(ao[0], sdO, 0, ks * 16, lane);
+    frag_a(ao[1], sdO, 16, ks * 16, lane);
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      if (nt < nkt) {
+        uint32_t bk[2], bv[2];
+        frag_b(bk, sK, nt * 8, ks * 16, lane);
+        frag_b(bv, sV, nt * 8, ks * 16, lane);
+        mma16816(s[0][nt], aq[0], bk);
+        mma16816(s[1][nt], aq[1], bk);
+        mma16816(dp[0][nt], ao[0], bv);
+        mma16816(dp[1][nt], ao[1], bv);
+      }
+    }
+  }
+  // ---- P, dP, D_i, dS; stage Pd and dS (bf16) as [query][key]
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const int i = mt * 16 + g + hh * 8;
+      const bool row_ok = i < a.Tq;
+      const float L = row_ok ? lse[(long long)unit * 32 + i] : 0.f;
+      float Di = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = nt * 8 + 2 * tq + e;
+          const bool ok = row_ok && (j < a.Tk) && (a.causal ? (j <= i && j < len) : true);
+          const float pr = ok ? __expf(s[mt][nt][hh * 2 + e] * a.scale - L) : 0.f;
+          const float mk = dropout_scale(a.p, inv_keep, seed, a.site, ((uint64_t)unit * 32 + i) * 64 + j);
+          const float dpr = dp[mt][nt][hh * 2 + e] * mk;  // dP = dPd * mask
+          Di += pr * dpr;
+          s[mt][nt][hh * 2 + e] = pr;
+          dp[mt][nt][hh * 2 + e] = dpr;
+          // Pd is consumed by dV only
+          sP[i * kLd + j] = f2bf(pr * mk);
+        }
+      Di += __shfl_xor_sync(0xffffffffu, Di, 1);
+      Di += __shfl_xor_sync(0xffffffffu, Di, 2);
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = nt * 8 + 2 * tq + e;
+          const float ds = s[mt][nt][hh * 2 + e] * (dp[mt][nt][hh * 2 + e] - Di) * a.scale;
+          s[mt][nt][hh * 2 + e] = ds;
+          sdS[i * kLd + j] = f2bf(ds);
+        }
+    }
+  __syncwarp();
+  // ---- dQ = dS K   (A = dS from registers, B = K [key][d] -> transposed fragments)
+  {
+    float acc[2][8][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      if (ks * 16 < Tk16) {
+        uint32_t pf[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          pf[mt][0] = pack_bf2(s[mt][2 * ks][0], s[mt][2 * ks][1]);
+          pf[mt][1] = pack_bf2(s[mt][2 * ks][2], s[mt][2 * ks][3]);
+          pf[mt][2] = pack_bf2(s[mt][2 * ks + 1][0], s[mt][2 * ks + 1][1]);
+          pf[mt][3] = pack_bf2(s[mt][2 * ks + 1][2], s[mt][2 * ks + 1][3]);
+        }
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          uint32_t bf[2];
+          frag_b_t(bf, sK, ks * 16, nt * 8, lane);
+          mma16816(acc[0][nt], pf[0], bf);
+          mma16816(acc[1][nt], pf[1], bf);
         }
       }
-      __nv_bfloat16* pk = dk + ((long long)b * a.Tk + j) * lddk + h * kD;
-      __nv_bfloat16* pv = dv + ((long long)b * a.Tk + j) * lddv + h * kD;
+    }
 #pragma unroll
-      for (int c = 0; c < kD; c += 8) {
-        *reinterpret_cast<bf16x8*>(pk + c) = pack8(dkv + c);
-        *reinterpret_cast<bf16x8*>(pv + c) = pack8(dvv + c);
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int i = mt * 16 + g + hh * 8;
+        if (i >= a.Tq) continue;
+        __nv_bfloat16* op = dq + ((long long)b * a.Tq + i) * lddq + h * kD + 2 * tq;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+          *reinterpret_cast<uint32_t*>(op + nt * 8) = pack_bf2(acc[mt][nt][hh * 2], acc[mt][nt][hh * 2 + 1]);
+      }
+  }
+  // ---- dV = Pd^T dO and dK = dS^T Q, one 16-key tile at a time (reduction over the 32 queries)
+  for (int kt = 0; kt * 16 < Tk16; ++kt) {
+    float av[8][4], ak[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) av[nt][e] = ak[nt][e] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      uint32_t ap[4], as_[4];
+      frag_a_t(ap, sP, kt * 16, ks * 16, lane);
+      frag_a_t(as_, sdS, kt * 16, ks * 16, lane);
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        uint32_t bo[2], bq[2];
+        frag_b_t(bo, sdO, ks * 16, nt * 8, lane);
+        frag_b_t(bq, sQ, ks * 16, nt * 8, lane);
+        mma16816(av[nt], ap, bo);
+        mma16816(ak[nt], as_, bq);
+      }
+    }
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const int j = kt * 16 + g + hh * 8;
+      if (j >= a.Tk) continue;
+      __nv_bfloat16* pk = dk + ((long long)b * a.Tk + j) * lddk + h * kD + 2 * tq;
+      __nv_bfloat16* pv = dv + ((long long)b * a.Tk + j) * lddv + h * kD + 2 * tq;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        *reinterpret_cast<uint32_t*>(pk + nt * 8) = pack_bf2(ak[nt][hh * 2], ak[nt][hh * 2 + 1]);
+        *reinterpret_cast<uint32_t*>(pv + nt * 8) = pack_bf2(av[nt][hh * 2], av[nt][hh * 2 + 1]);
       }
     }
   }
@@ -744,14 +914,14 @@ extern "C" int vtx_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t l
   int rc = fill_attn(&a, q, ldq, k, ldk, v, ldv, B, heads, Tq, Tk, lengths, causal, p, seed_ptr, site);
   if (rc) return rc;
   REQ(out && ldo % 8 == 0, "bad output");
-  const size_t smem = (size_t)kWarpsPerBlock * (2 * 64 * kD + 32 * kPS) * sizeof(float);
+  const size_t smem = (size_t)kAttnFwdWarps * kAttnFwdSmemPerWarp;
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr = true;
   }
   const int units = B * heads;
-  attn_fwd_kernel<<<(units + kWarpsPerBlock - 1) / kWarpsPerBlock, 32 * kWarpsPerBlock, smem, STREAM>>>(
+  attn_fwd_kernel<<<(units + kAttnFwdWarps - 1) / kAttnFwdWarps, 32 * kAttnFwdWarps, smem, STREAM>>>(
       a, (__nv_bfloat16*)out, ldo, lse);
   return check_launch("attn_fwd");
 }
@@ -763,15 +933,16 @@ extern "C" int vtx_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t l
   int rc = fill_attn(&a, q, ldq, k, ldk, v, ldv, B, heads, Tq, Tk, lengths, causal, p, seed_ptr, site);
   if (rc) return rc;
   REQ(dout && lse && dq && dk && dv && ldo % 8 == 0 && lddq % 8 == 0 && lddk % 8 == 0 && lddv % 8 == 0, "bad arguments");
-  const size_t smem = (size_t)2 * (2 * 64 * kD + 4 * 32 * kPS) * sizeof(float);
+  const size_t smem = (size_t)kAttnBwdWarps * kAttnBwdSmemPerWarp;
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr = true;
   }
   const int units = B * heads;
-  attn_bwd_kernel<<<(units + 1) / 2, 64, smem, STREAM>>>(a, (const __nv_bfloat16*)dout, ldo, lse, (__nv_bfloat16*)dq,
-                                                         lddq, (__nv_bfloat16*)dk, lddk, (__nv_bfloat16*)dv, lddv);
+  attn_bwd_kernel<<<(units + kAttnBwdWarps - 1) / kAttnBwdWarps, 32 * kAttnBwdWarps, smem, STREAM>>>(
+      a, (const __nv_bfloat16*)dout, ldo, lse, (__nv_bfloat16*)dq, lddq, (__nv_bfloat16*)dk, lddk, (__nv_bfloat16*)dv,
+      lddv);
   return check_launch("attn_bwd");
 }
 extern "C" int vtx_gelu_dropout_fwd(const void* u, void* h, int64_t n, float p, const uint64_t* seed_ptr, uint32_t site,

@@ -316,30 +316,32 @@ class Engine:
         sk = ops.split_k_for(tiles, (m_rows + 63) // 64)
         gemm(dY, X, dW, n_out, k_in, m_rows, a_mn=1, b_mn=1, atomic=True, split_k=sk, ldd=k_in, out_f32=True)
 
-    def _bn_bwd(self, dA, a, y, bnp, bn_name, M, C, dy, two=None, dz_out=None):
-        """dA -> dy through (ReLU mask from `a`) + train-mode BN; two = (y2, bnp2, bn2_name, dy2) shares dz."""
+    def _bn_bwd(self, dA, a, y, bnp, bn_name, M, C, dy, two=None, dz_out=None, mask_from_y=0):
+        """dA -> dy through (ReLU mask from `a`, or recomputed from y when mask_from_y) + train-mode BN;
+        two = (y2, bnp2, bn2_name, dy2) shares dz."""
         s = _stream()
         sums = self._slab_take(2 * C)
         coef = self.ws.get("coef:" + bn_name, (3, C), F32)
         if two is None:
             call("vtx_bn_bwd_reduce", dA.data_ptr(), _p(a), y.data_ptr(), bnp.data_ptr(), 0, 0, sums.data_ptr(), 0,
-                 M, C, s)
+                 M, C, mask_from_y, s)
             call("vtx_bn_bwd_finalize", sums.data_ptr(), bnp.data_ptr(), float(M), coef.data_ptr(),
                  self.G(bn_name + ".weight").data_ptr(), self.G(bn_name + ".bias").data_ptr(), C, s)
             call("vtx_bn_bwd_apply", dA.data_ptr(), _p(a), y.data_ptr(), bnp.data_ptr(), coef.data_ptr(),
-                 dy.data_ptr(), 0, 0, 0, 0, _p(dz_out), M, C, s)
+                 dy.data_ptr(), 0, 0, 0, 0, _p(dz_out), M, C, mask_from_y, s)
         else:
             y2, bnp2, bn2_name, dy2 = two
             sums2 = self._slab_take(2 * C)
             coef2 = self.ws.get("coef:" + bn2_name, (3, C), F32)
             call("vtx_bn_bwd_reduce", dA.data_ptr(), _p(a), y.data_ptr(), bnp.data_ptr(), y2.data_ptr(),
-                 bnp2.data_ptr(), sums.data_ptr(), sums2.data_ptr(), M, C, s)
+                 bnp2.data_ptr(), sums.data_ptr(), sums2.data_ptr(), M, C, mask_from_y, s)
             call("vtx_bn_bwd_finalize", sums.data_ptr(), bnp.data_ptr(), float(M), coef.data_ptr(),
                  self.G(bn_name + ".weight").data_ptr(), self.G(bn_name + ".bias").data_ptr(), C, s)
             call("vtx_bn_bwd_finalize", sums2.data_ptr(), bnp2.data_ptr(), float(M), coef2.data_ptr(),
                  self.G(bn2_name + ".weight").data_ptr(), self.G(bn2_name + ".bias").data_ptr(), C, s)
             call("vtx_bn_bwd_apply", dA.data_ptr(), _p(a), y.data_ptr(), bnp.data_ptr(), coef.data_ptr(),
-                 dy.data_ptr(), y2.data_ptr(), bnp2.data_ptr(), coef2.data_ptr(), dy2.data_ptr(), _p(dz_out), M, C, s)
+                 dy.data_ptr(), y2.data_ptr(), bnp2.data_ptr(), coef2.data_ptr(), dy2.data_ptr(), _p(dz_out), M, C,
+                 mask_from_y, s)
 
     def backbone_backward(self, dfeat: torch.Tensor, bucket_cb=None):
         """dfeat bf16 [B*h*w, C]: gradient w.r.t. the backbone output.  Accumulates into the gradient arena.
@@ -377,7 +379,7 @@ class Engine:
             gemm(dy3, self.W(name + ".conv3.weight").view(C4, planes), da2, Mout, planes, C4, b_mn=1)
             # ---- bn2 + ReLU backward
             dy2 = ws.get("bwd.dy2", (Mout, planes), BF16)
-            self._bn_bwd(da2, rec["a2"], rec["y2"], rec["bnp2"], name + ".bn2", Mout, planes, dy2)
+            self._bn_bwd(da2, None, rec["y2"], rec["bnp2"], name + ".bn2", Mout, planes, dy2, mask_from_y=1)
             # ---- conv2 (3x3): wgrad + dgrad
             dwp = ws.get("bwd.dwp", (planes, 9 * planes), F32)
             dwp.zero_()
@@ -398,7 +400,7 @@ class Engine:
                  3, 9 * planes, s)
             # ---- bn1 + ReLU backward
             dy1 = ws.get("bwd.dy1", (Min, planes), BF16)
-            self._bn_bwd(da1, rec["a1"], rec["y1"], rec["bnp1"], name + ".bn1", Min, planes, dy1)
+            self._bn_bwd(da1, None, rec["y1"], rec["bnp1"], name + ".bn1", Min, planes, dy1, mask_from_y=1)
             # ---- conv1 (1x1): wgrad + dgrad (+ shortcut gradient)
             self._wgrad(dy1, rec["x"], self.G(name + ".conv1.weight"), planes, Cin, Min)
             dx = ws.get(f"bwd.dx{scratch_i & 1}", (Min, Cin), BF16)
@@ -422,11 +424,8 @@ class Engine:
         M0 = st["M"]
         da0 = ws.get("bwd.da0", (M0, 64), BF16)
         call("vtx_maxpool_bwd", dOut.data_ptr(), st["idx"].data_ptr(), da0.data_ptr(), B, st["Ho"], st["Wo"], 64, s)
-        # ReLU mask of the stem comes from the BN output sign: recompute a = relu(bn(y)) into a scratch buffer
-        a0 = ws.get("bwd.a0", (M0, 64), BF16)
-        call("vtx_bn_act", st["y"].data_ptr(), st["bnp"].data_ptr(), 0, 0, a0.data_ptr(), M0, 64, 1, s)
         dy0 = ws.get("bwd.dy0", (M0, 64), BF16)
-        self._bn_bwd(da0, a0, st["y"], st["bnp"], "visual.cnn.bn1", M0, 64, dy0)
+        self._bn_bwd(da0, None, st["y"], st["bnp"], "visual.cnn.bn1", M0, 64, dy0, mask_from_y=1)
         dwp0 = ws.get("bwd.dwp0", (64, 160), F32)
         dwp0.zero_()
         self._wgrad(dy0, st["cols"], dwp0, 64, 160, M0)

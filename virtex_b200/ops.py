@@ -23,9 +23,9 @@ _PROTOS = {
     "vtx_bn_act": [P, P, P, P, P, I64, I, I, P],
     "vtx_bn_relu_maxpool": [P, P, P, P, I, I, I, I, P],
     "vtx_maxpool_bwd": [P, P, P, I, I, I, I, P],
-    "vtx_bn_bwd_reduce": [P, P, P, P, P, P, P, P, I64, I, P],
+    "vtx_bn_bwd_reduce": [P, P, P, P, P, P, P, P, I64, I, I, P],
     "vtx_bn_bwd_finalize": [P, P, F, P, P, P, I, P],
-    "vtx_bn_bwd_apply": [P, P, P, P, P, P, P, P, P, P, P, I64, I, P],
+    "vtx_bn_bwd_apply": [P, P, P, P, P, P, P, P, P, P, P, I64, I, I, P],
     "vtx_conv_w_pack": [P, P, I, I, I, I, I, P],
     "vtx_conv_w_pack_dgrad": [P, P, I, I, P],
     "vtx_conv_w_unpack_add": [P, P, I, I, I, I, I, P],
