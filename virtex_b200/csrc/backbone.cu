@@ -177,7 +177,9 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, float count,
 }
 
 // a = act( y*scale + shift  [+ res  |  + res*scale2 + shift2] )
-__global__ void bn_act_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ bnp,
+constexpr int kU = 4;  // independent 16-byte loads per tensor in flight per thread (memory-level parallelism)
+
+__global__ void __launch_bounds__(256, 2) bn_act_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ bnp,
                               const __nv_bfloat16* __restrict__ res, const float* __restrict__ bnp_res,
                               __nv_bfloat16* __restrict__ out, long long M, int C, int relu) {
   const int cg = C / 8;
@@ -185,6 +187,7 @@ __global__ void bn_act_kernel(const __nv_bfloat16* __restrict__ y, const float* 
   // blockDim.x (256) is a multiple of cg, so a thread's 8-channel group never changes across the grid-stride loop:
   // per-channel parameters live in registers.
   const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
   const int c0 = (int)(i0 % cg) * 8;
   float sc[8], sh[8], sc2[8], sh2[8];
 #pragma unroll
@@ -194,22 +197,36 @@ __global__ void bn_act_kernel(const __nv_bfloat16* __restrict__ y, const float* 
     sc2[j] = bnp_res ? bnp_res[2 * C + c0 + j] : 1.f;
     sh2[j] = bnp_res ? bnp_res[3 * C + c0 + j] : 0.f;
   }
-  for (long long i = i0; i < total; i += (long long)gridDim.x * blockDim.x) {
-    float v[8];
-    unpack8(*reinterpret_cast<const bf16x8*>(y + i * 8), v);
+  for (long long i = i0; i < total; i += stride * kU) {
+    bf16x8 vy[kU], vr[kU];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = v[j] * sc[j] + sh[j];
-    if (res != nullptr) {
-      float r[8];
-      unpack8(*reinterpret_cast<const bf16x8*>(res + i * 8), r);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] += r[j] * sc2[j] + sh2[j];
+    for (int u = 0; u < kU; ++u) {
+      const long long idx = i + u * stride;
+      if (idx < total) {
+        vy[u] = *reinterpret_cast<const bf16x8*>(y + idx * 8);
+        if (res != nullptr) vr[u] = *reinterpret_cast<const bf16x8*>(res + idx * 8);
+      }
     }
-    if (relu) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+    for (int u = 0; u < kU; ++u) {
+      const long long idx = i + u * stride;
+      if (idx >= total) break;
+      float v[8];
+      unpack8(vy[u], v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = v[j] * sc[j] + sh[j];
+      if (res != nullptr) {
+        float r[8];
+        unpack8(vr[u], r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += r[j] * sc2[j] + sh2[j];
+      }
+      if (relu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+      }
+      *reinterpret_cast<bf16x8*>(out + idx * 8) = pack8(v);
     }
-    *reinterpret_cast<bf16x8*>(out + i * 8) = pack8(v);
   }
 }
 
@@ -306,7 +323,7 @@ __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dpool, cons
 // sums[0,c] = sum_m dz, sums[1,c] = sum_m dz * xhat, with dz = dA * [a > 0] (a == null: no ReLU) and
 // xhat = (y - mean) * invstd.  Optionally the same for a second BN (y2, bnp2) sharing dz (downsample branch).
 template <int kTwo>
-__global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloat16* __restrict__ a,
+__global__ void __launch_bounds__(256, kTwo ? 1 : 2) bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloat16* __restrict__ a,
                                      const __nv_bfloat16* __restrict__ y, const float* __restrict__ bnp,
                                      const __nv_bfloat16* __restrict__ y2, const float* __restrict__ bnp2,
                                      float* __restrict__ sums, float* __restrict__ sums2, long long M, int C,
@@ -332,31 +349,48 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dA, const
     }
   }
   if (rr < rows_par) {
-    for (long long m = (long long)blockIdx.x * rows_par + rr; m < M; m += (long long)gridDim.x * rows_par) {
-      const long long off = m * C + c0;
-      float d[8], yy[8];
-      unpack8(*reinterpret_cast<const bf16x8*>(dA + off), d);
-      unpack8(*reinterpret_cast<const bf16x8*>(y + off), yy);
-      if (a != nullptr) {
-        float aa[8];
-        unpack8(*reinterpret_cast<const bf16x8*>(a + off), aa);
+    const long long mstride = (long long)gridDim.x * rows_par;
+    for (long long m0 = (long long)blockIdx.x * rows_par + rr; m0 < M; m0 += mstride * kU) {
+      bf16x8 vd[kU], vy[kU], va[kU], vy2[kU];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) d[j] = aa[j] > 0.f ? d[j] : 0.f;
-      } else if (mask_from_y) {  // ReLU mask recomputed from the BN output sign: a = relu(y*scale + shift)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) d[j] = (yy[j] * msc[j] + msh[j] > 0.f) ? d[j] : 0.f;
+      for (int u = 0; u < kU; ++u) {
+        const long long m = m0 + u * mstride;
+        if (m < M) {
+          const long long off = m * C + c0;
+          vd[u] = *reinterpret_cast<const bf16x8*>(dA + off);
+          vy[u] = *reinterpret_cast<const bf16x8*>(y + off);
+          if (a != nullptr) va[u] = *reinterpret_cast<const bf16x8*>(a + off);
+          if (kTwo) vy2[u] = *reinterpret_cast<const bf16x8*>(y2 + off);
+        }
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        s1[j] += d[j];
-        s2[j] += d[j] * (yy[j] - mean[j]) * istd[j];
-      }
-      if (kTwo) {
-        unpack8(*reinterpret_cast<const bf16x8*>(y2 + off), yy);
+      for (int u = 0; u < kU; ++u) {
+        const long long m = m0 + u * mstride;
+        if (m >= M) break;
+        float d[8], yy[8];
+        unpack8(vd[u], d);
+        unpack8(vy[u], yy);
+        if (a != nullptr) {
+          float aa[8];
+          unpack8(va[u], aa);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) d[j] = aa[j] > 0.f ? d[j] : 0.f;
+        } else if (mask_from_y) {  // ReLU mask recomputed from the BN output sign: a = relu(y*scale + shift)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) d[j] = (yy[j] * msc[j] + msh[j] > 0.f) ? d[j] : 0.f;
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          t1[j] += d[j];
-          t2[j] += d[j] * (yy[j] - mean2[j]) * istd2[j];
+          s1[j] += d[j];
+          s2[j] += d[j] * (yy[j] - mean[j]) * istd[j];
+        }
+        if (kTwo) {
+          unpack8(vy2[u], yy);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            t1[j] += d[j];
+            t2[j] += d[j] * (yy[j] - mean2[j]) * istd2[j];
+          }
         }
       }
     }
@@ -406,7 +440,7 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ sums, const flo
 
 // dy = scale * (dz - m1 - xhat * m2);  optional second BN sharing dz;  optional dz output (identity shortcut grad)
 template <int kTwo>
-__global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloat16* __restrict__ a,
+__global__ void __launch_bounds__(256, kTwo ? 1 : 2) bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloat16* __restrict__ a,
                                     const __nv_bfloat16* __restrict__ y, const float* __restrict__ bnp,
                                     const float* __restrict__ coef, __nv_bfloat16* __restrict__ dy,
                                     const __nv_bfloat16* __restrict__ y2, const float* __restrict__ bnp2,
@@ -438,29 +472,46 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dA, const 
       q2[j] = scl_b * (m2b * istd_b * mean_b - m1b);
     }
   }
-  for (long long i = i0; i < total; i += (long long)gridDim.x * blockDim.x) {
-    float d[8], yy[8], o[8];
-    unpack8(*reinterpret_cast<const bf16x8*>(dA + i * 8), d);
-    unpack8(*reinterpret_cast<const bf16x8*>(y + i * 8), yy);
-    if (a != nullptr) {
-      float aa[8];
-      unpack8(*reinterpret_cast<const bf16x8*>(a + i * 8), aa);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = i0; i < total; i += stride * kU) {
+    bf16x8 vd[kU], vy[kU], va[kU], vy2[kU];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) d[j] = aa[j] > 0.f ? d[j] : 0.f;
-    } else if (mask_from_y) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) d[j] = (yy[j] * msc[j] + msh[j] > 0.f) ? d[j] : 0.f;
+    for (int u = 0; u < kU; ++u) {
+      const long long idx = i + u * stride;
+      if (idx < total) {
+        vd[u] = *reinterpret_cast<const bf16x8*>(dA + idx * 8);
+        vy[u] = *reinterpret_cast<const bf16x8*>(y + idx * 8);
+        if (a != nullptr) va[u] = *reinterpret_cast<const bf16x8*>(a + idx * 8);
+        if (kTwo) vy2[u] = *reinterpret_cast<const bf16x8*>(y2 + idx * 8);
+      }
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = k0[j] * d[j] + k1[j] * yy[j] + k2[j];
-    *reinterpret_cast<bf16x8*>(dy + i * 8) = pack8(o);
-    if (kTwo) {
-      unpack8(*reinterpret_cast<const bf16x8*>(y2 + i * 8), yy);
+    for (int u = 0; u < kU; ++u) {
+      const long long idx = i + u * stride;
+      if (idx >= total) break;
+      float d[8], yy[8], o[8];
+      unpack8(vd[u], d);
+      unpack8(vy[u], yy);
+      if (a != nullptr) {
+        float aa[8];
+        unpack8(va[u], aa);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = q0[j] * d[j] + q1[j] * yy[j] + q2[j];
-      *reinterpret_cast<bf16x8*>(dy2 + i * 8) = pack8(o);
+        for (int j = 0; j < 8; ++j) d[j] = aa[j] > 0.f ? d[j] : 0.f;
+      } else if (mask_from_y) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] = (yy[j] * msc[j] + msh[j] > 0.f) ? d[j] : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = k0[j] * d[j] + k1[j] * yy[j] + k2[j];
+      *reinterpret_cast<bf16x8*>(dy + idx * 8) = pack8(o);
+      if (kTwo) {
+        unpack8(vy2[u], yy);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = q0[j] * d[j] + q1[j] * yy[j] + q2[j];
+        *reinterpret_cast<bf16x8*>(dy2 + idx * 8) = pack8(o);
+      }
+      if (dz_out != nullptr) *reinterpret_cast<bf16x8*>(dz_out + idx * 8) = pack8(d);
     }
-    if (dz_out != nullptr) *reinterpret_cast<bf16x8*>(dz_out + i * 8) = pack8(d);
   }
 }
 
