@@ -239,10 +239,11 @@ def test_backbone_backward_relu_open_vs_fp32_oracle():
 
 
 # -------------------------------------------------------------------------------------------------------------- head
-@pytest.mark.parametrize("layers,hidden,heads,ffn", [(1, 128, 2, 256), (2, 256, 4, 512)])
-def test_head_forward_backward_vs_oracle(layers, hidden, heads, ffn):
+@pytest.mark.parametrize("layers,hidden,heads,ffn,norm_first", [(1, 128, 2, 256, False), (2, 256, 4, 512, False),
+                                                                (2, 256, 4, 512, True)])
+def test_head_forward_backward_vs_oracle(layers, hidden, heads, ffn, norm_first):
     _need_cuda()
-    spec = O.Spec(hidden=hidden, layers=layers, heads=heads, ffn=ffn)
+    spec = O.Spec(hidden=hidden, layers=layers, heads=heads, ffn=ffn, norm_first=norm_first)
     state = O.synth_state(spec, 7)
     model = build_model(spec, state)
     model.train()

@@ -793,7 +793,20 @@ __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ X, long long ld,
   float acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-  for (int m = m0; m < m1; ++m) {
+  int m = m0;
+  for (; m + 4 <= m1; m += 4) {  // four independent 16-byte loads in flight per thread
+    bf16x8 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const bf16x8*>(X + (long long)(m + u) * ld + g * 8);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float f[8];
+      unpack8(v[u], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    }
+  }
+  for (; m < m1; ++m) {
     float f[8];
     unpack8(*reinterpret_cast<const bf16x8*>(X + (long long)m * ld + g * 8), f);
 #pragma unroll
@@ -983,7 +996,7 @@ extern "C" int vtx_colsum(const void* X, int64_t ld, int M, int N, float* out, v
   const int groups = (N + 7) / 8;
   const int threads = 128;
   const int gy = (groups + threads - 1) / threads;
-  int gx = (vtx_num_sms() * 4 + gy - 1) / gy;
+  int gx = (vtx_num_sms() * 8 + gy - 1) / gy;
   if (gx > M) gx = M;
   if (gx < 1) gx = 1;
   const int rows_per_block = (M + gx - 1) / gx;

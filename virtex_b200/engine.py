@@ -446,8 +446,6 @@ class Engine:
     def head_forward(self, direction, mem, tokens, lengths, training, want_logits_f32=False):
         """tokens int64 [B,T] -> bf16 logits [B*T, V] (and the tape for backward)."""
         mod = self._head_modules(direction)
-        if mod.norm_first:
-            raise NotImplementedError("transdec_prenorm forward is scheduled but not implemented in this round")
         B, T = tokens.shape
         M, H, Fd, V, A = B * T, mod.hidden_size, mod.feedforward_size, mod.vocab_size, mod.attention_heads
         S = mem.shape[0]
@@ -474,6 +472,9 @@ class Engine:
             q = f"{d}.transformer.layers.{l}."
             k = f"{d}.L{l}."
             sb = site + 10 * (l + 1)
+            if mod.norm_first:
+                x = self._prenorm_layer_forward(rec, q, k, sb, x, mem, lengths, p, B, T, A, H, Fd, S, Sk)
+                continue
             lr = dict(q=q, x_in=x, x_inb=xb)
             # self-attention block
             qkv = ws.get(k + "qkv", (M, 3 * H), BF16)
@@ -522,6 +523,13 @@ class Engine:
                       z2=z2, st2=st2, x2b=x2b, u=u, h=h, z3=z3, st3=st3, sb=sb)
             rec["layers"].append(lr)
             x, xb = x3, x3b
+        if mod.norm_first:  # final LayerNorm of pre-norm decoders (textual_heads.py:192-193)
+            qn = f"{d}.transformer.norm."
+            zf, stf = ws.get(d + ".zf", (M, H), F32), ws.get(d + ".stf", (M, 2), F32)
+            xb = ws.get(d + ".xfb", (M, H), BF16)
+            call("vtx_add_ln_fwd", x.data_ptr(), 0, self.P(qn + "weight").data_ptr(), self.P(qn + "bias").data_ptr(),
+                 zf.data_ptr(), stf.data_ptr(), 0, xb.data_ptr(), M, H, 1e-5, 0.0, seed, 0, 1, s)
+            rec.update(zf=zf, stf=stf)
         rec["x_out_b"] = xb
         # tied output projection
         wv = self.W("textual.embedding.words.weight")
@@ -534,6 +542,117 @@ class Engine:
         gemm(xb, wv, logits, M, V, H, bias=bo)
         rec["logits"] = logits
         return rec
+
+    def _prenorm_layer_forward(self, rec, q, k, sb, x, mem, lengths, p, B, T, A, H, Fd, S, Sk):
+        """x + f(LN(x)) for the three blocks (torch/nn/modules/transformer.py:1131-1143); returns the new fp32 x."""
+        s, ws, seed = _stream(), self.ws, self.seed.data_ptr()
+        M = B * T
+        e = 2
+        lr = dict(q=q, sb=sb, x0=x)
+
+        def norm(name, xin, tag):
+            z, st = ws.get(k + "z" + tag, (M, H), F32), ws.get(k + "st" + tag, (M, 2), F32)
+            nb = ws.get(k + "n" + tag + "b", (M, H), BF16)
+            call("vtx_add_ln_fwd", xin.data_ptr(), 0, self.P(q + name + ".weight").data_ptr(),
+                 self.P(q + name + ".bias").data_ptr(), z.data_ptr(), st.data_ptr(), 0, nb.data_ptr(), M, H, 1e-5, 0.0,
+                 seed, 0, 1, s)
+            return z, st, nb
+
+        def residual(xin, branch, tag, site):
+            xo = ws.get(k + "x" + tag, (M, H), F32)
+            call("vtx_add_ln_fwd", xin.data_ptr(), branch.data_ptr(), 0, 0, xo.data_ptr(), 0, 0, 0, M, H, 0.0, p, seed,
+                 site, 0, s)
+            return xo
+
+        pr = ws.get(k + "proj", (M, H), BF16)
+        # self attention
+        z1, st1, n1b = norm("norm1", x, "1")
+        qkv = ws.get(k + "qkv", (M, 3 * H), BF16)
+        gemm(n1b, self.W(q + "self_attn.in_proj_weight"), qkv, M, 3 * H, H, bias=self.P(q + "self_attn.in_proj_bias"))
+        o_s = ws.get(k + "o_s", (M, H), BF16)
+        lse_s = ws.get(k + "lse_s", (B * A * 32,), F32)
+        call("vtx_attn_fwd", qkv.data_ptr(), 3 * H, qkv.data_ptr() + H * e, 3 * H, qkv.data_ptr() + 2 * H * e, 3 * H,
+             o_s.data_ptr(), H, lse_s.data_ptr(), B, A, T, T, lengths.data_ptr(), 1, p, seed, sb + 0, s)
+        gemm(o_s, self.W(q + "self_attn.out_proj.weight"), pr, M, H, H, bias=self.P(q + "self_attn.out_proj.bias"))
+        x1 = residual(x, pr, "1", sb + 1)
+        # cross attention
+        z2, st2, n2b = norm("norm2", x1, "2")
+        wc, bc = self.W(q + "multihead_attn.in_proj_weight"), self.P(q + "multihead_attn.in_proj_bias")
+        qc = ws.get(k + "qc", (M, H), BF16)
+        gemm(n2b, wc[:H], qc, M, H, H, bias=bc[:H])
+        kv = ws.get(k + "kv", (S, 2 * H), BF16)
+        gemm(mem, wc[H:], kv, S, 2 * H, H, bias=bc[H:])
+        o_c = ws.get(k + "o_c", (M, H), BF16)
+        lse_c = ws.get(k + "lse_c", (B * A * 32,), F32)
+        call("vtx_attn_fwd", qc.data_ptr(), H, kv.data_ptr(), 2 * H, kv.data_ptr() + H * e, 2 * H, o_c.data_ptr(), H,
+             lse_c.data_ptr(), B, A, T, Sk, 0, 0, p, seed, sb + 2, s)
+        gemm(o_c, self.W(q + "multihead_attn.out_proj.weight"), pr, M, H, H,
+             bias=self.P(q + "multihead_attn.out_proj.bias"))
+        x2 = residual(x1, pr, "2", sb + 3)
+        # feed forward
+        z3, st3, n3b = norm("norm3", x2, "3")
+        u = ws.get(k + "u", (M, Fd), BF16)
+        gemm(n3b, self.W(q + "linear1.weight"), u, M, Fd, H, bias=self.P(q + "linear1.bias"))
+        h = ws.get(k + "h", (M, Fd), BF16)
+        call("vtx_gelu_dropout_fwd", u.data_ptr(), h.data_ptr(), M * Fd, p, seed, sb + 4, s)
+        gemm(h, self.W(q + "linear2.weight"), pr, M, H, Fd, bias=self.P(q + "linear2.bias"))
+        x3 = residual(x2, pr, "3", sb + 5)
+        lr.update(z1=z1, st1=st1, n1b=n1b, qkv=qkv, o_s=o_s, lse_s=lse_s, z2=z2, st2=st2, n2b=n2b, qc=qc, kv=kv, o_c=o_c,
+                  lse_c=lse_c, z3=z3, st3=st3, n3b=n3b, u=u, h=h)
+        rec["layers"].append(lr)
+        return x3
+
+    def _prenorm_layer_backward(self, rec, lr, g, dmem, dmem_started, mod):
+        """g = dL/dx_out (fp32 [M,H], updated in place to dL/dx_in)."""
+        B, T, M, S, Sk, p = rec["B"], rec["T"], rec["M"], rec["S"], rec["Sk"], rec["p"]
+        H, Fd, A = mod.hidden_size, mod.feedforward_size, mod.attention_heads
+        s, ws, seed = _stream(), self.ws, self.seed.data_ptr()
+        q, sb = lr["q"], lr["sb"]
+        e = 2
+        dbr = ws.get("hb.dbr", (M, H), BF16)
+        dxb = ws.get("hb.dxb", (M, H), BF16)
+        do = ws.get("hb.do", (M, H), BF16)
+
+        def branch_grad(site):  # d(branch) = g * dropout mask (bf16); g itself keeps flowing through the skip path
+            call("vtx_ln_bwd", g.data_ptr(), 0, 0, 0, 0, 0, 0, dbr.data_ptr(), 0, 0, M, H, p, seed, site, 0, s)
+
+        def norm_bwd(name, z, st, dn):  # g += LN_backward(dn)
+            call("vtx_ln_bwd", 0, dn.data_ptr(), z.data_ptr(), st.data_ptr(), self.P(q + name + ".weight").data_ptr(),
+                 g.data_ptr(), g.data_ptr(), 0, self.G(q + name + ".weight").data_ptr(),
+                 self.G(q + name + ".bias").data_ptr(), M, H, 0.0, seed, 0, 1, s)
+
+        # feed forward
+        branch_grad(sb + 5)
+        dh = ws.get("hb.dh", (M, Fd), BF16)
+        self._linear_bwd(dbr, lr["h"], q + "linear2.weight", q + "linear2.bias", dh, M, H, Fd)
+        call("vtx_gelu_dropout_bwd", dh.data_ptr(), lr["u"].data_ptr(), dh.data_ptr(), M * Fd, p, seed, sb + 4, s)
+        self._linear_bwd(dh, lr["n3b"], q + "linear1.weight", q + "linear1.bias", dxb, M, Fd, H)
+        norm_bwd("norm3", lr["z3"], lr["st3"], dxb)
+        # cross attention
+        branch_grad(sb + 3)
+        self._linear_bwd(dbr, lr["o_c"], q + "multihead_attn.out_proj.weight", q + "multihead_attn.out_proj.bias", do,
+                         M, H, H)
+        dqc = ws.get("hb.dqc", (M, H), BF16)
+        dkv = ws.get("hb.dkv", (S, 2 * H), BF16)
+        kv = lr["kv"]
+        call("vtx_attn_bwd", lr["qc"].data_ptr(), H, kv.data_ptr(), 2 * H, kv.data_ptr() + H * e, 2 * H, do.data_ptr(),
+             H, lr["lse_c"].data_ptr(), dqc.data_ptr(), H, dkv.data_ptr(), 2 * H, dkv.data_ptr() + H * e, 2 * H, B, A, T,
+             Sk, 0, 0, p, seed, sb + 2, s)
+        wn, bn = q + "multihead_attn.in_proj_weight", q + "multihead_attn.in_proj_bias"
+        self._linear_bwd(dqc, lr["n2b"], wn, bn, dxb, M, H, H, w_rows=slice(0, H))
+        self._linear_bwd(dkv, rec["mem"], wn, bn, dmem, S, 2 * H, H, w_rows=slice(H, 3 * H),
+                         residual=dmem if dmem_started else None)
+        norm_bwd("norm2", lr["z2"], lr["st2"], dxb)
+        # self attention
+        branch_grad(sb + 1)
+        self._linear_bwd(dbr, lr["o_s"], q + "self_attn.out_proj.weight", q + "self_attn.out_proj.bias", do, M, H, H)
+        dqkv = ws.get("hb.dqkv", (M, 3 * H), BF16)
+        qkv = lr["qkv"]
+        call("vtx_attn_bwd", qkv.data_ptr(), 3 * H, qkv.data_ptr() + H * e, 3 * H, qkv.data_ptr() + 2 * H * e, 3 * H,
+             do.data_ptr(), H, lr["lse_s"].data_ptr(), dqkv.data_ptr(), 3 * H, dqkv.data_ptr() + H * e, 3 * H,
+             dqkv.data_ptr() + 2 * H * e, 3 * H, B, A, T, T, rec["lengths"].data_ptr(), 1, p, seed, sb + 0, s)
+        self._linear_bwd(dqkv, lr["n1b"], q + "self_attn.in_proj_weight", q + "self_attn.in_proj_bias", dxb, M, 3 * H, H)
+        norm_bwd("norm1", lr["z1"], lr["st1"], dxb)
 
     def head_loss(self, rec, write_grad):
         di = 0 if rec["direction"] == "textual" else 1
@@ -574,7 +693,17 @@ class Engine:
         dbr = ws.get("hb.dbr", (M, H), BF16)
         dy_a, dy_b = None, dxb
         e = 2
-        for l in reversed(range(mod.num_layers)):
+        if mod.norm_first:
+            qn = f"{d}.transformer.norm."
+            g = dres_a
+            call("vtx_ln_bwd", 0, dxb.data_ptr(), rec["zf"].data_ptr(), rec["stf"].data_ptr(),
+                 self.P(qn + "weight").data_ptr(), 0, g.data_ptr(), 0, self.G(qn + "weight").data_ptr(),
+                 self.G(qn + "bias").data_ptr(), M, H, 0.0, seed, 0, 1, s)
+            for l in reversed(range(mod.num_layers)):
+                self._prenorm_layer_backward(rec, rec["layers"][l], g, dmem, dmem_started, mod)
+                dmem_started = True
+            dy_a, dy_b = g, None
+        for l in (reversed(range(mod.num_layers)) if not mod.norm_first else ()):
             lr = rec["layers"][l]
             q, sb = lr["q"], lr["sb"]
             # LN3 / FFN
