@@ -20,32 +20,47 @@ static inline int grid_for(long long work_items, int threads, int per_sm = 16) {
 
 // ---------------------------------------------------------------------------------------------- stem im2col
 // image fp32 NCHW [N,3,H,W] -> cols bf16 [N*Ho*Wo, ldc], k = (kh*7 + kw)*3 + c for the 7x7/stride 2/pad 3 stem,
-// columns [147, ldc) zero.
-__global__ void stem_im2col_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ cols, int N, int H, int W,
-                                   int Ho, int Wo, int ldc) {
-  const long long total = (long long)N * Ho * Wo * (ldc / 8);
+// columns [147, ldc) zero.  One CTA per output row (n, ho): the 7 x 3 input rows it needs are staged in shared memory
+// with coalesced float4 loads, then the ldc-wide column rows are written as coalesced 16-byte vectors.
+__global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ cols,
+                                                         int N, int H, int W, int Ho, int Wo, int ldc) {
+  extern __shared__ float tile[];  // [3][7][Wp], Wp = W + 8: 4 zero columns on each side (left pad 3 -> x offset 4)
+  __shared__ int lut[160];         // k -> (c*7 + kh)*Wp + kw  or -1
+  const int Wp = W + 8;
+  const int n = blockIdx.x / Ho, ho = blockIdx.x % Ho;
+  for (int k = threadIdx.x; k < 160; k += blockDim.x) {
+    int v = -1;
+    if (k < 147) {
+      const int c = k % 3, t = k / 3, kw = t % 7, kh = t / 7;
+      v = (c * 7 + kh) * Wp + kw;
+    }
+    lut[k] = v;
+  }
+  // stage rows: tile[c][r][4 + w] = img[n][c][2*ho - 3 + r][w]
+  const int quads = Wp / 4;
+  for (int e = threadIdx.x; e < 21 * quads; e += blockDim.x) {
+    const int cr = e / quads, qd = e % quads;
+    const int c = cr / 7, r = cr % 7;
+    const int h = 2 * ho - 3 + r;
+    const int w0 = qd * 4 - 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (h >= 0 && h < H && w0 >= 0 && w0 + 3 < W)
+      v = *reinterpret_cast<const float4*>(img + (((long long)n * 3 + c) * H + h) * W + w0);
+    *reinterpret_cast<float4*>(tile + cr * Wp + qd * 4) = v;
+  }
+  __syncthreads();
   const int groups = ldc / 8;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(i % groups);
-    const long long pos = i / groups;
-    const int wo = (int)(pos % Wo);
-    const int ho = (int)((pos / Wo) % Ho);
-    const int n = (int)(pos / ((long long)Wo * Ho));
+  const long long row0 = ((long long)n * Ho + ho) * Wo;
+  for (int e = threadIdx.x; e < Wo * groups; e += blockDim.x) {
+    const int wo = e / groups, g = e % groups;
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int k = g * 8 + j;
-      float x = 0.f;
-      if (k < 147) {
-        const int c = k % 3;
-        const int t = k / 3;
-        const int kw = t % 7, kh = t / 7;
-        const int h = ho * 2 - 3 + kh, w = wo * 2 - 3 + kw;
-        if (h >= 0 && h < H && w >= 0 && w < W) x = __ldg(img + (((long long)n * 3 + c) * H + h) * W + w);
-      }
-      v[j] = x;
+      const int o = k < 160 ? lut[k] : -1;
+      v[j] = o >= 0 ? tile[o + 2 * wo + 1] : 0.f;  // x = 2*wo - 3 + kw  ->  tile column 4 + x = 2*wo + 1 + kw
     }
-    *reinterpret_cast<bf16x8*>(cols + pos * ldc + g * 8) = pack8(v);
+    *reinterpret_cast<bf16x8*>(cols + (row0 + wo) * ldc + g * 8) = pack8(v);
   }
 }
 
@@ -588,9 +603,11 @@ using namespace vtx;
 
 extern "C" int vtx_stem_im2col(const float* img, void* cols, int N, int H, int W, int ldc, void* stream) {
   REQ(img && cols && ldc >= 152 && ldc % 8 == 0, "bad arguments");
+  REQ(W % 4 == 0 && ldc <= 160 + 96, "stem im2col needs W %% 4 == 0");
   const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
-  const long long total = (long long)N * Ho * Wo * (ldc / 8);
-  stem_im2col_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>(img, (__nv_bfloat16*)cols, N, H, W, Ho, Wo, ldc);
+  const size_t smem = (size_t)21 * (W + 8) * sizeof(float);
+  REQ(smem <= 48 * 1024, "image too wide for the stem im2col tile");
+  stem_im2col_kernel<<<N * Ho, 256, smem, STREAM>>>(img, (__nv_bfloat16*)cols, N, H, W, Ho, Wo, ldc);
   return check_launch("stem_im2col");
 }
 extern "C" int vtx_im2col3x3(const void* x, void* cols, int N, int H, int W, int C, int stride, void* stream) {
@@ -636,7 +653,7 @@ extern "C" int vtx_bn_finalize(const float* stats, float count, const float* gam
 extern "C" int vtx_bn_act(const void* y, const float* bnp, const void* res, const float* bnp_res, void* out,
                           int64_t M, int C, int relu, void* stream) {
   REQ(y && bnp && out && C % 8 == 0, "bad arguments");
-  bn_act_kernel<<<grid_for(M * (C / 8), 256), 256, 0, STREAM>>>((const __nv_bfloat16*)y, bnp,
+  bn_act_kernel<<<grid_for((M * (C / 8) + kU - 1) / kU, 256, 2), 256, 0, STREAM>>>((const __nv_bfloat16*)y, bnp,
                                                                 (const __nv_bfloat16*)res, bnp_res,
                                                                 (__nv_bfloat16*)out, M, C, relu);
   return check_launch("bn_act");
@@ -667,8 +684,8 @@ extern "C" int vtx_bn_bwd_reduce(const void* dA, const void* a, const void* y, c
   const int rows_par = threads / (C / 8);
   const bool two = (y2 != nullptr);
   const size_t smem = (size_t)rows_par * C * (two ? 4 : 2) * sizeof(float);
-  long long blocks = (M + rows_par - 1) / rows_par;
-  const long long cap = (long long)vtx_num_sms() * 4;
+  long long blocks = (M + (long long)rows_par * kU - 1) / ((long long)rows_par * kU);
+  const long long cap = (long long)vtx_num_sms() * (two ? 1 : 2);
   if (blocks > cap) blocks = cap;
   if (two) {
     REQ(bnp2 && sums2, "second BN needs bnp2/sums2");
@@ -693,7 +710,7 @@ extern "C" int vtx_bn_bwd_apply(const void* dA, const void* a, const void* y, co
                                 void* dy, const void* y2, const float* bnp2, const float* coef2, void* dy2,
                                 void* dz_out, int64_t M, int C, int mask_from_y, void* stream) {
   REQ(dA && y && bnp && coef && dy && C % 8 == 0, "bad arguments");
-  const int grid = grid_for(M * (C / 8), 256);
+  const int grid = grid_for((M * (C / 8) + kU - 1) / kU, 256, y2 != nullptr ? 1 : 2);
   if (y2 != nullptr) {
     REQ(bnp2 && coef2 && dy2, "second BN needs bnp2/coef2/dy2");
     bn_bwd_apply_kernel<1><<<grid, 256, 0, STREAM>>>((const __nv_bfloat16*)dA, (const __nv_bfloat16*)a,
