@@ -29,5 +29,10 @@ for _ in range(2):
         A, B, D = bf(M, K), bf(N, K), torch.empty(M, N, device=dev, dtype=torch.bfloat16)
         bias = torch.randn(N, device=dev)
         ops.gemm(A, B, D, M, N, K, bias=bias)
+    if "l1conv" in cases:  # layer1 3x3 implicit conv 64->64 with BN statistics
+        x, w = bf(256, 56, 56, 64), bf(64, 576)
+        D = torch.empty(256 * 3136, 64, device=dev, dtype=torch.bfloat16)
+        st = torch.zeros(2, 64, device=dev)
+        ops.gemm(x, w, D, 256 * 3136, 64, 576, lda=64, stats=st, conv=(256, 56, 56, 64), conv_mode=1)
     torch.cuda.synchronize()
 print("done")

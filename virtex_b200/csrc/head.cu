@@ -996,7 +996,7 @@ extern "C" int vtx_colsum(const void* X, int64_t ld, int M, int N, float* out, v
   const int groups = (N + 7) / 8;
   const int threads = 128;
   const int gy = (groups + threads - 1) / threads;
-  int gx = (vtx_num_sms() * 8 + gy - 1) / gy;
+  int gx = (vtx_num_sms() * 2 + gy - 1) / gy;  // few row blocks: every block ends with one atomic per column
   if (gx > M) gx = M;
   if (gx < 1) gx = 1;
   const int rows_per_block = (M + gx - 1) / gx;
