@@ -392,7 +392,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
       const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)as * 256u;
-      uint8_t* srow = cbuf + r_in_tile * 128;
+      const uint32_t srow = smem_u32(cbuf) + r_in_tile * 128;
       const int sw = r_in_tile & 7;
       float va[32], vb[32];
       int j = hf;
@@ -409,10 +409,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const bool full = col0 + 32 <= p.N;
           epi_math(va, p, grow, col0, full);
           if (staged) {
-            uint8_t* sp = srow + (j >> 1) * 16384;
+            const uint32_t sp = srow + (j >> 1) * 16384;
             const int cb = (j & 1) * 4;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) *reinterpret_cast<bf16x8*>(sp + (((cb + i) ^ sw) << 4)) = pack8(va + 8 * i);
+            for (int i = 0; i < 4; ++i) {
+              const bf16x8 pk = pack8(va + 8 * i);
+              const uint32_t* w = reinterpret_cast<const uint32_t*>(&pk);
+              sts128(sp + (((cb + i) ^ sw) << 4), w[0], w[1], w[2], w[3]);
+            }
           } else if (grow >= 0) {
             epi_store_f32(va, p, grow, col0, full);
           }
@@ -426,10 +430,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const bool full = col0 + 32 <= p.N;
           epi_math(vb, p, grow, col0, full);
           if (staged) {
-            uint8_t* sp = srow + ((j + 2) >> 1) * 16384;
+            const uint32_t sp = srow + ((j + 2) >> 1) * 16384;
             const int cb = ((j + 2) & 1) * 4;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) *reinterpret_cast<bf16x8*>(sp + (((cb + i) ^ sw) << 4)) = pack8(vb + 8 * i);
+            for (int i = 0; i < 4; ++i) {
+              const bf16x8 pk = pack8(vb + 8 * i);
+              const uint32_t* w = reinterpret_cast<const uint32_t*>(&pk);
+              sts128(sp + (((cb + i) ^ sw) << 4), w[0], w[1], w[2], w[3]);
+            }
           } else if (grow >= 0) {
             epi_store_f32(vb, p, grow, col0, full);
           }
@@ -456,12 +464,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ---------------- BN statistics of the staged (bf16-rounded) tile, accumulated in registers.
         // Rows outside the problem are exact zeros (TMA zero fill; stats forbids bias/residual): no masking needed.
         if (p.stats != nullptr && scg * 8 < p.bn) {
-          const uint8_t* cp = cbuf + (scg >> 3) * 16384 + (srg * 16) * 128;
+          const uint32_t cp = smem_u32(cbuf) + (scg >> 3) * 16384 + (srg * 16) * 128;
           const int c8 = scg & 7;
 #pragma unroll 4
           for (int r = 0; r < 16; ++r) {
             float f[8];
-            unpack8(*reinterpret_cast<const bf16x8*>(cp + r * 128 + ((c8 ^ (r & 7)) << 4)), f);
+            const uint4 raw = lds128(cp + r * 128 + ((c8 ^ (r & 7)) << 4));
+            unpack8(*reinterpret_cast<const bf16x8*>(&raw), f);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               st_s[i] += f[i];
