@@ -51,6 +51,7 @@ struct GemmKParams {
   int dbg;  // developer knobs (VTX_GEMM_DBG): selectively disable epilogue parts for attribution experiments
   int stages, stage_bytes;   // smem ring depth / bytes per stage
   int cbytes, nbuf;          // bytes of one bf16 staging buffer (0: no staging) / number of staging buffers
+  int res_tma;               // residual tile is TMA-loaded into the staging buffer and added there
   float alpha;
   void* D;
   long long ldd;
@@ -102,7 +103,7 @@ __device__ __forceinline__ void epi_math(float* v, const GemmKParams& p, long lo
         if (col0 + i < p.N) v[i] += p.bias[col0 + i];
     }
   }
-  if (p.residual != nullptr && grow >= 0) {
+  if (p.residual != nullptr && !p.res_tma && grow >= 0) {
     const __nv_bfloat16* rp = p.residual + grow * p.ldr + col0;
     if (full) {
 #pragma unroll
@@ -155,7 +156,8 @@ __device__ __forceinline__ void epi_store_f32(const float* v, const GemmKParams&
 
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmD, const GemmKParams p) {
+               const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR,
+               const GemmKParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(base);
@@ -163,7 +165,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* empty_bar = bars + kMaxStages;       // [kMaxStages]
   uint64_t* tfull_bar = bars + 2 * kMaxStages;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;          // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* res_bar = tempty_bar + 2;            // [2] residual tile landed in staging buffer b
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2);
   uint8_t* smem = base + kCtrlBytes;                       // stage ring (1024-aligned)
   uint8_t* cstage0 = smem + p.stages * p.stage_bytes;      // bf16 staging: nbuf x [bn/64 slabs][128 rows][128 B], SW128
 
@@ -176,6 +179,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (p.cbytes) tma_prefetch_desc(&tmD);
+    if (p.res_tma) tma_prefetch_desc(&tmR);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < nstages; ++i) {
@@ -185,6 +189,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], kEpiThreads);
+      mbar_init(&res_bar[i], 1);
     }
     fence_mbar_init();
   }
@@ -372,14 +377,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (st_nt >= 0) flush_stats(cbuf);
           st_nt = nt;
         }
+        if (p.res_tma && et == 0) {
+          // asynchronous, coalesced load of the residual tile into the (now free) staging buffer
+          const int bi = p.nbuf > 1 ? (it & 1) : 0;
+          const int slabs = (min(p.bn, p.N - n_base) + 63) >> 6;
+          mbar_arrive_expect_tx(&res_bar[bi], (uint32_t)slabs * 16384u);
+          for (int sl = 0; sl < slabs; ++sl) {
+            if (p.mode == 1)
+              tma_load_4d(cbuf + sl * 16384, &tmR, &res_bar[bi], n_base + sl * 64, tw << p.lbw, th << p.lbh, tn << p.lbn);
+            else
+              tma_load_2d(cbuf + sl * 16384, &tmR, &res_bar[bi], n_base + sl * 64, mt * kBM);
+          }
+        }
       }
       mbar_wait(&tfull_bar[as], (it >> 1) & 1);
       tc_fence_after();
+      if (p.res_tma) {
+        const int bi = p.nbuf > 1 ? (it & 1) : 0;
+        const int uses = p.nbuf > 1 ? (it >> 1) : it;
+        mbar_wait(&res_bar[bi], uses & 1);
+      }
 
       // ---------------- phase 1: TMEM -> registers -> fp32 epilogue math -> swizzled bf16 staging (or fp32 global)
       const int r_in_tile = ew * 32 + lane;
       long long grow = -1;
-      if (!staged || p.residual != nullptr) {
+      if (!staged || (p.residual != nullptr && !p.res_tma)) {
         if (p.mode == 1) {
           const int dw = r_in_tile & ((1 << p.lbw) - 1);
           const int dh = (r_in_tile >> p.lbw) & ((1 << p.lbh) - 1);
@@ -407,10 +429,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         {
           const int col0 = n_base + c0;
           const bool full = col0 + 32 <= p.N;
+          const uint32_t sp = srow + (j >> 1) * 16384;
+          const int cb = (j & 1) * 4;
+          if (p.res_tma) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint4 raw = lds128(sp + (((cb + i) ^ sw) << 4));
+              float f[8];
+              unpack8(*reinterpret_cast<const bf16x8*>(&raw), f);
+#pragma unroll
+              for (int e2 = 0; e2 < 8; ++e2) va[8 * i + e2] += f[e2];
+            }
+          }
           epi_math(va, p, grow, col0, full);
           if (staged) {
-            const uint32_t sp = srow + (j >> 1) * 16384;
-            const int cb = (j & 1) * 4;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const bf16x8 pk = pack8(va + 8 * i);
@@ -428,10 +460,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         {
           const int col0 = n_base + c1;
           const bool full = col0 + 32 <= p.N;
+          const uint32_t sp = srow + ((j + 2) >> 1) * 16384;
+          const int cb = ((j + 2) & 1) * 4;
+          if (p.res_tma) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint4 raw = lds128(sp + (((cb + i) ^ sw) << 4));
+              float f[8];
+              unpack8(*reinterpret_cast<const bf16x8*>(&raw), f);
+#pragma unroll
+              for (int e2 = 0; e2 < 8; ++e2) vb[8 * i + e2] += f[e2];
+            }
+          }
           epi_math(vb, p, grow, col0, full);
           if (staged) {
-            const uint32_t sp = srow + ((j + 2) >> 1) * 16384;
-            const int cb = ((j + 2) & 1) * 4;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const bf16x8 pk = pack8(vb + 8 * i);
@@ -689,7 +731,7 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
     p.nbuf = 1;
     if (p.cbytes) {
       const int st2 = (budget - 2 * p.cbytes) / p.stage_bytes;
-      if (st2 >= 4 || st2 >= kb_tile + 1) { p.nbuf = 2; st = st2; }
+      if (st2 >= 4 || (st2 >= 2 && st2 >= kb_tile)) { p.nbuf = 2; st = st2; }
     }
     {
       const char* e = getenv("VTX_GEMM_NBUF");
@@ -700,19 +742,30 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
     if (st < 2) return set_error(VTX_EUNSUPPORTED, "vtx_gemm: not enough shared memory for a 2-stage pipeline");
     p.stages = st;
   }
-  CUtensorMap tmD;
+  CUtensorMap tmD, tmR;
   memset(&tmD, 0, sizeof(tmD));
+  memset(&tmR, 0, sizeof(tmR));
+  p.res_tma = (p.cbytes && g->residual != nullptr && g->ldr % 8 == 0 &&
+               (reinterpret_cast<uintptr_t>(g->residual) & 15) == 0) ? 1 : 0;
   if (p.cbytes) {
     if (p.mode == 1) {
       uint64_t dd[4] = {(uint64_t)g->N, (uint64_t)g->conv_w, (uint64_t)g->conv_h, (uint64_t)g->conv_n};
       uint64_t ds[3] = {(uint64_t)g->ldd, (uint64_t)g->conv_w * g->ldd, (uint64_t)g->conv_h * g->conv_w * g->ldd};
       uint32_t db[4] = {64, 1u << p.lbw, 1u << p.lbh, 1u << p.lbn};
       if ((rc = make_tmap(&tmD, g->D, 4, dd, ds, db)) != VTX_OK) return rc;
+      if (p.res_tma) {
+        uint64_t rs[3] = {(uint64_t)g->ldr, (uint64_t)g->conv_w * g->ldr, (uint64_t)g->conv_h * g->conv_w * g->ldr};
+        if ((rc = make_tmap(&tmR, g->residual, 4, dd, rs, db)) != VTX_OK) return rc;
+      }
     } else {
       uint64_t dd[2] = {(uint64_t)g->N, (uint64_t)g->M};
       uint64_t ds[1] = {(uint64_t)g->ldd};
       uint32_t db[2] = {64, 128};
       if ((rc = make_tmap(&tmD, g->D, 2, dd, ds, db)) != VTX_OK) return rc;
+      if (p.res_tma) {
+        uint64_t rs[1] = {(uint64_t)g->ldr};
+        if ((rc = make_tmap(&tmR, g->residual, 2, dd, rs, db)) != VTX_OK) return rc;
+      }
     }
   }
   static bool attr_set = false;
@@ -724,7 +777,7 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
   const long total = (long)p.m_tiles * p.n_tiles * p.k_splits;
   const int sms = vtx_num_sms();
   const int grid = (int)(total < sms ? total : sms);
-  gemm_tc_kernel<<<grid, kThreads, kSmemTotal, stream>>>(tmA, tmB, tmD, p);
+  gemm_tc_kernel<<<grid, kThreads, kSmemTotal, stream>>>(tmA, tmB, tmD, tmR, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(VTX_ECUDA, "gemm_tc_kernel launch: %s", cudaGetErrorString(e));
   return VTX_OK;
