@@ -49,11 +49,12 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -61,18 +62,27 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append([time.perf_counter()] + [x.strip() for x in line.split(",")])
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
         self.proc.terminate()
-        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        inside = [r[1:] for r in self.rows if self.t0 is not None and self.t0 <= r[0] <= (self.t1 or r[0])]
+        rows = inside if inside else [r[1:] for r in self.rows]  # sampler started under load (warm-up) as a fallback
+        sm = sorted(float(r[0]) for r in rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in rows)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+                "reasons": reasons, "samples": len(rows), "samples_in_timed_region": len(inside)}
 
 
 def measured_peaks():
@@ -166,20 +176,22 @@ def main_ours(args, rank, world, local):
         return ms
 
     # ---- warm-up (allocates every workspace buffer), then the device-resident timed region
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()  # started before the warm-up so that it is already sampling when the timed region begins
     for _ in range(max(args.warmup, 3)):
         trainer.step(dev_batch)
     barrier()
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
     launches0 = ops.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    clocks.mark_begin()
     e0.record()
     for _ in range(args.steps):
         loss = trainer.step(dev_batch)
     e1.record()
     barrier()
+    clocks.mark_end()
     ms = max_over_ranks(e0.elapsed_time(e1))
     launches = ops.launch_count - launches0
     clk = clocks.stop() if rank == 0 else None
