@@ -232,13 +232,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           // stage buffer is filled once and never reloaded
           const bool skip_b = (p.dbg & 16) && fills >= nstages;
           ++fills;
-          mbar_arrive_expect_tx(&full_bar[stage], kABytes + (skip_b ? 0u : b_bytes));
+          // MN-major A tiles are loaded as two 64-row atoms; when the second lies entirely beyond M it is not fetched
+          // (its accumulator rows are garbage, and masked by the epilogue)
+          const bool half_a = p.a_mn && (mt * kBM + 64 >= p.M);
+          mbar_arrive_expect_tx(&full_bar[stage], (half_a ? kABytes / 2 : kABytes) + (skip_b ? 0u : b_bytes));
           if (p.mode == 0) {
             if (!p.a_mn) {
               tma_load_2d(sA, &tmA, &full_bar[stage], kb * kBK, mt * kBM);
             } else {
               tma_load_2d(sA, &tmA, &full_bar[stage], mt * kBM, kb * kBK);
-              tma_load_2d(sA + 8192, &tmA, &full_bar[stage], mt * kBM + 64, kb * kBK);
+              if (!half_a) tma_load_2d(sA + 8192, &tmA, &full_bar[stage], mt * kBM + 64, kb * kBK);
             }
             if (skip_b) {
             } else if (!p.b_mn) {
@@ -260,7 +263,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int tn = kb / (p.tiles_w * p.tiles_h);
             const int bw0 = tw << p.lbw, bh0 = th << p.lbh, bn0 = tn << p.lbn;
             tma_load_4d(sA, &tmA, &full_bar[stage], mt * kBM, bw0, bh0, bn0);
-            tma_load_4d(sA + 8192, &tmA, &full_bar[stage], mt * kBM + 64, bw0, bh0, bn0);
+            if (!half_a) tma_load_4d(sA + 8192, &tmA, &full_bar[stage], mt * kBM + 64, bw0, bh0, bn0);
             for (int j = 0; j < (p.bn >> 6); ++j) {
               const int atom = nt * (p.bn >> 6) + j;
               const int tap = atom / p.cpb;
@@ -629,6 +632,11 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
     const int gran = p.b_mn ? 64 : 16;
     if (g->N >= 256) bn = 256;
     else bn = ((g->N + gran - 1) / gran) * gran;
+    if (p.b_mn && bn == 256 && g->N % 256 != 0) {
+      // MN-major B is fetched in 64-column atoms: a 192-wide tile wastes nothing on N = 576 / 1152 (3x3 wgrads)
+      if (g->N % 192 == 0) bn = 192;
+      else if (g->N % 128 == 0) bn = 128;
+    }
     // prefer 128-wide tiles when that fills the machine noticeably better
     if (bn == 256) {
       const long mt = (g->M + kBM - 1) / kBM;
