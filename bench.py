@@ -136,7 +136,8 @@ def main_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": round(v, 3), "unit": "pairs/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": round(sec * 1e3, 2), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "bicaptioning R50_L1_H1024 full optimisation step, reference algorithm on host cores",
+            "config": {"workload": "bicaptioning R50_L1_H1024 full optimisation step, batch 256 per GPU",
+                       "sample": f"reference algorithm on the host cores, each step = {B} pairs of that workload",
                        "global_batch": B},
             "cpu_baseline": {"value": round(v, 3), "unit": "pairs/s", "cores": threads, "kind": "port",
                              "sample": f"{steps} full steps at batch {B} after {warm} warm-up (oracle port of the reference, fp32)"},

@@ -357,3 +357,95 @@ def test_dropout_runs_and_is_unbiased():
     assert math.isfinite(out["loss"].item())
     for p in model.parameters():
         assert p.grad is not None and torch.isfinite(p.grad).all()
+
+
+# ------------------------------------------------------------------------------------------------- optimiser / trainer
+def test_sgd_step_kernel_matches_reference_arithmetic():
+    """vtx_sgd_step == torch.optim.SGD(momentum, per-tensor lr/wd) + Lookahead arithmetic on random arenas."""
+    _need_cuda()
+    import struct
+    from virtex_b200.ops import call, _stream
+    torch.manual_seed(3)
+    dev = "cuda"
+    n = 3 * 70000 + 13
+    p = torch.randn(n, device=dev); g = torch.randn(n, device=dev); m = torch.randn(n, device=dev)
+    slow = torch.randn(n, device=dev)
+    bf = torch.zeros(n, device=dev, dtype=torch.bfloat16)
+    bounds = [(0, 70000, 0.2, 1e-4), (70000, 140000, 0.001, 0.0), (140000, n, 0.001, 1e-4)]
+    segs = []
+    for b, e, lr, wd in bounds:
+        for c in range(b, e, 65536):
+            segs.append((c, min(e, c + 65536), lr, wd))
+    blob = torch.frombuffer(bytearray(b"".join(struct.pack("<qqff", *s) for s in segs)), dtype=torch.uint8).to(dev)
+    for first, do_la in ((1.0, 0.0), (0.0, 0.0), (0.0, 1.0)):
+        p0, m0, s0 = p.clone(), m.clone(), slow.clone()
+        ssq = (g.double() ** 2).sum().float().reshape(1)
+        ctl = torch.zeros(2, device=dev)
+        call("vtx_clip_coef", ssq.data_ptr(), 2, 10.0, ctl.data_ptr(), _stream())
+        hyper = torch.tensor([0.37, first, do_la, 0.0], device=dev)
+        call("vtx_sgd_step", p.data_ptr(), g.data_ptr(), m.data_ptr(), slow.data_ptr(), bf.data_ptr(), blob.data_ptr(),
+             len(segs), ctl.data_ptr(), hyper.data_ptr(), 0.9, 0.5, _stream())
+        torch.cuda.synchronize()
+        norm = ssq.sqrt().item() / 2
+        scale = min(1.0, 10.0 / (norm + 1e-6)) / 2
+        assert abs(ctl[1].item() - norm) < 1e-3 * norm
+        for b, e, lr, wd in bounds:
+            gg = g[b:e] * scale + wd * p0[b:e]
+            mm = gg if first else 0.9 * m0[b:e] + gg
+            pp = p0[b:e] - lr * 0.37 * mm
+            if do_la:
+                pp = 0.5 * pp + 0.5 * s0[b:e]
+                assert torch.allclose(slow[b:e], pp, rtol=1e-5, atol=1e-6)
+            assert torch.allclose(m[b:e], mm, rtol=1e-5, atol=1e-6)
+            assert torch.allclose(p[b:e], pp, rtol=1e-5, atol=1e-6)
+            assert torch.allclose(bf[b:e].float(), pp, rtol=1e-2, atol=1e-2)
+
+
+def test_trainer_trajectory_vs_oracle():
+    """6 fused optimiser steps (crossing the Lookahead boundary) track the CPU oracle trainer."""
+    _need_cuda()
+    from virtex_b200.config import Config
+    from virtex_b200.trainer import Trainer
+    spec = O.Spec(hidden=128, layers=1, heads=2, ffn=256)
+    state = O.synth_state(spec, 3, bn3_gain=0.25)
+    model = build_model(spec, state)
+    model.train()
+    cfg = Config(None, ["MODEL.TEXTUAL.NAME", "transdec_postnorm::L1_H128_A2_F256", "MODEL.TEXTUAL.DROPOUT", 0.0,
+                        "OPTIM.WARMUP_STEPS", 3, "OPTIM.NUM_ITERATIONS", 20, "OPTIM.BATCH_SIZE", 4, "OPTIM.CNN_LR", 0.005])
+    tr = Trainer(model, cfg)
+    ora = O.OracleTrainer(state, spec, O.OptimCfg(warmup_steps=3, num_iterations=20, cnn_lr=0.005))
+    for it in range(6):
+        batch = O.synth_batch(4, seed=30 + it, ragged=True)
+        loss = tr.step(to_cuda(batch)).sum().item()
+        ref = ora.step(batch)
+        assert abs(loss - ref["loss"].item()) < 3e-3 * ref["loss"].item(), (it, loss, ref["loss"].item())
+        assert abs(tr.grad_norm.item() - ref["grad_norm"].item()) < 0.1 * ref["grad_norm"].item(), it
+    k = "textual.transformer.layers.0.linear1.weight"
+    d_ours = dict(model.named_parameters())[k].detach().cpu() - state[k]
+    d_ref = ora.state[k] - state[k]
+    assert cos(d_ours, d_ref) > 0.99, cos(d_ours, d_ref)
+
+
+def test_frozen_backbone_and_forward_only_model():
+    _need_cuda()
+    from virtex_b200.models import ForwardCaptioningModel
+    from virtex_b200.modules import TorchvisionVisualBackbone, TransformerDecoderTextualHead
+    spec = O.Spec(hidden=128, layers=1, heads=2, ffn=256, caption_backward=False)
+    state = O.synth_state(spec, 19, bn3_gain=0.25)
+    visual = TorchvisionVisualBackbone("resnet50", 2048, frozen=True)
+    textual = TransformerDecoderTextualHead(2048, spec.vocab, 128, 1, 2, 256, dropout=0.0)
+    model = ForwardCaptioningModel(visual, textual)
+    model.load_state_dict(O.to_reference_state_dict(state, spec), strict=True)
+    model = model.cuda().train()
+    batch = O.synth_batch(3, seed=14, ragged=True)
+    out = model(to_cuda(batch))
+    with torch.no_grad():  # frozen backbone == eval-mode BN
+        vf = O.backbone_forward(state, batch["image"], spec, training=False)
+        ref = O.caption_loss(O.head_forward(state, vf, batch["caption_tokens"], batch["caption_lengths"], spec), batch["caption_tokens"])
+    assert "captioning_backward" not in out["loss_components"]
+    assert abs(out["loss"].item() - ref.item()) < 2e-3 * ref.item(), (out["loss"].item(), ref.item())
+    out["loss"].backward()
+    named = dict(model.named_parameters())
+    assert named["visual.cnn.conv1.weight"].grad is None
+    assert torch.isfinite(named["textual.embedding.words.weight"].grad).all()
+    assert int(model.visual.cnn.bn1.num_batches_tracked) == 0
