@@ -89,6 +89,11 @@ int vtx_bn_finalize(const float* stats, float count, const float* gamma, const f
 /* out = act(y*scale + shift [+ res | + res*scale_r + shift_r]) */
 int vtx_bn_act(const void* y, const float* bnp, const void* res, const float* bnp_res, void* out, int64_t M, int C,
                int relu, void* stream);
+/* vtx_bn_finalize + vtx_bn_act fused into one launch */
+int vtx_bn_finalize_act(const float* stats, float count, const float* gamma, const float* beta, float* running_mean,
+                        float* running_var, int64_t* num_batches_tracked, float momentum, float eps, int training,
+                        float* bnp, const void* y, const void* res, const float* bnp_res, void* out, int64_t M, int C,
+                        int relu, void* stream);
 int vtx_bn_relu_maxpool(const void* y, const float* bnp, void* out, uint8_t* idx, int N, int H, int W, int C,
                         void* stream);
 int vtx_maxpool_bwd(const void* dpool, const uint8_t* idx, void* da, int N, int H, int W, int C, void* stream);
@@ -103,6 +108,11 @@ int vtx_bn_bwd_finalize(const float* sums, const float* bnp, float count, float*
 int vtx_bn_bwd_apply(const void* dA, const void* a, const void* y, const float* bnp, const float* coef, void* dy,
                      const void* y2, const float* bnp2, const float* coef2, void* dy2, void* dz_out, int64_t M, int C,
                      int mask_from_y, void* stream);
+/* vtx_bn_bwd_finalize + vtx_bn_bwd_apply fused into one launch (dgamma/dbeta accumulated by the first thread block) */
+int vtx_bn_bwd_finalize_apply(const float* sums, const float* sums2, float count, float* dgamma, float* dbeta,
+                              float* dgamma2, float* dbeta2, const void* dA, const void* a, const void* y,
+                              const float* bnp, void* dy, const void* y2, const float* bnp2, void* dy2, void* dz_out,
+                              int64_t M, int C, int mask_from_y, void* stream);
 /* conv weight layouts: fp32 OIHW <-> bf16 [O, (kh,kw,I)] GEMM operand; flipped/transposed dgrad operand */
 int vtx_conv_w_pack(const float* w, void* out, int O, int I, int KH, int KW, int ldk, void* stream);
 int vtx_conv_w_pack_dgrad(const float* w, void* out, int O, int I, void* stream);

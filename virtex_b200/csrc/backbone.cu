@@ -194,9 +194,23 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, float count,
 // a = act( y*scale + shift  [+ res  |  + res*scale2 + shift2] )
 constexpr int kU = 4;  // independent 16-byte loads per tensor in flight per thread (memory-level parallelism)
 
-__global__ void __launch_bounds__(256, 2) bn_act_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ bnp,
+// Optional fold of bn_finalize into the apply kernel: every thread derives scale/shift of its 8 channels from the raw
+// batch sums (or the running statistics in eval mode); block 0 also publishes bnp and updates the running buffers.
+struct BnFwdFold {
+  const float* stats;  // [2,C] sum, sumsq (training) -- may be null in eval mode
+  const float* gamma;
+  const float* beta;
+  float* rmean;
+  float* rvar;
+  long long* nbt;
+  float count, momentum, eps;
+  int training;
+};
+
+template <bool kFold>
+__global__ void __launch_bounds__(256, 2) bn_act_kernel(const __nv_bfloat16* __restrict__ y, float* __restrict__ bnp,
                               const __nv_bfloat16* __restrict__ res, const float* __restrict__ bnp_res,
-                              __nv_bfloat16* __restrict__ out, long long M, int C, int relu) {
+                              __nv_bfloat16* __restrict__ out, long long M, int C, int relu, const BnFwdFold f) {
   const int cg = C / 8;
   const long long total = M * cg;
   // blockDim.x (256) is a multiple of cg, so a thread's 8-channel group never changes across the grid-stride loop:
@@ -207,11 +221,37 @@ __global__ void __launch_bounds__(256, 2) bn_act_kernel(const __nv_bfloat16* __r
   float sc[8], sh[8], sc2[8], sh2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    sc[j] = bnp[2 * C + c0 + j];
-    sh[j] = bnp[3 * C + c0 + j];
-    sc2[j] = bnp_res ? bnp_res[2 * C + c0 + j] : 1.f;
-    sh2[j] = bnp_res ? bnp_res[3 * C + c0 + j] : 0.f;
+    const int c = c0 + j;
+    if (kFold) {
+      float mean, var;
+      if (f.training) {
+        mean = f.stats[c] / f.count;
+        var = fmaxf(f.stats[C + c] / f.count - mean * mean, 0.f);
+      } else {
+        mean = f.rmean[c];
+        var = f.rvar[c];
+      }
+      const float invstd = rsqrtf(var + f.eps);
+      sc[j] = f.gamma[c] * invstd;
+      sh[j] = f.beta[c] - mean * sc[j];
+      if (blockIdx.x == 0 && threadIdx.x < cg) {  // thread t < cg of block 0 owns channels [8t, 8t+8)
+        bnp[c] = mean;
+        bnp[C + c] = invstd;
+        bnp[2 * C + c] = sc[j];
+        bnp[3 * C + c] = sh[j];
+        if (f.training) {
+          f.rmean[c] = (1.f - f.momentum) * f.rmean[c] + f.momentum * mean;
+          f.rvar[c] = (1.f - f.momentum) * f.rvar[c] + f.momentum * var * (f.count / fmaxf(f.count - 1.f, 1.f));
+        }
+      }
+    } else {
+      sc[j] = bnp[2 * C + c];
+      sh[j] = bnp[3 * C + c];
+    }
+    sc2[j] = bnp_res ? bnp_res[2 * C + c] : 1.f;
+    sh2[j] = bnp_res ? bnp_res[3 * C + c] : 0.f;
   }
+  if (kFold && blockIdx.x == 0 && threadIdx.x == 0 && f.training && f.nbt != nullptr) *f.nbt += 1;
   for (long long i = i0; i < total; i += stride * kU) {
     bf16x8 vy[kU], vr[kU];
 #pragma unroll
@@ -454,13 +494,25 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ sums, const flo
 }
 
 // dy = scale * (dz - m1 - xhat * m2);  optional second BN sharing dz;  optional dz output (identity shortcut grad)
-template <int kTwo>
+// Optional fold of bn_bwd_finalize: coefficients derived from the raw sums in the prologue; block 0 accumulates dgamma/dbeta
+struct BnBwdFold {
+  const float* sums;
+  const float* sums2;
+  float* dgamma;
+  float* dbeta;
+  float* dgamma2;
+  float* dbeta2;
+  float count;
+};
+
+template <int kTwo, bool kFold>
 __global__ void __launch_bounds__(256, kTwo ? 1 : 2) bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloat16* __restrict__ a,
                                     const __nv_bfloat16* __restrict__ y, const float* __restrict__ bnp,
                                     const float* __restrict__ coef, __nv_bfloat16* __restrict__ dy,
                                     const __nv_bfloat16* __restrict__ y2, const float* __restrict__ bnp2,
                                     const float* __restrict__ coef2, __nv_bfloat16* __restrict__ dy2,
-                                    __nv_bfloat16* __restrict__ dz_out, long long M, int C, int mask_from_y) {
+                                    __nv_bfloat16* __restrict__ dz_out, long long M, int C, int mask_from_y,
+                                    const BnBwdFold f) {
   const int cg = C / 8;
   const long long total = M * cg;
   const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -476,12 +528,38 @@ __global__ void __launch_bounds__(256, kTwo ? 1 : 2) bn_bwd_apply_kernel(const _
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = c0 + j;
-    const float mean = bnp[c], istd = bnp[C + c], scl = coef[c], m1 = coef[C + c], m2 = coef[2 * C + c];
+    const float mean = bnp[c], istd = bnp[C + c];
+    float scl, m1, m2;
+    if (kFold) {
+      const float s1 = f.sums[c], s2 = f.sums[C + c];
+      scl = bnp[2 * C + c];
+      m1 = s1 / f.count;
+      m2 = s2 / f.count;
+      if (blockIdx.x == 0 && threadIdx.x < cg) {
+        if (f.dgamma) f.dgamma[c] += s2;
+        if (f.dbeta) f.dbeta[c] += s1;
+      }
+    } else {
+      scl = coef[c]; m1 = coef[C + c]; m2 = coef[2 * C + c];
+    }
     k0[j] = scl;
     k1[j] = -scl * m2 * istd;
     k2[j] = scl * (m2 * istd * mean - m1);
     if (kTwo) {
-      const float mean_b = bnp2[c], istd_b = bnp2[C + c], scl_b = coef2[c], m1b = coef2[C + c], m2b = coef2[2 * C + c];
+      const float mean_b = bnp2[c], istd_b = bnp2[C + c];
+      float scl_b, m1b, m2b;
+      if (kFold) {
+        const float s1 = f.sums2[c], s2 = f.sums2[C + c];
+        scl_b = bnp2[2 * C + c];
+        m1b = s1 / f.count;
+        m2b = s2 / f.count;
+        if (blockIdx.x == 0 && threadIdx.x < cg) {
+          if (f.dgamma2) f.dgamma2[c] += s2;
+          if (f.dbeta2) f.dbeta2[c] += s1;
+        }
+      } else {
+        scl_b = coef2[c]; m1b = coef2[C + c]; m2b = coef2[2 * C + c];
+      }
       q0[j] = scl_b;
       q1[j] = -scl_b * m2b * istd_b;
       q2[j] = scl_b * (m2b * istd_b * mean_b - m1b);
@@ -653,10 +731,26 @@ extern "C" int vtx_bn_finalize(const float* stats, float count, const float* gam
 extern "C" int vtx_bn_act(const void* y, const float* bnp, const void* res, const float* bnp_res, void* out,
                           int64_t M, int C, int relu, void* stream) {
   REQ(y && bnp && out && C % 8 == 0, "bad arguments");
-  bn_act_kernel<<<grid_for((M * (C / 8) + kU - 1) / kU, 256, 2), 256, 0, STREAM>>>((const __nv_bfloat16*)y, bnp,
-                                                                (const __nv_bfloat16*)res, bnp_res,
-                                                                (__nv_bfloat16*)out, M, C, relu);
+  BnFwdFold f;
+  memset(&f, 0, sizeof(f));
+  bn_act_kernel<false><<<grid_for((M * (C / 8) + kU - 1) / kU, 256, 2), 256, 0, STREAM>>>(
+      (const __nv_bfloat16*)y, const_cast<float*>(bnp), (const __nv_bfloat16*)res, bnp_res, (__nv_bfloat16*)out, M, C,
+      relu, f);
   return check_launch("bn_act");
+}
+// bn_finalize + bn_act in one launch (the statistics -> scale/shift step runs in every thread's prologue)
+extern "C" int vtx_bn_finalize_act(const float* stats, float count, const float* gamma, const float* beta, float* rmean,
+                                   float* rvar, int64_t* nbt, float momentum, float eps, int training, float* bnp,
+                                   const void* y, const void* res, const float* bnp_res, void* out, int64_t M, int C,
+                                   int relu, void* stream) {
+  REQ(y && bnp && out && gamma && beta && rmean && rvar && C % 8 == 0 && C / 8 <= 256 && (stats || !training),
+      "bad arguments");
+  BnFwdFold f;
+  f.stats = stats; f.gamma = gamma; f.beta = beta; f.rmean = rmean; f.rvar = rvar; f.nbt = (long long*)nbt;
+  f.count = count; f.momentum = momentum; f.eps = eps; f.training = training;
+  bn_act_kernel<true><<<grid_for((M * (C / 8) + kU - 1) / kU, 256, 2), 256, 0, STREAM>>>(
+      (const __nv_bfloat16*)y, bnp, (const __nv_bfloat16*)res, bnp_res, (__nv_bfloat16*)out, M, C, relu, f);
+  return check_launch("bn_finalize_act");
 }
 extern "C" int vtx_bn_relu_maxpool(const void* y, const float* bnp, void* out, uint8_t* idx, int N, int H, int W, int C,
                                    void* stream) {
@@ -706,23 +800,45 @@ extern "C" int vtx_bn_bwd_finalize(const float* sums, const float* bnp, float co
   bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, STREAM>>>(sums, bnp, count, coef, dgamma, dbeta, C);
   return check_launch("bn_bwd_finalize");
 }
+static int launch_bn_bwd_apply(bool fold, const BnBwdFold& f, const void* dA, const void* a, const void* y,
+                               const float* bnp, const float* coef, void* dy, const void* y2, const float* bnp2,
+                               const float* coef2, void* dy2, void* dz_out, int64_t M, int C, int mask_from_y,
+                               cudaStream_t st) {
+  const int grid = grid_for((M * (C / 8) + kU - 1) / kU, 256, y2 != nullptr ? 1 : 2);
+#define VTX_APPLY_ARGS (const __nv_bfloat16*)dA, (const __nv_bfloat16*)a, (const __nv_bfloat16*)y, bnp, coef,          \
+                       (__nv_bfloat16*)dy, (const __nv_bfloat16*)y2, bnp2, coef2, (__nv_bfloat16*)dy2,                  \
+                       (__nv_bfloat16*)dz_out, M, C, mask_from_y, f
+  if (y2 != nullptr) {
+    if (fold) bn_bwd_apply_kernel<1, true><<<grid, 256, 0, st>>>(VTX_APPLY_ARGS);
+    else bn_bwd_apply_kernel<1, false><<<grid, 256, 0, st>>>(VTX_APPLY_ARGS);
+  } else {
+    if (fold) bn_bwd_apply_kernel<0, true><<<grid, 256, 0, st>>>(VTX_APPLY_ARGS);
+    else bn_bwd_apply_kernel<0, false><<<grid, 256, 0, st>>>(VTX_APPLY_ARGS);
+  }
+#undef VTX_APPLY_ARGS
+  return check_launch("bn_bwd_apply");
+}
 extern "C" int vtx_bn_bwd_apply(const void* dA, const void* a, const void* y, const float* bnp, const float* coef,
                                 void* dy, const void* y2, const float* bnp2, const float* coef2, void* dy2,
                                 void* dz_out, int64_t M, int C, int mask_from_y, void* stream) {
   REQ(dA && y && bnp && coef && dy && C % 8 == 0, "bad arguments");
-  const int grid = grid_for((M * (C / 8) + kU - 1) / kU, 256, y2 != nullptr ? 1 : 2);
-  if (y2 != nullptr) {
-    REQ(bnp2 && coef2 && dy2, "second BN needs bnp2/coef2/dy2");
-    bn_bwd_apply_kernel<1><<<grid, 256, 0, STREAM>>>((const __nv_bfloat16*)dA, (const __nv_bfloat16*)a,
-                                                     (const __nv_bfloat16*)y, bnp, coef, (__nv_bfloat16*)dy,
-                                                     (const __nv_bfloat16*)y2, bnp2, coef2, (__nv_bfloat16*)dy2,
-                                                     (__nv_bfloat16*)dz_out, M, C, mask_from_y);
-  } else {
-    bn_bwd_apply_kernel<0><<<grid, 256, 0, STREAM>>>((const __nv_bfloat16*)dA, (const __nv_bfloat16*)a,
-                                                     (const __nv_bfloat16*)y, bnp, coef, (__nv_bfloat16*)dy, nullptr,
-                                                     nullptr, nullptr, nullptr, (__nv_bfloat16*)dz_out, M, C, mask_from_y);
-  }
-  return check_launch("bn_bwd_apply");
+  if (y2 != nullptr) REQ(bnp2 && coef2 && dy2, "second BN needs bnp2/coef2/dy2");
+  BnBwdFold f;
+  memset(&f, 0, sizeof(f));
+  return launch_bn_bwd_apply(false, f, dA, a, y, bnp, coef, dy, y2, bnp2, coef2, dy2, dz_out, M, C, mask_from_y, STREAM);
+}
+// bn_bwd_finalize + bn_bwd_apply in one launch: sums [2,C] (and sums2) straight from vtx_bn_bwd_reduce
+extern "C" int vtx_bn_bwd_finalize_apply(const float* sums, const float* sums2, float count, float* dgamma, float* dbeta,
+                                         float* dgamma2, float* dbeta2, const void* dA, const void* a, const void* y,
+                                         const float* bnp, void* dy, const void* y2, const float* bnp2, void* dy2,
+                                         void* dz_out, int64_t M, int C, int mask_from_y, void* stream) {
+  REQ(sums && dA && y && bnp && dy && C % 8 == 0 && C / 8 <= 256, "bad arguments");
+  if (y2 != nullptr) REQ(bnp2 && sums2 && dy2, "second BN needs bnp2/sums2/dy2");
+  BnBwdFold f;
+  f.sums = sums; f.sums2 = sums2; f.dgamma = dgamma; f.dbeta = dbeta; f.dgamma2 = dgamma2; f.dbeta2 = dbeta2;
+  f.count = count;
+  return launch_bn_bwd_apply(true, f, dA, a, y, bnp, nullptr, dy, y2, bnp2, nullptr, dy2, dz_out, M, C, mask_from_y,
+                             STREAM);
 }
 extern "C" int vtx_conv_w_pack(const float* w, void* out, int O, int I, int KH, int KW, int ldk, void* stream) {
   REQ(w && out && ldk >= KH * KW * I, "bad arguments");

@@ -355,6 +355,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       epi_bar();
     };
+    // asynchronous, coalesced TMA load of the residual tile of schedule slot `t_` into staging buffer `bi_`
+    // (called by ONE thread, only once the TMA store that last read that buffer has finished reading it)
+    auto issue_residual = [&](int t_, int bi_) {
+      const int rem_ = t_ % (p.m_tiles * p.n_tiles);
+      const int mt_ = rem_ / p.n_tiles;
+      const int nb_ = (rem_ - mt_ * p.n_tiles) * p.bn;
+      uint8_t* buf_ = cstage0 + (size_t)bi_ * p.cbytes;
+      const int slabs = (min(p.bn, p.N - nb_) + 63) >> 6;
+      mbar_arrive_expect_tx(&res_bar[bi_], (uint32_t)slabs * 16384u);
+      for (int sl = 0; sl < slabs; ++sl) {
+        if (p.mode == 1) {
+          const int tw_ = mt_ % p.tiles_w, th_ = (mt_ / p.tiles_w) % p.tiles_h, tn_ = mt_ / (p.tiles_w * p.tiles_h);
+          tma_load_4d(buf_ + sl * 16384, &tmR, &res_bar[bi_], nb_ + sl * 64, tw_ << p.lbw, th_ << p.lbh, tn_ << p.lbn);
+        } else {
+          tma_load_2d(buf_ + sl * 16384, &tmR, &res_bar[bi_], nb_ + sl * 64, mt_ * kBM);
+        }
+      }
+    };
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const int rem = t % (p.m_tiles * p.n_tiles);
@@ -380,18 +398,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (st_nt >= 0) flush_stats(cbuf);
           st_nt = nt;
         }
-        if (p.res_tma && et == 0) {
-          // asynchronous, coalesced load of the residual tile into the (now free) staging buffer
-          const int bi = p.nbuf > 1 ? (it & 1) : 0;
-          const int slabs = (min(p.bn, p.N - n_base) + 63) >> 6;
-          mbar_arrive_expect_tx(&res_bar[bi], (uint32_t)slabs * 16384u);
-          for (int sl = 0; sl < slabs; ++sl) {
-            if (p.mode == 1)
-              tma_load_4d(cbuf + sl * 16384, &tmR, &res_bar[bi], n_base + sl * 64, tw << p.lbw, th << p.lbh, tn << p.lbn);
-            else
-              tma_load_2d(cbuf + sl * 16384, &tmR, &res_bar[bi], n_base + sl * 64, mt * kBM);
-          }
-        }
+        // with two staging buffers the residual of this tile was prefetched one tile ago (see below); otherwise, and
+        // for the CTA's first tile, it is requested now that the buffer is free
+        if (p.res_tma && et == 0 && (p.nbuf == 1 || it == 0)) issue_residual(t, p.nbuf > 1 ? (it & 1) : 0);
       }
       mbar_wait(&tfull_bar[as], (it >> 1) & 1);
       tc_fence_after();
@@ -505,6 +514,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               tma_store_2d(&tmD, cbuf + sl * 16384, n_base + sl * 64, mt * kBM);
           }
           tma_store_commit();
+          if (p.res_tma && p.nbuf > 1 && t + (int)gridDim.x < total_tiles) {
+            // prefetch the next tile's residual into the other buffer as soon as its previous store has been read
+            tma_store_wait_read<1>();
+            issue_residual(t + gridDim.x, (it + 1) & 1);
+          }
         }
         // ---------------- BN statistics of the staged (bf16-rounded) tile, accumulated in registers.
         // Rows outside the problem are exact zeros (TMA zero fill; stats forbids bias/residual): no masking needed.

@@ -206,6 +206,16 @@ class Engine:
              bnp.data_ptr(), C, _stream())
         return bnp
 
+    def _bn_act_fwd(self, y, bn_name, M, C, training, stats, out, res=None, bnp_res=None, relu=1):
+        """BN finalize (batch or running statistics -> bnp, running-stat update) + apply + ReLU (+ residual), one launch."""
+        bnp = self.ws.get("bnp:" + bn_name, (4, C), F32)
+        call("vtx_bn_finalize_act", _p(stats), float(M), self.P(bn_name + ".weight").data_ptr(),
+             self.P(bn_name + ".bias").data_ptr(), self.buffers[bn_name + ".running_mean"].data_ptr(),
+             self.buffers[bn_name + ".running_var"].data_ptr(),
+             self.buffers[bn_name + ".num_batches_tracked"].data_ptr(), 0.1, 1e-5, int(training), bnp.data_ptr(),
+             y.data_ptr(), _p(res), _p(bnp_res), out.data_ptr(), M, C, relu, _stream())
+        return bnp
+
     def _stats_slab(self, training):
         """One zeroed fp32 slab per step holding every BN's [2,C] sum/sumsq (fwd) and [2,C] dz sums (bwd)."""
         total = 2 * 64 * 2
@@ -260,9 +270,8 @@ class Engine:
             y1 = ws.get(name + ".y1", (Min, planes), BF16)
             st1 = self._slab_take(2 * planes) if training else None
             gemm(x, self.W(name + ".conv1.weight").view(planes, Cin), y1, Min, planes, Cin, stats=st1)
-            bnp1 = self._bn_fwd(y1, name + ".bn1", Min, planes, training, st1)
             a1 = ws.get(name + ".a1", (Min, planes), BF16)
-            call("vtx_bn_act", y1.data_ptr(), bnp1.data_ptr(), 0, 0, a1.data_ptr(), Min, planes, 1, s)
+            bnp1 = self._bn_act_fwd(y1, name + ".bn1", Min, planes, training, st1, a1)
             # conv2 3x3 (stride)
             y2 = ws.get(name + ".y2", (Mout, planes), BF16)
             st2 = self._slab_take(2 * planes) if training else None
@@ -275,15 +284,13 @@ class Engine:
                 call("vtx_im2col3x3", a1.data_ptr(), cols2.data_ptr(), B, Hc, Wc, planes, stride, s)
                 gemm(cols2, w2, y2, Mout, planes, 9 * planes, stats=st2)
                 rec["cols2"] = cols2
-            bnp2 = self._bn_fwd(y2, name + ".bn2", Mout, planes, training, st2)
             a2 = ws.get(name + ".a2", (Mout, planes), BF16)
-            call("vtx_bn_act", y2.data_ptr(), bnp2.data_ptr(), 0, 0, a2.data_ptr(), Mout, planes, 1, s)
+            bnp2 = self._bn_act_fwd(y2, name + ".bn2", Mout, planes, training, st2, a2)
             # conv3 1x1
             C4 = 4 * planes
             y3 = ws.get(name + ".y3", (Mout, C4), BF16)
             st3 = self._slab_take(2 * C4) if training else None
             gemm(a2, self.W(name + ".conv3.weight").view(C4, planes), y3, Mout, C4, planes, stats=st3)
-            bnp3 = self._bn_fwd(y3, name + ".bn3", Mout, C4, training, st3)
             out = ws.get(name + ".out", (Mout, C4), BF16)
             if blk.downsample is not None:
                 if stride == 1:
@@ -295,11 +302,10 @@ class Engine:
                 std = self._slab_take(2 * C4) if training else None
                 gemm(xs, self.W(name + ".downsample.0.weight").view(C4, Cin), yd, Mout, C4, Cin, stats=std)
                 bnpd = self._bn_fwd(yd, name + ".downsample.1", Mout, C4, training, std)
-                call("vtx_bn_act", y3.data_ptr(), bnp3.data_ptr(), yd.data_ptr(), bnpd.data_ptr(), out.data_ptr(),
-                     Mout, C4, 1, s)
+                bnp3 = self._bn_act_fwd(y3, name + ".bn3", Mout, C4, training, st3, out, res=yd, bnp_res=bnpd)
                 rec.update(xs=xs, yd=yd, bnpd=bnpd)
             else:
-                call("vtx_bn_act", y3.data_ptr(), bnp3.data_ptr(), x.data_ptr(), 0, out.data_ptr(), Mout, C4, 1, s)
+                bnp3 = self._bn_act_fwd(y3, name + ".bn3", Mout, C4, training, st3, out, res=x)
             rec.update(y1=y1, bnp1=bnp1, a1=a1, y2=y2, bnp2=bnp2, a2=a2, y3=y3, bnp3=bnp3, out=out)
             tape["blocks"].append(rec)
             x, Hc, Wc, Cin = out, Hn, Wn, C4
@@ -321,27 +327,22 @@ class Engine:
         two = (y2, bnp2, bn2_name, dy2) shares dz."""
         s = _stream()
         sums = self._slab_take(2 * C)
-        coef = self.ws.get("coef:" + bn_name, (3, C), F32)
         if two is None:
             call("vtx_bn_bwd_reduce", dA.data_ptr(), _p(a), y.data_ptr(), bnp.data_ptr(), 0, 0, sums.data_ptr(), 0,
                  M, C, mask_from_y, s)
-            call("vtx_bn_bwd_finalize", sums.data_ptr(), bnp.data_ptr(), float(M), coef.data_ptr(),
-                 self.G(bn_name + ".weight").data_ptr(), self.G(bn_name + ".bias").data_ptr(), C, s)
-            call("vtx_bn_bwd_apply", dA.data_ptr(), _p(a), y.data_ptr(), bnp.data_ptr(), coef.data_ptr(),
-                 dy.data_ptr(), 0, 0, 0, 0, _p(dz_out), M, C, mask_from_y, s)
+            call("vtx_bn_bwd_finalize_apply", sums.data_ptr(), 0, float(M), self.G(bn_name + ".weight").data_ptr(),
+                 self.G(bn_name + ".bias").data_ptr(), 0, 0, dA.data_ptr(), _p(a), y.data_ptr(), bnp.data_ptr(),
+                 dy.data_ptr(), 0, 0, 0, _p(dz_out), M, C, mask_from_y, s)
         else:
             y2, bnp2, bn2_name, dy2 = two
             sums2 = self._slab_take(2 * C)
-            coef2 = self.ws.get("coef:" + bn2_name, (3, C), F32)
             call("vtx_bn_bwd_reduce", dA.data_ptr(), _p(a), y.data_ptr(), bnp.data_ptr(), y2.data_ptr(),
                  bnp2.data_ptr(), sums.data_ptr(), sums2.data_ptr(), M, C, mask_from_y, s)
-            call("vtx_bn_bwd_finalize", sums.data_ptr(), bnp.data_ptr(), float(M), coef.data_ptr(),
-                 self.G(bn_name + ".weight").data_ptr(), self.G(bn_name + ".bias").data_ptr(), C, s)
-            call("vtx_bn_bwd_finalize", sums2.data_ptr(), bnp2.data_ptr(), float(M), coef2.data_ptr(),
-                 self.G(bn2_name + ".weight").data_ptr(), self.G(bn2_name + ".bias").data_ptr(), C, s)
-            call("vtx_bn_bwd_apply", dA.data_ptr(), _p(a), y.data_ptr(), bnp.data_ptr(), coef.data_ptr(),
-                 dy.data_ptr(), y2.data_ptr(), bnp2.data_ptr(), coef2.data_ptr(), dy2.data_ptr(), _p(dz_out), M, C,
-                 mask_from_y, s)
+            call("vtx_bn_bwd_finalize_apply", sums.data_ptr(), sums2.data_ptr(), float(M),
+                 self.G(bn_name + ".weight").data_ptr(), self.G(bn_name + ".bias").data_ptr(),
+                 self.G(bn2_name + ".weight").data_ptr(), self.G(bn2_name + ".bias").data_ptr(), dA.data_ptr(), _p(a),
+                 y.data_ptr(), bnp.data_ptr(), dy.data_ptr(), y2.data_ptr(), bnp2.data_ptr(), dy2.data_ptr(),
+                 _p(dz_out), M, C, mask_from_y, s)
 
     def backbone_backward(self, dfeat: torch.Tensor, bucket_cb=None):
         """dfeat bf16 [B*h*w, C]: gradient w.r.t. the backbone output.  Accumulates into the gradient arena.

@@ -21,6 +21,8 @@ _PROTOS = {
     "vtx_upsample_add": [P, P, I, I, I, I, I, P],
     "vtx_bn_finalize": [P, F, P, P, P, P, P, F, F, I, P, I, P],
     "vtx_bn_act": [P, P, P, P, P, I64, I, I, P],
+    "vtx_bn_finalize_act": [P, F, P, P, P, P, P, F, F, I, P, P, P, P, P, I64, I, I, P],
+    "vtx_bn_bwd_finalize_apply": [P, P, F, P, P, P, P, P, P, P, P, P, P, P, P, P, I64, I, I, P],
     "vtx_bn_relu_maxpool": [P, P, P, P, I, I, I, I, P],
     "vtx_maxpool_bwd": [P, P, P, I, I, I, I, P],
     "vtx_bn_bwd_reduce": [P, P, P, P, P, P, P, P, I64, I, I, P],
