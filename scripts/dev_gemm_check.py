@@ -100,7 +100,7 @@ gemm(dY, X, N, K, Mred, a_mn=1, b_mn=1, out_f32=True, atomic=True, split_k=8, D=
 report("wgrad (A,B MN-major, split-K)", rel(out, dY.float().t() @ X.float()), 1e-4)
 
 # ---- 5. implicit 3x3 conv fprop / wgrad
-for (NI, H, W_, C, Co) in [(4, 56, 56, 64, 64), (8, 28, 28, 128, 128), (33, 14, 14, 256, 256), (130, 7, 7, 512, 512),
+for (NI, H, W_, C, Co) in [(4, 56, 56, 64, 64), (3, 20, 20, 64, 64), (5, 7, 7, 64, 64), (8, 28, 28, 128, 128), (33, 14, 14, 256, 256), (130, 7, 7, 512, 512),
                            (2, 14, 14, 64, 128)]:
     x = bf(NI, H, W_, C)
     w = (torch.randn(Co, 3, 3, C, device=dev) * 0.05).to(torch.bfloat16)
@@ -108,6 +108,9 @@ for (NI, H, W_, C, Co) in [(4, 56, 56, 64, 64), (8, 28, 28, 128, 128), (33, 14, 
     ref = ref.permute(0, 2, 3, 1).reshape(-1, Co)
     D = gemm(x, w.reshape(Co, 9 * C), NI * H * W_, Co, 9 * C, conv=(NI, H, W_, C), conv_mode=1)
     report(f"conv3x3 fprop N{NI} {H}x{W_} C{C}->{Co}", rel(D, ref))
+    st = torch.zeros(2, Co, device=dev)
+    D = gemm(x, w.reshape(Co, 9 * C), NI * H * W_, Co, 9 * C, conv=(NI, H, W_, C), conv_mode=1, stats=st)
+    report(f"   + stats sum/sumsq", max(rel(st[0], D.float().sum(0)), rel(st[1], (D.float() ** 2).sum(0))), 1e-3)
     dy = bf(NI, H, W_, Co)
     out = torch.zeros(Co, 9 * C, device=dev)
     gemm(dy, x, Co, 9 * C, NI * H * W_, out_f32=True, atomic=True, split_k=4, D=out, conv=(NI, H, W_, C),

@@ -36,6 +36,8 @@ constexpr int kSmemTotal = 232448;            // 227 KB: the per-CTA maximum on 
 constexpr int kCtrlBytes = 1024;              // barriers + TMEM slot, placed right after the 1024-aligned base
 constexpr int kThreads = 384;
 constexpr int kEpiThreads = 256;
+constexpr int kHaloW = 16, kHaloH = 18;                 // mode 3: halo tile of an 8 x 16 output tile, rows padded to 16
+constexpr int kHaloBytes = kHaloW * kHaloH * 128;        // 36864: [18 lines][16 pixels][64 channels] bf16
 
 struct GemmKParams {
   int M, N, K;
@@ -52,6 +54,7 @@ struct GemmKParams {
   int stages, stage_bytes;   // smem ring depth / bytes per stage
   int cbytes, nbuf;          // bytes of one bf16 staging buffer (0: no staging) / number of staging buffers
   int res_tma;               // residual tile is TMA-loaded into the staging buffer and added there
+  int bstat_bytes;           // mode 3: bytes of the stationary weight region (0 otherwise)
   float alpha;
   void* D;
   long long ldd;
@@ -166,9 +169,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tfull_bar = bars + 2 * kMaxStages;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;          // [2]
   uint64_t* res_bar = tempty_bar + 2;            // [2] residual tile landed in staging buffer b
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2);
+  uint64_t* bst_bar = res_bar + 2;               // [1] stationary weights landed (mode 3)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bst_bar + 1);
   uint8_t* smem = base + kCtrlBytes;                       // stage ring (1024-aligned)
-  uint8_t* cstage0 = smem + p.stages * p.stage_bytes;      // bf16 staging: nbuf x [bn/64 slabs][128 rows][128 B], SW128
+  uint8_t* bstat = smem + p.stages * p.stage_bytes;        // mode 3: stationary weights [9 taps][bn rows][128 B]
+  uint8_t* cstage0 = bstat + p.bstat_bytes;                // bf16 staging: nbuf x [bn/64 slabs][128 rows][128 B], SW128
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -191,6 +196,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&tempty_bar[i], kEpiThreads);
       mbar_init(&res_bar[i], 1);
     }
+    mbar_init(bst_bar, 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -210,7 +216,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0;
       int fills = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      if (p.mode == 3) {
+        // halo-reuse 3x3 conv: weights are loaded once and stay resident; every tile needs ONE halo'd input tile
+        mbar_arrive_expect_tx(bst_bar, 9u * (uint32_t)p.bn * 128u);
+        for (int tap = 0; tap < 9; ++tap) tma_load_2d(bstat + tap * p.bn * 128, &tmB, bst_bar, tap * 64, 0);
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+          const int tw = t % p.tiles_w;
+          const int th = (t / p.tiles_w) % p.tiles_h;
+          const int tn = t / (p.tiles_w * p.tiles_h);
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], kHaloBytes);
+          tma_load_4d(smem + stage * p.stage_bytes, &tmA, &full_bar[stage], 0, (tw << 3) - 1, (th << 4) - 1, tn);
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
+        }
+      }
+      for (int t = blockIdx.x; t < total_tiles && p.mode != 3; t += gridDim.x) {
         const int ks = t / (p.m_tiles * p.n_tiles);
         const int rem = t - ks * (p.m_tiles * p.n_tiles);
         const int mt = rem / p.n_tiles;
@@ -290,7 +310,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      if (p.mode == 3) {
+        mbar_wait(bst_bar, 0);
+        const uint32_t sBst = smem_u32(bstat);
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+          const int as = it & 1;
+          mbar_wait(&tempty_bar[as], ((it >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)as * 256u;
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sA = smem_u32(smem + stage * p.stage_bytes);
+#pragma unroll 1
+          for (int tap = 0; tap < 9; ++tap) {
+            const int kh = tap / 3, kw = tap - kh * 3;
+            // output row (dh, dw) of the 16 x 8 tile reads halo row (dh + kh) * 16 + (dw + kw): 8-row groups are
+            // contiguous, groups are one halo line (16 rows = 2048 B) apart, the view starts kw rows into a swizzle atom
+            const uint32_t a0 = sA + (uint32_t)(kh * kHaloW + kw) * 128u;
+            const uint32_t b0 = sBst + (uint32_t)tap * (uint32_t)p.bn * 128u;
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k) {
+              const uint64_t ad = make_smem_desc(a0 + k * 32, 16, kHaloW * 128, (p.dbg & 32) ? 0u : (uint32_t)kw);
+              const uint64_t bd = make_smem_desc(b0 + k * 32, 16, 1024);
+              umma_bf16(d_tmem, ad, bd, idesc, (tap > 0 || k > 0) ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
+          umma_commit(&tfull_bar[as]);
+        }
+      }
+      for (int t = blockIdx.x; t < total_tiles && p.mode != 3; t += gridDim.x, ++it) {
         const int ks = t / (p.m_tiles * p.n_tiles);
         const int kb0 = ks * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
@@ -365,7 +415,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int slabs = (min(p.bn, p.N - nb_) + 63) >> 6;
       mbar_arrive_expect_tx(&res_bar[bi_], (uint32_t)slabs * 16384u);
       for (int sl = 0; sl < slabs; ++sl) {
-        if (p.mode == 1) {
+        if (p.mode & 1) {
           const int tw_ = mt_ % p.tiles_w, th_ = (mt_ / p.tiles_w) % p.tiles_h, tn_ = mt_ / (p.tiles_w * p.tiles_h);
           tma_load_4d(buf_ + sl * 16384, &tmR, &res_bar[bi_], nb_ + sl * 64, tw_ << p.lbw, th_ << p.lbh, tn_ << p.lbn);
         } else {
@@ -381,7 +431,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int as = it & 1;
       const int n_base = nt * p.bn;
       int tw = 0, th = 0, tn = 0;
-      if (p.mode == 1) {
+      if (p.mode & 1) {
         tw = mt % p.tiles_w;
         th = (mt / p.tiles_w) % p.tiles_h;
         tn = mt / (p.tiles_w * p.tiles_h);
@@ -413,8 +463,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // ---------------- phase 1: TMEM -> registers -> fp32 epilogue math -> swizzled bf16 staging (or fp32 global)
       const int r_in_tile = ew * 32 + lane;
       long long grow = -1;
+      bool row_dead = false;  // mode 3: rows of a partial tile that lie outside the image must not reach the BN statistics
+      if (p.mode == 3) {
+        const int w = (tw << 3) + (r_in_tile & 7), h = (th << 4) + (r_in_tile >> 3);
+        row_dead = (w >= p.cW) || (h >= p.cH);
+      }
       if (!staged || (p.residual != nullptr && !p.res_tma)) {
-        if (p.mode == 1) {
+        if (p.mode & 1) {
           const int dw = r_in_tile & ((1 << p.lbw) - 1);
           const int dh = (r_in_tile >> p.lbw) & ((1 << p.lbh) - 1);
           const int dn = r_in_tile >> (p.lbw + p.lbh);
@@ -454,6 +509,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
           epi_math(va, p, grow, col0, full);
+          if (row_dead) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) va[i] = 0.f;
+          }
           if (staged) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -485,6 +544,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
           epi_math(vb, p, grow, col0, full);
+          if (row_dead) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) vb[i] = 0.f;
+          }
           if (staged) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -508,7 +571,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (et == 0) {
           const int slabs = (min(p.bn, p.N - n_base) + 63) >> 6;
           for (int sl = 0; sl < slabs; ++sl) {
-            if (p.mode == 1)
+            if (p.mode & 1)
               tma_store_4d(&tmD, cbuf + sl * 16384, n_base + sl * 64, tw << p.lbw, th << p.lbh, tn << p.lbn);
             else
               tma_store_2d(&tmD, cbuf + sl * 16384, n_base + sl * 64, mt * kBM);
@@ -696,20 +759,25 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
     const int C = g->conv_c, H = g->conv_h, W = g->conv_w, NI = g->conv_n;
     if (C <= 0 || C % 64 != 0) return set_error(VTX_EINVAL, "vtx_gemm: implicit conv needs channels %% 64 == 0");
     p.cH = H; p.cW = W; p.cN = NI; p.cpb = C / 64;
+    // halo-reuse variant (mode 3): C = 64 -> 64 convs whose 9 weight taps (72 KB) stay resident in shared memory and
+    // whose input is fetched ONCE per 8 x 16 output tile as an 18 x 16 halo tile (instead of once per tap)
+    const bool halo = p.mode == 1 && C == 64 && g->N == 64 && bn == 64 && !g->out_f32 && g->residual == nullptr &&
+                      getenv("VTX_GEMM_NO_HALO") == nullptr;
     int bw, bh, bnn;
     choose_box(H, W, p.mode == 1 ? 128 : 64, &bw, &bh, &bnn);
+    if (halo) { p.mode = 3; bw = 8; bh = 16; bnn = 1; }
     p.lbw = ilog2(bw); p.lbh = ilog2(bh); p.lbn = ilog2(bnn);
     p.tiles_w = (W + bw - 1) / bw;
     p.tiles_h = (H + bh - 1) / bh;
     const int tiles_n = (NI + bnn - 1) / bnn;
-    if (p.mode == 1) {
+    if (p.mode & 1) {
       // A: activation [NI,H,W,C]; M = NI*H*W (tiled as boxes); K = 9*C; B: weights [N, 9*C] K-major
       if (g->M != NI * H * W || g->K != 9 * C) return set_error(VTX_EINVAL, "vtx_gemm: conv fprop shape mismatch");
       p.m_tiles = p.tiles_w * p.tiles_h * tiles_n;
-      p.kb_total = 9 * p.cpb;
+      p.kb_total = halo ? 1 : 9 * p.cpb;
       uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)NI};
       uint64_t str[3] = {(uint64_t)C, (uint64_t)W * C, (uint64_t)H * W * C};
-      uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bh, (uint32_t)bnn};
+      uint32_t box[4] = {64, (uint32_t)(halo ? kHaloW : bw), (uint32_t)(halo ? kHaloH : bh), (uint32_t)bnn};
       if ((rc = make_tmap(&tmA, g->A, 4, dims, str, box)) != VTX_OK) return rc;
       uint64_t bd[2] = {(uint64_t)g->K, (uint64_t)g->N};
       uint64_t bs[1] = {(uint64_t)g->ldb};
@@ -742,13 +810,14 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
     const char* e = getenv("VTX_GEMM_DBG");
     p.dbg = e ? atoi(e) : 0;
   }
-  p.stage_bytes = kABytes + bn * kBK * 2;
+  p.stage_bytes = p.mode == 3 ? kHaloBytes : kABytes + bn * kBK * 2;
+  p.bstat_bytes = p.mode == 3 ? 9 * bn * 128 : 0;
   p.cbytes = p.out_f32 ? 0 : ((bn + 63) / 64) * 16384;
   {
     // two staging buffers (the TMA store of tile i overlaps the epilogue of tile i+1) whenever the operand ring still
     // gets >= 4 stages, or holds a whole tile's K loop
     const int kb_tile = p.kb_per_split;
-    const int budget = kSmemTotal - 1024 /*alignment slack*/ - kCtrlBytes;
+    const int budget = kSmemTotal - 1024 /*alignment slack*/ - kCtrlBytes - p.bstat_bytes;
     int st = 0;
     p.nbuf = 1;
     if (p.cbytes) {
@@ -770,7 +839,7 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
   p.res_tma = (p.cbytes && g->residual != nullptr && g->ldr % 8 == 0 &&
                (reinterpret_cast<uintptr_t>(g->residual) & 15) == 0) ? 1 : 0;
   if (p.cbytes) {
-    if (p.mode == 1) {
+    if (p.mode & 1) {
       uint64_t dd[4] = {(uint64_t)g->N, (uint64_t)g->conv_w, (uint64_t)g->conv_h, (uint64_t)g->conv_n};
       uint64_t ds[3] = {(uint64_t)g->ldd, (uint64_t)g->conv_w * g->ldd, (uint64_t)g->conv_h * g->conv_w * g->ldd};
       uint32_t db[4] = {64, 1u << p.lbw, 1u << p.lbh, 1u << p.lbn};
