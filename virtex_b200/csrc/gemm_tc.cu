@@ -36,8 +36,7 @@ constexpr int kSmemTotal = 232448;            // 227 KB: the per-CTA maximum on 
 constexpr int kCtrlBytes = 1024;              // barriers + TMEM slot, placed right after the 1024-aligned base
 constexpr int kThreads = 384;
 constexpr int kEpiThreads = 256;
-constexpr int kHaloW = 16, kHaloH = 18;                 // mode 3: halo tile of an 8 x 16 output tile, rows padded to 16
-constexpr int kHaloBytes = kHaloW * kHaloH * 128;        // 36864: [18 lines][16 pixels][64 channels] bf16
+constexpr int kHaloH = 18;  // mode 3: halo tile of an 8 x 16 output tile = 18 lines x halo_w pixels x 64 channels (bf16)
 
 struct GemmKParams {
   int M, N, K;
@@ -55,6 +54,7 @@ struct GemmKParams {
   int cbytes, nbuf;          // bytes of one bf16 staging buffer (0: no staging) / number of staging buffers
   int res_tma;               // residual tile is TMA-loaded into the staging buffer and added there
   int bstat_bytes;           // mode 3: bytes of the stationary weight region (0 otherwise)
+  int halo_w;                // mode 3: pixels per halo line in shared memory (10 = exact, 16 = padded)
   float alpha;
   void* D;
   long long ldd;
@@ -225,7 +225,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int th = (t / p.tiles_w) % p.tiles_h;
           const int tn = t / (p.tiles_w * p.tiles_h);
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], kHaloBytes);
+          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(p.halo_w * kHaloH * 128));
           tma_load_4d(smem + stage * p.stage_bytes, &tmA, &full_bar[stage], 0, (tw << 3) - 1, (th << 4) - 1, tn);
           if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
@@ -324,13 +324,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll 1
           for (int tap = 0; tap < 9; ++tap) {
             const int kh = tap / 3, kw = tap - kh * 3;
-            // output row (dh, dw) of the 16 x 8 tile reads halo row (dh + kh) * 16 + (dw + kw): 8-row groups are
-            // contiguous, groups are one halo line (16 rows = 2048 B) apart, the view starts kw rows into a swizzle atom
-            const uint32_t a0 = sA + (uint32_t)(kh * kHaloW + kw) * 128u;
+            // output row (dh, dw) of the 16 x 8 tile reads halo row (dh + kh) * halo_w + (dw + kw): 8-row groups are
+            // contiguous, consecutive groups are one halo line apart (SBO), and the view starts at an arbitrary row of
+            // the TMA-written tile.  The 128B swizzle is a function of absolute shared-memory address bits (verified
+            // on B200: base_offset must stay 0), so row-shifted views of one tile serve all nine taps.
+            const uint32_t a0 = sA + (uint32_t)(kh * p.halo_w + kw) * 128u;
             const uint32_t b0 = sBst + (uint32_t)tap * (uint32_t)p.bn * 128u;
 #pragma unroll
             for (int k = 0; k < kBK / 16; ++k) {
-              const uint64_t ad = make_smem_desc(a0 + k * 32, 16, kHaloW * 128, (p.dbg & 32) ? 0u : (uint32_t)kw);
+              const uint64_t ad = make_smem_desc(a0 + k * 32, 16, (uint32_t)p.halo_w * 128u);
               const uint64_t bd = make_smem_desc(b0 + k * 32, 16, 1024);
               umma_bf16(d_tmem, ad, bd, idesc, (tap > 0 || k > 0) ? 1u : 0u);
             }
@@ -765,7 +767,11 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
                       getenv("VTX_GEMM_NO_HALO") == nullptr;
     int bw, bh, bnn;
     choose_box(H, W, p.mode == 1 ? 128 : 64, &bw, &bh, &bnn);
-    if (halo) { p.mode = 3; bw = 8; bh = 16; bnn = 1; }
+    if (halo) {
+      p.mode = 3; bw = 8; bh = 16; bnn = 1;
+      const char* e = getenv("VTX_GEMM_HALO_W");
+      p.halo_w = e ? atoi(e) : 10;
+    }
     p.lbw = ilog2(bw); p.lbh = ilog2(bh); p.lbn = ilog2(bnn);
     p.tiles_w = (W + bw - 1) / bw;
     p.tiles_h = (H + bh - 1) / bh;
@@ -777,7 +783,7 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
       p.kb_total = halo ? 1 : 9 * p.cpb;
       uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)NI};
       uint64_t str[3] = {(uint64_t)C, (uint64_t)W * C, (uint64_t)H * W * C};
-      uint32_t box[4] = {64, (uint32_t)(halo ? kHaloW : bw), (uint32_t)(halo ? kHaloH : bh), (uint32_t)bnn};
+      uint32_t box[4] = {64, (uint32_t)(halo ? p.halo_w : bw), (uint32_t)(halo ? kHaloH : bh), (uint32_t)bnn};
       if ((rc = make_tmap(&tmA, g->A, 4, dims, str, box)) != VTX_OK) return rc;
       uint64_t bd[2] = {(uint64_t)g->K, (uint64_t)g->N};
       uint64_t bs[1] = {(uint64_t)g->ldb};
@@ -810,7 +816,8 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
     const char* e = getenv("VTX_GEMM_DBG");
     p.dbg = e ? atoi(e) : 0;
   }
-  p.stage_bytes = p.mode == 3 ? kHaloBytes : kABytes + bn * kBK * 2;
+  // mode 3 stages hold one halo tile, rounded up to whole 1024-byte swizzle atoms
+  p.stage_bytes = p.mode == 3 ? ((p.halo_w * kHaloH * 128 + 1023) / 1024) * 1024 : kABytes + bn * kBK * 2;
   p.bstat_bytes = p.mode == 3 ? 9 * bn * 128 : 0;
   p.cbytes = p.out_f32 ? 0 : ((bn + 63) / 64) * 16384;
   {

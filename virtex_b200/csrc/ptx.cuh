@@ -156,8 +156,9 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 //   K-major  tile [rows][64 bf16]: LBO unused (=1), SBO = 1024 B (8 rows x 128 B).
 //   MN-major tile [k rows][64 bf16] atoms: SBO = 1024 B between 8-k-row groups, LBO = byte stride between
 //   consecutive 64-element atoms along M/N.
-// `base_offset` (bits 49..51) = (start address >> 7) & 7 when the start is not 1024-byte aligned (row-shifted views of a
-// TMA-written tile): it restores the absolute row phase of the 128B swizzle pattern.
+// `base_offset` (bits 49..51) stays 0: measured on B200, the 128B swizzle is applied on absolute shared-memory address
+// bits, so descriptors whose start address is not 1024-byte aligned (row-shifted views of a TMA-written tile) read
+// correctly with base_offset = 0 and INcorrectly with base_offset = (start >> 7) & 7.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
                                                    uint32_t base_offset = 0) {
   uint64_t d = (uint64_t)(base_offset & 7) << 49;
