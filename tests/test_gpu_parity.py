@@ -95,6 +95,28 @@ def test_gemm_wgrad_dgrad_conv():
     assert rel(y, ref.permute(0, 2, 3, 1).reshape(-1, Co)) < 4e-3
 
 
+@pytest.mark.parametrize("NI,H,W", [(3, 56, 56), (5, 20, 20), (4, 7, 7)])
+def test_conv3x3_halo_reuse_mode(NI, H, W):
+    """64 -> 64 channel 3x3 convs take the halo-reuse path (stationary weights, one 18x10 halo tile per 8x16 output tile,
+    nine row-shifted UMMA views); partial tiles at the image border must neither be stored nor reach the BN statistics."""
+    _need_cuda()
+    from virtex_b200 import ops
+    torch.manual_seed(4)
+    dev = "cuda"
+    C = Co = 64
+    x = (torch.randn(NI, H, W, C, device=dev) * 0.5).bfloat16()
+    w = (torch.randn(Co, 3, 3, C, device=dev) * 0.05).bfloat16()
+    y = torch.full((NI * H * W + 64, Co), 7.0, device=dev, dtype=torch.bfloat16)  # guard rows behind the output
+    st = torch.zeros(2, Co, device=dev)
+    ops.gemm(x, w.view(Co, 9 * C), y, NI * H * W, Co, 9 * C, lda=C, stats=st, conv=(NI, H, W, C), conv_mode=1)
+    ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), padding=1)
+    ref = ref.permute(0, 2, 3, 1).reshape(-1, Co)
+    out = y[:NI * H * W]
+    assert rel(out, ref) < 4e-3
+    assert torch.all(y[NI * H * W:] == 7.0)
+    assert rel(st[0], out.float().sum(0)) < 1e-3 and rel(st[1], (out.float() ** 2).sum(0)) < 1e-3
+
+
 def test_attention_and_ce_kernels():
     _need_cuda()
     from virtex_b200.ops import call, _stream

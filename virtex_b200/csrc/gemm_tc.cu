@@ -49,7 +49,6 @@ struct GemmKParams {
   int lbw, lbh, lbn;
   int tiles_w, tiles_h;
   int out_f32, atomic, act;
-  int dbg;  // developer knobs (VTX_GEMM_DBG): selectively disable epilogue parts for attribution experiments
   int stages, stage_bytes;   // smem ring depth / bytes per stage
   int cbytes, nbuf;          // bytes of one bf16 staging buffer (0: no staging) / number of staging buffers
   int res_tma;               // residual tile is TMA-loaded into the staging buffer and added there
@@ -65,22 +64,6 @@ struct GemmKParams {
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
-
-// Per-warp transpose-reduce: every lane holds v[0..31] (one row, 32 columns); on return lane l holds, in v[0],
-// the sum over the warp's 32 rows of column l.
-__device__ __forceinline__ float warp_colsum32(float* v, int lane) {
-#pragma unroll
-  for (int s = 16; s >= 1; s >>= 1) {
-    const bool hi = (lane & s) != 0;
-#pragma unroll
-    for (int i = 0; i < s; ++i) {
-      float send = hi ? v[i] : v[i + s];
-      float keep = hi ? v[i + s] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-    }
-  }
-  return v[0];
-}
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -214,7 +197,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================================================== TMA producer
     if (lane == 0) {
       int stage = 0;
-      int fills = 0;
       uint32_t phase = 0;
       if (p.mode == 3) {
         // halo-reuse 3x3 conv: weights are loaded once and stay resident; every tile needs ONE halo'd input tile
@@ -248,14 +230,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sA = smem + stage * p.stage_bytes;
           uint8_t* sB = sA + kABytes;
-          // dbg&16 (experiment; valid only for n_tiles == 1 && kb_total == 1): B is identical for every tile, so each
-          // stage buffer is filled once and never reloaded
-          const bool skip_b = (p.dbg & 16) && fills >= nstages;
-          ++fills;
           // MN-major A tiles are loaded as two 64-row atoms; when the second lies entirely beyond M it is not fetched
           // (its accumulator rows are garbage, and masked by the epilogue)
           const bool half_a = p.a_mn && (mt * kBM + 64 >= p.M);
-          mbar_arrive_expect_tx(&full_bar[stage], (half_a ? kABytes / 2 : kABytes) + (skip_b ? 0u : b_bytes));
+          mbar_arrive_expect_tx(&full_bar[stage], (half_a ? kABytes / 2 : kABytes) + b_bytes);
           if (p.mode == 0) {
             if (!p.a_mn) {
               tma_load_2d(sA, &tmA, &full_bar[stage], kb * kBK, mt * kBM);
@@ -263,8 +241,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               tma_load_2d(sA, &tmA, &full_bar[stage], mt * kBM, kb * kBK);
               if (!half_a) tma_load_2d(sA + 8192, &tmA, &full_bar[stage], mt * kBM + 64, kb * kBK);
             }
-            if (skip_b) {
-            } else if (!p.b_mn) {
+            if (!p.b_mn) {
               tma_load_2d(sB, &tmB, &full_bar[stage], kb * kBK, nt * p.bn);
             } else {
               for (int j = 0; j < (p.bn >> 6); ++j)
@@ -769,8 +746,7 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
     choose_box(H, W, p.mode == 1 ? 128 : 64, &bw, &bh, &bnn);
     if (halo) {
       p.mode = 3; bw = 8; bh = 16; bnn = 1;
-      const char* e = getenv("VTX_GEMM_HALO_W");
-      p.halo_w = e ? atoi(e) : 10;
+      p.halo_w = 10;
     }
     p.lbw = ilog2(bw); p.lbh = ilog2(bh); p.lbn = ilog2(bnn);
     p.tiles_w = (W + bw - 1) / bw;
@@ -812,10 +788,6 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
   p.k_splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
 
   // ---- shared-memory carve-up: [1 KB control][stages x (A 16 KB + B bn*128 B)][bf16 staging tile 128 x (bn*2+16) B]
-  {
-    const char* e = getenv("VTX_GEMM_DBG");
-    p.dbg = e ? atoi(e) : 0;
-  }
   // mode 3 stages hold one halo tile, rounded up to whole 1024-byte swizzle atoms
   p.stage_bytes = p.mode == 3 ? ((p.halo_w * kHaloH * 128 + 1023) / 1024) * 1024 : kABytes + bn * kBK * 2;
   p.bstat_bytes = p.mode == 3 ? 9 * bn * 128 : 0;
@@ -830,10 +802,6 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
     if (p.cbytes) {
       const int st2 = (budget - 2 * p.cbytes) / p.stage_bytes;
       if (st2 >= 4 || (st2 >= 2 && st2 >= kb_tile)) { p.nbuf = 2; st = st2; }
-    }
-    {
-      const char* e = getenv("VTX_GEMM_NBUF");
-      if (e && p.cbytes) { p.nbuf = atoi(e) == 2 ? 2 : 1; st = 0; }
     }
     if (st == 0) st = (budget - p.nbuf * p.cbytes) / p.stage_bytes;
     if (st > kMaxStages) st = kMaxStages;
