@@ -67,3 +67,36 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(so, name), f"{name} declared in include/virtex_b200.h but not exported"
     assert declared == set(ops.exported_symbols())
     assert so.vtx_version() >= 100
+
+
+def test_virtex_alias_package_and_hubconf():
+    """`import virtex.*` paths of the reference resolve to this implementation; hubconf exposes resnet50()."""
+    import importlib
+    import sys
+    for m in [k for k in sys.modules if k == "virtex" or k.startswith("virtex.")]:
+        del sys.modules[m]
+    from virtex.config import Config
+    from virtex.factories import PretrainingModelFactory, TextualHeadFactory
+    from virtex.models import VirTexModel
+    from virtex.modules.textual_heads import TransformerDecoderTextualHead
+    import virtex_b200.models as vm
+    assert VirTexModel is vm.VirTexModel
+    assert set(TextualHeadFactory.PRODUCTS) == {"transdec_prenorm", "transdec_postnorm"}
+    assert {"virtex", "bicaptioning", "captioning"} <= set(PretrainingModelFactory.PRODUCTS)
+    with pytest.raises(KeyError):
+        PretrainingModelFactory.create("does_not_exist")
+    with pytest.raises(ValueError):
+        PretrainingModelFactory()
+    cfg = Config(None, ["MODEL.TEXTUAL.NAME", "transdec_prenorm::L2_H128_A2_F256"])
+    head = TextualHeadFactory.from_config(cfg)
+    assert isinstance(head, TransformerDecoderTextualHead) and head.norm_first and head.num_layers == 2
+    with pytest.raises(KeyError):
+        Config(None, ["OPTIM.DOES_NOT_EXIST", 1])
+    with pytest.raises(ValueError):
+        Config(None, ["OPTIM.BATCH_SIZE", "not-an-int"])
+    hub = importlib.import_module("hubconf")
+    m = hub.resnet50()
+    sd = m.state_dict()
+    assert "conv1.weight" in sd and "layer4.2.bn3.running_var" in sd and not any(k.startswith("fc.") for k in sd)
+    assert len(sd) == 318
+    assert m.layer3[0].conv1.weight.shape == (256, 512, 1, 1)
