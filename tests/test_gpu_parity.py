@@ -471,3 +471,84 @@ def test_frozen_backbone_and_forward_only_model():
     assert named["visual.cnn.conv1.weight"].grad is None
     assert torch.isfinite(named["textual.embedding.words.weight"].grad).all()
     assert int(model.visual.cnn.bn1.num_batches_tracked) == 0
+
+
+# ------------------------------------------------------------------------------------------- full-size properties
+def test_full_size_eval_loss_is_chunk_consistent():
+    """BASELINE.json config #2 size (R50-L1-H1024, batch 256) through a size-independent property: in eval mode (running
+    BN statistics) the token-mean loss of the whole batch equals the valid-target-weighted mean of the losses of its
+    chunks, per direction; and repeating the forward reproduces the loss."""
+    _need_cuda()
+    from virtex_b200.config import Config
+    from virtex_b200.factories import PretrainingModelFactory
+    torch.manual_seed(0)
+    cfg = Config("_base_bicaptioning_R_50_L1_H1024.yaml", [])
+    model = PretrainingModelFactory.from_config(cfg).cuda().eval()
+    with torch.no_grad():  # make BN/zero-init-residual non-trivial
+        for n, p in model.named_parameters():
+            if "bn3.weight" in n:
+                p.fill_(0.25)
+    B = 256
+    batch = to_cuda(O.synth_batch(B, seed=77, ragged=True))
+    with torch.no_grad():
+        full = model(batch)
+        again = model(batch)
+    lf, lb = full["loss_components"]["captioning_forward"].item(), full["loss_components"]["captioning_backward"].item()
+    assert abs(again["loss"].item() - full["loss"].item()) < 1e-5 * full["loss"].item()
+    acc_f = acc_b = 0.0
+    tot_f = tot_b = 0
+    for i in range(0, B, 64):
+        sub = {k: v[i:i + 64].contiguous() for k, v in batch.items()}
+        with torch.no_grad():
+            o = model(sub)
+        nf = int((sub["caption_tokens"][:, 1:] != 0).sum())
+        nb = int((sub["noitpac_tokens"][:, 1:] != 0).sum())
+        acc_f += o["loss_components"]["captioning_forward"].item() * nf
+        acc_b += o["loss_components"]["captioning_backward"].item() * nb
+        tot_f += nf
+        tot_b += nb
+    assert abs(acc_f / tot_f - lf) < 1e-3 * lf, (acc_f / tot_f, lf)
+    assert abs(acc_b / tot_b - lb) < 1e-3 * lb, (acc_b / tot_b, lb)
+    assert full["predictions"].shape == (B, 30) and full["predictions"].dtype == torch.int64
+
+
+def test_full_size_train_step_gradients_are_finite_and_scale():
+    """Batch-256 training step of the named config: finite loss near ln-scale, every gradient finite and non-zero where
+    it must be, and the loss gradient is linear: backward with upstream 2.0 doubles every gradient."""
+    _need_cuda()
+    from virtex_b200.config import Config
+    from virtex_b200.factories import PretrainingModelFactory
+    torch.manual_seed(0)
+    cfg = Config("_base_bicaptioning_R_50_L1_H1024.yaml", ["MODEL.TEXTUAL.DROPOUT", 0.0])
+    model = PretrainingModelFactory.from_config(cfg).cuda().train()
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if "bn3.weight" in n:
+                p.fill_(0.25)
+    batch = to_cuda(O.synth_batch(256, seed=78))
+    out = model(batch)
+    assert 15.0 < out["loss"].item() < 40.0
+    out["loss"].backward()
+    g1 = {n: p.grad.clone() for n, p in model.named_parameters()}
+    for n, g in g1.items():
+        assert torch.isfinite(g).all(), n
+    assert g1["visual.cnn.conv1.weight"].abs().sum() > 0 and g1["textual.output.bias"].abs().sum() > 0
+    model.zero_grad()
+    for b in model.visual.cnn.buffers():  # same BN running state is irrelevant in train mode; just rerun
+        pass
+    out2 = model(batch)
+    (2.0 * out2["loss"]).backward()
+    for n in ("textual.transformer.layers.0.linear2.weight", "visual.cnn.layer4.2.conv3.weight", "textual.embedding.words.weight"):
+        g2 = dict(model.named_parameters())[n].grad
+        assert rel(g2, 2.0 * g1[n]) < 2e-2, (n, rel(g2, 2.0 * g1[n]))
+
+
+def test_hub_resnet50_forward():
+    _need_cuda()
+    import importlib
+    hub = importlib.import_module("hubconf")
+    m = hub.resnet50().cuda().eval()
+    x = torch.randn(2, 3, 224, 224, device="cuda")
+    with torch.no_grad():
+        y = m(x)
+    assert y.shape == (2, 2048 * 7 * 7) and torch.isfinite(y).all()
