@@ -100,3 +100,42 @@ def test_virtex_alias_package_and_hubconf():
     assert "conv1.weight" in sd and "layer4.2.bn3.running_var" in sd and not any(k.startswith("fc.") for k in sd)
     assert len(sd) == 318
     assert m.layer3[0].conv1.weight.shape == (256, 512, 1, 1)
+
+
+def test_config_yaml_inheritance_dump_and_freeze(tmp_path):
+    from virtex_b200.config import Config
+    c = Config("depth_ablations/bicaptioning_R_50_L4_H1024.yaml", ["OPTIM.BATCH_SIZE", 2048, "OPTIM.LR", "0.002"])
+    assert c.MODEL.TEXTUAL.NAME == "transdec_postnorm::L4_H1024_A16_F4096"   # delta file
+    assert c.MODEL.VISUAL.NAME == "torchvision::resnet50" and c.OPTIM.CNN_LR == 0.2  # inherited through _BASE_
+    assert c.OPTIM.BATCH_SIZE == 2048 and c.OPTIM.LR == 0.002                  # override list, literal-evaluated
+    with pytest.raises(AttributeError):
+        c.OPTIM.LR = 1.0
+    out = tmp_path / "dump.yaml"
+    c.dump(str(out))
+    c2 = Config(str(out))
+    assert str(c2) == str(c)
+    assert "BATCH_SIZE: 2048" in str(c)
+
+
+def test_lr_schedules_and_lookahead_match_oracle_formulas():
+    import torch
+    from virtex_b200 import optim as vo
+    cfg = O.OptimCfg(warmup_steps=5, num_iterations=40)
+    fn = vo.lr_multiplier_fn("cosine", 40, 5)
+    for s in range(0, 40):
+        assert abs(fn(s) - O.lr_multiplier(s, cfg)) < 1e-12
+    assert vo.lr_multiplier_fn("linear", 40, 5)(40) == 0.0 and vo.lr_multiplier_fn("none", 40, 5)(20) == 1.0
+    assert abs(vo.lr_multiplier_fn("multistep", 40, 5, [10, 20], 0.1)(25) - 0.01) < 1e-12
+    # Lookahead wrapper: k fast steps then interpolation towards the slow weights
+    p = torch.nn.Parameter(torch.ones(4))
+    opt = vo.Lookahead(torch.optim.SGD([p], lr=0.5), k=2, alpha=0.5)
+    sched = vo.LinearWarmupCosineAnnealingLR(opt, total_steps=40, warmup_steps=5)
+    assert opt.param_groups[0]["lr"] == 0.0     # lambda(0) = 0: the first step runs at lr 0
+    for g in opt.param_groups:
+        g["lr"] = 0.5
+    p.grad = torch.ones(4); opt.step()           # fast: 1 - 0.5 = 0.5
+    assert torch.allclose(p.data, torch.full((4,), 0.5))
+    p.grad = torch.ones(4); opt.step()           # fast: 0.0 -> lookahead: 0.5*0.0 + 0.5*1.0 = 0.5
+    assert torch.allclose(p.data, torch.full((4,), 0.5))
+    assert torch.allclose(opt.state[p]["slow_params"], torch.full((4,), 0.5))
+    assert sched is not None
