@@ -65,7 +65,10 @@ typedef struct VtxGemm {
      A is the activation [conv_n, conv_h, conv_w, conv_c]; M = n*h*w, K = 9*conv_c, B = weights [N, (kh,kw,c)].
      conv_wgrad = 1 swaps roles for the weight gradient (see gemm_tc.cu). */
   int32_t conv_n, conv_h, conv_w, conv_c;
-  int32_t conv_mode; /* 0 = plain GEMM, 1 = implicit fprop/dgrad gather on A, 2 = wgrad gather on B */
+  int32_t conv_mode; /* 0 = plain GEMM, 1 = implicit fprop/dgrad gather on A (64->64 channel problems run the halo-reuse
+                        variant automatically), 2 = wgrad gather on B,
+                        4 = halo-reuse wgrad for C = Cout = 64: A = dy, B = x, D[9*C, Cout] fp32 += (atomic),
+                            i.e. the TRANSPOSE of mode 2's [Cout, 9*C] output */
 } VtxGemm;
 
 int vtx_gemm(const VtxGemm* g, void* stream);
@@ -117,6 +120,8 @@ int vtx_bn_bwd_finalize_apply(const float* sums, const float* sums2, float count
 int vtx_conv_w_pack(const float* w, void* out, int O, int I, int KH, int KW, int ldk, void* stream);
 int vtx_conv_w_pack_dgrad(const float* w, void* out, int O, int I, void* stream);
 int vtx_conv_w_unpack_add(const float* dwp, float* grad, int O, int I, int KH, int KW, int ldk, void* stream);
+/* same for the transposed [(tap, I), O] weight-gradient layout written by vtx_gemm conv_mode 4 */
+int vtx_conv_w_unpack_add_t(const float* dwt, float* grad, int O, int I, int KH, int KW, void* stream);
 int vtx_cast_bf16(const float* in, void* out, int64_t n, void* stream);
 int vtx_nhwc_to_nchw_f32(const void* in, float* out, int N, int HW, int C, void* stream);
 

@@ -118,6 +118,10 @@ for (NI, H, W_, C, Co) in [(4, 56, 56, 64, 64), (3, 20, 20, 64, 64), (5, 7, 7, 6
     xr = x.float().permute(0, 3, 1, 2).requires_grad_(False)
     wref = torch.nn.grad.conv2d_weight(xr, (Co, C, 3, 3), dy.float().permute(0, 3, 1, 2), padding=1)
     report(f"conv3x3 wgrad N{NI} {H}x{W_}", rel(out, wref.permute(0, 2, 3, 1).reshape(Co, 9 * C)), 1e-4)
+    if C == 64 and Co == 64:
+        out_t = torch.zeros(9 * C, Co, device=dev)
+        gemm(dy, x, 9 * C, Co, NI * H * W_, out_f32=True, atomic=True, D=out_t, conv=(NI, H, W_, C), conv_mode=4)
+        report(f"   halo wgrad (mode 4) N{NI} {H}x{W_}", rel(out_t, wref.permute(2, 3, 1, 0).reshape(9 * C, Co)), 1e-4)
 
 # ---- 6. timing of a few representative shapes
 def bench(name, fn, flops, iters=20):
@@ -150,5 +154,11 @@ w = bf(256, 9 * 256)
 D = torch.empty(256 * 196, 256, device=dev, dtype=torch.bfloat16)
 bench("vtx conv3x3 l3", lambda: gemm(x, w, 256 * 196, 256, 2304, D=D, conv=(256, 14, 14, 256), conv_mode=1),
       2.0 * 256 * 196 * 256 * 2304)
+x = bf(256, 56, 56, 64); dy = bf(256, 56, 56, 64)
+out = torch.zeros(64, 576, device=dev); out_t = torch.zeros(576, 64, device=dev)
+bench("vtx conv3x3 l1 wgrad mode 2", lambda: gemm(dy, x, 64, 576, 256 * 3136, out_f32=True, atomic=True, split_k=49, D=out,
+                                                    conv=(256, 56, 56, 64), conv_mode=2), 2.0 * 256 * 3136 * 64 * 576)
+bench("vtx conv3x3 l1 wgrad mode 4", lambda: gemm(dy, x, 576, 64, 256 * 3136, out_f32=True, atomic=True, D=out_t,
+                                                    conv=(256, 56, 56, 64), conv_mode=4), 2.0 * 256 * 3136 * 64 * 576)
 print("ALL OK" if ok else "SOME FAILED")
 sys.exit(0 if ok else 1)

@@ -647,6 +647,17 @@ __global__ void conv_w_unpack_add_kernel(const float* __restrict__ dwp, float* _
     grad[t] += dwp[(long long)o * ldk + (long long)tap * I + i];
   }
 }
+// grad OIHW += dwt [(tap, i), O]   (transposed layout produced by the halo-reuse wgrad, conv_mode 4)
+__global__ void conv_w_unpack_add_t_kernel(const float* __restrict__ dwt, float* __restrict__ grad, int O, int I, int KH,
+                                           int KW) {
+  const long long total = (long long)O * I * KH * KW;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int tap = (int)(t % (KH * KW));
+    const int i = (int)((t / (KH * KW)) % I);
+    const int o = (int)(t / ((long long)KH * KW * I));
+    grad[t] += dwt[((long long)tap * I + i) * O + o];
+  }
+}
 __global__ void cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
   const long long n4 = n / 4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -855,6 +866,11 @@ extern "C" int vtx_conv_w_unpack_add(const float* dwp, float* grad, int O, int I
   REQ(dwp && grad && ldk >= KH * KW * I, "bad arguments");
   conv_w_unpack_add_kernel<<<grid_for((long long)O * I * KH * KW, 256), 256, 0, STREAM>>>(dwp, grad, O, I, KH, KW, ldk);
   return check_launch("conv_w_unpack_add");
+}
+extern "C" int vtx_conv_w_unpack_add_t(const float* dwt, float* grad, int O, int I, int KH, int KW, void* stream) {
+  REQ(dwt && grad, "bad arguments");
+  conv_w_unpack_add_t_kernel<<<grid_for((long long)O * I * KH * KW, 256), 256, 0, STREAM>>>(dwt, grad, O, I, KH, KW);
+  return check_launch("conv_w_unpack_add_t");
 }
 extern "C" int vtx_cast_bf16(const float* in, void* out, int64_t n, void* stream) {
   REQ(in && out && n >= 0, "bad arguments");

@@ -36,7 +36,7 @@ constexpr int kSmemTotal = 232448;            // 227 KB: the per-CTA maximum on 
 constexpr int kCtrlBytes = 1024;              // barriers + TMEM slot, placed right after the 1024-aligned base
 constexpr int kThreads = 384;
 constexpr int kEpiThreads = 256;
-constexpr int kHaloH = 18;  // mode 3: halo tile of an 8 x 16 output tile = 18 lines x halo_w pixels x 64 channels (bf16)
+constexpr int kHaloH = 18, kHaloW = 10;  // mode 3: halo tile of an 8 x 16 output tile = 18 lines x halo_w pixels x 64 channels (bf16)
 
 struct GemmKParams {
   int M, N, K;
@@ -53,7 +53,8 @@ struct GemmKParams {
   int cbytes, nbuf;          // bytes of one bf16 staging buffer (0: no staging) / number of staging buffers
   int res_tma;               // residual tile is TMA-loaded into the staging buffer and added there
   int bstat_bytes;           // mode 3: bytes of the stationary weight region (0 otherwise)
-  int halo_w;                // mode 3: pixels per halo line in shared memory (10 = exact, 16 = padded)
+  int halo_w;                // modes 3/4: pixels per halo line in shared memory
+  int dy_off;                // mode 4: byte offset of the dy tile inside a stage (1024-aligned)
   float alpha;
   void* D;
   long long ldd;
@@ -212,7 +213,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
       }
-      for (int t = blockIdx.x; t < total_tiles && p.mode != 3; t += gridDim.x) {
+      if (p.mode == 4) {
+        // halo-reuse 3x3 wgrad (64 -> 64 channels): every spatial tile of 8 x 16 positions needs ONE halo'd input tile
+        // and ONE output-gradient tile; all nine taps are row-shifted views of the halo tile
+        const uint32_t halo_bytes = (uint32_t)(p.halo_w * kHaloH * 128);
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+          const int tw = t % p.tiles_w;
+          const int th = (t / p.tiles_w) % p.tiles_h;
+          const int tn = t / (p.tiles_w * p.tiles_h);
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sX = smem + stage * p.stage_bytes;
+          mbar_arrive_expect_tx(&full_bar[stage], halo_bytes + 16384u);
+          tma_load_4d(sX, &tmB, &full_bar[stage], 0, (tw << 3) - 1, (th << 4) - 1, tn);        // x halo tile
+          tma_load_4d(sX + p.dy_off, &tmA, &full_bar[stage], 0, tw << 3, th << 4, tn);          // dy tile [128 pos][64]
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
+        }
+      }
+      for (int t = blockIdx.x; t < total_tiles && p.mode < 3; t += gridDim.x) {
         const int ks = t / (p.m_tiles * p.n_tiles);
         const int rem = t - ks * (p.m_tiles * p.n_tiles);
         const int mt = rem / p.n_tiles;
@@ -289,7 +306,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int it = 0;
       if (p.mode == 3) {
         mbar_wait(bst_bar, 0);
-        const uint32_t sBst = smem_u32(bstat);
+        const uint64_t bd0 = make_smem_desc(smem_u32(bstat), 16, 1024);  // mode 3 always runs bn = 64
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
           const int as = it & 1;
           mbar_wait(&tempty_bar[as], ((it >> 1) & 1) ^ 1);
@@ -298,19 +315,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sA = smem_u32(smem + stage * p.stage_bytes);
-#pragma unroll 1
+          // output row (dh, dw) of the 16 x 8 tile reads halo row (dh + kh) * kHaloW + (dw + kw): 8-row groups are
+          // contiguous, consecutive groups are one halo line apart (SBO), and the view starts at an arbitrary row of
+          // the TMA-written tile.  The 128B swizzle is a function of absolute shared-memory address bits (verified
+          // on B200: base_offset must stay 0), so row-shifted views of one tile serve all nine taps.
+          // An N = 64 MMA takes only ~32 clk, so the issuing thread must not spend more than a few instructions per
+          // MMA: both loops are fully unrolled and every descriptor is the tile's base descriptor plus a constant.
+          const uint64_t ad0 = make_smem_desc(sA, 16, (uint32_t)kHaloW * 128u);
+#pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
-            const int kh = tap / 3, kw = tap - kh * 3;
-            // output row (dh, dw) of the 16 x 8 tile reads halo row (dh + kh) * halo_w + (dw + kw): 8-row groups are
-            // contiguous, consecutive groups are one halo line apart (SBO), and the view starts at an arbitrary row of
-            // the TMA-written tile.  The 128B swizzle is a function of absolute shared-memory address bits (verified
-            // on B200: base_offset must stay 0), so row-shifted views of one tile serve all nine taps.
-            const uint32_t a0 = sA + (uint32_t)(kh * p.halo_w + kw) * 128u;
-            const uint32_t b0 = sBst + (uint32_t)tap * (uint32_t)p.bn * 128u;
 #pragma unroll
             for (int k = 0; k < kBK / 16; ++k) {
-              const uint64_t ad = make_smem_desc(a0 + k * 32, 16, (uint32_t)p.halo_w * 128u);
-              const uint64_t bd = make_smem_desc(b0 + k * 32, 16, 1024);
+              const uint64_t ad = ad0 + (uint64_t)((((tap / 3) * kHaloW + tap % 3) * 128 + k * 32) >> 4);
+              const uint64_t bd = bd0 + (uint64_t)((tap * 64 * 128 + k * 32) >> 4);
               umma_bf16(d_tmem, ad, bd, idesc, (tap > 0 || k > 0) ? 1u : 0u);
             }
           }
@@ -319,7 +336,41 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           umma_commit(&tfull_bar[as]);
         }
       }
-      for (int t = blockIdx.x; t < total_tiles && p.mode != 3; t += gridDim.x, ++it) {
+      if (p.mode == 4) {
+        // D[(tap, cin) = 576 rows -> 5 M-tiles][cout = 64] accumulates in TMEM over ALL spatial tiles of this CTA.
+        // A = x^T views (MN-major: M = cin contiguous, K = positions): the two 64-row atoms of an M-tile are two taps,
+        // i.e. two row offsets into the same halo tile (LBO = their distance); a K step is 16 positions = 2 image lines
+        // of 8 pixels, one halo line apart (SBO).  B = dy^T (MN-major, one 64-cout atom, SBO 1024).
+        const uint32_t idesc4 = make_idesc_bf16(64, 1, 1);
+        constexpr uint32_t line = (uint32_t)kHaloW * 128u;
+        uint32_t acc0 = 0;  // the first MMA of every M-tile of this CTA's first spatial tile overwrites
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sX = smem_u32(smem + stage * p.stage_bytes);
+          const uint64_t ad0 = make_smem_desc(sX, 0, line);
+          const uint64_t bd0 = make_smem_desc(sX + (uint32_t)p.dy_off, 16, 1024);
+          // fully unrolled, constant descriptor increments (see mode 3): ~3 instructions per 32-clk MMA
+#pragma unroll
+          for (int j = 0; j < 5; ++j) {
+            const int t0 = 2 * j, t1 = (2 * j + 1 < 9) ? 2 * j + 1 : 2 * j;  // M-tile 4: second atom is padding
+            const uint32_t o0 = (uint32_t)((t0 / 3) * kHaloW + t0 % 3) * 128u;
+            const uint32_t o1 = (uint32_t)((t1 / 3) * kHaloW + t1 % 3) * 128u;
+            const uint32_t lbo = (o1 > o0) ? (o1 - o0) : 128u;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const uint64_t ad = ad0 + (uint64_t)((o0 + (uint32_t)(2 * k) * line) >> 4) + ((uint64_t)(lbo >> 4) << 16);
+              const uint64_t bd = bd0 + (uint64_t)((k * 2048) >> 4);
+              umma_bf16(tmem_base + (uint32_t)j * 64u, ad, bd, idesc4, k == 0 ? acc0 : 1u);
+            }
+          }
+          acc0 = 1;
+          umma_commit(&empty_bar[stage]);
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[0]);
+      }
+      for (int t = blockIdx.x; t < total_tiles && p.mode < 3; t += gridDim.x, ++it) {
         const int ks = t / (p.m_tiles * p.n_tiles);
         const int kb0 = ks * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
@@ -403,7 +454,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     };
     int it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+    if (p.mode == 4) {
+      // one epilogue for the whole CTA: 5 M-tiles x 64 fp32 columns -> red.add into D[(tap,cin), cout]
+      if (blockIdx.x < total_tiles) {
+        mbar_wait(&tfull_bar[0], 0);
+        tc_fence_after();
+        float* D = reinterpret_cast<float*>(p.D);
+        for (int j = 0; j < 5; ++j) {
+          float v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(j * 64 + hf * 32), v);
+          tmem_ld_wait();
+          const int row = j * 128 + ew * 32 + lane;
+          if (row < p.M) {
+            float* op = D + (long long)row * p.ldd + hf * 32;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) red_add_v4(op + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+          }
+        }
+        tc_fence_before();
+      }
+    }
+    for (int t = blockIdx.x; t < total_tiles && p.mode != 4; t += gridDim.x, ++it) {
       const int rem = t % (p.m_tiles * p.n_tiles);
       const int mt = rem / p.n_tiles;
       const int nt = rem - mt * p.n_tiles;
@@ -681,7 +752,7 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
   p.a_mn = g->a_mn; p.b_mn = g->b_mn;
   p.mode = g->conv_mode;
   if (p.mode == 1) { p.a_mn = 0; p.b_mn = 0; }
-  if (p.mode == 2) { p.a_mn = 1; p.b_mn = 1; }
+  if (p.mode == 2 || p.mode == 4) { p.a_mn = 1; p.b_mn = 1; }
   // ---- tile_n
   int bn = g->tile_n;
   if (bn == 0) {
@@ -746,13 +817,31 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
     choose_box(H, W, p.mode == 1 ? 128 : 64, &bw, &bh, &bnn);
     if (halo) {
       p.mode = 3; bw = 8; bh = 16; bnn = 1;
-      p.halo_w = 10;
+      p.halo_w = kHaloW;
     }
     p.lbw = ilog2(bw); p.lbh = ilog2(bh); p.lbn = ilog2(bnn);
     p.tiles_w = (W + bw - 1) / bw;
     p.tiles_h = (H + bh - 1) / bh;
     const int tiles_n = (NI + bnn - 1) / bnn;
-    if (p.mode & 1) {
+    if (p.mode == 4) {
+      // halo-reuse wgrad: D[9*C, Cout] (fp32, +=) ; A = dy [NI,H,W,Cout=64], B = x [NI,H,W,C=64]
+      if (C != 64 || g->N != 64 || g->M != 9 * C || !g->out_f32 || !g->atomic)
+        return set_error(VTX_EINVAL, "vtx_gemm: conv_mode 4 needs C = Cout = 64, M = 576, fp32 atomic output");
+      bw = 8; bh = 16; bnn = 1;
+      p.lbw = 3; p.lbh = 4; p.lbn = 0;
+      p.tiles_w = (W + 7) / 8;
+      p.tiles_h = (H + 15) / 16;
+      p.m_tiles = p.tiles_w * p.tiles_h * NI;  // spatial tiles: the schedule's only dimension
+      p.n_tiles = 1;
+      p.kb_total = 1;
+      p.halo_w = kHaloW;
+      uint64_t ad[4] = {64, (uint64_t)W, (uint64_t)H, (uint64_t)NI};
+      uint64_t as_[3] = {64, (uint64_t)W * 64, (uint64_t)H * W * 64};
+      uint32_t abox[4] = {64, 8, 16, 1};
+      if ((rc = make_tmap(&tmA, g->A, 4, ad, as_, abox)) != VTX_OK) return rc;
+      uint32_t xbox[4] = {64, 10, (uint32_t)kHaloH, 1};
+      if ((rc = make_tmap(&tmB, g->B, 4, ad, as_, xbox)) != VTX_OK) return rc;
+    } else if (p.mode & 1) {
       // A: activation [NI,H,W,C]; M = NI*H*W (tiled as boxes); K = 9*C; B: weights [N, 9*C] K-major
       if (g->M != NI * H * W || g->K != 9 * C) return set_error(VTX_EINVAL, "vtx_gemm: conv fprop shape mismatch");
       p.m_tiles = p.tiles_w * p.tiles_h * tiles_n;
@@ -790,6 +879,11 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
   // ---- shared-memory carve-up: [1 KB control][stages x (A 16 KB + B bn*128 B)][bf16 staging tile 128 x (bn*2+16) B]
   // mode 3 stages hold one halo tile, rounded up to whole 1024-byte swizzle atoms
   p.stage_bytes = p.mode == 3 ? ((p.halo_w * kHaloH * 128 + 1023) / 1024) * 1024 : kABytes + bn * kBK * 2;
+  p.dy_off = 0;
+  if (p.mode == 4) {
+    p.dy_off = ((p.halo_w * kHaloH * 128 + 1023) / 1024) * 1024;
+    p.stage_bytes = p.dy_off + 16384;
+  }
   p.bstat_bytes = p.mode == 3 ? 9 * bn * 128 : 0;
   p.cbytes = p.out_f32 ? 0 : ((bn + 63) / 64) * 16384;
   {

@@ -385,11 +385,18 @@ class Engine:
             dwp = ws.get("bwd.dwp", (planes, 9 * planes), F32)
             dwp.zero_()
             da1 = ws.get("bwd.da1", (Min, planes), BF16)
+            transposed = False
             if rec["cols2"] is None:
-                tiles = ((planes + 127) // 128) * ((9 * planes + 255) // 256)
-                sk = ops.split_k_for(tiles, (Mout + 63) // 64)
-                gemm(dy2, rec["a1"], dwp, planes, 9 * planes, Mout, atomic=True, split_k=sk, lda=planes, ldb=planes,
-                     conv=(B, Hc, Wc, planes), conv_mode=2, out_f32=True)
+                if planes == 64:
+                    # halo-reuse wgrad: D[(tap, cin), cout], accumulated in TMEM over all spatial tiles of a CTA
+                    gemm(dy2, rec["a1"], dwp, 9 * planes, planes, Mout, atomic=True, lda=planes, ldb=planes, ldd=planes,
+                         conv=(B, Hc, Wc, planes), conv_mode=4, out_f32=True)
+                    transposed = True
+                else:
+                    tiles = ((planes + 127) // 128) * ((9 * planes + 255) // 256)
+                    sk = ops.split_k_for(tiles, (Mout + 63) // 64)
+                    gemm(dy2, rec["a1"], dwp, planes, 9 * planes, Mout, atomic=True, split_k=sk, lda=planes,
+                         ldb=planes, conv=(B, Hc, Wc, planes), conv_mode=2, out_f32=True)
                 gemm(dy2, self._packed[name + ".conv2.weight#dgrad"], da1, Min, planes, 9 * planes, lda=planes,
                      conv=(B, Hc, Wc, planes), conv_mode=1)
             else:
@@ -397,8 +404,12 @@ class Engine:
                 dcols = ws.get("bwd.dcols", (Mout, 9 * planes), BF16)
                 gemm(dy2, self._packed[name + ".conv2.weight"], dcols, Mout, 9 * planes, planes, b_mn=1)
                 call("vtx_col2im3x3", dcols.data_ptr(), da1.data_ptr(), B, Hc, Wc, planes, stride, s)
-            call("vtx_conv_w_unpack_add", dwp.data_ptr(), self.G(name + ".conv2.weight").data_ptr(), planes, planes, 3,
-                 3, 9 * planes, s)
+            if transposed:
+                call("vtx_conv_w_unpack_add_t", dwp.data_ptr(), self.G(name + ".conv2.weight").data_ptr(), planes,
+                     planes, 3, 3, s)
+            else:
+                call("vtx_conv_w_unpack_add", dwp.data_ptr(), self.G(name + ".conv2.weight").data_ptr(), planes, planes,
+                     3, 3, 9 * planes, s)
             # ---- bn1 + ReLU backward
             dy1 = ws.get("bwd.dy1", (Min, planes), BF16)
             self._bn_bwd(da1, None, rec["y1"], rec["bnp1"], name + ".bn1", Min, planes, dy1, mask_from_y=1)

@@ -31,6 +31,7 @@ _PROTOS = {
     "vtx_conv_w_pack": [P, P, I, I, I, I, I, P],
     "vtx_conv_w_pack_dgrad": [P, P, I, I, P],
     "vtx_conv_w_unpack_add": [P, P, I, I, I, I, I, P],
+    "vtx_conv_w_unpack_add_t": [P, P, I, I, I, I, P],
     "vtx_cast_bf16": [P, P, I64, P],
     "vtx_nhwc_to_nchw_f32": [P, P, I, I, I, P],
     "vtx_embed_fwd": [P, P, P, P, P, P, P, P, P, I, I, I, I, F, F, P, U32, P],
