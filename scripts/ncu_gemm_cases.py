@@ -34,5 +34,10 @@ for _ in range(2):
         D = torch.empty(256 * 3136, 64, device=dev, dtype=torch.bfloat16)
         st = torch.zeros(2, 64, device=dev)
         ops.gemm(x, w, D, 256 * 3136, 64, 576, lda=64, stats=st, conv=(256, 56, 56, 64), conv_mode=1)
+    if "l1wgrad" in cases:  # layer1 3x3 halo-reuse wgrad (conv_mode 4)
+        x, dy = bf(256, 56, 56, 64), bf(256, 56, 56, 64)
+        D = torch.zeros(576, 64, device=dev)
+        ops.gemm(dy, x, D, 576, 64, 256 * 3136, lda=64, ldb=64, ldd=64, atomic=True, out_f32=True,
+                 conv=(256, 56, 56, 64), conv_mode=4)
     torch.cuda.synchronize()
 print("done")

@@ -159,7 +159,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* bstat = smem + p.stages * p.stage_bytes;        // mode 3: stationary weights [9 taps][bn rows][128 B]
   uint8_t* cstage0 = bstat + p.bstat_bytes;                // bf16 staging: nbuf x [bn/64 slabs][128 rows][128 B], SW128
 
-  const int warp = threadIdx.x >> 5;
+  // broadcast from lane 0 so that the compiler sees the warp index (and every role branch on it) as warp-uniform
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.m_tiles * p.n_tiles * p.k_splits;
   const int nstages = p.stages;
@@ -295,7 +296,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncwarp();
   } else if (warp == 1) {
     // ===================================================== MMA issuer
-    if (lane == 0) {
+    // The WHOLE warp walks the schedule (so stage / phase / descriptors are warp-uniform and live in uniform
+    // registers); only the tcgen05.mma / tcgen05.commit instructions themselves are issued by lane 0.  With the loop
+    // inside an `if (lane == 0)` region the compiler kept the descriptors in vector registers and needed ~10
+    // instructions (R2UR + ELECT/BRA.U.ANY loops) per MMA, which paced the 32-clk N = 64 MMAs of the halo modes.
+    // lane-0 broadcast: the TMEM base (read from shared memory, hence a vector register) becomes a value the compiler
+    // can treat as warp-uniform and feed to tcgen05.mma without a per-instruction ELECT / R2UR.BROADCAST sequence
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    {
       const uint32_t idesc = make_idesc_bf16(p.bn, p.a_mn, p.b_mn);
       const uint32_t a_step = p.a_mn ? 2048u : 32u;
       const uint32_t b_step = p.b_mn ? 2048u : 32u;
@@ -311,7 +319,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int as = it & 1;
           mbar_wait(&tempty_bar[as], ((it >> 1) & 1) ^ 1);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + (uint32_t)as * 256u;
+          const uint32_t d_tmem = tmem_u + (uint32_t)as * 256u;
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sA = smem_u32(smem + stage * p.stage_bytes);
@@ -322,18 +330,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           // An N = 64 MMA takes only ~32 clk, so the issuing thread must not spend more than a few instructions per
           // MMA: both loops are fully unrolled and every descriptor is the tile's base descriptor plus a constant.
           const uint64_t ad0 = make_smem_desc(sA, 16, (uint32_t)kHaloW * 128u);
-#pragma unroll
+#pragma unroll 1
           for (int tap = 0; tap < 9; ++tap) {
+            const uint64_t ad_t = ad0 + (uint64_t)((uint32_t)((tap / 3) * kHaloW + tap % 3) * 8u);  // rows * 128 B >> 4
+            const uint64_t bd_t = bd0 + (uint64_t)((uint32_t)tap * 512u);                            // 64 * 128 B >> 4
 #pragma unroll
-            for (int k = 0; k < kBK / 16; ++k) {
-              const uint64_t ad = ad0 + (uint64_t)((((tap / 3) * kHaloW + tap % 3) * 128 + k * 32) >> 4);
-              const uint64_t bd = bd0 + (uint64_t)((tap * 64 * 128 + k * 32) >> 4);
-              umma_bf16(d_tmem, ad, bd, idesc, (tap > 0 || k > 0) ? 1u : 0u);
-            }
+            for (int k = 0; k < kBK / 16; ++k)
+              umma_bf16_ws(d_tmem, ad_t + (uint64_t)(2 * k), bd_t + (uint64_t)(2 * k), idesc, (tap | k) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);
+          umma_commit_ws(&empty_bar[stage]);
+          umma_commit_ws(&tfull_bar[as]);
           if (++stage == nstages) { stage = 0; phase ^= 1; }
-          umma_commit(&tfull_bar[as]);
         }
       }
       if (p.mode == 4) {
@@ -351,24 +358,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint64_t ad0 = make_smem_desc(sX, 0, line);
           const uint64_t bd0 = make_smem_desc(sX + (uint32_t)p.dy_off, 16, 1024);
           // fully unrolled, constant descriptor increments (see mode 3): ~3 instructions per 32-clk MMA
-#pragma unroll
+#pragma unroll 1
           for (int j = 0; j < 5; ++j) {
             const int t0 = 2 * j, t1 = (2 * j + 1 < 9) ? 2 * j + 1 : 2 * j;  // M-tile 4: second atom is padding
             const uint32_t o0 = (uint32_t)((t0 / 3) * kHaloW + t0 % 3) * 128u;
             const uint32_t o1 = (uint32_t)((t1 / 3) * kHaloW + t1 % 3) * 128u;
             const uint32_t lbo = (o1 > o0) ? (o1 - o0) : 128u;
+            const uint64_t ad_j = ad0 + (uint64_t)(o0 >> 4) + ((uint64_t)(lbo >> 4) << 16);
+            const uint32_t d_j = tmem_u + (uint32_t)j * 64u;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const uint64_t ad = ad0 + (uint64_t)((o0 + (uint32_t)(2 * k) * line) >> 4) + ((uint64_t)(lbo >> 4) << 16);
-              const uint64_t bd = bd0 + (uint64_t)((k * 2048) >> 4);
-              umma_bf16(tmem_base + (uint32_t)j * 64u, ad, bd, idesc4, k == 0 ? acc0 : 1u);
-            }
+            for (int k = 0; k < 8; ++k)
+              umma_bf16_ws(d_j, ad_j + (uint64_t)(((uint32_t)(2 * k) * line) >> 4), bd0 + (uint64_t)(k * 128), idesc4,
+                           k == 0 ? acc0 : 1u);
           }
+          umma_commit_ws(&empty_bar[stage]);
           acc0 = 1;
-          umma_commit(&empty_bar[stage]);
           if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[0]);
+        umma_commit_ws(&tfull_bar[0]);
       }
       for (int t = blockIdx.x; t < total_tiles && p.mode < 3; t += gridDim.x, ++it) {
         const int ks = t / (p.m_tiles * p.n_tiles);
@@ -377,7 +384,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int as = it & 1;
         mbar_wait(&tempty_bar[as], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)as * 256u;
+        const uint32_t d_tmem = tmem_u + (uint32_t)as * 256u;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -387,12 +394,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int k = 0; k < kBK / 16; ++k) {
             const uint64_t ad = make_smem_desc(sA + k * a_step, a_lbo, 1024);
             const uint64_t bd = make_smem_desc(sB + k * b_step, b_lbo, 1024);
-            umma_bf16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            umma_bf16_ws(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);
+          umma_commit_ws(&empty_bar[stage]);
           if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[as]);
+        umma_commit_ws(&tfull_bar[as]);
       }
     }
     __syncwarp();
