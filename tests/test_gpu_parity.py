@@ -121,6 +121,42 @@ def test_conv3x3_halo_reuse_mode(NI, H, W):
     assert rel(st[0], out.float().sum(0)) < 1e-3 and rel(st[1], (out.float() ** 2).sum(0)) < 1e-3
 
 
+def _conv_weight_grad_ref(x, dy, Co, C):
+    """OIHW weight gradient of a 3x3 / pad-1 conv from NHWC x, dy (fp32 math on the bf16-rounded inputs)."""
+    return torch.nn.grad.conv2d_weight(x.float().permute(0, 3, 1, 2), (Co, C, 3, 3), dy.float().permute(0, 3, 1, 2),
+                                       padding=1)
+
+
+@pytest.mark.parametrize("NI,H,W", [(3, 56, 56), (5, 20, 20), (4, 7, 7)])
+def test_conv3x3_halo_reuse_wgrad(NI, H, W):
+    """conv_mode 4: weight gradient of a 64 -> 64 3x3 conv from one x halo tile + one dy tile per 8x16 spatial tile,
+    accumulated in TMEM over all tiles of a CTA; output layout [(tap, cin), cout], folded into OIHW by
+    vtx_conv_w_unpack_add_t.  Image sizes that are not multiples of the 8x16 tile exercise the zero-filled borders."""
+    _need_cuda()
+    from virtex_b200 import ops
+    torch.manual_seed(5)
+    dev = "cuda"
+    C = Co = 64
+    x = (torch.randn(NI, H, W, C, device=dev) * 0.5).bfloat16()
+    dy = (torch.randn(NI, H, W, Co, device=dev) * 0.5).bfloat16()
+    dwt = torch.zeros(9 * C, Co, device=dev)
+    ops.gemm(dy, x, dwt, 9 * C, Co, NI * H * W, lda=Co, ldb=C, ldd=Co, atomic=True, out_f32=True,
+             conv=(NI, H, W, C), conv_mode=4)
+    ref = _conv_weight_grad_ref(x, dy, Co, C)                       # [Co, C, 3, 3]
+    assert rel(dwt, ref.permute(2, 3, 1, 0).reshape(9 * C, Co)) < 1e-4
+    # += semantics of both the kernel and the unpack
+    ops.gemm(dy, x, dwt, 9 * C, Co, NI * H * W, lda=Co, ldb=C, ldd=Co, atomic=True, out_f32=True,
+             conv=(NI, H, W, C), conv_mode=4)
+    grad = torch.ones(Co, C, 3, 3, device=dev)
+    ops.call("vtx_conv_w_unpack_add_t", dwt.data_ptr(), grad.data_ptr(), Co, C, 3, 3, ops._stream())
+    assert rel(grad, 1.0 + 2.0 * ref) < 1e-4
+    # the split-K implicit wgrad (conv_mode 2) must agree with it
+    dw2 = torch.zeros(Co, 9 * C, device=dev)
+    ops.gemm(dy, x, dw2, Co, 9 * C, NI * H * W, lda=Co, ldb=C, atomic=True, split_k=4, out_f32=True,
+             conv=(NI, H, W, C), conv_mode=2)
+    assert rel(dw2, ref.permute(0, 2, 3, 1).reshape(Co, 9 * C)) < 1e-4
+
+
 def test_attention_and_ce_kernels():
     _need_cuda()
     from virtex_b200.ops import call, _stream
