@@ -5,7 +5,8 @@
 // Structure (persistent, warp specialised, one CTA per SM, 384 threads):
 //   warp 0 : TMA producer   (one elected lane)  global -> 128B-swizzled smem ring of (A 16 KB, B = tile_n*128 B) stages;
 //                           the ring depth is whatever fits next to the output staging tile (3..8 stages)
-//   warp 1 : MMA issuer     (one elected lane)  tcgen05.mma.cta_group::1.kind::f16, M=128, N=tile_n, K=16 per issue
+//   warp 1 : MMA issuer     tcgen05.mma.cta_group::1.kind::f16, M=128, N=tile_n, K=16 per issue; the whole warp walks
+//                           the schedule (uniform-datapath descriptors), one elect.sync lane issues
 //   warp 2 : TMEM allocator (512 columns = 2 accumulator stages of up to 256 fp32 columns)
 //   warps 4-11 : epilogue   tcgen05.ld (double buffered) -> bias / residual / activation in fp32 -> bf16 tile in
 //                           128B-swizzled smem (TMEM is released to the MMA warp here) -> one elected thread issues
@@ -21,6 +22,10 @@
 // kernel serves fprop (A,B K-major), dgrad (B MN-major) and wgrad (A,B MN-major) without transposing activations.
 // conv_mode 1/2 replace the 2D TMA loads by 4D NHWC box loads whose out-of-bounds elements are zero-filled by the
 // TMA unit: that *is* the im2col of a 3x3/stride-1/pad-1 convolution, with no extra HBM traffic.
+// 64 -> 64 channel 3x3 convs (ResNet layer1) additionally have halo-reuse variants that fetch the input ONCE per
+// 8 x 16 spatial tile and address the nine taps as row-shifted descriptor views of that tile: mode 3 (fprop / dgrad,
+// selected automatically from mode 1; weights stationary in shared memory) and mode 4 (wgrad; accumulators stay in
+// TMEM across all spatial tiles of the CTA).
 #include <stdlib.h>
 #include "ptx.cuh"
 #include "vtx_common.cuh"
@@ -36,7 +41,7 @@ constexpr int kSmemTotal = 232448;            // 227 KB: the per-CTA maximum on 
 constexpr int kCtrlBytes = 1024;              // barriers + TMEM slot, placed right after the 1024-aligned base
 constexpr int kThreads = 384;
 constexpr int kEpiThreads = 256;
-constexpr int kHaloH = 18, kHaloW = 10;  // mode 3: halo tile of an 8 x 16 output tile = 18 lines x halo_w pixels x 64 channels (bf16)
+constexpr int kHaloH = 18, kHaloW = 10;  // modes 3/4: halo of an 8 (w) x 16 (h) tile = 18 lines x 10 pixels x 64 ch (bf16)
 
 struct GemmKParams {
   int M, N, K;
