@@ -139,3 +139,111 @@ def test_lr_schedules_and_lookahead_match_oracle_formulas():
     assert torch.allclose(p.data, torch.full((4,), 0.5))
     assert torch.allclose(opt.state[p]["slow_params"], torch.full((4,), 0.5))
     assert sched is not None
+
+
+# ------------------------------------------------------------------------------------------ checkpoint interchange
+def _tiny_config():
+    from virtex_b200.config import Config
+    return Config(None, ["MODEL.TEXTUAL.NAME", "transdec_postnorm::L1_H128_A2_F256", "OPTIM.CNN_LR", 0.1,
+                         "OPTIM.LR", 0.001, "OPTIM.WARMUP_STEPS", 4, "OPTIM.NUM_ITERATIONS", 20])
+
+
+def _fake_trainer(model, config, device="cpu"):
+    """The host-side state of `Trainer` without a GPU: real Arena (on the CPU) + the fields the state views read."""
+    import types
+    from virtex_b200.engine import Arena
+    from virtex_b200.optim import lr_multiplier_fn
+    named = [(n, p) for n, p in model.named_parameters()]
+    t = types.SimpleNamespace()
+    t.config = config
+    t.arena = Arena(named, device)
+    t.mom = torch.zeros_like(t.arena.params)
+    t.slow = t.arena.params.clone()
+    t.momentum = float(config.OPTIM.SGD_MOMENTUM)
+    O = config.OPTIM
+    t.lr_fn = lr_multiplier_fn(O.LR_DECAY_NAME, O.NUM_ITERATIONS, O.WARMUP_STEPS, O.LR_STEPS, O.LR_GAMMA)
+    t.iteration, t._k_counter, t.momentum_ready = 0, 3, False
+
+    def reset_lookahead():
+        t._k_counter = 0
+        t.slow.copy_(t.arena.params)
+    t.reset_lookahead = reset_lookahead
+    return t
+
+
+def test_checkpoint_interchange_with_torch_optimizer_and_scheduler(tmp_path):
+    """A checkpoint written by the reference's recipe (torch SGD in Lookahead + LambdaLR, one group per parameter) loads
+    into the fused-tail state views, and what the views write loads back into the torch objects unchanged."""
+    from virtex_b200.checkpointing import CheckpointManager, FusedOptimizerState, FusedSchedulerState
+    from virtex_b200.factories import LRSchedulerFactory, OptimizerFactory, PretrainingModelFactory
+    cfg = _tiny_config()
+    torch.manual_seed(0)
+    model = PretrainingModelFactory.from_config(cfg)
+    opt = OptimizerFactory.from_config(cfg, model.named_parameters())
+    sch = LRSchedulerFactory.from_config(cfg, opt)
+    for it in range(3):  # momentum buffers + an advanced schedule
+        for p in model.parameters():
+            p.grad = torch.randn_like(p) * 0.01
+        opt.step()
+        sch.step()
+    CheckpointManager(str(tmp_path / "ref"), model=model, optimizer=opt, scheduler=sch).step(3)
+
+    # ---- "reference" checkpoint -> fused-tail views
+    model2 = PretrainingModelFactory.from_config(cfg)
+    tr = _fake_trainer(model2, cfg)
+    mgr = CheckpointManager(str(tmp_path / "ours"), keep_recent=2, model=model2, optimizer=FusedOptimizerState(tr),
+                            scheduler=FusedSchedulerState(tr))
+    assert mgr.load(str(tmp_path / "ref" / "checkpoint_3.pth")) == 3
+    assert mgr.not_loaded == [] and mgr.not_found == []
+    assert tr.iteration == 3 and tr.momentum_ready and tr._k_counter == 0
+    sd = opt.state_dict()
+    names = tr.arena.names
+    assert len(sd["param_groups"]) == len(names) == len(list(model.named_parameters()))
+    for i, n in enumerate(names):
+        assert torch.equal(tr.arena.view(tr.mom, n), sd["state"][i]["momentum_buffer"]), n
+        assert torch.equal(tr.arena.p(n), dict(model.named_parameters())[n]), n
+    assert torch.equal(tr.slow, tr.arena.params)  # Lookahead restarts from the loaded weights (as in the reference)
+
+    # ---- fused-tail views -> file -> fresh torch optimizer / scheduler
+    for it in (3, 4, 5):
+        mgr.step(it, metric=1.0 / it)
+    assert sorted(p.name for p in (tmp_path / "ours").iterdir()) == ["checkpoint_4.pth", "checkpoint_5.pth",
+                                                                      "checkpoint_best.pth"]
+    ck = torch.load(tmp_path / "ours" / "checkpoint_best.pth", weights_only=False)
+    assert ck["iteration"] == 3  # 1/3 is the best ("higher is better") metric
+    model3 = PretrainingModelFactory.from_config(cfg)
+    opt3 = OptimizerFactory.from_config(cfg, model3.named_parameters())
+    sch3 = LRSchedulerFactory.from_config(cfg, opt3)
+    mgr3 = CheckpointManager(str(tmp_path / "x"), model=model3, optimizer=opt3, scheduler=sch3)
+    assert mgr3.load(str(tmp_path / "ours" / "checkpoint_5.pth")) == 5
+    sd3 = opt3.state_dict()
+    for g, g3 in zip(sd["param_groups"], sd3["param_groups"]):
+        for k in ("lr", "weight_decay", "momentum", "initial_lr", "params", "nesterov", "dampening"):
+            assert g[k] == pytest.approx(g3[k], rel=1e-12, abs=0), k
+    for i in range(len(names)):
+        assert torch.equal(sd["state"][i]["momentum_buffer"], sd3["state"][i]["momentum_buffer"])
+    assert sch3.last_epoch == 3 and sch3.get_last_lr() == pytest.approx(sch.get_last_lr())
+    # and the schedule keeps going where it stopped
+    opt3.step(); sch3.step(); opt.step(); sch.step()
+    assert sch3.get_last_lr() == pytest.approx(sch.get_last_lr())
+
+
+def test_fused_optimizer_state_is_empty_before_the_first_step_and_skips_frozen_parameters():
+    from virtex_b200.checkpointing import FusedOptimizerState
+    from virtex_b200.factories import PretrainingModelFactory
+    cfg = _tiny_config()
+    model = PretrainingModelFactory.from_config(cfg)
+    for p in model.visual.parameters():
+        p.requires_grad = False
+    tr = _fake_trainer(model, cfg)
+    view = FusedOptimizerState(tr)
+    sd = view.state_dict()
+    assert sd["state"] == {} and len(sd["param_groups"]) == len(tr.arena.names)
+    assert all(g["lr"] == 0.0 for g in sd["param_groups"])  # LambdaLR: the first step runs at lambda(0) = 0
+    tr.momentum_ready, tr.iteration = True, 2
+    sd = view.state_dict()
+    frozen = [i for i, n in enumerate(tr.arena.names) if n.startswith("visual.")]
+    assert frozen and all(i not in sd["state"] for i in frozen)
+    assert sd["param_groups"][frozen[0]]["lr"] == pytest.approx(0.1 * 2 / 4)
+    with pytest.raises(ValueError):
+        view.load_state_dict({"state": {}, "param_groups": sd["param_groups"][:-1]})

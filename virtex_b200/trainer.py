@@ -87,6 +87,7 @@ class Trainer:
         self._hyper_ring = [torch.zeros(4, dtype=torch.float32).pin_memory() for _ in range(16)]
         self.iteration = 0
         self._k_counter = 0
+        self.momentum_ready = False  # torch.optim.SGD: the first step with a gradient initialises the buffer to it
         self.comm_stream = torch.cuda.Stream(device=dev) if self.world > 1 else None
         self._pending = []
         self._ranges = self._bucket_ranges()
@@ -140,14 +141,33 @@ class Trainer:
             self._k_counter = 0
         h = self._hyper_ring[self.iteration % len(self._hyper_ring)]
         h[0] = self.lr_fn(self.iteration)  # the optimiser step of iteration i uses lambda(i - 1 + 1 - 1) = lambda(i)
-        h[1] = 1.0 if self.iteration == 0 else 0.0
+        h[1] = 0.0 if self.momentum_ready else 1.0
         h[2] = 1.0 if do_la else 0.0
         self.hyper.copy_(h, non_blocking=True)
         call("vtx_sgd_step", arena.params.data_ptr(), arena.grads.data_ptr(), self.mom.data_ptr(),
              0 if self.slow is None else self.slow.data_ptr(), arena.mirror.data_ptr(), self.segs.data_ptr(), self.nseg,
              self.ctl.data_ptr(), self.hyper.data_ptr(), self.momentum, self.la_alpha, s)
         eng.prepare_weights(mirror=False)  # the step kernel refreshed the bf16 mirror; re-pack the k>1 conv weights
+        self.momentum_ready = True
         self.iteration += 1
+
+    # ------------------------------------------------------------------------------------------- checkpoint views
+    def reset_lookahead(self):
+        """Slow weights restart from the current parameters (what the reference's Lookahead does after a load)."""
+        self._k_counter = 0
+        if self.slow is not None:
+            self.slow.copy_(self.arena.params)
+
+    @property
+    def optimizer(self):
+        """`torch.optim.SGD`-layout state view for checkpoint interchange (virtex_b200/checkpointing.py)."""
+        from .checkpointing import FusedOptimizerState
+        return FusedOptimizerState(self)
+
+    @property
+    def scheduler(self):
+        from .checkpointing import FusedSchedulerState
+        return FusedSchedulerState(self)
 
     @property
     def grad_norm(self) -> torch.Tensor:
