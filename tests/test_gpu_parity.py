@@ -595,3 +595,74 @@ def test_hub_resnet50_forward():
     with torch.no_grad():
         y = m(x)
     assert y.shape == (2, 2048 * 7 * 7) and torch.isfinite(y).all()
+
+
+# ------------------------------------------------------------------------- experimental kernels (opt-in, see header)
+def _need_experimental(feature):
+    """Experimental kernels (include/virtex_b200_x.h) were written without hardware access; their tests run only when
+    VTX_EXPERIMENTAL names the feature:  VTX_EXPERIMENTAL=all python -m pytest tests -m gpu -q"""
+    _need_cuda()
+    from virtex_b200 import experimental as X
+    if not X.enabled(feature):
+        pytest.skip(f"experimental feature {feature} not enabled (set VTX_EXPERIMENTAL={feature})")
+    return X
+
+
+def _s2d_ref(x):
+    """S[n, i, j, (r*2+q)*3 + c] = x[n, c, 2i + r - 3, 2j + q - 3] (zero padded), [N, H/2+3, W/2+3, 16]."""
+    N, _, H, W = x.shape
+    Hs, Ws = H // 2 + 3, W // 2 + 3
+    xp = torch.zeros(N, 3, 2 * Hs, 2 * Ws, dtype=x.dtype, device=x.device)
+    xp[:, :, 3:3 + H, 3:3 + W] = x
+    S = torch.zeros(N, Hs, Ws, 16, dtype=x.dtype, device=x.device)
+    for r in range(2):
+        for q in range(2):
+            for c in range(3):
+                S[..., (r * 2 + q) * 3 + c] = xp[:, c, r::2, q::2]
+    return S
+
+
+def _stem_wpack_ref(w):
+    wp = torch.zeros(w.shape[0], 256, dtype=w.dtype, device=w.device)
+    for kh in range(7):
+        for kw in range(7):
+            for c in range(3):
+                wp[:, (kh >> 1) * 64 + (kw >> 1) * 16 + ((kh & 1) * 2 + (kw & 1)) * 3 + c] = w[:, c, kh, kw]
+    return wp
+
+
+@pytest.mark.parametrize("N,H,W", [(3, 224, 224), (2, 64, 96)])
+def test_experimental_stem_space_to_depth_conv(N, H, W):
+    X = _need_experimental("stem_s2d")
+    torch.manual_seed(6)
+    dev = "cuda"
+    s = torch.cuda.current_stream().cuda_stream
+    x = torch.randn(N, 3, H, W, device=dev)
+    w = torch.randn(64, 3, 7, 7, device=dev) * 0.05
+    Ho, Wo = H // 2, W // 2
+    S = torch.full((N, Ho + 3, Wo + 3, 16), 9.0, device=dev, dtype=torch.bfloat16)
+    X.call("vtx_x_stem_s2d", x.data_ptr(), S.data_ptr(), N, H, W, s)
+    assert torch.equal(S, _s2d_ref(x).bfloat16())
+    wp = torch.empty(64, 256, device=dev, dtype=torch.bfloat16)
+    X.call("vtx_x_stem_w_pack", w.data_ptr(), wp.data_ptr(), 64, s)
+    assert torch.equal(wp, _stem_wpack_ref(w).bfloat16())
+    # fprop (+ BN statistics) against conv2d on the bf16-rounded operands
+    M = N * Ho * Wo
+    y = torch.full((M + 64, 64), 7.0, device=dev, dtype=torch.bfloat16)
+    st = torch.zeros(2, 64, device=dev)
+    X.gemm(S, wp, y, M, 64, 256, lda=64, ldb=256, stats=st, conv=(N, Ho, Wo, 64), conv_mode=5)
+    ref = torch.nn.functional.conv2d(x.bfloat16().float(), w.bfloat16().float(), stride=2, padding=3)
+    ref = ref.permute(0, 2, 3, 1).reshape(M, 64)
+    assert rel(y[:M], ref) < 4e-3
+    assert torch.all(y[M:] == 7.0)
+    assert rel(st[0], y[:M].float().sum(0)) < 1e-3 and rel(st[1], (y[:M].float() ** 2).sum(0)) < 1e-3
+    # wgrad
+    dy = (torch.randn(N, Ho, Wo, 64, device=dev) * 0.5).bfloat16()
+    dwp = torch.zeros(64, 256, device=dev)
+    X.gemm(dy, S, dwp, 64, 256, M, lda=64, ldb=64, atomic=True, out_f32=True, split_k=16, conv=(N, Ho, Wo, 64),
+           conv_mode=6)
+    grad = torch.ones(64, 3, 7, 7, device=dev)
+    X.call("vtx_x_stem_w_unpack_add", dwp.data_ptr(), grad.data_ptr(), 64, s)
+    gref = torch.nn.grad.conv2d_weight(x.bfloat16().float(), (64, 3, 7, 7), dy.float().permute(0, 3, 1, 2), stride=2,
+                                       padding=3)
+    assert rel(grad, 1.0 + gref) < 1e-4

@@ -247,3 +247,19 @@ def test_fused_optimizer_state_is_empty_before_the_first_step_and_skips_frozen_p
     assert sd["param_groups"][frozen[0]]["lr"] == pytest.approx(0.1 * 2 / 4)
     with pytest.raises(ValueError):
         view.load_state_dict({"state": {}, "param_groups": sd["param_groups"][:-1]})
+
+
+def test_experimental_library_exports_and_is_off_by_default(monkeypatch):
+    from virtex_b200 import experimental as X
+    hdr = open(os.path.join(ROOT, "include", "virtex_b200_x.h")).read()
+    declared = sorted(set(re.findall(r"\b(vtx_[a-z0-9_]+)\s*\(", hdr)))
+    assert declared == X.exported_symbols()
+    lib = ctypes.CDLL(X.lib_path())
+    for name in declared:
+        assert hasattr(lib, name), name
+    monkeypatch.delenv("VTX_EXPERIMENTAL", raising=False)
+    assert not X.any_enabled()
+    monkeypatch.setenv("VTX_EXPERIMENTAL", "stem_s2d")
+    assert X.enabled("stem_s2d")
+    monkeypatch.setenv("VTX_EXPERIMENTAL", "all")
+    assert X.enabled("stem_s2d")

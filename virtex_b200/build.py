@@ -15,6 +15,10 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OBJ_DIR = os.path.join(ROOT, "build", "obj")
 LIB_PATH = os.path.join(HERE, "libvirtex_b200.so")
+# experimental kernels (not on the default path, see include/virtex_b200_x.h) live in a SEPARATE library so that the
+# validated one is bit-for-bit what was tested: csrc_x/*.cu + gemm_tc.cu compiled with -DVTX_GEMM_X + common.cu
+CSRC_X = os.path.join(HERE, "csrc_x")
+LIB_X_PATH = os.path.join(HERE, "libvirtex_b200_x.so")
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = [
@@ -35,20 +39,33 @@ def _headers_digest():
     return h.hexdigest()
 
 
-def _compile_one(src, hdr_digest, verbose):
+def _compile_one(src, hdr_digest, verbose, extra=(), tag=""):
     with open(src, "rb") as f:
-        digest = hashlib.sha1(f.read() + hdr_digest.encode()).hexdigest()[:16]
-    base = os.path.splitext(os.path.basename(src))[0]
+        digest = hashlib.sha1(f.read() + hdr_digest.encode() + " ".join(extra).encode()).hexdigest()[:16]
+    base = os.path.splitext(os.path.basename(src))[0] + tag
     obj = os.path.join(OBJ_DIR, f"{base}.{digest}.o")
     if not os.path.exists(obj):
         for old in os.listdir(OBJ_DIR):
             if old.startswith(base + ".") and old.endswith(".o"):
                 os.remove(os.path.join(OBJ_DIR, old))
-        cmd = [NVCC] + NVCC_FLAGS + ["-c", src, "-o", obj]
+        cmd = [NVCC] + NVCC_FLAGS + list(extra) + ["-c", src, "-o", obj]
         if verbose:
             print(" ".join(cmd), flush=True)
         subprocess.run(cmd, check=True)
     return obj
+
+
+def _link(objs, lib_path, stamp_name, verbose):
+    stamp = os.path.join(OBJ_DIR, stamp_name)
+    want = "\n".join(objs)
+    have = open(stamp).read() if os.path.exists(stamp) else ""
+    if want != have or not os.path.exists(lib_path):
+        cmd = [NVCC, "-shared", "-o", lib_path] + objs
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        subprocess.run(cmd, check=True)
+        with open(stamp, "w") as f:
+            f.write(want)
 
 
 def build(verbose=False, force=False):
@@ -58,18 +75,15 @@ def build(verbose=False, force=False):
     if force:
         for old in os.listdir(OBJ_DIR):
             os.remove(os.path.join(OBJ_DIR, old))
-    with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
-        objs = list(ex.map(lambda s: _compile_one(s, hdr, verbose), srcs))
-    stamp = os.path.join(OBJ_DIR, "link.stamp")
-    want = "\n".join(objs)
-    have = open(stamp).read() if os.path.exists(stamp) else ""
-    if want != have or not os.path.exists(LIB_PATH):
-        cmd = [NVCC, "-shared", "-o", LIB_PATH] + objs
-        if verbose:
-            print(" ".join(cmd), flush=True)
-        subprocess.run(cmd, check=True)
-        with open(stamp, "w") as f:
-            f.write(want)
+    jobs = [(s, (), "") for s in srcs]
+    # experimental library: its own sources + the GEMM with runtime tap geometry + its own copy of the error helpers
+    jobs += [(os.path.join(CSRC_X, n), (), "") for n in sorted(os.listdir(CSRC_X)) if n.endswith(".cu")]
+    jobs += [(os.path.join(CSRC, "gemm_tc.cu"), ("-DVTX_GEMM_X",), "_x")]
+    with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
+        objs = list(ex.map(lambda j: _compile_one(j[0], hdr, verbose, j[1], j[2]), jobs))
+    _link(objs[:len(srcs)], LIB_PATH, "link.stamp", verbose)
+    common = [o for o in objs[:len(srcs)] if os.path.basename(o).startswith("common.")]
+    _link(objs[len(srcs):] + common, LIB_X_PATH, "link_x.stamp", verbose)
     return LIB_PATH
 
 

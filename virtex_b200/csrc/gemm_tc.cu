@@ -31,6 +31,23 @@
 #include "vtx_common.cuh"
 #include "../../include/virtex_b200.h"
 
+// Experimental build (-DVTX_GEMM_X, linked into libvirtex_b200_x.so only): the tap geometry of the implicit-conv modes
+// becomes a runtime parameter, which adds conv_mode 5 / 6 -- the 7x7/2 stem conv as a 4-tap implicit GEMM over a
+// space-to-depth view of the image (include/virtex_b200_x.h).  The regular build sees the literal constants below, i.e.
+// exactly the code that was validated on hardware.
+#ifdef VTX_GEMM_X
+#define gemm_tc_kernel gemm_tc_kernel_x
+#define GemmKParams GemmKParamsX
+#define vtx_gemm vtx_gemm_x
+#define KP_TAPS_W p.taps_w
+#define KP_PAD p.pad
+#define KP_NTAPS p.ntaps
+#else
+#define KP_TAPS_W 3
+#define KP_PAD 1
+#define KP_NTAPS 9
+#endif
+
 namespace vtx {
 
 constexpr int kBM = 128;
@@ -67,6 +84,9 @@ struct GemmKParams {
   const __nv_bfloat16* residual;
   long long ldr;
   float* stats;
+#ifdef VTX_GEMM_X
+  int taps_w, pad, ntaps;    // taps per kernel row / zero padding / number of taps of the implicit conv (3, 1, 9 for 3x3)
+#endif
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
@@ -273,8 +293,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           } else if (p.mode == 1) {
             const int tap = kb / p.cpb;
             const int cb = kb - tap * p.cpb;
-            const int kh = tap / 3, kw = tap - kh * 3;
-            tma_load_4d(sA, &tmA, &full_bar[stage], cb * 64, w0 + kw - 1, h0 + kh - 1, n0);
+            const int kh = tap / KP_TAPS_W, kw = tap - kh * KP_TAPS_W;
+            tma_load_4d(sA, &tmA, &full_bar[stage], cb * 64, w0 + kw - KP_PAD, h0 + kh - KP_PAD, n0);
             tma_load_2d(sB, &tmB, &full_bar[stage], kb * kBK, nt * p.bn);
           } else {
             // wgrad: reduction block kb is a spatial box of 64 output positions
@@ -288,10 +308,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const int atom = nt * (p.bn >> 6) + j;
               const int tap = atom / p.cpb;
               const int cb = atom - tap * p.cpb;
-              const int kh = tap / 3, kw = tap - kh * 3;
+              const int kh = tap / KP_TAPS_W, kw = tap - kh * KP_TAPS_W;
               // atoms past the 9 taps are loaded fully out of bounds (zero fill) to keep the tx count fixed
-              const int nn = tap < 9 ? bn0 : p.cN + 1;
-              tma_load_4d(sB + j * 8192, &tmB, &full_bar[stage], cb * 64, bw0 + kw - 1, bh0 + kh - 1, nn);
+              const int nn = tap < KP_NTAPS ? bn0 : p.cN + 1;
+              tma_load_4d(sB + j * 8192, &tmB, &full_bar[stage], cb * 64, bw0 + kw - KP_PAD, bh0 + kh - KP_PAD, nn);
             }
           }
           if (++stage == nstages) { stage = 0; phase ^= 1; }
@@ -763,6 +783,15 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
   p.M = g->M; p.N = g->N; p.K = g->K;
   p.a_mn = g->a_mn; p.b_mn = g->b_mn;
   p.mode = g->conv_mode;
+#ifdef VTX_GEMM_X
+  // conv_mode 5 / 6: stem conv over the space-to-depth view = modes 1 / 2 with 4 x 1 taps, no padding
+  const bool stem = g->conv_mode == 5 || g->conv_mode == 6;
+  p.taps_w = 3; p.pad = 1; p.ntaps = 9;
+  if (stem) { p.mode = g->conv_mode == 5 ? 1 : 2; p.taps_w = 1; p.pad = 0; p.ntaps = 4; }
+#else
+  constexpr bool stem = false;
+#endif
+  const int ntaps = stem ? 4 : 9;
   if (p.mode == 1) { p.a_mn = 0; p.b_mn = 0; }
   if (p.mode == 2 || p.mode == 4) { p.a_mn = 1; p.b_mn = 1; }
   // ---- tile_n
@@ -823,8 +852,13 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
     p.cH = H; p.cW = W; p.cN = NI; p.cpb = C / 64;
     // halo-reuse variant (mode 3): C = 64 -> 64 convs whose 9 weight taps (72 KB) stay resident in shared memory and
     // whose input is fetched ONCE per 8 x 16 output tile as an 18 x 16 halo tile (instead of once per tap)
-    const bool halo = p.mode == 1 && C == 64 && g->N == 64 && bn == 64 && !g->out_f32 && g->residual == nullptr &&
-                      getenv("VTX_GEMM_NO_HALO") == nullptr;
+    const bool halo = p.mode == 1 && !stem && C == 64 && g->N == 64 && bn == 64 && !g->out_f32 &&
+                      g->residual == nullptr && getenv("VTX_GEMM_NO_HALO") == nullptr;
+    // the activation operand of the implicit convs: [NI, H, W, C] NHWC; for the stem view [NI, H + 3, W + 3, 16] whose
+    // "channel" extent is 4 pixels x 16 channels and whose W stride is ONE pixel (overlapping rows, legal for TMA)
+    const uint64_t xdims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)(stem ? H + 3 : H), (uint64_t)NI};
+    const uint64_t xstr[3] = {(uint64_t)(stem ? 16 : C), stem ? (uint64_t)(W + 3) * 16 : (uint64_t)W * C,
+                              stem ? (uint64_t)(H + 3) * (W + 3) * 16 : (uint64_t)H * W * C};
     int bw, bh, bnn;
     choose_box(H, W, p.mode == 1 ? 128 : 64, &bw, &bh, &bnn);
     if (halo) {
@@ -855,13 +889,16 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
       if ((rc = make_tmap(&tmB, g->B, 4, ad, as_, xbox)) != VTX_OK) return rc;
     } else if (p.mode & 1) {
       // A: activation [NI,H,W,C]; M = NI*H*W (tiled as boxes); K = 9*C; B: weights [N, 9*C] K-major
-      if (g->M != NI * H * W || g->K != 9 * C) return set_error(VTX_EINVAL, "vtx_gemm: conv fprop shape mismatch");
+      if (g->M != NI * H * W || g->K != ntaps * C) return set_error(VTX_EINVAL, "vtx_gemm: conv fprop shape mismatch");
+#ifdef VTX_GEMM_X
+      // rows of a partial box below the image are real rows of the padded view: they would reach the BN statistics
+      if (stem && g->stats && (W % bw != 0 || H % bh != 0))
+        return set_error(VTX_EUNSUPPORTED, "vtx_gemm_x: conv_mode 5 with stats needs an output size tiled exactly by %dx%d", bw, bh);
+#endif
       p.m_tiles = p.tiles_w * p.tiles_h * tiles_n;
-      p.kb_total = halo ? 1 : 9 * p.cpb;
-      uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)NI};
-      uint64_t str[3] = {(uint64_t)C, (uint64_t)W * C, (uint64_t)H * W * C};
+      p.kb_total = halo ? 1 : ntaps * p.cpb;
       uint32_t box[4] = {64, (uint32_t)(halo ? p.halo_w : bw), (uint32_t)(halo ? kHaloH : bh), (uint32_t)bnn};
-      if ((rc = make_tmap(&tmA, g->A, 4, dims, str, box)) != VTX_OK) return rc;
+      if ((rc = make_tmap(&tmA, g->A, 4, xdims, xstr, box)) != VTX_OK) return rc;
       uint64_t bd[2] = {(uint64_t)g->K, (uint64_t)g->N};
       uint64_t bs[1] = {(uint64_t)g->ldb};
       uint32_t bb[2] = {64, (uint32_t)bn};
@@ -869,7 +906,7 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
     } else {
       // wgrad: D[M = Cout, N = 9*C] += sum over positions dy[pos, Cout] * x_shift[pos, C]
       //   A = dy [NI,H,W,Cout] (lda = Cout), B = x [NI,H,W,C]
-      if (g->N != 9 * C) return set_error(VTX_EINVAL, "vtx_gemm: conv wgrad shape mismatch");
+      if (g->N != ntaps * C) return set_error(VTX_EINVAL, "vtx_gemm: conv wgrad shape mismatch");
       const int Cout = g->M;
       if (Cout % 64 != 0) return set_error(VTX_EINVAL, "vtx_gemm: conv wgrad needs Cout %% 64 == 0");
       p.m_tiles = (Cout + kBM - 1) / kBM;
@@ -878,9 +915,7 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
       uint64_t as[3] = {(uint64_t)Cout, (uint64_t)W * Cout, (uint64_t)H * W * Cout};
       uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bh, (uint32_t)bnn};
       if ((rc = make_tmap(&tmA, g->A, 4, ad, as, box)) != VTX_OK) return rc;
-      uint64_t bd[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)NI};
-      uint64_t bs[3] = {(uint64_t)C, (uint64_t)W * C, (uint64_t)H * W * C};
-      if ((rc = make_tmap(&tmB, g->B, 4, bd, bs, box)) != VTX_OK) return rc;
+      if ((rc = make_tmap(&tmB, g->B, 4, xdims, xstr, box)) != VTX_OK) return rc;
     }
   }
   p.k_splits = split_k;

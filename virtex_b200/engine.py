@@ -22,6 +22,7 @@ import torch
 from torch import nn
 
 from . import ops
+from . import experimental as X
 from .ops import call, gemm, _p, _stream
 
 BF16, F32 = torch.bfloat16, torch.float32
@@ -145,6 +146,7 @@ class Engine:
         self._packed: Dict[str, torch.Tensor] = {}
         self._tape = None
         self._weights_fresh = False
+        self._x_stem = X.enabled("stem_s2d")  # opt-in experimental stem path (virtex_b200/experimental.py)
         self._build_backbone_plan()
 
     # ------------------------------------------------------------------------------------------------ parameters
@@ -179,6 +181,9 @@ class Engine:
             w = self.P("visual.cnn.conv1.weight")
             pk = self._pack_buf("visual.cnn.conv1.weight", (64, 160))
             call("vtx_conv_w_pack", w.data_ptr(), pk.data_ptr(), 64, 3, 7, 7, 160, s)
+            if self._x_stem:
+                px = self._pack_buf("visual.cnn.conv1.weight#s2d", (64, 256))
+                X.call("vtx_x_stem_w_pack", w.data_ptr(), px.data_ptr(), 64, s)
             for name, blk in self.blocks:
                 w = self.P(name + ".conv2.weight")
                 planes = w.shape[0]
@@ -246,17 +251,25 @@ class Engine:
         # ---- stem: im2col -> GEMM(+stats) -> BN finalize -> BN+ReLU+maxpool
         Ho, Wo = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
         M0 = B * Ho * Wo
-        cols = ws.get("stem.cols", (M0, 160), BF16)
-        call("vtx_stem_im2col", image.data_ptr(), cols.data_ptr(), B, H, W, 160, s)
         y0 = ws.get("stem.y", (M0, 64), BF16)
         st = self._slab_take(128) if training else None
-        gemm(cols, self._packed["visual.cnn.conv1.weight"], y0, M0, 64, 160, stats=st)
+        cols = s2d = None
+        if self._x_stem and H % 2 == 0 and W % 4 == 0 and Ho % 8 == 0 and Wo % 16 == 0:  # boxes tile the output exactly
+            # EXPERIMENTAL (VTX_EXPERIMENTAL=stem_s2d): 4-tap implicit GEMM over the space-to-depth view of the image
+            s2d = ws.get("stem.s2d", (B, H // 2 + 3, W // 2 + 3, 16), BF16)
+            X.call("vtx_x_stem_s2d", image.data_ptr(), s2d.data_ptr(), B, H, W, s)
+            X.gemm(s2d, self._packed["visual.cnn.conv1.weight#s2d"], y0, M0, 64, 256, lda=64, ldb=256, stats=st,
+                   conv=(B, Ho, Wo, 64), conv_mode=5)
+        else:
+            cols = ws.get("stem.cols", (M0, 160), BF16)
+            call("vtx_stem_im2col", image.data_ptr(), cols.data_ptr(), B, H, W, 160, s)
+            gemm(cols, self._packed["visual.cnn.conv1.weight"], y0, M0, 64, 160, stats=st)
         bnp0 = self._bn_fwd(y0, "visual.cnn.bn1", M0, 64, training, st)
         Hp, Wp = (Ho - 1) // 2 + 1, (Wo - 1) // 2 + 1
         x = ws.get("stem.pool", (B * Hp * Wp, 64), BF16)
         idx = ws.get("stem.idx", (B * Hp * Wp, 64), torch.uint8)
         call("vtx_bn_relu_maxpool", y0.data_ptr(), bnp0.data_ptr(), x.data_ptr(), idx.data_ptr(), B, Ho, Wo, 64, s)
-        tape["stem"] = dict(cols=cols, y=y0, bnp=bnp0, idx=idx, Ho=Ho, Wo=Wo, Hp=Hp, Wp=Wp, M=M0)
+        tape["stem"] = dict(cols=cols, s2d=s2d, y=y0, bnp=bnp0, idx=idx, Ho=Ho, Wo=Wo, Hp=Hp, Wp=Wp, M=M0)
         Hc, Wc, Cin = Hp, Wp, 64
         # ---- bottleneck blocks
         for name, blk in self.blocks:
@@ -438,6 +451,13 @@ class Engine:
         call("vtx_maxpool_bwd", dOut.data_ptr(), st["idx"].data_ptr(), da0.data_ptr(), B, st["Ho"], st["Wo"], 64, s)
         dy0 = ws.get("bwd.dy0", (M0, 64), BF16)
         self._bn_bwd(da0, None, st["y"], st["bnp"], "visual.cnn.bn1", M0, 64, dy0, mask_from_y=1)
+        if st["s2d"] is not None:  # EXPERIMENTAL: implicit wgrad over the space-to-depth view
+            dwx = ws.get("bwd.dwp0x", (64, 256), F32)
+            dwx.zero_()
+            X.gemm(dy0, st["s2d"], dwx, 64, 256, M0, lda=64, ldb=64, atomic=True, out_f32=True,
+                   split_k=ops.split_k_for(1, M0 // 64), conv=(B, st["Ho"], st["Wo"], 64), conv_mode=6)
+            X.call("vtx_x_stem_w_unpack_add", dwx.data_ptr(), self.G("visual.cnn.conv1.weight").data_ptr(), 64, s)
+            return
         dwp0 = ws.get("bwd.dwp0", (64, 160), F32)
         dwp0.zero_()
         self._wgrad(dy0, st["cols"], dwp0, 64, 160, M0)

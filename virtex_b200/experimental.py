@@ -1,0 +1,91 @@
+"""Opt-in experimental kernels (libvirtex_b200_x.so, include/virtex_b200_x.h).
+
+Nothing here is on the default path.  A feature is used only when the environment variable `VTX_EXPERIMENTAL` names it
+(comma separated, or `all`); its GPU tests are skipped otherwise.  Features:
+
+  stem_s2d   the 7x7/2 stem conv as a 4-tap implicit GEMM over a space-to-depth view of the image (vtx_gemm_x
+             conv_mode 5 / 6) instead of im2col + GEMM: ~2 GB less HBM traffic per step and no 1 GB im2col buffer.
+
+Validation procedure on a B200: `VTX_EXPERIMENTAL=all python -m pytest tests -m gpu -q` and
+`VTX_EXPERIMENTAL=all python bench.py`; then move the kernels into the main library.
+"""
+import ctypes
+import os
+
+import torch
+
+from . import lib as L
+from . import ops
+
+FEATURES = ("stem_s2d",)
+_P, _I = ctypes.c_void_p, ctypes.c_int
+_PROTOS = {
+    "vtx_gemm_x": [_P, _P],
+    "vtx_x_stem_s2d": [_P, _P, _I, _I, _I, _P],
+    "vtx_x_stem_w_pack": [_P, _P, _I, _P],
+    "vtx_x_stem_w_unpack_add": [_P, _P, _I, _P],
+}
+_lib = None
+
+
+def enabled(feature: str) -> bool:
+    assert feature in FEATURES, feature
+    v = os.environ.get("VTX_EXPERIMENTAL", "")
+    return v == "all" or feature in [t.strip() for t in v.split(",")]
+
+
+def any_enabled() -> bool:
+    return any(enabled(f) for f in FEATURES)
+
+
+def lib_path() -> str:
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libvirtex_b200_x.so")
+
+
+def load():
+    global _lib
+    if _lib is None:
+        path = lib_path()
+        if not os.path.exists(path):
+            raise L.VtxError(f"{path} is missing: run `python -m virtex_b200.build`")
+        lib = ctypes.CDLL(path)
+        for name, argtypes in _PROTOS.items():
+            fn = getattr(lib, name)
+            fn.argtypes, fn.restype = argtypes, ctypes.c_int
+        lib.vtx_last_error.restype = ctypes.c_char_p
+        _lib = lib
+    return _lib
+
+
+def exported_symbols():
+    return sorted(_PROTOS)
+
+
+def call(name, *args):
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise L.VtxError(f"{name} failed ({rc}): {lib.vtx_last_error().decode()}")
+    ops.launch_count += 1
+
+
+_gemm_struct = L.VtxGemm()
+
+
+def gemm(A, B, D, M, N, K, *, lda, ldb, ldd=None, stats=None, atomic=False, split_k=1, conv=None, conv_mode=0,
+         out_f32=None):
+    """vtx_gemm_x: same contract as ops.gemm plus conv_mode 5 / 6 (stem conv over the space-to-depth view)."""
+    g = _gemm_struct
+    g.A, g.B, g.D = A.data_ptr(), B.data_ptr(), D.data_ptr()
+    g.bias, g.residual, g.stats = 0, 0, (0 if stats is None else stats.data_ptr())
+    g.lda, g.ldb = lda, ldb
+    g.ldd = D.stride(0) if ldd is None else ldd
+    g.ldr = 0
+    g.M, g.N, g.K = M, N, K
+    g.a_mn = g.b_mn = 0
+    g.out_f32 = int(D.dtype == torch.float32) if out_f32 is None else int(out_f32)
+    g.atomic, g.act, g.split_k, g.tile_n = int(atomic), 0, split_k, 0
+    g.alpha = 1.0
+    g.conv_n, g.conv_h, g.conv_w, g.conv_c = conv if conv is not None else (0, 0, 0, 0)
+    g.conv_mode = conv_mode
+    call("vtx_gemm_x", ctypes.addressof(g), ops._stream())
