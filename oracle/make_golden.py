@@ -25,6 +25,10 @@ CASES = {
     "r50_l2_h256_pre_b3_ragged": (dict(hidden=256, layers=2, heads=4, ffn=512, norm_first=True),
                                   dict(batch_size=3, seed=1, ragged=True), 1),
     "r50_l1_h128_post_b4_ragged": (dict(hidden=128, layers=1, heads=2, ffn=256), dict(batch_size=4, seed=2, ragged=True), 2),
+    # the architectures of BASELINE.json configs #4 / #5 (C4 = R50-L4-H1024, C5 = R101-L1-H2048)
+    "r50_l4_h1024_post_b2_ragged": (dict(layers=4), dict(batch_size=2, seed=3, ragged=True), 3),
+    "r101_l1_h2048_post_b2": (dict(backbone="resnet101", hidden=2048, heads=32, ffn=8192),
+                              dict(batch_size=2, seed=4, ragged=False), 4),
 }
 
 

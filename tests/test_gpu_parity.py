@@ -666,3 +666,72 @@ def test_experimental_stem_space_to_depth_conv(N, H, W):
     gref = torch.nn.grad.conv2d_weight(x.bfloat16().float(), (64, 3, 7, 7), dy.float().permute(0, 3, 1, 2), stride=2,
                                        padding=3)
     assert rel(grad, 1.0 + gref) < 1e-4
+
+
+# ---------------------------------------------------------------- written after round 1's GPU budget ran out (opt-in)
+def _need_unverified():
+    """Tests added after the last GPU run of round 1: they exercise validated kernels on new shapes, but their
+    tolerances have not been seen to pass on hardware yet.  Run with VTX_RUN_UNVERIFIED=1, then drop this gate."""
+    import os
+    _need_cuda()
+    if os.environ.get("VTX_RUN_UNVERIFIED", "") != "1":
+        pytest.skip("not yet run on hardware (set VTX_RUN_UNVERIFIED=1)")
+
+
+@pytest.mark.parametrize("spec_kw,B,ragged", [
+    (dict(layers=4), 2, True),                                              # BASELINE.json config #4: R50-L4-H1024
+    (dict(backbone="resnet101", hidden=2048, heads=32, ffn=8192), 2, False),  # config #5: R101-L1-H2048
+])
+def test_baseline_config_architectures_vs_oracle(spec_kw, B, ragged):
+    _need_unverified()
+    spec = O.Spec(**spec_kw)
+    state = O.synth_state(spec, 12, bn3_gain=0.25)
+    model = build_model(spec, state)
+    model.train()
+    batch = O.synth_batch(B, seed=8, ragged=ragged)
+    out = model(to_cuda(batch))
+    ref, grads, _ = O.loss_and_grads(state, batch, spec)
+    assert abs(out["loss"].item() - ref["loss"].item()) < 1e-3 * ref["loss"].item(), (out["loss"].item(), ref["loss"].item())
+    out["loss"].backward()
+    named = dict(model.named_parameters())
+    bad = []
+    for name, gref in grads.items():
+        if name.startswith("visual."):
+            continue
+        r, c = rel(named[name].grad, gref), cos(named[name].grad, gref)
+        if not (c > 0.998 and r < 5e-2):
+            bad.append((name, r, c))
+    assert not bad, bad
+
+
+def test_trainer_checkpoint_resume_matches_uninterrupted_run(tmp_path):
+    """3 steps -> CheckpointManager.step -> fresh model + Trainer -> load -> 3 more steps == 6 uninterrupted steps
+    (Lookahead off: the reference does not serialise its slow weights either)."""
+    _need_unverified()
+    from virtex_b200.checkpointing import CheckpointManager
+    from virtex_b200.config import Config
+    from virtex_b200.factories import PretrainingModelFactory
+    from virtex_b200.trainer import Trainer
+    over = ["MODEL.TEXTUAL.NAME", "transdec_postnorm::L1_H128_A2_F256", "MODEL.TEXTUAL.DROPOUT", 0.0,
+            "OPTIM.WARMUP_STEPS", 2, "OPTIM.NUM_ITERATIONS", 20, "OPTIM.BATCH_SIZE", 2, "OPTIM.CNN_LR", 0.005,
+            "OPTIM.LOOKAHEAD.USE", False]
+    cfg = Config(None, over)
+    batch = to_cuda(O.synth_batch(2, seed=9, ragged=True))
+
+    def fresh():
+        torch.manual_seed(3)
+        m = PretrainingModelFactory.from_config(cfg).cuda().train()
+        return m, Trainer(m, cfg)
+
+    m_a, tr_a = fresh()
+    losses_a = [tr_a.step(batch).sum().item() for _ in range(6)]
+    m_b, tr_b = fresh()
+    losses_b = [tr_b.step(batch).sum().item() for _ in range(3)]
+    CheckpointManager(str(tmp_path), model=m_b, optimizer=tr_b.optimizer, scheduler=tr_b.scheduler).step(3)
+    m_c, tr_c = fresh()
+    mgr = CheckpointManager(str(tmp_path), model=m_c, optimizer=tr_c.optimizer, scheduler=tr_c.scheduler)
+    assert mgr.load(str(tmp_path / "checkpoint_3.pth")) == 3 and tr_c.iteration == 3 and tr_c.momentum_ready
+    tr_c.engine.mark_weights_dirty()
+    losses_b += [tr_c.step(batch).sum().item() for _ in range(3)]
+    for a, b in zip(losses_a, losses_b):
+        assert abs(a - b) < 2e-3 * abs(a), (losses_a, losses_b)

@@ -7,7 +7,8 @@ import torch
 
 from oracle import virtex_oracle as O
 
-CASES = ["r50_l1_h1024_post_b2", "r50_l2_h256_pre_b3_ragged", "r50_l1_h128_post_b4_ragged"]
+CASES = ["r50_l1_h1024_post_b2", "r50_l2_h256_pre_b3_ragged", "r50_l1_h128_post_b4_ragged",
+         "r50_l4_h1024_post_b2_ragged", "r101_l1_h2048_post_b2"]  # the last two: BASELINE.json configs #4 / #5
 
 
 def _load(golden_dir, name):
