@@ -263,3 +263,11 @@ def test_experimental_library_exports_and_is_off_by_default(monkeypatch):
     assert X.enabled("stem_s2d")
     monkeypatch.setenv("VTX_EXPERIMENTAL", "all")
     assert X.enabled("stem_s2d")
+
+
+def test_pdl_library_exports_the_same_abi():
+    from virtex_b200 import lib as L, ops
+    assert os.path.exists(L.LIB_PDL_PATH)
+    pdl = ctypes.CDLL(L.LIB_PDL_PATH)
+    for name in ops.exported_symbols():
+        assert hasattr(pdl, name), name

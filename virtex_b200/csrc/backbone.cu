@@ -24,6 +24,7 @@ static inline int grid_for(long long work_items, int threads, int per_sm = 16) {
 // with coalesced float4 loads, then the ldc-wide column rows are written as coalesced 16-byte vectors.
 __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ cols,
                                                          int N, int H, int W, int Ho, int Wo, int ldc) {
+  VTX_PDL_TRIGGER();
   extern __shared__ float tile[];  // [3][7][Wp], Wp = W + 8: 4 zero columns on each side (left pad 3 -> x offset 4)
   __shared__ int lut[160];         // k -> (c*7 + kh)*Wp + kw  or -1
   const int Wp = W + 8;
@@ -68,6 +69,7 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
 // x bf16 NHWC [N,H,W,C] -> cols [N*Ho*Wo, 9*C], k = (kh*3+kw)*C + c, pad 1, given stride.
 __global__ void im2col3x3_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ cols, int N, int H,
                                  int W, int C, int Ho, int Wo, int stride) {
+  VTX_PDL_TRIGGER();
   const int cg = C / 8;
   const long long total = (long long)N * Ho * Wo * 9 * cg;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -90,6 +92,7 @@ __global__ void im2col3x3_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloa
 // dcols [N*Ho*Wo, 9*C] -> dx [N,H,W,C]  (gather form: every input pixel sums the taps that touched it)
 __global__ void col2im3x3_kernel(const __nv_bfloat16* __restrict__ dcols, __nv_bfloat16* __restrict__ dx, int N, int H,
                                  int W, int C, int Ho, int Wo, int stride) {
+  VTX_PDL_TRIGGER();
   const int cg = C / 8;
   const long long total = (long long)N * H * W * cg;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -128,6 +131,7 @@ __global__ void col2im3x3_kernel(const __nv_bfloat16* __restrict__ dcols, __nv_b
 // xs[n,ho,wo,:] = x[n,ho*s,wo*s,:]
 __global__ void subsample_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ xs, int N, int H,
                                  int W, int C, int Ho, int Wo, int stride) {
+  VTX_PDL_TRIGGER();
   const int cg = C / 8;
   const long long total = (long long)N * Ho * Wo * cg;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -144,6 +148,7 @@ __global__ void subsample_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloa
 // dx[n,ho*s,wo*s,:] += dxs[n,ho,wo,:]
 __global__ void upsample_add_kernel(const __nv_bfloat16* __restrict__ dxs, __nv_bfloat16* __restrict__ dx, int N, int H,
                                     int W, int C, int Ho, int Wo, int stride) {
+  VTX_PDL_TRIGGER();
   const int cg = C / 8;
   const long long total = (long long)N * Ho * Wo * cg;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -170,6 +175,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, float count,
                                    const float* __restrict__ beta, float* __restrict__ rmean, float* __restrict__ rvar,
                                    long long* __restrict__ nbt, float momentum, float eps, int training,
                                    float* __restrict__ bnp, int C) {
+  VTX_PDL_TRIGGER();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c == 0 && training && nbt != nullptr) *nbt += 1;
   if (c >= C) return;
@@ -211,6 +217,7 @@ template <bool kFold>
 __global__ void __launch_bounds__(256, 2) bn_act_kernel(const __nv_bfloat16* __restrict__ y, float* __restrict__ bnp,
                               const __nv_bfloat16* __restrict__ res, const float* __restrict__ bnp_res,
                               __nv_bfloat16* __restrict__ out, long long M, int C, int relu, const BnFwdFold f) {
+  VTX_PDL_TRIGGER();
   const int cg = C / 8;
   const long long total = M * cg;
   // blockDim.x (256) is a multiple of cg, so a thread's 8-channel group never changes across the grid-stride loop:
@@ -289,6 +296,7 @@ __global__ void __launch_bounds__(256, 2) bn_act_kernel(const __nv_bfloat16* __r
 __global__ void bn_relu_maxpool_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ bnp,
                                        __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ idx, int N, int H, int W,
                                        int C, int Ho, int Wo) {
+  VTX_PDL_TRIGGER();
   const int cg = C / 8;
   const long long total = (long long)N * Ho * Wo * cg;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -336,6 +344,7 @@ __global__ void bn_relu_maxpool_kernel(const __nv_bfloat16* __restrict__ y, cons
 // da[n,h,w,:] = sum over pooled windows (ph,pw) whose argmax slot points at (h,w) of dpool[n,ph,pw,:]
 __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dpool, const uint8_t* __restrict__ idx,
                                    __nv_bfloat16* __restrict__ da, int N, int H, int W, int C, int Ho, int Wo) {
+  VTX_PDL_TRIGGER();
   const int cg = C / 8;
   const long long total = (long long)N * H * W * cg;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -383,6 +392,7 @@ __global__ void __launch_bounds__(256, kTwo ? 1 : 2) bn_bwd_reduce_kernel(const 
                                      const __nv_bfloat16* __restrict__ y2, const float* __restrict__ bnp2,
                                      float* __restrict__ sums, float* __restrict__ sums2, long long M, int C,
                                      int mask_from_y) {
+  VTX_PDL_TRIGGER();
   extern __shared__ float red[];  // [rows_par][C][2 or 4]
   const int cg = C / 8;
   const int rows_par = blockDim.x / cg;  // rows handled in parallel by one CTA
@@ -483,6 +493,7 @@ __global__ void __launch_bounds__(256, kTwo ? 1 : 2) bn_bwd_reduce_kernel(const 
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ sums, const float* __restrict__ bnp, float count,
                                        float* __restrict__ coef, float* __restrict__ dgamma, float* __restrict__ dbeta,
                                        int C) {
+  VTX_PDL_TRIGGER();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float s1 = sums[c], s2 = sums[C + c];
@@ -513,6 +524,7 @@ __global__ void __launch_bounds__(256, kTwo ? 1 : 2) bn_bwd_apply_kernel(const _
                                     const float* __restrict__ coef2, __nv_bfloat16* __restrict__ dy2,
                                     __nv_bfloat16* __restrict__ dz_out, long long M, int C, int mask_from_y,
                                     const BnBwdFold f) {
+  VTX_PDL_TRIGGER();
   const int cg = C / 8;
   const long long total = M * cg;
   const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -612,6 +624,7 @@ __global__ void __launch_bounds__(256, kTwo ? 1 : 2) bn_bwd_apply_kernel(const _
 // fp32 OIHW [O,I,KH,KW] -> bf16 [O, ldk] with k = (kh*KW + kw)*I + i   (columns >= KH*KW*I zero)
 __global__ void conv_w_pack_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int O, int I, int KH,
                                    int KW, int ldk) {
+  VTX_PDL_TRIGGER();
   const long long total = (long long)O * ldk;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
     const int k = (int)(t % ldk);
@@ -627,6 +640,7 @@ __global__ void conv_w_pack_kernel(const float* __restrict__ w, __nv_bfloat16* _
 }
 // fp32 OIHW [O,I,3,3] -> bf16 [I, 9*O] with k = ((2-kh)*3 + (2-kw))*O + o   (flipped + transposed: dgrad weights)
 __global__ void conv_w_pack_dgrad_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int O, int I) {
+  VTX_PDL_TRIGGER();
   const long long total = (long long)I * 9 * O;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
     const int o = (int)(t % O);
@@ -639,6 +653,7 @@ __global__ void conv_w_pack_dgrad_kernel(const float* __restrict__ w, __nv_bfloa
 // grad OIHW += dwp [O, ldk] (k = tap*I + i)
 __global__ void conv_w_unpack_add_kernel(const float* __restrict__ dwp, float* __restrict__ grad, int O, int I, int KH,
                                          int KW, int ldk) {
+  VTX_PDL_TRIGGER();
   const long long total = (long long)O * I * KH * KW;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
     const int tap = (int)(t % (KH * KW));
@@ -650,6 +665,7 @@ __global__ void conv_w_unpack_add_kernel(const float* __restrict__ dwp, float* _
 // grad OIHW += dwt [(tap, i), O]   (transposed layout produced by the halo-reuse wgrad, conv_mode 4)
 __global__ void conv_w_unpack_add_t_kernel(const float* __restrict__ dwt, float* __restrict__ grad, int O, int I, int KH,
                                            int KW) {
+  VTX_PDL_TRIGGER();
   const long long total = (long long)O * I * KH * KW;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
     const int tap = (int)(t % (KH * KW));
@@ -659,6 +675,7 @@ __global__ void conv_w_unpack_add_t_kernel(const float* __restrict__ dwt, float*
   }
 }
 __global__ void cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
+  VTX_PDL_TRIGGER();
   const long long n4 = n / 4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const float4 v = reinterpret_cast<const float4*>(in)[i];
@@ -674,6 +691,7 @@ __global__ void cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __
 // NHWC bf16 [N,H,W,C] -> NCHW fp32 (the reference-shaped `visual_features` handed back to callers)
 __global__ void nhwc_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, int N, int HW,
                                         int C) {
+  VTX_PDL_TRIGGER();
   const long long total = (long long)N * HW * C;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
     const int p = (int)(t % HW);

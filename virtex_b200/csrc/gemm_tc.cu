@@ -170,6 +170,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR,
                const GemmKParams p) {
+  VTX_PDL_TRIGGER();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(base);
@@ -217,6 +218,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  VTX_PDL_WAIT();  // (PDL build) everything above overlapped the previous kernel's tail; its results are visible from here
 
   const uint32_t b_bytes = (uint32_t)p.bn * kBK * 2;
 
@@ -984,7 +986,25 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
   const long total = (long)p.m_tiles * p.n_tiles * p.k_splits;
   const int sms = vtx_num_sms();
   const int grid = (int)(total < sms ? total : sms);
+#ifdef VTX_PDL
+  {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmemTotal;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel, tmA, tmB, tmD, tmR, p);
+    if (le != cudaSuccess) return set_error(VTX_ECUDA, "gemm_tc_kernel PDL launch: %s", cudaGetErrorString(le));
+  }
+#else
   gemm_tc_kernel<<<grid, kThreads, kSmemTotal, stream>>>(tmA, tmB, tmD, tmR, p);
+#endif
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(VTX_ECUDA, "gemm_tc_kernel launch: %s", cudaGetErrorString(e));
   return VTX_OK;

@@ -37,6 +37,7 @@ __global__ void embed_fwd_kernel(const long long* __restrict__ tokens, const flo
                                  const float* __restrict__ beta, float* __restrict__ z, float* __restrict__ stats,
                                  float* __restrict__ out, __nv_bfloat16* __restrict__ out_bf, int M, int T, int H,
                                  int pad, float eps, float p, const uint64_t* seed_ptr, uint32_t site) {
+  VTX_PDL_TRIGGER();
   const uint64_t seed = seed_ptr ? *seed_ptr : 0ull;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
@@ -82,6 +83,7 @@ __global__ void embed_bwd_kernel(const float* __restrict__ dy_a, const __nv_bflo
                                  float* __restrict__ d_words, float* __restrict__ d_pos, float* __restrict__ d_gamma,
                                  float* __restrict__ d_beta, int M, int T, int H, int pad, float p, const uint64_t* seed_ptr,
                                  uint32_t site) {
+  VTX_PDL_TRIGGER();
   const uint64_t seed = seed_ptr ? *seed_ptr : 0ull;
   extern __shared__ float acc[];  // [2][H] : dgamma, dbeta partials of this CTA
   for (int i = threadIdx.x; i < 2 * H; i += blockDim.x) acc[i] = 0.f;
@@ -133,6 +135,7 @@ __global__ void add_ln_fwd_kernel(const float* __restrict__ res, const __nv_bflo
                                   float* __restrict__ z, float* __restrict__ stats, float* __restrict__ out,
                                   __nv_bfloat16* __restrict__ out_bf, int M, int H, float eps, float p, const uint64_t* seed_ptr,
                                   uint32_t site, int ln) {
+  VTX_PDL_TRIGGER();
   const uint64_t seed = seed_ptr ? *seed_ptr : 0ull;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
@@ -193,6 +196,7 @@ __global__ void ln_bwd_kernel(const float* __restrict__ dy_a, const __nv_bfloat1
                               float* __restrict__ d_res, __nv_bfloat16* __restrict__ d_branch,
                               float* __restrict__ d_gamma, float* __restrict__ d_beta, int M, int H, float p,
                               const uint64_t* seed_ptr, uint32_t site, int ln) {
+  VTX_PDL_TRIGGER();
   const uint64_t seed = seed_ptr ? *seed_ptr : 0ull;
   extern __shared__ float acc[];  // [warps][2][H] per-warp partial dgamma / dbeta (no atomics in the row loop)
   const int lane = threadIdx.x & 31;
@@ -371,6 +375,7 @@ constexpr int kAttnFwdSmemPerWarp = (32 + 64 + 64) * kLd * 2;  // Q, K, V
 
 __global__ void __launch_bounds__(32 * kAttnFwdWarps) attn_fwd_kernel(const AttnArgs a, __nv_bfloat16* __restrict__ out,
                                                                         long long ldo, float* __restrict__ lse) {
+  VTX_PDL_TRIGGER();
   const uint64_t seed = a.seed_ptr ? *a.seed_ptr : 0ull;
   extern __shared__ __align__(16) uint8_t sm_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -498,6 +503,7 @@ __global__ void __launch_bounds__(32 * kAttnBwdWarps) attn_bwd_kernel(const Attn
                                                                         __nv_bfloat16* __restrict__ dq, long long lddq,
                                                                         __nv_bfloat16* __restrict__ dk, long long lddk,
                                                                         __nv_bfloat16* __restrict__ dv, long long lddv) {
+  VTX_PDL_TRIGGER();
   const uint64_t seed = a.seed_ptr ? *a.seed_ptr : 0ull;
   extern __shared__ __align__(16) uint8_t sm_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -665,6 +671,7 @@ __global__ void __launch_bounds__(32 * kAttnBwdWarps) attn_bwd_kernel(const Attn
 // ------------------------------------------------------------------------------------------------ GELU + dropout
 __global__ void gelu_dropout_fwd_kernel(const __nv_bfloat16* __restrict__ u, __nv_bfloat16* __restrict__ h,
                                         long long n8, float p, const uint64_t* seed_ptr, uint32_t site) {
+  VTX_PDL_TRIGGER();
   const uint64_t seed = seed_ptr ? *seed_ptr : 0ull;
   const float inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
@@ -683,6 +690,7 @@ __global__ void gelu_dropout_fwd_kernel(const __nv_bfloat16* __restrict__ u, __n
 __global__ void gelu_dropout_bwd_kernel(const __nv_bfloat16* __restrict__ dh, const __nv_bfloat16* __restrict__ u,
                                         __nv_bfloat16* __restrict__ du, long long n8, float p, const uint64_t* seed_ptr,
                                         uint32_t site) {
+  VTX_PDL_TRIGGER();
   const uint64_t seed = seed_ptr ? *seed_ptr : 0ull;
   const float inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
@@ -702,6 +710,7 @@ __global__ void gelu_dropout_bwd_kernel(const __nv_bfloat16* __restrict__ dh, co
 // ------------------------------------------------------------------------------------------------ cross entropy
 // counts[0] = number of targets tokens[b, t>=1] != pad
 __global__ void count_valid_kernel(const long long* __restrict__ tokens, int B, int T, int pad, float* __restrict__ count) {
+  VTX_PDL_TRIGGER();
   float c = 0.f;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B * T; i += gridDim.x * blockDim.x)
     if ((i % T) >= 1 && tokens[i] != pad) c += 1.f;
@@ -713,6 +722,7 @@ __global__ void count_valid_kernel(const long long* __restrict__ tokens, int B, 
 // == pad.  loss += nll / count;  if write_grad: logits row overwritten by dlogits = (softmax - onehot)/count (or 0).
 __global__ void ce_kernel(__nv_bfloat16* __restrict__ logits, long long ldl, const long long* __restrict__ tokens, int T,
                           int V, int pad, const float* __restrict__ count, float* __restrict__ loss, int write_grad) {
+  VTX_PDL_TRIGGER();
   __shared__ float red[32];
   __shared__ float bcast;
   const int row = blockIdx.x;
@@ -786,6 +796,7 @@ __global__ void ce_kernel(__nv_bfloat16* __restrict__ logits, long long ldl, con
 // out[n] += sum_m X[m,n]    X bf16 [M, ld]
 __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ X, long long ld, int M, int N, float* __restrict__ out,
                               int rows_per_block) {
+  VTX_PDL_TRIGGER();
   const int g = blockIdx.y * blockDim.x + threadIdx.x;  // 8-column group
   if (g * 8 >= N) return;
   const int m0 = blockIdx.x * rows_per_block;
@@ -819,6 +830,7 @@ __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ X, long long ld,
 
 // first-index argmax of each fp32 row
 __global__ void argmax_rows_kernel(const float* __restrict__ X, long long ld, int N, long long* __restrict__ out) {
+  VTX_PDL_TRIGGER();
   __shared__ float bv[32];
   __shared__ int bi[32];
   const float* x = X + (long long)blockIdx.x * ld;

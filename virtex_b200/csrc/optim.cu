@@ -9,6 +9,7 @@
 namespace vtx {
 
 __global__ void sumsq_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
+  VTX_PDL_TRIGGER();
   float acc = 0.f;
   const long long n4 = n / 4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -30,6 +31,7 @@ __global__ void sumsq_kernel(const float* __restrict__ x, long long n, float* __
 
 // ctl[0] = grad scale applied in the update = (1/world) * min(1, max_norm / (norm + 1e-6)),  ctl[1] = norm of the mean grad
 __global__ void clip_coef_kernel(const float* __restrict__ sumsq, float inv_world, float max_norm, float* __restrict__ ctl) {
+  VTX_PDL_TRIGGER();
   const float norm = sqrtf(*sumsq) * inv_world;
   float c = max_norm > 0.f ? max_norm / (norm + 1e-6f) : 1.f;
   c = fminf(c, 1.f);
@@ -48,6 +50,7 @@ __global__ void sgd_step_kernel(float* __restrict__ p, const float* __restrict__
                                 float* __restrict__ slow, __nv_bfloat16* __restrict__ p_bf, const Seg* __restrict__ segs,
                                 int nseg, const float* __restrict__ ctl, const float* __restrict__ hyper, float momentum,
                                 float la_alpha) {
+  VTX_PDL_TRIGGER();
   const float gscale = ctl[0];
   const float mult = hyper[0];
   const bool first = hyper[1] != 0.f;

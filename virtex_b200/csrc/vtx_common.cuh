@@ -5,6 +5,18 @@
 #include <stdint.h>
 #include <string.h>
 
+// Programmatic dependent launch -- EXPERIMENTAL, only in the -DVTX_PDL build (libvirtex_b200_pdl.so); both macros are
+// empty in the regular build.  Every kernel signals at its first instruction that dependents may be scheduled; the GEMM
+// (the only kernel launched with the programmatic-serialisation attribute) runs its prologue -- barrier init, TMEM
+// allocation, tensor-map prefetch -- while the previous kernel drains and then waits for it to complete and flush.
+#ifdef VTX_PDL
+#define VTX_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+#define VTX_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+#else
+#define VTX_PDL_TRIGGER() ((void)0)
+#define VTX_PDL_WAIT() ((void)0)
+#endif
+
 namespace vtx {
 // printf-style error recording; returns `code` so call sites can `return set_error(...)`.
 int set_error(int code, const char* fmt, ...);

@@ -6,6 +6,11 @@ Nothing here is on the default path.  A feature is used only when the environmen
   stem_s2d   the 7x7/2 stem conv as a 4-tap implicit GEMM over a space-to-depth view of the image (vtx_gemm_x
              conv_mode 5 / 6) instead of im2col + GEMM: ~2 GB less HBM traffic per step and no 1 GB im2col buffer.
 
+  pdl        programmatic dependent launch: the library compiled with -DVTX_PDL (libvirtex_b200_pdl.so) is loaded
+             instead of libvirtex_b200.so (virtex_b200/lib.py); every kernel triggers its dependents at entry and the
+             GEMM -- launched with the programmatic-serialisation attribute -- overlaps its prologue with the
+             previous kernel's tail, then `griddepcontrol.wait`s.
+
 Validation procedure on a B200: `VTX_EXPERIMENTAL=all python -m pytest tests -m gpu -q` and
 `VTX_EXPERIMENTAL=all python bench.py`; then move the kernels into the main library.
 """
@@ -17,7 +22,7 @@ import torch
 from . import lib as L
 from . import ops
 
-FEATURES = ("stem_s2d",)
+FEATURES = ("stem_s2d", "pdl")
 _P, _I = ctypes.c_void_p, ctypes.c_int
 _PROTOS = {
     "vtx_gemm_x": [_P, _P],
