@@ -148,6 +148,7 @@ def main_reference(args, rank, world):
 # ---------------------------------------------------------------------------------------------------------------- ours
 def main_ours(args, rank, world, local):
     import torch.distributed as dist
+    from virtex_b200 import experimental as X
     from virtex_b200 import ops
     from virtex_b200.config import Config
     from virtex_b200.factories import PretrainingModelFactory
@@ -305,7 +306,8 @@ def main_ours(args, rank, world, local):
                 "config": {"workload": f"bicaptioning R50_L1_H1024 full optimisation step, batch {B} per GPU",
                            "config_file": args.config, "global_batch": B * world, "seq_len": T,
                            "parallelism": f"dp{world}", "dropout": cfg.MODEL.TEXTUAL.DROPOUT,
-                           "l2_policy": "per-step working set (>= 150 MB of inputs, GBs of activations) exceeds the 126 MB L2"},
+                           "l2_policy": "per-step working set (>= 150 MB of inputs, GBs of activations) exceeds the 126 MB L2",
+                           "experimental": [f for f in X.FEATURES if X.enabled(f)]},
                 "loss": round(loss_val, 4), "clocks": clk,
                 "e2e": {"value": round(e2e_value, 1), "unit": "pairs/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": 8, "ms_per_step": round(ms_e2e / args.steps, 3),
