@@ -29,6 +29,10 @@ int vtx_x_stem_w_pack(const float* w, void* wp, int O, void* stream);
 /* grad fp32 [O, 3, 7, 7] += dwp fp32 [O, 256] (same index map) */
 int vtx_x_stem_w_unpack_add(const float* dwp, float* grad, int O, void* stream);
 
+/* Feature `head_x`: this library also exports vtx_ln_bwd and vtx_embed_bwd with the signatures of virtex_b200.h,
+ * implemented by register-accumulating kernels (csrc/head.cu, -DVTX_HEAD_X); virtex_b200/ops.py routes those two
+ * entry points here when the feature is enabled. */
+
 #ifdef __cplusplus
 }
 #endif

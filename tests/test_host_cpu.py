@@ -271,3 +271,15 @@ def test_pdl_library_exports_the_same_abi():
     pdl = ctypes.CDLL(L.LIB_PDL_PATH)
     for name in ops.exported_symbols():
         assert hasattr(pdl, name), name
+
+
+def test_routed_entry_points_default_to_the_main_library(monkeypatch):
+    from virtex_b200 import experimental as X, ops
+    xlib = ctypes.CDLL(X.lib_path())
+    for name, feature in X.ROUTED.items():
+        assert feature in X.FEATURES and name in ops._PROTOS and hasattr(xlib, name)
+    monkeypatch.delenv("VTX_EXPERIMENTAL", raising=False)
+    assert all(X.routed_lib(n) is None for n in X.ROUTED)
+    monkeypatch.setenv("VTX_EXPERIMENTAL", "head_x")
+    assert all(X.routed_lib(n) is not None for n in X.ROUTED)
+    assert X.routed_lib("vtx_gemm") is None

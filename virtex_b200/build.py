@@ -82,6 +82,7 @@ def build(verbose=False, force=False):
     # experimental library: its own sources + the GEMM with runtime tap geometry + its own copy of the error helpers
     jobs += [(os.path.join(CSRC_X, n), (), "") for n in sorted(os.listdir(CSRC_X)) if n.endswith(".cu")]
     jobs += [(os.path.join(CSRC, "gemm_tc.cu"), ("-DVTX_GEMM_X",), "_x")]
+    jobs += [(os.path.join(CSRC, "head.cu"), ("-DVTX_HEAD_X",), "_x")]
     n_x = len(jobs)
     jobs += [(s, ("-DVTX_PDL",), "_pdl") for s in srcs]
     with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:

@@ -293,6 +293,202 @@ __global__ void ln_bwd_kernel(const float* __restrict__ dy_a, const __nv_bfloat1
   }
 }
 
+#ifdef VTX_HEAD_X
+// ------------------------------------------------------------------------------- EXPERIMENTAL variants (head_x)
+// Compiled only into libvirtex_b200_x.so (-DVTX_HEAD_X) and used only when VTX_EXPERIMENTAL names `head_x`; written
+// without hardware access.  Same arithmetic as ln_bwd_kernel / embed_bwd_kernel above, different data movement:
+//   * every lane owns the columns {lane*4 + 128*k}: the upstream gradient and z are read ONCE per row (they were read
+//     twice) and the dgamma / dbeta (/ dposition) partial sums of all rows of a warp stay in REGISTERS; the validated
+//     kernels do two shared-memory read-modify-writes per element, 4-way bank conflicted (ln_bwd) or shared-memory
+//     atomics (embed_bwd);
+//   * embed_bwd: a warp only handles rows of ONE position t, so d_positions gets one atomic per column per warp instead
+//     of one per element (7.8 M atomics on 30 x 1024 addresses), and the word-table scatter uses red.global.add.v4.f32.
+__device__ __forceinline__ void red_add_v4_head(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// loads the 4 upstream-gradient values of columns [i, i+4) of one row: g = dy_a (fp32, optional) + dy_b (bf16, optional)
+__device__ __forceinline__ void load_g4(const float* dy_a, const __nv_bfloat16* dy_b, long long off, float* g) {
+  g[0] = g[1] = g[2] = g[3] = 0.f;
+  if (dy_a) {
+    const float4 t = *reinterpret_cast<const float4*>(dy_a + off);
+    g[0] = t.x; g[1] = t.y; g[2] = t.z; g[3] = t.w;
+  }
+  if (dy_b) {
+    const uint2 u = *reinterpret_cast<const uint2*>(dy_b + off);
+    const float2 b0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+    const float2 b1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+    g[0] += b0.x; g[1] += b0.y; g[2] += b1.x; g[3] += b1.y;
+  }
+}
+
+// cross-warp reduction of per-lane column partials through shared memory, then one atomic per column per CTA
+template <int KB>
+__device__ __forceinline__ void flush_columns(float* smem, const float* part, float* dst, int H) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < KB; ++k)
+    *reinterpret_cast<float4*>(smem + warp * H + lane * 4 + 128 * k) =
+        make_float4(part[4 * k], part[4 * k + 1], part[4 * k + 2], part[4 * k + 3]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < H; i += blockDim.x) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarpsPerBlock; ++w) t += smem[w * H + i];
+    atomicAdd(dst + i, t);
+  }
+}
+
+template <int KB>
+__global__ void __launch_bounds__(32 * kWarpsPerBlock)
+ln_bwd_reg_kernel(const float* __restrict__ dy_a, const __nv_bfloat16* __restrict__ dy_b, const float* __restrict__ z,
+                  const float* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ d_skip,
+                  float* __restrict__ d_res, __nv_bfloat16* __restrict__ d_branch, float* __restrict__ d_gamma,
+                  float* __restrict__ d_beta, int M, float p, const uint64_t* seed_ptr, uint32_t site) {
+  VTX_PDL_TRIGGER();
+  constexpr int H = KB * 128;
+  extern __shared__ float acc[];  // [warps][H] scratch of the final cross-warp reduction
+  const uint64_t seed = seed_ptr ? *seed_ptr : 0ull;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  float dg[KB * 4], db[KB * 4];
+#pragma unroll
+  for (int j = 0; j < KB * 4; ++j) dg[j] = db[j] = 0.f;
+  for (int row = blockIdx.x * kWarpsPerBlock + warp; row < M; row += gridDim.x * kWarpsPerBlock) {
+    const long long base = (long long)row * H;
+    const float mean = stats[2 * row], rstd = stats[2 * row + 1];
+    float g[KB * 4], xh[KB * 4];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < KB; ++k) {
+      const int i = lane * 4 + 128 * k;
+      load_g4(dy_a, dy_b, base + i, g + 4 * k);
+      const float4 zz = *reinterpret_cast<const float4*>(z + base + i);
+      const float4 gm = *reinterpret_cast<const float4*>(gamma + i);
+      xh[4 * k] = (zz.x - mean) * rstd; xh[4 * k + 1] = (zz.y - mean) * rstd;
+      xh[4 * k + 2] = (zz.z - mean) * rstd; xh[4 * k + 3] = (zz.w - mean) * rstd;
+      const float gw[4] = {gm.x, gm.y, gm.z, gm.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        dg[4 * k + j] += g[4 * k + j] * xh[4 * k + j];
+        db[4 * k + j] += g[4 * k + j];
+        const float dxh = g[4 * k + j] * gw[j];
+        s1 += dxh;
+        s2 += dxh * xh[4 * k + j];
+      }
+    }
+    s1 = warp_sum(s1) / H;
+    s2 = warp_sum(s2) / H;
+#pragma unroll
+    for (int k = 0; k < KB; ++k) {
+      const int i = lane * 4 + 128 * k;
+      const float4 gm = *reinterpret_cast<const float4*>(gamma + i);  // L1 hit: same addresses as above
+      const float gw[4] = {gm.x, gm.y, gm.z, gm.w};
+      float dz[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dz[j] = rstd * (g[4 * k + j] * gw[j] - s1 - xh[4 * k + j] * s2);
+      if (d_branch) {
+        float t[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) t[j] = dz[j] * dropout_scale(p, inv_keep, seed, site, (uint64_t)base + i + j);
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(t[0], t[1]), h1 = __floats2bfloat162_rn(t[2], t[3]);
+        uint2 u;
+        u.x = *reinterpret_cast<uint32_t*>(&h0);
+        u.y = *reinterpret_cast<uint32_t*>(&h1);
+        *reinterpret_cast<uint2*>(d_branch + base + i) = u;
+      }
+      if (d_res) {
+        float4 o = make_float4(dz[0], dz[1], dz[2], dz[3]);
+        if (d_skip) {
+          const float4 sk = *reinterpret_cast<const float4*>(d_skip + base + i);
+          o.x += sk.x; o.y += sk.y; o.z += sk.z; o.w += sk.w;
+        }
+        *reinterpret_cast<float4*>(d_res + base + i) = o;
+      }
+    }
+  }
+  flush_columns<KB>(acc, dg, d_gamma, H);
+  flush_columns<KB>(acc, db, d_beta, H);
+}
+
+// warp w handles position t = w % T and the batch entries {w / T, w / T + NC, ...}: rows b*T + t
+template <int KB>
+__global__ void __launch_bounds__(32 * kWarpsPerBlock)
+embed_bwd_reg_kernel(const float* __restrict__ dy_a, const __nv_bfloat16* __restrict__ dy_b,
+                     const long long* __restrict__ tokens, const float* __restrict__ z, const float* __restrict__ stats,
+                     const float* __restrict__ gamma, float* __restrict__ d_words, float* __restrict__ d_pos,
+                     float* __restrict__ d_gamma, float* __restrict__ d_beta, int M, int T, int pad, float p,
+                     const uint64_t* seed_ptr, uint32_t site) {
+  VTX_PDL_TRIGGER();
+  constexpr int H = KB * 128;
+  extern __shared__ float acc[];  // [warps][H]
+  const uint64_t seed = seed_ptr ? *seed_ptr : 0ull;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  const int gw_id = blockIdx.x * kWarpsPerBlock + warp;
+  const int nc = (gridDim.x * kWarpsPerBlock) / T;  // batch chunks (host guarantees >= 1)
+  const int t = gw_id % T, chunk = gw_id / T;
+  const int B = M / T;
+  float dg[KB * 4], db[KB * 4], dp[KB * 4];
+#pragma unroll
+  for (int j = 0; j < KB * 4; ++j) dg[j] = db[j] = dp[j] = 0.f;
+  if (chunk < nc) {
+    for (int b = chunk; b < B; b += nc) {
+      const int row = b * T + t;
+      const long long tok = tokens[row];
+      if (tok == pad) continue;  // zero upstream gradient: contributes nothing anywhere
+      const long long base = (long long)row * H;
+      const float mean = stats[2 * row], rstd = stats[2 * row + 1];
+      float g[KB * 4], xh[KB * 4];
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int k = 0; k < KB; ++k) {
+        const int i = lane * 4 + 128 * k;
+        load_g4(dy_a, dy_b, base + i, g + 4 * k);
+        const float4 zz = *reinterpret_cast<const float4*>(z + base + i);
+        const float4 gm = *reinterpret_cast<const float4*>(gamma + i);
+        const float zv[4] = {zz.x, zz.y, zz.z, zz.w};
+        const float gwv[4] = {gm.x, gm.y, gm.z, gm.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float gj = g[4 * k + j] * dropout_scale(p, inv_keep, seed, site, (uint64_t)base + i + j);
+          const float x = (zv[j] - mean) * rstd;
+          g[4 * k + j] = gj;
+          xh[4 * k + j] = x;
+          dg[4 * k + j] += gj * x;
+          db[4 * k + j] += gj;
+          const float dxh = gj * gwv[j];
+          s1 += dxh;
+          s2 += dxh * x;
+        }
+      }
+      s1 = warp_sum(s1) / H;
+      s2 = warp_sum(s2) / H;
+#pragma unroll
+      for (int k = 0; k < KB; ++k) {
+        const int i = lane * 4 + 128 * k;
+        const float4 gm = *reinterpret_cast<const float4*>(gamma + i);
+        const float gwv[4] = {gm.x, gm.y, gm.z, gm.w};
+        float dz[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          dz[j] = rstd * (g[4 * k + j] * gwv[j] - s1 - xh[4 * k + j] * s2);
+          dp[4 * k + j] += dz[j];
+        }
+        red_add_v4_head(d_words + tok * H + i, dz[0], dz[1], dz[2], dz[3]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < KB; ++k)
+      red_add_v4_head(d_pos + (long long)t * H + lane * 4 + 128 * k, dp[4 * k], dp[4 * k + 1], dp[4 * k + 2],
+                      dp[4 * k + 3]);
+  }
+  flush_columns<KB>(acc, dg, d_gamma, H);
+  flush_columns<KB>(acc, db, d_beta, H);
+}
+#endif  // VTX_HEAD_X
+
 // ------------------------------------------------------------------------------------------------ attention
 // One warp per (batch b, head h); head_dim = 64; Tq <= 32 queries, Tk <= 64 keys.  The five small matrix products
 // (S = Q K^T, O = P V; backward: dP = dO V^T, dQ = dS K, dK = dS^T Q, dV = P^T dO) run on mma.sync.m16n8k16 bf16
@@ -884,6 +1080,25 @@ extern "C" int vtx_embed_bwd(const float* dy_a, const void* dy_b, const int64_t*
   int blocks = (M + kWarpsPerBlock - 1) / kWarpsPerBlock;
   const int cap = vtx_num_sms() * 2;
   if (blocks > cap) blocks = cap;
+#ifdef VTX_HEAD_X
+  if (H % 128 == 0 && H <= 1024 && (H / 128 == 1 || H / 128 == 2 || H / 128 == 4 || H / 128 == 8) && T > 0 && M % T == 0) {
+    int xb = cap;
+    if (xb * kWarpsPerBlock < T) xb = (T + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    const size_t xs = (size_t)kWarpsPerBlock * H * sizeof(float);
+#define VTX_EMB_X(KB)                                                                                                  \
+  embed_bwd_reg_kernel<KB><<<xb, 32 * kWarpsPerBlock, xs, STREAM>>>(dy_a, (const __nv_bfloat16*)dy_b,                   \
+                                                                      (const long long*)tokens, z, stats, gamma, d_words, \
+                                                                      d_pos, d_gamma, d_beta, M, T, pad, p, seed_ptr, site)
+    switch (H / 128) {
+      case 1: VTX_EMB_X(1); break;
+      case 2: VTX_EMB_X(2); break;
+      case 4: VTX_EMB_X(4); break;
+      default: VTX_EMB_X(8); break;
+    }
+#undef VTX_EMB_X
+    return check_launch("embed_bwd_reg");
+  }
+#endif
   embed_bwd_kernel<<<blocks, 32 * kWarpsPerBlock, 2 * H * sizeof(float), STREAM>>>(
       dy_a, (const __nv_bfloat16*)dy_b, (const long long*)tokens, z, stats, gamma, d_words, d_pos, d_gamma, d_beta, M, T,
       H, pad, p, seed_ptr, site);
@@ -905,6 +1120,23 @@ extern "C" int vtx_ln_bwd(const float* dy_a, const void* dy_b, const float* z, c
   int blocks = (M + kWarpsPerBlock - 1) / kWarpsPerBlock;
   const int cap = vtx_num_sms() * 2;
   if (blocks > cap) blocks = cap;
+#ifdef VTX_HEAD_X
+  if (ln && H % 128 == 0 && (H / 128 == 1 || H / 128 == 2 || H / 128 == 4 || H / 128 == 8)) {
+    const size_t xs = (size_t)kWarpsPerBlock * H * sizeof(float);
+#define VTX_LN_X(KB)                                                                                                   \
+  ln_bwd_reg_kernel<KB><<<blocks, 32 * kWarpsPerBlock, xs, STREAM>>>(dy_a, (const __nv_bfloat16*)dy_b, z, stats, gamma,  \
+                                                                     d_skip, d_res, (__nv_bfloat16*)d_branch, d_gamma,   \
+                                                                     d_beta, M, p, seed_ptr, site)
+    switch (H / 128) {
+      case 1: VTX_LN_X(1); break;
+      case 2: VTX_LN_X(2); break;
+      case 4: VTX_LN_X(4); break;
+      default: VTX_LN_X(8); break;
+    }
+#undef VTX_LN_X
+    return check_launch("ln_bwd_reg");
+  }
+#endif
   const size_t ln_smem = ln ? (size_t)kWarpsPerBlock * 2 * H * sizeof(float) : 0;
   static size_t ln_attr = 0;
   if (ln_smem > 48 * 1024 && ln_smem > ln_attr) {

@@ -11,6 +11,9 @@ Nothing here is on the default path.  A feature is used only when the environmen
              GEMM -- launched with the programmatic-serialisation attribute -- overlaps its prologue with the
              previous kernel's tail, then `griddepcontrol.wait`s.
 
+  head_x     register-accumulating LayerNorm / embedding backward kernels (head.cu compiled with -DVTX_HEAD_X): the
+             entry points vtx_ln_bwd / vtx_embed_bwd are routed to libvirtex_b200_x.so.
+
 Validation procedure on a B200: `VTX_EXPERIMENTAL=all python -m pytest tests -m gpu -q` and
 `VTX_EXPERIMENTAL=all python bench.py`; then move the kernels into the main library.
 """
@@ -22,7 +25,10 @@ import torch
 from . import lib as L
 from . import ops
 
-FEATURES = ("stem_s2d", "pdl")
+FEATURES = ("stem_s2d", "pdl", "head_x")
+# entry points of the MAIN ABI that libvirtex_b200_x.so re-implements (same signature); routed there by ops._get when
+# the feature is enabled
+ROUTED = {"vtx_ln_bwd": "head_x", "vtx_embed_bwd": "head_x"}
 _P, _I = ctypes.c_void_p, ctypes.c_int
 _PROTOS = {
     "vtx_gemm_x": [_P, _P],
@@ -64,6 +70,18 @@ def load():
 
 def exported_symbols():
     return sorted(_PROTOS)
+
+
+def routed_lib(name):
+    """The experimental library if entry point `name` is re-implemented there and its feature is enabled, else None."""
+    feature = ROUTED.get(name)
+    if feature is None or not enabled(feature):
+        return None
+    return load()
+
+
+def last_error() -> str:
+    return load().vtx_last_error().decode("utf-8", "replace")
 
 
 def call(name, *args):

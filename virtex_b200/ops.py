@@ -57,7 +57,9 @@ _fn = {}
 def _get(name):
     f = _fn.get(name)
     if f is None:
-        f = getattr(L.load(), name)
+        from . import experimental as X  # opt-in re-implementations of a few entry points (off by default)
+        lib = X.routed_lib(name) or L.load()
+        f = getattr(lib, name)
         f.argtypes = _PROTOS[name]
         f.restype = c_int
         _fn[name] = f
