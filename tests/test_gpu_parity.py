@@ -735,3 +735,57 @@ def test_trainer_checkpoint_resume_matches_uninterrupted_run(tmp_path):
     losses_b += [tr_c.step(batch).sum().item() for _ in range(3)]
     for a, b in zip(losses_a, losses_b):
         assert abs(a - b) < 2e-3 * abs(a), (losses_a, losses_b)
+
+
+@pytest.mark.parametrize("H,p", [(1024, 0.1), (256, 0.0)])
+def test_experimental_head_x_kernels_match_the_validated_ones(H, p):
+    """A/B: the register-accumulating LayerNorm / embedding backward kernels against the validated kernels of the main
+    library on the same inputs (same arithmetic, different summation order)."""
+    X = _need_experimental("head_x")
+    import ctypes
+    from virtex_b200 import lib as L, ops
+    main = ctypes.CDLL(L.LIB_PATH)
+    xlib = X.load()
+    torch.manual_seed(8)
+    dev = "cuda"
+    B, T = 37, 30
+    M = B * T
+    s = torch.cuda.current_stream().cuda_stream
+    dy_a = torch.randn(M, H, device=dev)
+    dy_b = torch.randn(M, H, device=dev).bfloat16()
+    z = torch.randn(M, H, device=dev) * 2 + 0.5
+    stats = torch.stack([z.mean(1), 1.0 / torch.sqrt(z.var(1, unbiased=False) + 1e-5)], 1).contiguous()
+    gamma = torch.rand(H, device=dev) + 0.5
+    d_skip = torch.randn(M, H, device=dev)
+    seed = torch.full((1,), 1234, dtype=torch.int64, device=dev)
+    outs = []
+    for lib in (main, xlib):
+        fn = lib.vtx_ln_bwd
+        fn.argtypes, fn.restype = ops._PROTOS["vtx_ln_bwd"], ctypes.c_int
+        d_res = torch.zeros(M, H, device=dev)
+        d_branch = torch.zeros(M, H, device=dev, dtype=torch.bfloat16)
+        d_gamma, d_beta = torch.zeros(H, device=dev), torch.zeros(H, device=dev)
+        rc = fn(dy_a.data_ptr(), dy_b.data_ptr(), z.data_ptr(), stats.data_ptr(), gamma.data_ptr(), d_skip.data_ptr(),
+                d_res.data_ptr(), d_branch.data_ptr(), d_gamma.data_ptr(), d_beta.data_ptr(), M, H, p, seed.data_ptr(), 7,
+                1, s)
+        assert rc == 0
+        outs.append((d_res, d_branch.float(), d_gamma, d_beta))
+    for a, b in zip(*outs):
+        assert rel(b, a) < 2e-5
+    # embedding backward
+    tokens = torch.randint(4, 500, (B, T), device=dev)
+    tokens[:, -3:] = 0  # padding
+    outs = []
+    for lib in (main, xlib):
+        fn = lib.vtx_embed_bwd
+        fn.argtypes, fn.restype = ops._PROTOS["vtx_embed_bwd"], ctypes.c_int
+        d_words, d_pos = torch.zeros(500, H, device=dev), torch.zeros(T, H, device=dev)
+        d_gamma, d_beta = torch.zeros(H, device=dev), torch.zeros(H, device=dev)
+        rc = fn(dy_a.data_ptr(), dy_b.data_ptr(), tokens.data_ptr(), z.data_ptr(), stats.data_ptr(), gamma.data_ptr(),
+                d_words.data_ptr(), d_pos.data_ptr(), d_gamma.data_ptr(), d_beta.data_ptr(), M, T, H, 0, p,
+                seed.data_ptr(), 9, s)
+        assert rc == 0
+        outs.append((d_words, d_pos, d_gamma, d_beta))
+    for a, b in zip(*outs):
+        assert rel(b, a) < 2e-5
+    assert torch.all(outs[1][0][0] == 0)  # the padding row of the word table receives nothing
