@@ -9,7 +9,7 @@ cd "$(dirname "$0")/.."
 run() { echo "=== $*"; timeout -k 5 "${T:-420}" "$@" 2>&1 | tail -${TAIL:-6}; echo "--- exit ${PIPESTATUS[0]}"; }
 
 T=300 run python bench.py --skip-cpu --steps 10 --warmup 3
-VTX_RUN_UNVERIFIED=1 run python -m pytest tests -m gpu -q -x -k "baseline_config or checkpoint_resume"
+VTX_RUN_UNVERIFIED=1 run python -m pytest tests -m gpu -q -x -k "baseline_config or checkpoint_resume or edge_batch"
 for f in head_x stem_s2d pdl; do
   export VTX_EXPERIMENTAL=$f
   T=200 run python -m pytest tests -m gpu -q -x -k "experimental"

@@ -789,3 +789,27 @@ def test_experimental_head_x_kernels_match_the_validated_ones(H, p):
     for a, b in zip(*outs):
         assert rel(b, a) < 2e-5
     assert torch.all(outs[1][0][0] == 0)  # the padding row of the word table receives nothing
+
+
+@pytest.mark.parametrize("B,max_len", [(1, 30), (3, 13), (5, 2)])
+def test_edge_batch_shapes_vs_oracle(B, max_len):
+    """Batch of one; captions shorter than MAX_CAPTION_LENGTH (the collate pads to the longest caption of the batch,
+    virtex/data/datasets/captioning.py:84-100); and the shortest legal caption `[SOS] [EOS]` (one target per row)."""
+    _need_unverified()
+    spec = O.Spec(hidden=128, layers=1, heads=2, ffn=256)
+    state = O.synth_state(spec, 13, bn3_gain=0.25)
+    model = build_model(spec, state)
+    model.train()
+    batch = O.synth_batch(B, seed=10, max_len=max_len, ragged=max_len > 4)
+    out = model(to_cuda(batch))
+    ref, grads, _ = O.loss_and_grads(state, batch, spec)
+    assert abs(out["loss"].item() - ref["loss"].item()) < 1e-3 * ref["loss"].item(), (out["loss"].item(), ref["loss"].item())
+    out["loss"].backward()
+    named = dict(model.named_parameters())
+    for name in ("textual.transformer.layers.0.linear1.weight", "textual.embedding.words.weight",
+                 "backward_textual.transformer.layers.0.self_attn.in_proj_weight"):
+        assert cos(named[name].grad, grads[name]) > 0.998, name
+    model.eval()
+    with torch.no_grad():
+        ev = model(to_cuda(batch))
+    assert ev["predictions"].shape == (B, max_len)
