@@ -1,0 +1,176 @@
+"""Host-logic dry run of the engine on the CPU box: every kernel launcher is replaced by a recorder that checks the
+call against the C-ABI prototype (argument count) and the GEMM operands against the buffer sizes they imply.  No
+arithmetic runs -- this is not a CPU path (the product refuses CPU tensors, tests/test_host_cpu.py::test_no_cpu_fallback);
+it exercises the Python schedule (shapes, workspaces, tape, optional branches) for configurations and edge shapes that
+the GPU suite also runs, plus the opt-in experimental branches."""
+import pytest
+import torch
+
+from oracle import virtex_oracle as O
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+class Recorder:
+    def __init__(self):
+        self.calls = []
+
+    def names(self):
+        return [c if isinstance(c, str) else c[0] for c in self.calls]
+
+
+def _check_gemm(A, B, D, M, N, K, lda=None, ldb=None, ldd=None, a_mn=0, b_mn=0, bias=None, act=0, residual=None, ldr=0,
+                stats=None, atomic=False, split_k=1, tile_n=0, conv=None, conv_mode=0, out_f32=None):
+    assert A.dtype == BF16 and B.dtype == BF16, (A.dtype, B.dtype)
+    f32 = (D.dtype == F32) if out_f32 is None else bool(out_f32)
+    assert D.dtype == (F32 if f32 else BF16)
+    assert not atomic or f32
+    assert split_k >= 1 and (split_k == 1 or atomic)
+    ldd = D.stride(0) if ldd is None else ldd
+    assert M > 0 and N > 0 and K > 0
+    if conv_mode == 0:
+        lda = A.stride(0) if lda is None else lda
+        ldb = B.stride(0) if ldb is None else ldb
+        assert A.numel() >= ((K - 1) * lda + M if a_mn else (M - 1) * lda + K), "A too small"
+        assert B.numel() >= ((K - 1) * ldb + N if b_mn else (N - 1) * ldb + K), "B too small"
+        assert D.numel() >= (M - 1) * ldd + N, "D too small"
+    else:
+        NI, H, W, C = conv
+        assert C % 64 == 0
+        if conv_mode == 1:
+            assert M == NI * H * W and K == 9 * C and A.numel() >= NI * H * W * C and B.numel() >= N * K
+            assert D.numel() >= (M - 1) * ldd + N
+        elif conv_mode == 2:
+            assert N == 9 * C and K == NI * H * W and A.numel() >= K * M and B.numel() >= K * C and f32 and atomic
+            assert D.numel() >= (M - 1) * ldd + N
+        elif conv_mode == 4:
+            assert C == 64 and N == 64 and M == 9 * C and K == NI * H * W and f32 and atomic
+            assert A.numel() >= K * N and B.numel() >= K * C and D.numel() >= M * N
+        elif conv_mode == 5:   # experimental stem fprop over the space-to-depth view
+            assert C == 64 and N == 64 and K == 256 and M == NI * H * W
+            assert A.numel() >= NI * (H + 3) * (W + 3) * 16 and B.numel() >= 64 * 256 and D.numel() >= M * N
+        elif conv_mode == 6:   # experimental stem wgrad
+            assert C == 64 and M == 64 and N == 256 and K == NI * H * W and f32 and atomic
+            assert A.numel() >= K * 64 and B.numel() >= NI * (H + 3) * (W + 3) * 16 and D.numel() >= M * N
+        else:
+            raise AssertionError(conv_mode)
+    if stats is not None:
+        assert stats.dtype == F32 and stats.numel() >= 2 * N and not f32 and bias is None and residual is None
+    if bias is not None:
+        assert bias.dtype == F32 and bias.numel() >= N
+    if residual is not None:
+        assert residual.dtype == BF16 and residual.numel() >= M * N
+
+
+@pytest.fixture
+def dry(monkeypatch):
+    """Patch the launchers of virtex_b200.engine (and the experimental module) with checking recorders."""
+    from virtex_b200 import engine as E, experimental as X, ops
+    rec = Recorder()
+
+    def fake_call(name, *args):
+        assert len(args) == len(ops._PROTOS[name]), (name, len(args), len(ops._PROTOS[name]))
+        rec.calls.append(name)
+
+    def fake_gemm(A, B, D, M, N, K, **kw):
+        _check_gemm(A, B, D, M, N, K, **kw)
+        rec.calls.append(("gemm", M, N, K, kw.get("conv_mode", 0)))
+
+    def fake_xcall(name, *args):
+        assert len(args) == len(X._PROTOS[name]), (name, len(args))
+        rec.calls.append(name)
+
+    def fake_xgemm(A, B, D, M, N, K, **kw):
+        _check_gemm(A, B, D, M, N, K, **kw)
+        rec.calls.append(("gemm_x", M, N, K, kw.get("conv_mode", 0)))
+
+    monkeypatch.setattr(E, "call", fake_call)
+    monkeypatch.setattr(E, "gemm", fake_gemm)
+    monkeypatch.setattr(E, "_stream", lambda: 0)
+    monkeypatch.setattr(E, "_require_cuda", lambda dev: None)
+    monkeypatch.setattr(X, "call", fake_xcall)
+    monkeypatch.setattr(X, "gemm", fake_xgemm)
+    monkeypatch.setattr(ops, "num_sms", lambda: 148)
+    return rec
+
+
+def _model(spec, frozen=False, bidirectional=True):
+    from virtex_b200.models import BidirectionalCaptioningModel, ForwardCaptioningModel
+    from virtex_b200.modules import TorchvisionVisualBackbone, TransformerDecoderTextualHead
+    visual = TorchvisionVisualBackbone(spec.backbone, visual_feature_size=spec.visual_feature_size, frozen=frozen)
+    textual = TransformerDecoderTextualHead(
+        visual_feature_size=spec.visual_feature_size, vocab_size=spec.vocab, hidden_size=spec.hidden,
+        num_layers=spec.layers, attention_heads=spec.heads, feedforward_size=spec.ffn, dropout=0.1,
+        norm_first=spec.norm_first, max_caption_length=spec.max_len, padding_idx=spec.pad)
+    return (BidirectionalCaptioningModel if bidirectional else ForwardCaptioningModel)(visual, textual)
+
+
+def _run(model, batch, training=True, backward=True):
+    eng = model.engine
+    loss = eng.forward(batch["image"], batch["caption_tokens"],
+                       batch["noitpac_tokens"] if model.caption_backward else batch["caption_tokens"],
+                       batch["caption_lengths"], training=training, with_grad=backward)
+    assert tuple(loss.shape) == (2,)
+    if backward:
+        eng.backward(zero_grads=True)
+    return eng
+
+
+SMALL = dict(hidden=128, layers=1, heads=2, ffn=256)
+
+
+@pytest.mark.parametrize("spec_kw,batch_kw", [
+    (SMALL, dict(batch_size=2, seed=0)),
+    (SMALL, dict(batch_size=1, seed=1)),                                   # batch of one
+    (SMALL, dict(batch_size=3, seed=2, max_len=13, ragged=True)),          # captions shorter than the maximum
+    (SMALL, dict(batch_size=5, seed=3, max_len=2)),                        # [SOS] [EOS] only
+    (dict(hidden=256, layers=2, heads=4, ffn=512, norm_first=True), dict(batch_size=2, seed=4, ragged=True)),
+    (dict(layers=4), dict(batch_size=2, seed=5)),                          # BASELINE config #4 architecture
+    (dict(backbone="resnet101", hidden=2048, heads=32, ffn=8192), dict(batch_size=2, seed=6)),  # config #5
+])
+def test_training_step_schedule(dry, spec_kw, batch_kw):
+    spec = O.Spec(**spec_kw)
+    model = _model(spec)
+    batch = O.synth_batch(**batch_kw)
+    _run(model, batch)
+    names = dry.names()
+    n_blocks = sum(spec.blocks)
+    gemms = [c for c in dry.calls if not isinstance(c, str)]
+    # every conv has one fprop GEMM and one wgrad GEMM (stem: no dgrad); 3 convs (+ downsample in 4 blocks) per block
+    assert len([g for g in gemms if g[0] == "gemm"]) >= 3 * (3 * n_blocks + 4 + 1) - 1
+    assert names.count("vtx_cross_entropy") == 2 and names.count("vtx_embed_fwd") == 2
+    assert names.count("vtx_attn_fwd") == 2 * 2 * spec.layers == names.count("vtx_attn_bwd")
+    assert "vtx_stem_im2col" in names and not any(g[0] == "gemm_x" for g in gemms)
+    # layer1's three 64 -> 64 3x3 convs use the halo-reuse wgrad
+    assert len([g for g in gemms if g[4] == 4]) == 3
+
+
+def test_eval_forward_only_and_frozen_backbone(dry):
+    spec = O.Spec(**SMALL)
+    batch = O.synth_batch(3, seed=7, ragged=True)
+    model = _model(spec)
+    eng = _run(model, batch, training=False, backward=False)
+    assert "vtx_argmax_rows" not in dry.names()  # predictions are computed on demand
+    eng.predictions()
+    assert "vtx_argmax_rows" in dry.names()
+    assert not any(n.startswith("vtx_bn_bwd") for n in dry.names())
+    dry.calls.clear()
+    _run(_model(spec, frozen=True), batch)
+    assert not any(n.startswith("vtx_bn_bwd") for n in dry.names())          # no backbone backward at all
+    dry.calls.clear()
+    _run(_model(spec, bidirectional=False), batch)
+    assert dry.names().count("vtx_cross_entropy") == 1
+
+
+def test_experimental_stem_branch_schedule(dry, monkeypatch):
+    monkeypatch.setenv("VTX_EXPERIMENTAL", "stem_s2d")
+    spec = O.Spec(**SMALL)
+    _run(_model(spec), O.synth_batch(2, seed=8))
+    names = dry.names()
+    gemms = [c for c in dry.calls if not isinstance(c, str)]
+    assert "vtx_stem_im2col" not in names and "vtx_x_stem_s2d" in names and "vtx_x_stem_w_pack" in names
+    assert [g[4] for g in gemms if g[0] == "gemm_x"] == [5, 6] and "vtx_x_stem_w_unpack_add" in names
+    # an image size whose output is not tiled exactly by the TMA boxes falls back to the validated path
+    dry.calls.clear()
+    _run(_model(spec), O.synth_batch(2, seed=9, image_size=200))
+    assert "vtx_stem_im2col" in dry.names() and "vtx_x_stem_s2d" not in dry.names()

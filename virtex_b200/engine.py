@@ -114,6 +114,11 @@ class _Workspace:
         return sum(t.numel() * t.element_size() for t in self.flat.values())
 
 
+def _require_cuda(dev):
+    if dev is None or dev.type != "cuda":
+        raise RuntimeError("virtex_b200 has no CPU path: move the model to a CUDA device first (model.cuda())")
+
+
 class Engine:
     """Forward/backward of (backbone) + (forward head) + (backward head) on one GPU.  Any part may be absent."""
 
@@ -130,8 +135,7 @@ class Engine:
         for _, p in named:
             dev = p.device
             break
-        if dev is None or dev.type != "cuda":
-            raise RuntimeError("virtex_b200 has no CPU path: move the model to a CUDA device first (model.cuda())")
+        _require_cuda(dev)
         self.device = dev
         self.arena = Arena(named, dev)
         self.ws = _Workspace(dev)
