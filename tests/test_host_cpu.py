@@ -277,9 +277,11 @@ def test_routed_entry_points_default_to_the_main_library(monkeypatch):
     from virtex_b200 import experimental as X, ops
     xlib = ctypes.CDLL(X.lib_path())
     for name, feature in X.ROUTED.items():
-        assert feature in X.FEATURES and name in ops._PROTOS and hasattr(xlib, name)
+        assert feature in X.FEATURES and name in ops._PROTOS and hasattr(xlib, X.routed_symbol(name))
     monkeypatch.delenv("VTX_EXPERIMENTAL", raising=False)
     assert all(X.routed_lib(n) is None for n in X.ROUTED)
     monkeypatch.setenv("VTX_EXPERIMENTAL", "head_x")
     assert all(X.routed_lib(n) is not None for n in X.ROUTED)
-    assert X.routed_lib("vtx_gemm") is None
+    assert X.routed_lib("vtx_gemm") is None and X.routed_lib("vtx_colsum") is None
+    monkeypatch.setenv("VTX_EXPERIMENTAL", "gemm_x")
+    assert X.routed_lib("vtx_gemm") is not None and X.routed_symbol("vtx_gemm") == "vtx_gemm_x"

@@ -440,7 +440,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // BN statistics: thread (scg, srg) owns 8 columns x 16 rows of every staged tile and keeps running partial sums in
     // registers across all tiles of this CTA that share the same column block; they are reduced through shared
     // memory and flushed with one atomic per column only when the column block changes (or at the end).
+#ifdef VTX_GEMM_X
+    // experimental: for 64- / 128-wide tiles ALL 256 threads take part (8 / 16 column groups x 32 / 16 row groups of
+    // 4 / 8 rows) instead of only the threads whose column group exists (8 column groups x 8 row groups x 16 rows)
+    const int st_cgs = (p.bn == 64) ? 8 : (p.bn == 128) ? 16 : 32;   // column groups of 8 columns
+    const int st_rgs = 256 / st_cgs;                                   // row groups
+    const int st_rpt = 128 / st_rgs;                                   // rows per thread
+    const int scg = et % st_cgs, srg = et / st_cgs;
+#else
+    constexpr int st_rgs = 8, st_rpt = 16;
     const int scg = et & 31, srg = et >> 5;
+#endif
     float st_s[8], st_q[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) st_s[i] = st_q[i] = 0.f;
@@ -460,7 +470,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (et < p.bn && st_nt * p.bn + et < p.N) {
         float a = 0.f, b = 0.f;
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
+        for (int g = 0; g < st_rgs; ++g) {
           a += scr[(g * p.bn + et) * 2];
           b += scr[(g * p.bn + et) * 2 + 1];
         }
@@ -670,12 +680,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ---------------- BN statistics of the staged (bf16-rounded) tile, accumulated in registers.
         // Rows outside the problem are exact zeros (TMA zero fill; stats forbids bias/residual): no masking needed.
         if (p.stats != nullptr && scg * 8 < p.bn) {
-          const uint32_t cp = smem_u32(cbuf) + (scg >> 3) * 16384 + (srg * 16) * 128;
+          const int r0 = srg * st_rpt;  // first row of this thread (a multiple of 8 in the regular build)
+          const uint32_t cp = smem_u32(cbuf) + (scg >> 3) * 16384 + r0 * 128;
           const int c8 = scg & 7;
 #pragma unroll 4
-          for (int r = 0; r < 16; ++r) {
+          for (int r = 0; r < st_rpt; ++r) {
             float f[8];
-            const uint4 raw = lds128(cp + r * 128 + ((c8 ^ (r & 7)) << 4));
+            const uint4 raw = lds128(cp + r * 128 + ((c8 ^ ((r0 + r) & 7)) << 4));
             unpack8(*reinterpret_cast<const bf16x8*>(&raw), f);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {

@@ -58,8 +58,8 @@ def _get(name):
     f = _fn.get(name)
     if f is None:
         from . import experimental as X  # opt-in re-implementations of a few entry points (off by default)
-        lib = X.routed_lib(name) or L.load()
-        f = getattr(lib, name)
+        xlib = X.routed_lib(name)
+        f = getattr(xlib, X.routed_symbol(name)) if xlib is not None else getattr(L.load(), name)
         f.argtypes = _PROTOS[name]
         f.restype = c_int
         _fn[name] = f
