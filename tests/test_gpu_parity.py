@@ -789,6 +789,16 @@ def test_experimental_head_x_kernels_match_the_validated_ones(H, p):
     for a, b in zip(*outs):
         assert rel(b, a) < 2e-5
     assert torch.all(outs[1][0][0] == 0)  # the padding row of the word table receives nothing
+    # bias-gradient column sums (+= semantics), incl. a strided input and a column count that is not a multiple of 256
+    for (Mc, Nc, ldc) in [(7680, 1024, 1024), (7424, 10000, 10000), (870, 128, 384), (100, 3072, 3072)]:
+        Xc = (torch.randn(Mc, ldc, device=dev) * 0.5).bfloat16()
+        ref = Xc[:, :Nc].float().sum(0)
+        for lib in (main, xlib):
+            fn = lib.vtx_colsum
+            fn.argtypes, fn.restype = ops._PROTOS["vtx_colsum"], ctypes.c_int
+            out = torch.ones(Nc, device=dev)
+            assert fn(Xc.data_ptr(), ldc, Mc, Nc, out.data_ptr(), s) == 0
+            assert rel(out, 1.0 + ref) < 1e-5
 
 
 @pytest.mark.parametrize("B,max_len", [(1, 30), (3, 13), (5, 2)])

@@ -282,6 +282,6 @@ def test_routed_entry_points_default_to_the_main_library(monkeypatch):
     assert all(X.routed_lib(n) is None for n in X.ROUTED)
     monkeypatch.setenv("VTX_EXPERIMENTAL", "head_x")
     assert all((X.routed_lib(n) is not None) == (f == "head_x") for n, f in X.ROUTED.items())
-    assert X.routed_lib("vtx_gemm") is None and X.routed_lib("vtx_colsum") is None
+    assert X.routed_lib("vtx_gemm") is None and X.routed_lib("vtx_sumsq") is None
     monkeypatch.setenv("VTX_EXPERIMENTAL", "gemm_x")
     assert X.routed_lib("vtx_gemm") is not None and X.routed_symbol("vtx_gemm") == "vtx_gemm_x"

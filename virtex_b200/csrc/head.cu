@@ -1024,6 +1024,56 @@ __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ X, long long ld,
     if (g * 8 + j < N) atomicAdd(out + g * 8 + j, acc[j]);
 }
 
+#ifdef VTX_HEAD_X
+// EXPERIMENTAL (head_x): a CTA covers 256 columns x a row slice with 8 row lanes (one per warp) and reduces the lanes in
+// shared memory, so the number of atomics per output column drops from (row blocks) = 296 to 296 / (N / 256) -- the
+// validated kernel is bound by those atomics (31 us for a 15.7 MB input).
+__global__ void __launch_bounds__(256) colsum_lanes_kernel(const __nv_bfloat16* __restrict__ X, long long ld, int M, int N,
+                                                          float* __restrict__ out, int rows_per_block) {
+  VTX_PDL_TRIGGER();
+  __shared__ float red[8][256];
+  const int cgrp = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int col0 = blockIdx.y * 256 + cgrp * 8;
+  const int m0 = blockIdx.x * rows_per_block;
+  const int m1 = min(M, m0 + rows_per_block);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (col0 < N) {
+    const __nv_bfloat16* xp = X + col0;
+    int m = m0 + rl;
+    for (; m + 24 < m1; m += 32) {  // four independent 16-byte loads in flight per thread
+      bf16x8 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const bf16x8*>(xp + (long long)(m + 8 * u) * ld);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float f[8];
+        unpack8(v[u], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += f[j];
+      }
+    }
+    for (; m < m1; m += 8) {
+      float f[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(xp + (long long)m * ld), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    }
+  }
+  *reinterpret_cast<float4*>(&red[rl][cgrp * 8]) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  *reinterpret_cast<float4*>(&red[rl][cgrp * 8 + 4]) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  __syncthreads();
+  const int c = blockIdx.y * 256 + threadIdx.x;
+  if (c < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    atomicAdd(out + c, t);
+  }
+}
+#endif
+
 // first-index argmax of each fp32 row
 __global__ void argmax_rows_kernel(const float* __restrict__ X, long long ld, int N, long long* __restrict__ out) {
   VTX_PDL_TRIGGER();
@@ -1237,6 +1287,17 @@ extern "C" int vtx_cross_entropy(void* logits, int64_t ldl, const int64_t* token
 }
 extern "C" int vtx_colsum(const void* X, int64_t ld, int M, int N, float* out, void* stream) {
   REQ(X && out && ld % 8 == 0, "bad arguments");
+#ifdef VTX_HEAD_X
+  if (N % 8 == 0 && M >= 64) {
+    const int by = (N + 255) / 256;
+    int bx = (vtx_num_sms() * 2 + by - 1) / by;
+    if (bx > M / 8) bx = M / 8;
+    const int rpb = (M + bx - 1) / bx;
+    bx = (M + rpb - 1) / rpb;
+    colsum_lanes_kernel<<<dim3(bx, by), 256, 0, STREAM>>>((const __nv_bfloat16*)X, ld, M, N, out, rpb);
+    return check_launch("colsum_lanes");
+  }
+#endif
   const int groups = (N + 7) / 8;
   const int threads = 128;
   const int gy = (groups + threads - 1) / threads;
