@@ -789,6 +789,20 @@ def test_experimental_head_x_kernels_match_the_validated_ones(H, p):
     for a, b in zip(*outs):
         assert rel(b, a) < 2e-5
     assert torch.all(outs[1][0][0] == 0)  # the padding row of the word table receives nothing
+    # cross-entropy with in-place dlogits (identical arithmetic: expect bit-equal gradients)
+    Bc, Tc, V = 9, 30, 10000
+    logits0 = (torch.randn(Bc * Tc, V, device=dev) * 3).bfloat16()
+    toks = torch.randint(4, V, (Bc, Tc), device=dev)
+    toks[:, 20:] = 0
+    cnt = torch.tensor([float((toks[:, 1:] != 0).sum())], device=dev)
+    res = []
+    for lib in (main, xlib):
+        fn = lib.vtx_cross_entropy
+        fn.argtypes, fn.restype = ops._PROTOS["vtx_cross_entropy"], ctypes.c_int
+        lg, loss = logits0.clone(), torch.zeros(1, device=dev)
+        assert fn(lg.data_ptr(), V, toks.data_ptr(), Bc, Tc, V, 0, cnt.data_ptr(), loss.data_ptr(), 1, s) == 0
+        res.append((lg, loss))
+    assert torch.equal(res[0][0], res[1][0]) and abs(res[0][1].item() - res[1][1].item()) < 1e-5 * res[0][1].item()
     # bias-gradient column sums (+= semantics), incl. a strided input and a column count that is not a multiple of 256
     for (Mc, Nc, ldc) in [(7680, 1024, 1024), (7424, 10000, 10000), (870, 128, 384), (100, 3072, 3072)]:
         Xc = (torch.randn(Mc, ldc, device=dev) * 0.5).bfloat16()

@@ -989,6 +989,98 @@ __global__ void ce_kernel(__nv_bfloat16* __restrict__ logits, long long ldl, con
   }
 }
 
+#ifdef VTX_HEAD_X
+// EXPERIMENTAL (head_x): same arithmetic as ce_kernel with the row held in registers -- one global read pass with all
+// of a thread's loads in flight (the validated kernel walks the row three times with one dependent load at a time,
+// ~3 x 5 x memory latency per CTA) and exp() evaluated once.  Rows of up to 256 * 8 * IT logits.
+template <int IT>
+__global__ void __launch_bounds__(256) ce_reg_kernel(__nv_bfloat16* __restrict__ logits, long long ldl,
+                                                    const long long* __restrict__ tokens, int T, int V, int pad,
+                                                    const float* __restrict__ count, float* __restrict__ loss,
+                                                    int write_grad) {
+  VTX_PDL_TRIGGER();
+  __shared__ float red[32];
+  __shared__ float bcast;
+  const int row = blockIdx.x;
+  const int t = row % T;
+  __nv_bfloat16* z = logits + (long long)row * ldl;
+  const long long target = (t < T - 1) ? tokens[row + 1] : (long long)pad;
+  const bool valid = target != pad;
+  const int nv = V / 8;
+  if (!valid) {
+    if (write_grad)
+      for (int i = threadIdx.x; i < nv; i += blockDim.x) *reinterpret_cast<uint4*>(z + i * 8) = make_uint4(0, 0, 0, 0);
+    return;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  float f[IT][8];
+#pragma unroll
+  for (int k = 0; k < IT; ++k) {
+    const int i = threadIdx.x + k * 256;
+    if (i < nv) {
+      unpack8(*reinterpret_cast<const bf16x8*>(z + i * 8), f[k]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[k][j] = -INFINITY;
+    }
+  }
+  const float zt = threadIdx.x == 0 ? bf2f(z[target]) : 0.f;  // read before anybody overwrites the row
+  float mx = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < IT; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mx = fmaxf(mx, f[k][j]);
+  mx = warp_max(mx);
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  if (warp == 0) {
+    float v = lane < nwarps ? red[lane] : -INFINITY;
+    v = warp_max(v);
+    if (lane == 0) bcast = v;
+  }
+  __syncthreads();
+  mx = bcast;
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < IT; ++k) {
+    if (threadIdx.x + k * 256 < nv) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        f[k][j] = __expf(f[k][j] - mx);
+        s += f[k][j];
+      }
+    }
+  }
+  s = warp_sum(s);
+  __syncthreads();
+  if (lane == 0) red[warp] = s;
+  __syncthreads();
+  if (warp == 0) {
+    float v = lane < nwarps ? red[lane] : 0.f;
+    v = warp_sum(v);
+    if (lane == 0) bcast = v;
+  }
+  __syncthreads();
+  s = bcast;
+  const float inv_n = 1.f / fmaxf(*count, 1.f);
+  if (threadIdx.x == 0) atomicAdd(loss, (mx + __logf(s) - zt) * inv_n);
+  if (write_grad) {
+    const float inv_s = 1.f / s;
+#pragma unroll
+    for (int k = 0; k < IT; ++k) {
+      const int i = threadIdx.x + k * 256;
+      if (i < nv) {
+        float g[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          g[j] = (f[k][j] * inv_s - ((long long)(i * 8 + j) == target ? 1.f : 0.f)) * inv_n;
+        *reinterpret_cast<bf16x8*>(z + i * 8) = pack8(g);
+      }
+    }
+  }
+}
+#endif
+
 // out[n] += sum_m X[m,n]    X bf16 [M, ld]
 __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ X, long long ld, int M, int N, float* __restrict__ out,
                               int rows_per_block) {
@@ -1281,6 +1373,13 @@ extern "C" int vtx_count_valid(const int64_t* tokens, int B, int T, int pad, flo
 extern "C" int vtx_cross_entropy(void* logits, int64_t ldl, const int64_t* tokens, int B, int T, int V, int pad,
                                  const float* count, float* loss, int write_grad, void* stream) {
   REQ(logits && tokens && count && loss && V % 8 == 0 && ldl % 8 == 0, "bad arguments");
+#ifdef VTX_HEAD_X
+  if (V / 8 <= 256 * 5) {
+    ce_reg_kernel<5><<<B * T, 256, 0, STREAM>>>((__nv_bfloat16*)logits, ldl, (const long long*)tokens, T, V, pad, count,
+                                                loss, write_grad);
+    return check_launch("cross_entropy_reg");
+  }
+#endif
   ce_kernel<<<B * T, 256, 0, STREAM>>>((__nv_bfloat16*)logits, ldl, (const long long*)tokens, T, V, pad, count, loss,
                                        write_grad);
   return check_launch("cross_entropy");

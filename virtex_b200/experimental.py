@@ -13,7 +13,8 @@ Nothing here is on the default path.  A feature is used only when the environmen
 
   head_x     register-accumulating LayerNorm / embedding backward kernels (head.cu compiled with -DVTX_HEAD_X): the
              entry points vtx_ln_bwd / vtx_embed_bwd / vtx_colsum (bias gradients: row lanes reduced in
-             shared memory, 4-40x fewer atomics) are routed to libvirtex_b200_x.so.
+             shared memory, 4-40x fewer atomics) / vtx_cross_entropy (row held in registers: one read pass) are routed to
+             libvirtex_b200_x.so.
 
   gemm_x     every vtx_gemm call goes to vtx_gemm_x (gemm_tc.cu compiled with -DVTX_GEMM_X): BN-statistics pass of
              64- / 128-wide tiles spread over all 256 epilogue threads (4 / 8 rows each instead of 16 rows on a
@@ -33,7 +34,8 @@ from . import ops
 FEATURES = ("stem_s2d", "pdl", "head_x", "gemm_x")
 # entry points of the MAIN ABI that libvirtex_b200_x.so re-implements (same signature); routed there by ops._get when
 # the feature is enabled
-ROUTED = {"vtx_ln_bwd": "head_x", "vtx_embed_bwd": "head_x", "vtx_colsum": "head_x", "vtx_gemm": "gemm_x"}
+ROUTED = {"vtx_ln_bwd": "head_x", "vtx_embed_bwd": "head_x", "vtx_colsum": "head_x", "vtx_cross_entropy": "head_x",
+          "vtx_gemm": "gemm_x"}
 _ROUTED_SYMBOL = {"vtx_gemm": "vtx_gemm_x"}  # where the name differs in the experimental library
 _P, _I = ctypes.c_void_p, ctypes.c_int
 _PROTOS = {
