@@ -10,7 +10,7 @@ run() { echo "=== $*"; timeout -k 5 "${T:-420}" "$@" 2>&1 | tail -${TAIL:-6}; ec
 
 T=300 run python bench.py --skip-cpu --steps 10 --warmup 3
 VTX_RUN_UNVERIFIED=1 run python -m pytest tests -m gpu -q -x -k "baseline_config or checkpoint_resume or edge_batch"
-for f in head_x gemm_x stem_s2d pdl; do
+for f in head_x gemm_x backbone_x stem_s2d pdl; do
   export VTX_EXPERIMENTAL=$f
   T=200 run python -m pytest tests -m gpu -q -x -k "experimental"
   run python -m pytest tests -m gpu -q -x

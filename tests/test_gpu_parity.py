@@ -837,3 +837,25 @@ def test_edge_batch_shapes_vs_oracle(B, max_len):
     with torch.no_grad():
         ev = model(to_cuda(batch))
     assert ev["predictions"].shape == (B, max_len)
+
+
+@pytest.mark.parametrize("N,H,W,C", [(3, 112, 112, 64), (2, 30, 22, 64), (2, 7, 9, 16)])
+def test_experimental_backbone_x_maxpool_backward_matches_the_validated_kernel(N, H, W, C):
+    X = _need_experimental("backbone_x")
+    import ctypes
+    from virtex_b200 import lib as L, ops
+    main, xlib = ctypes.CDLL(L.LIB_PATH), X.load()
+    torch.manual_seed(9)
+    dev = "cuda"
+    s = torch.cuda.current_stream().cuda_stream
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    dpool = torch.randn(N, Ho, Wo, C, device=dev).bfloat16()
+    idx = torch.randint(0, 9, (N, Ho, Wo, C), device=dev, dtype=torch.uint8)
+    outs = []
+    for lib in (main, xlib):
+        fn = lib.vtx_maxpool_bwd
+        fn.argtypes, fn.restype = ops._PROTOS["vtx_maxpool_bwd"], ctypes.c_int
+        da = torch.full((N, H, W, C), 5.0, device=dev, dtype=torch.bfloat16)
+        assert fn(dpool.data_ptr(), idx.data_ptr(), da.data_ptr(), N, H, W, C, s) == 0
+        outs.append(da)
+    assert torch.equal(outs[0], outs[1])

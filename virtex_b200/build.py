@@ -83,6 +83,7 @@ def build(verbose=False, force=False):
     jobs += [(os.path.join(CSRC_X, n), (), "") for n in sorted(os.listdir(CSRC_X)) if n.endswith(".cu")]
     jobs += [(os.path.join(CSRC, "gemm_tc.cu"), ("-DVTX_GEMM_X",), "_x")]
     jobs += [(os.path.join(CSRC, "head.cu"), ("-DVTX_HEAD_X",), "_x")]
+    jobs += [(os.path.join(CSRC, "backbone.cu"), ("-DVTX_BACKBONE_X",), "_x")]
     n_x = len(jobs)
     jobs += [(s, ("-DVTX_PDL",), "_pdl") for s in srcs]
     with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:

@@ -383,6 +383,71 @@ __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dpool, cons
   }
 }
 
+#ifdef VTX_BACKBONE_X
+// EXPERIMENTAL (backbone_x): same arithmetic as maxpool_bwd_kernel, but a CTA first stages the kTP + 1 pooled rows
+// (gradients + argmax slots) it needs in shared memory with linear coalesced copies and then produces 2 * kTP input
+// rows from them.  The validated kernel gathers every pooled element from L2 up to nine times (1.4 GB of L2 -> SM
+// traffic for 565 MB of algorithmic bytes at batch 256).
+constexpr int kTP = 4;
+__global__ void __launch_bounds__(256) maxpool_bwd_tiled_kernel(const __nv_bfloat16* __restrict__ dpool,
+                                                               const uint8_t* __restrict__ idx,
+                                                               __nv_bfloat16* __restrict__ da, int N, int H, int W, int C,
+                                                               int Ho, int Wo) {
+  VTX_PDL_TRIGGER();
+  extern __shared__ __align__(16) uint8_t pool_smem[];
+  const int row_elems = Wo * C;                                   // elements of one pooled row
+  __nv_bfloat16* sd = reinterpret_cast<__nv_bfloat16*>(pool_smem);            // [kTP + 1][Wo][C] gradients
+  uint8_t* si = pool_smem + (size_t)(kTP + 1) * row_elems * 2;               // [kTP + 1][Wo][C] argmax slots
+  const int tiles = (Ho + kTP - 1) / kTP;
+  const int n = blockIdx.x / tiles, ph0 = (blockIdx.x % tiles) * kTP;
+  const int prow = min(kTP + 1, Ho - ph0);                        // pooled rows that exist
+  {
+    const uint4* gd = reinterpret_cast<const uint4*>(dpool + ((long long)n * Ho + ph0) * row_elems);
+    uint4* d4 = reinterpret_cast<uint4*>(sd);
+    for (int i = threadIdx.x; i < prow * row_elems / 8; i += blockDim.x) d4[i] = gd[i];
+    const uint4* gi = reinterpret_cast<const uint4*>(idx + ((long long)n * Ho + ph0) * row_elems);
+    uint4* i4 = reinterpret_cast<uint4*>(si);
+    for (int i = threadIdx.x; i < prow * row_elems / 16; i += blockDim.x) i4[i] = gi[i];
+  }
+  __syncthreads();
+  const int cg = C / 8;
+  const int h0 = 2 * ph0, h1 = min(H, 2 * (ph0 + kTP));
+  const int items = (h1 - h0) * W * cg;
+  for (int it = threadIdx.x; it < items; it += blockDim.x) {
+    const int g = it % cg;
+    const int w = (it / cg) % W;
+    const int h = h0 + it / (cg * W);
+    const int c0 = g * 8;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int hn = h + 1 - kh;
+      if (hn < 0 || (hn & 1)) continue;
+      const int ph = hn >> 1;
+      if (ph >= Ho) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int wn = w + 1 - kw;
+        if (wn < 0 || (wn & 1)) continue;
+        const int pw = wn >> 1;
+        if (pw >= Wo) continue;
+        const int off = ((ph - ph0) * Wo + pw) * C + c0;
+        const uint2 raw = *reinterpret_cast<const uint2*>(si + off);
+        const uint8_t* b = reinterpret_cast<const uint8_t*>(&raw);
+        float d[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(sd + off), d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (b[j] == kh * 3 + kw) acc[j] += d[j];
+      }
+    }
+    *reinterpret_cast<bf16x8*>(da + (((long long)n * H + h) * W + w) * C + c0) = pack8(acc);
+  }
+}
+#endif
+
 // ---------------------------------------------------------------------------------------------- BatchNorm backward
 // sums[0,c] = sum_m dz, sums[1,c] = sum_m dz * xhat, with dz = dA * [a > 0] (a == null: no ReLU) and
 // xhat = (y - mean) * invstd.  Optionally the same for a second BN (y2, bnp2) sharing dz (downsample branch).
@@ -794,6 +859,22 @@ extern "C" int vtx_maxpool_bwd(const void* dpool, const uint8_t* idx, void* da, 
                                void* stream) {
   REQ(dpool && idx && da && C % 8 == 0, "bad arguments");
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+#ifdef VTX_BACKBONE_X
+  {
+    const size_t smem = (size_t)(kTP + 1) * Wo * C * 3;  // bf16 gradients + u8 slots
+    if (C % 16 == 0 && smem <= 200 * 1024) {
+      static size_t attr = 0;
+      if (smem > 48 * 1024 && smem > attr) {
+        cudaFuncSetAttribute(maxpool_bwd_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = smem;
+      }
+      const int tiles = (Ho + kTP - 1) / kTP;
+      maxpool_bwd_tiled_kernel<<<N * tiles, 256, smem, STREAM>>>((const __nv_bfloat16*)dpool, idx, (__nv_bfloat16*)da, N,
+                                                                 H, W, C, Ho, Wo);
+      return check_launch("maxpool_bwd_tiled");
+    }
+  }
+#endif
   const long long total = (long long)N * H * W * (C / 8);
   maxpool_bwd_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>((const __nv_bfloat16*)dpool, idx, (__nv_bfloat16*)da, N,
                                                                H, W, C, Ho, Wo);
