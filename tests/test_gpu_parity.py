@@ -859,3 +859,15 @@ def test_experimental_backbone_x_maxpool_backward_matches_the_validated_kernel(N
         assert fn(dpool.data_ptr(), idx.data_ptr(), da.data_ptr(), N, H, W, C, s) == 0
         outs.append(da)
     assert torch.equal(outs[0], outs[1])
+    # forward: BN + ReLU + 3x3/2 max-pool with argmax slots
+    y = torch.randn(N, H, W, C, device=dev).bfloat16()
+    bnp = torch.cat([torch.zeros(2 * C, device=dev), torch.rand(C, device=dev) + 0.5, torch.randn(C, device=dev) * 0.3])
+    outs = []
+    for lib in (main, xlib):
+        fn = lib.vtx_bn_relu_maxpool
+        fn.argtypes, fn.restype = ops._PROTOS["vtx_bn_relu_maxpool"], ctypes.c_int
+        out = torch.full((N, Ho, Wo, C), 5.0, device=dev, dtype=torch.bfloat16)
+        slot = torch.full((N, Ho, Wo, C), 77, device=dev, dtype=torch.uint8)
+        assert fn(y.data_ptr(), bnp.data_ptr(), out.data_ptr(), slot.data_ptr(), N, H, W, C, s) == 0
+        outs.append((out, slot))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])

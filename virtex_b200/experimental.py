@@ -20,8 +20,9 @@ Nothing here is on the default path.  A feature is used only when the environmen
              64- / 128-wide tiles spread over all 256 epilogue threads (4 / 8 rows each instead of 16 rows on a
              quarter / half of the threads).
 
-  backbone_x shared-memory tiled max-pool backward (backbone.cu compiled with -DVTX_BACKBONE_X): pooled gradients and
-             argmax slots are staged once per CTA instead of being gathered from L2 up to nine times.
+  backbone_x shared-memory tiled stem max-pool (backbone.cu compiled with -DVTX_BACKBONE_X).  Backward: pooled gradients
+             and argmax slots are staged once per CTA instead of being gathered from L2 up to nine times; forward:
+             BN + ReLU applied once per input element into shared memory, pooled from there.
 
 Validation procedure on a B200: `VTX_EXPERIMENTAL=all python -m pytest tests -m gpu -q` and
 `VTX_EXPERIMENTAL=all python bench.py`; then move the kernels into the main library.
@@ -38,7 +39,7 @@ FEATURES = ("stem_s2d", "pdl", "head_x", "gemm_x", "backbone_x")
 # entry points of the MAIN ABI that libvirtex_b200_x.so re-implements (same signature); routed there by ops._get when
 # the feature is enabled
 ROUTED = {"vtx_ln_bwd": "head_x", "vtx_embed_bwd": "head_x", "vtx_colsum": "head_x", "vtx_cross_entropy": "head_x",
-          "vtx_gemm": "gemm_x", "vtx_maxpool_bwd": "backbone_x"}
+          "vtx_gemm": "gemm_x", "vtx_maxpool_bwd": "backbone_x", "vtx_bn_relu_maxpool": "backbone_x"}
 _ROUTED_SYMBOL = {"vtx_gemm": "vtx_gemm_x"}  # where the name differs in the experimental library
 _P, _I = ctypes.c_void_p, ctypes.c_int
 _PROTOS = {
