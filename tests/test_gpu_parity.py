@@ -871,3 +871,19 @@ def test_experimental_backbone_x_maxpool_backward_matches_the_validated_kernel(N
         assert fn(y.data_ptr(), bnp.data_ptr(), out.data_ptr(), slot.data_ptr(), N, H, W, C, s) == 0
         outs.append((out, slot))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    # strided 3x3 gathers with 32-bit index arithmetic
+    for stride in (1, 2):
+        Hs, Ws = (H - 1) // stride + 1, (W - 1) // stride + 1
+        x = torch.randn(N, H, W, C, device=dev).bfloat16()
+        dcols = torch.randn(N * Hs * Ws, 9 * C, device=dev).bfloat16()
+        res = []
+        for lib in (main, xlib):
+            f1, f2 = lib.vtx_im2col3x3, lib.vtx_col2im3x3
+            f1.argtypes, f1.restype = ops._PROTOS["vtx_im2col3x3"], ctypes.c_int
+            f2.argtypes, f2.restype = ops._PROTOS["vtx_col2im3x3"], ctypes.c_int
+            cols = torch.full((N * Hs * Ws, 9 * C), 3.0, device=dev, dtype=torch.bfloat16)
+            dx = torch.full((N, H, W, C), 3.0, device=dev, dtype=torch.bfloat16)
+            assert f1(x.data_ptr(), cols.data_ptr(), N, H, W, C, stride, s) == 0
+            assert f2(dcols.data_ptr(), dx.data_ptr(), N, H, W, C, stride, s) == 0
+            res.append((cols, dx))
+        assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
