@@ -887,3 +887,16 @@ def test_experimental_backbone_x_maxpool_backward_matches_the_validated_kernel(N
             assert f2(dcols.data_ptr(), dx.data_ptr(), N, H, W, C, stride, s) == 0
             res.append((cols, dx))
         assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+        if stride == 2:
+            dxs = torch.randn(N, Hs, Ws, C, device=dev).bfloat16()
+            res = []
+            for lib in (main, xlib):
+                f1, f2 = lib.vtx_subsample, lib.vtx_upsample_add
+                f1.argtypes, f1.restype = ops._PROTOS["vtx_subsample"], ctypes.c_int
+                f2.argtypes, f2.restype = ops._PROTOS["vtx_upsample_add"], ctypes.c_int
+                xs = torch.full((N, Hs, Ws, C), 3.0, device=dev, dtype=torch.bfloat16)
+                dxx = x.clone()
+                assert f1(x.data_ptr(), xs.data_ptr(), N, H, W, C, stride, s) == 0
+                assert f2(dxs.data_ptr(), dxx.data_ptr(), N, H, W, C, stride, s) == 0
+                res.append((xs, dxx))
+            assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])

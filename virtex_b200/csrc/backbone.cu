@@ -233,6 +233,47 @@ __global__ void upsample_add_kernel(const __nv_bfloat16* __restrict__ dxs, __nv_
   }
 }
 
+#ifdef VTX_BACKBONE_X
+// EXPERIMENTAL (backbone_x): 32-bit index arithmetic, see im2col3x3_i32_kernel
+__global__ void subsample_i32_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ xs, int N, int H,
+                                     int W, int C, int Ho, int Wo, int stride) {
+  VTX_PDL_TRIGGER();
+  const int cg = C / 8;
+  const int total = N * Ho * Wo * cg;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int g = i % cg;
+    const int pos = i / cg;
+    const int wo = pos % Wo;
+    const int t2 = pos / Wo;
+    const int ho = t2 % Ho;
+    const int n = t2 / Ho;
+    *reinterpret_cast<uint4*>(xs + (long long)pos * C + g * 8) =
+        *reinterpret_cast<const uint4*>(x + (((long long)n * H + ho * stride) * W + wo * stride) * C + g * 8);
+  }
+}
+__global__ void upsample_add_i32_kernel(const __nv_bfloat16* __restrict__ dxs, __nv_bfloat16* __restrict__ dx, int N, int H,
+                                        int W, int C, int Ho, int Wo, int stride) {
+  VTX_PDL_TRIGGER();
+  const int cg = C / 8;
+  const int total = N * Ho * Wo * cg;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int g = i % cg;
+    const int pos = i / cg;
+    const int wo = pos % Wo;
+    const int t2 = pos / Wo;
+    const int ho = t2 % Ho;
+    const int n = t2 / Ho;
+    __nv_bfloat16* p = dx + (((long long)n * H + ho * stride) * W + wo * stride) * C + g * 8;
+    float a[8], b[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(p), a);
+    unpack8(*reinterpret_cast<const bf16x8*>(dxs + (long long)pos * C + g * 8), b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] += b[j];
+    *reinterpret_cast<bf16x8*>(p) = pack8(a);
+  }
+}
+#endif
+
 // ---------------------------------------------------------------------------------------------- BatchNorm forward
 // stats [2,C] (sum, sumsq over `count` samples)  ->  bnp [4,C] = mean, invstd, scale = gamma*invstd, shift
 // training: also running_mean/var (momentum, unbiased var) and num_batches_tracked.  eval: statistics come from
@@ -943,6 +984,13 @@ extern "C" int vtx_subsample(const void* x, void* xs, int N, int H, int W, int C
   REQ(x && xs && C % 8 == 0, "bad arguments");
   const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
   const long long total = (long long)N * Ho * Wo * (C / 8);
+#ifdef VTX_BACKBONE_X
+  if (total < (1LL << 31) - (1LL << 24)) {
+    subsample_i32_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)xs, N, H, W, C,
+                                                                   Ho, Wo, stride);
+    return check_launch("subsample_i32");
+  }
+#endif
   subsample_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)xs, N, H, W, C,
                                                              Ho, Wo, stride);
   return check_launch("subsample");
@@ -951,6 +999,13 @@ extern "C" int vtx_upsample_add(const void* dxs, void* dx, int N, int H, int W, 
   REQ(dxs && dx && C % 8 == 0, "bad arguments");
   const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
   const long long total = (long long)N * Ho * Wo * (C / 8);
+#ifdef VTX_BACKBONE_X
+  if (total < (1LL << 31) - (1LL << 24)) {
+    upsample_add_i32_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>((const __nv_bfloat16*)dxs, (__nv_bfloat16*)dx, N, H,
+                                                                      W, C, Ho, Wo, stride);
+    return check_launch("upsample_add_i32");
+  }
+#endif
   upsample_add_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>((const __nv_bfloat16*)dxs, (__nv_bfloat16*)dx, N, H, W,
                                                                 C, Ho, Wo, stride);
   return check_launch("upsample_add");

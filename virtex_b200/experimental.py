@@ -23,7 +23,7 @@ Nothing here is on the default path.  A feature is used only when the environmen
   backbone_x shared-memory tiled stem max-pool (backbone.cu compiled with -DVTX_BACKBONE_X).  Backward: pooled gradients
              and argmax slots are staged once per CTA instead of being gathered from L2 up to nine times; forward:
              BN + ReLU applied once per input element into shared memory, pooled from there.  im2col3x3 /
-             col2im3x3 with 32-bit index arithmetic (the validated kernels are bound by 64-bit integer division).
+             col2im3x3 / subsample / upsample_add with 32-bit index arithmetic (the validated kernels are bound by 64-bit integer division).
 
 Validation procedure on a B200: `VTX_EXPERIMENTAL=all python -m pytest tests -m gpu -q` and
 `VTX_EXPERIMENTAL=all python bench.py`; then move the kernels into the main library.
@@ -41,7 +41,8 @@ FEATURES = ("stem_s2d", "pdl", "head_x", "gemm_x", "backbone_x")
 # the feature is enabled
 ROUTED = {"vtx_ln_bwd": "head_x", "vtx_embed_bwd": "head_x", "vtx_colsum": "head_x", "vtx_cross_entropy": "head_x",
           "vtx_gemm": "gemm_x", "vtx_maxpool_bwd": "backbone_x", "vtx_bn_relu_maxpool": "backbone_x",
-          "vtx_im2col3x3": "backbone_x", "vtx_col2im3x3": "backbone_x"}
+          "vtx_im2col3x3": "backbone_x", "vtx_col2im3x3": "backbone_x", "vtx_subsample": "backbone_x",
+          "vtx_upsample_add": "backbone_x"}
 _ROUTED_SYMBOL = {"vtx_gemm": "vtx_gemm_x"}  # where the name differs in the experimental library
 _P, _I = ctypes.c_void_p, ctypes.c_int
 _PROTOS = {
