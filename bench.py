@@ -145,10 +145,63 @@ def main_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------- incumbent (eager GPU)
+def run_incumbent(args, cfg):
+    """The reference's own GPU path on the same box: eager PyTorch (cuDNN / cuBLASLt / SDPA) under bf16 autocast,
+    channels_last -- scripts/gpu_incumbent.py in a subprocess (its own CUDA context and memory), N = 1 only."""
+    m = __import__("re").match(r"L(\d+)_H(\d+)_A(\d+)_F(\d+)", cfg.MODEL.TEXTUAL.NAME.split("::")[1])
+    cmd = [sys.executable, os.path.join(ROOT, "scripts", "gpu_incumbent.py"), "--variant", "channels_last",
+           "--arch", cfg.MODEL.VISUAL.NAME.split("::")[-1], "--layers", m.group(1), "--hidden", m.group(2),
+           "--batch", str(args.batch_per_gpu), "--steps", "10", "--warmup", "4"]
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+        for line in reversed(out.stdout.strip().splitlines()):
+            if line.startswith("{"):
+                return json.loads(line)["incumbent"]
+        return {"unavailable": (out.stderr.strip().splitlines() or ["no output"])[-1][:200]}
+    except Exception as e:  # noqa: BLE001 -- a reported baseline must never take the bench line down
+        return {"unavailable": repr(e)[:200]}
+
+
+def dp_gradient_check(trainer, dev_batch, world):
+    """Data-parallel parity on real NCCL (scripts/pretrain_virtex.py:121-123, DDP semantics): the gradients the
+    optimiser consumes -- bucketed SUM all-reduce on the side stream, 1/world folded in afterwards -- must equal the
+    mean over ranks of the per-rank gradients.  Checked on every bucket; the reference value comes from an
+    all_gather of the un-reduced gradients."""
+    import torch.distributed as dist
+    eng = trainer.engine
+    eng.seed.add_(1)
+    eng.forward(dev_batch["image"], dev_batch["caption_tokens"], dev_batch["noitpac_tokens"],
+                dev_batch["caption_lengths"], training=True, with_grad=True)
+    eng.backward(zero_grads=True, bucket_cb=None)
+    torch.cuda.synchronize()
+    local = eng.arena.grads.clone()
+    worst = 0.0
+    for tag in trainer._ranges:
+        trainer._on_bucket(tag)
+    for w in trainer._pending:
+        w.wait()
+    trainer._pending.clear()
+    torch.cuda.synchronize()
+    for tag, r in trainer._ranges.items():
+        if r is None:
+            continue
+        n = min(r[1] - r[0], 1 << 22)  # first 4 Mi elements of every bucket: all_gather of the whole arena is not needed
+        mine = local[r[0]:r[0] + n].contiguous()
+        gathered = torch.empty(world * n, dtype=mine.dtype, device=mine.device)
+        dist.all_gather_into_tensor(gathered, mine)
+        mean = gathered.view(world, n).double().mean(0)
+        got = eng.arena.grads[r[0]:r[0] + n].double() / world
+        err = ((got - mean).abs().max() / (mean.abs().max() + 1e-30)).item()
+        worst = max(worst, err)
+    t = torch.tensor([worst], device=local.device, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return {"max_rel_err": float(t.item()), "ok": bool(t.item() < 1e-6), "buckets": [k for k, v in trainer._ranges.items() if v]}
+
+
 # ---------------------------------------------------------------------------------------------------------------- ours
 def main_ours(args, rank, world, local):
     import torch.distributed as dist
-    from virtex_b200 import experimental as X
     from virtex_b200 import ops
     from virtex_b200.config import Config
     from virtex_b200.factories import PretrainingModelFactory
@@ -278,14 +331,20 @@ def main_ours(args, rank, world, local):
 
         g_by = sum(min_bytes(*p) for p in half)
         t_min = sum(max(p[1] / (peak_tf * 1e12), min_bytes(*p) / (peak_bw * 1e9)) for p in half) * 1e3  # ms
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r01_gemm_dram_traffic.json")
-        if os.path.exists(tpath):
-            with open(tpath) as f:
-                traffic = json.load(f).get("dram_bytes_per_launch")
+        # DRAM bytes cannot be counted without ncu: `traffic` is the per-launch average of the committed ncu capture of
+        # this same command (profiles/, newest round first); traffic_source says which capture and at which commit
+        traffic = traffic_src = None
+        for tname in ("r02_gemm_dram_traffic.json", "r01_gemm_dram_traffic.json"):
+            tpath = os.path.join(ROOT, "profiles", tname)
+            if os.path.exists(tpath):
+                with open(tpath) as f:
+                    tj = json.load(f)
+                traffic, traffic_src = tj.get("dram_bytes_per_launch"), f"profiles/{tname} @ {tj.get('commit', 'round-1 kernel')}"
+                break
         roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 GEMM: all convs + linears)",
                 "achieved": round(g_fl / (g_ms * 1e-3) / 1e12, 1), "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": round(g_fl / (g_ms * 1e-3) / 1e12 / peak_tf, 4), "traffic": traffic, "peak_source": peak_src,
+                "frac": round(g_fl / (g_ms * 1e-3) / 1e12 / peak_tf, 4), "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": peak_src,
                 "launches_per_step": len(prof) // 2, "gemm_ms_per_step": round(g_ms, 3),
                 "gemm_share_of_step": round(g_ms / prof_ms, 3),
                 "algorithmic_gflop_per_launch": round(g_fl / 1e9 / (len(prof) // 2), 2),
@@ -297,23 +356,32 @@ def main_ours(args, rank, world, local):
                         "launches (layer1-2 convs, all wgrads) are HBM-bound, so per_launch_roofline_frac = "
                         "sum(max(flops/peak_tf, min_bytes/peak_bw))/sum(time) is the tighter figure"}
     barrier()
+    dp = dp_gradient_check(trainer, dev_batch, world) if world > 1 else None
+    name = f"{cfg.MODEL.VISUAL.NAME.split('::')[-1]} + {cfg.MODEL.TEXTUAL.NAME}"
 
     if rank == 0:
+        incumbent = None
+        if world == 1 and not args.skip_incumbent:
+            del trainer, model
+            torch.cuda.empty_cache()
+            incumbent = run_incumbent(args, cfg)
         cpu_v, cpu_sec, cpu_threads = run_cpu_reference(2, 1, args.cpu_batch) if not args.skip_cpu else (None, None, 0)
         line = {"metric": METRIC, "value": round(value, 1), "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": f"bicaptioning R50_L1_H1024 full optimisation step, batch {B} per GPU",
+                "config": {"workload": f"bicaptioning {name} full optimisation step, batch {B} per GPU",
                            "config_file": args.config, "global_batch": B * world, "seq_len": T,
                            "parallelism": f"dp{world}", "dropout": cfg.MODEL.TEXTUAL.DROPOUT,
-                           "l2_policy": "per-step working set (>= 150 MB of inputs, GBs of activations) exceeds the 126 MB L2",
-                           "experimental": [f for f in X.FEATURES if X.enabled(f)]},
+                           "l2_policy": "per-step working set (>= 150 MB of inputs, GBs of activations) exceeds the 126 MB L2"},
                 "loss": round(loss_val, 4), "clocks": clk,
                 "e2e": {"value": round(e2e_value, 1), "unit": "pairs/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": 8, "ms_per_step": round(ms_e2e / args.steps, 3),
                         "api": "virtex_b200.trainer.Trainer.step on pinned host batches"},
                 "gpu_launches": launches, "roofline": roof,
-                "model_tflops": round(value * GFLOP_PER_PAIR / 1e3, 1),
+                "model_tflops": round(value * (roof["algorithmic_gflop_per_launch"] * roof["launches_per_step"] / B) / 1e3, 1),
+                "incumbent": incumbent,
+                "vs_incumbent": (round(value / incumbent["pairs_s"], 3) if incumbent and "pairs_s" in incumbent else None),
+                "dp_check": dp,
                 "cpu_baseline": None if cpu_v is None else {
                     "value": round(cpu_v, 3), "unit": "pairs/s", "cores": cpu_threads, "kind": "port",
                     "sample": f"2 full steps at batch {args.cpu_batch} after 1 warm-up (oracle port of the reference, fp32)"}}
@@ -333,6 +401,7 @@ def main():
     ap.add_argument("--config", default="_base_bicaptioning_R_50_L1_H1024.yaml")
     ap.add_argument("--config-override", nargs="*", default=[])
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-incumbent", action="store_true")
     ap.add_argument("--dump-gemm-profile", default="")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))

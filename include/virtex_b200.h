@@ -68,7 +68,12 @@ typedef struct VtxGemm {
   int32_t conv_mode; /* 0 = plain GEMM, 1 = implicit fprop/dgrad gather on A (64->64 channel problems run the halo-reuse
                         variant automatically), 2 = wgrad gather on B,
                         4 = halo-reuse wgrad for C = Cout = 64: A = dy, B = x, D[9*C, Cout] fp32 += (atomic),
-                            i.e. the TRANSPOSE of mode 2's [Cout, 9*C] output */
+                            i.e. the TRANSPOSE of mode 2's [Cout, 9*C] output,
+                        5 = 7x7/2 stem fprop over the space-to-depth view S written by vtx_stem_s2d: A = S
+                            [conv_n, conv_h + 3, conv_w + 3, 16] (conv_h x conv_w = OUTPUT size, conv_c = 64 = 4 pixels
+                            x 16 channels), B = packed weights [64, 256] (vtx_stem_s2d_w_pack), D [n*h*w, 64] NHWC
+                            (torchvision resnet.py:197 conv1 forward, BN statistics through `stats`),
+                        6 = stem wgrad: A = dy [conv_n, conv_h, conv_w, 64], B = S; D [64, 256] fp32 += (atomic) */
 } VtxGemm;
 
 int vtx_gemm(const VtxGemm* g, void* stream);
@@ -79,6 +84,14 @@ int vtx_gemm(const VtxGemm* g, void* stream);
  * ------------------------------------------------------------------------------------------------------------------ */
 /* 7x7/stride 2/pad 3 stem: image fp32 NCHW -> cols bf16 [N*Ho*Wo, ldc], k = (kh*7+kw)*3 + c, zero padded to ldc */
 int vtx_stem_im2col(const float* img, void* cols, int N, int H, int W, int ldc, void* stream);
+/* space-to-depth view of the image for the 4-tap implicit stem conv (vtx_gemm conv_mode 5 / 6):
+   image fp32 NCHW [N, 3, H, W] -> S bf16 [N, H/2 + 3, W/2 + 3, 16],
+   S[n, i, j, (r*2+q)*3 + c] = img[n, c, 2i + r - 3, 2j + q - 3], zero outside the image and in channels 12..15 */
+int vtx_stem_s2d(const float* img, void* S, int N, int H, int W, void* stream);
+/* conv1.weight fp32 [O, 3, 7, 7] -> bf16 [O, 256], k = a*64 + b*16 + (r*2+q)*3 + c for tap (kh, kw) = (2a+r, 2b+q) */
+int vtx_stem_s2d_w_pack(const float* w, void* wp, int O, void* stream);
+/* grad fp32 [O, 3, 7, 7] += dwp fp32 [O, 256] (same index map) */
+int vtx_stem_s2d_w_unpack_add(const float* dwp, float* grad, int O, void* stream);
 /* 3x3 / pad 1 / given stride: x [N,H,W,C] -> cols [N*Ho*Wo, 9*C] (k = tap*C + c) and its adjoint */
 int vtx_im2col3x3(const void* x, void* cols, int N, int H, int W, int C, int stride, void* stream);
 int vtx_col2im3x3(const void* dcols, void* dx, int N, int H, int W, int C, int stride, void* stream);
@@ -89,31 +102,33 @@ int vtx_upsample_add(const void* dxs, void* dx, int N, int H, int W, int C, int 
 int vtx_bn_finalize(const float* stats, float count, const float* gamma, const float* beta, float* running_mean,
                     float* running_var, int64_t* num_batches_tracked, float momentum, float eps, int training,
                     float* bnp, int C, void* stream);
-/* out = act(y*scale + shift [+ res | + res*scale_r + shift_r]) */
-int vtx_bn_act(const void* y, const float* bnp, const void* res, const float* bnp_res, void* out, int64_t M, int C,
-               int relu, void* stream);
+/* out = act(y*scale + shift [+ res | + res*scale_r + shift_r]).  relu_mask (optional, relu only): uint8 [M, C/8], bit j
+   of byte (m, g) = [pre-activation of channel 8g + j > 0] -- all that BN backward needs of `out` (1/16 of its bytes) */
+int vtx_bn_act(const void* y, const float* bnp, const void* res, const float* bnp_res, void* out, uint8_t* relu_mask,
+               int64_t M, int C, int relu, void* stream);
 /* vtx_bn_finalize + vtx_bn_act fused into one launch */
 int vtx_bn_finalize_act(const float* stats, float count, const float* gamma, const float* beta, float* running_mean,
                         float* running_var, int64_t* num_batches_tracked, float momentum, float eps, int training,
-                        float* bnp, const void* y, const void* res, const float* bnp_res, void* out, int64_t M, int C,
-                        int relu, void* stream);
+                        float* bnp, const void* y, const void* res, const float* bnp_res, void* out, uint8_t* relu_mask,
+                        int64_t M, int C, int relu, void* stream);
 int vtx_bn_relu_maxpool(const void* y, const float* bnp, void* out, uint8_t* idx, int N, int H, int W, int C,
                         void* stream);
 int vtx_maxpool_bwd(const void* dpool, const uint8_t* idx, void* da, int N, int H, int W, int C, void* stream);
-/* BN backward in three steps: per-channel sums of dz and dz*xhat (dz = dA*[a>0]); coefficients + dgamma/dbeta;
+/* BN backward in three steps: per-channel sums of dz and dz*xhat (dz = dA*[relu_mask bit]); coefficients + dgamma/dbeta;
    dy = scale*(dz - mean(dz) - xhat*mean(dz*xhat)).  A second BN sharing dz (downsample branch) rides along.
-   a == NULL && mask_from_y: the ReLU mask is recomputed as [y*scale + shift > 0] instead of being read. */
-int vtx_bn_bwd_reduce(const void* dA, const void* a, const void* y, const float* bnp, const void* y2,
+   relu_mask: the uint8 bit mask written by vtx_bn_act / vtx_bn_finalize_act, or NULL;
+   relu_mask == NULL && mask_from_y: the ReLU mask is recomputed as [y*scale + shift > 0] instead of being read. */
+int vtx_bn_bwd_reduce(const void* dA, const uint8_t* relu_mask, const void* y, const float* bnp, const void* y2,
                       const float* bnp2, float* sums, float* sums2, int64_t M, int C, int mask_from_y,
                       void* stream);
 int vtx_bn_bwd_finalize(const float* sums, const float* bnp, float count, float* coef, float* dgamma, float* dbeta,
                         int C, void* stream);
-int vtx_bn_bwd_apply(const void* dA, const void* a, const void* y, const float* bnp, const float* coef, void* dy,
+int vtx_bn_bwd_apply(const void* dA, const uint8_t* relu_mask, const void* y, const float* bnp, const float* coef, void* dy,
                      const void* y2, const float* bnp2, const float* coef2, void* dy2, void* dz_out, int64_t M, int C,
                      int mask_from_y, void* stream);
 /* vtx_bn_bwd_finalize + vtx_bn_bwd_apply fused into one launch (dgamma/dbeta accumulated by the first thread block) */
 int vtx_bn_bwd_finalize_apply(const float* sums, const float* sums2, float count, float* dgamma, float* dbeta,
-                              float* dgamma2, float* dbeta2, const void* dA, const void* a, const void* y,
+                              float* dgamma2, float* dbeta2, const void* dA, const uint8_t* relu_mask, const void* y,
                               const float* bnp, void* dy, const void* y2, const float* bnp2, void* dy2, void* dz_out,
                               int64_t M, int C, int mask_from_y, void* stream);
 /* conv weight layouts: fp32 OIHW <-> bf16 [O, (kh,kw,I)] GEMM operand; flipped/transposed dgrad operand */
@@ -161,6 +176,28 @@ int vtx_cross_entropy(void* logits, int64_t ldl, const int64_t* tokens, int B, i
                       const float* count, float* loss, int write_grad, void* stream);
 int vtx_colsum(const void* X, int64_t ld, int M, int N, float* out, void* stream);
 int vtx_argmax_rows(const float* X, int64_t ld, int M, int N, int64_t* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * GPU input pipeline (csrc/input_pipe.cu): decoded uint8 HWC images -> fp32 NCHW network input, token lists -> padded
+ * matrices.  Replaces the per-sample albumentations / cv2 transforms and the collate of
+ * virtex/data/datasets/captioning.py:51-100 with the transform lists of virtex/factories.py:131-155.  Random parameters
+ * are sampled on the host.  src: all images of the batch back to back (uint8, RGB, HWC), image n at src + src_off[n];
+ * geom_i [B,8] = {H, W, region y0, x0, h, w, window offset y, x}; geom_d [B,2] = {region h / resized h, region w /
+ * resized w}; jit_i [B,6] = {flip, apply-jitter, op order[4] (0 brightness, 1 contrast, 2 saturation, 3 hue)};
+ * jit_d [B,4] = the four factors.  Integer paths are bit-exact with OpenCV's uint8 resize / cvtColor / addWeighted.
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* crop + cv2.resize(INTER_LINEAR) (+ horizontal flip): out uint8 [B, S, S, 3] */
+int vtx_image_resample(const uint8_t* src, const int64_t* src_off, const int32_t* geom_i, const double* geom_d,
+                       const int32_t* jit_i, uint8_t* out, int B, int S, void* stream);
+/* gray_sum[n] += sum of grey values of image n at the contrast stage of its jitter (caller zero-initialises) */
+int vtx_image_gray_sum(const uint8_t* img, const int32_t* jit_i, const double* jit_d, uint64_t* gray_sum, int B, int S,
+                       void* stream);
+/* colour jitter in the sampled op order + (v - mean*255) / (std*255), written as fp32 NCHW; norm = {m[3], 1/s[3]} */
+int vtx_image_jitter_normalize(const uint8_t* img, const int32_t* jit_i, const double* jit_d, const uint64_t* gray_sum,
+                               const float* norm, float* out, int B, int S, void* stream);
+/* flat token ids + offsets [B+1] -> caption / reversed caption [B, T] right-padded with pad, lengths [B] (<= max_len) */
+int vtx_collate_tokens(const int64_t* flat, const int64_t* offs, int64_t* cap, int64_t* rev, int64_t* lengths, int B,
+                       int T, int max_len, int64_t pad, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Fused optimiser tail over flat fp32 arenas (scripts/pretrain_virtex.py:157-162; virtex/factories.py:529-545;

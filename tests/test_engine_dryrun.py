@@ -2,7 +2,7 @@
 call against the C-ABI prototype (argument count) and the GEMM operands against the buffer sizes they imply.  No
 arithmetic runs -- this is not a CPU path (the product refuses CPU tensors, tests/test_host_cpu.py::test_no_cpu_fallback);
 it exercises the Python schedule (shapes, workspaces, tape, optional branches) for configurations and edge shapes that
-the GPU suite also runs, plus the opt-in experimental branches."""
+the GPU suite also runs."""
 import pytest
 import torch
 
@@ -46,10 +46,10 @@ def _check_gemm(A, B, D, M, N, K, lda=None, ldb=None, ldd=None, a_mn=0, b_mn=0, 
         elif conv_mode == 4:
             assert C == 64 and N == 64 and M == 9 * C and K == NI * H * W and f32 and atomic
             assert A.numel() >= K * N and B.numel() >= K * C and D.numel() >= M * N
-        elif conv_mode == 5:   # experimental stem fprop over the space-to-depth view
+        elif conv_mode == 5:   # stem fprop over the space-to-depth view
             assert C == 64 and N == 64 and K == 256 and M == NI * H * W
             assert A.numel() >= NI * (H + 3) * (W + 3) * 16 and B.numel() >= 64 * 256 and D.numel() >= M * N
-        elif conv_mode == 6:   # experimental stem wgrad
+        elif conv_mode == 6:   # stem wgrad
             assert C == 64 and M == 64 and N == 256 and K == NI * H * W and f32 and atomic
             assert A.numel() >= K * 64 and B.numel() >= NI * (H + 3) * (W + 3) * 16 and D.numel() >= M * N
         else:
@@ -64,8 +64,8 @@ def _check_gemm(A, B, D, M, N, K, lda=None, ldb=None, ldd=None, a_mn=0, b_mn=0, 
 
 @pytest.fixture
 def dry(monkeypatch):
-    """Patch the launchers of virtex_b200.engine (and the experimental module) with checking recorders."""
-    from virtex_b200 import engine as E, experimental as X, ops
+    """Patch the launchers of virtex_b200.engine with checking recorders."""
+    from virtex_b200 import engine as E, ops
     rec = Recorder()
 
     def fake_call(name, *args):
@@ -76,20 +76,10 @@ def dry(monkeypatch):
         _check_gemm(A, B, D, M, N, K, **kw)
         rec.calls.append(("gemm", M, N, K, kw.get("conv_mode", 0)))
 
-    def fake_xcall(name, *args):
-        assert len(args) == len(X._PROTOS[name]), (name, len(args))
-        rec.calls.append(name)
-
-    def fake_xgemm(A, B, D, M, N, K, **kw):
-        _check_gemm(A, B, D, M, N, K, **kw)
-        rec.calls.append(("gemm_x", M, N, K, kw.get("conv_mode", 0)))
-
     monkeypatch.setattr(E, "call", fake_call)
     monkeypatch.setattr(E, "gemm", fake_gemm)
     monkeypatch.setattr(E, "_stream", lambda: 0)
     monkeypatch.setattr(E, "_require_cuda", lambda dev: None)
-    monkeypatch.setattr(X, "call", fake_xcall)
-    monkeypatch.setattr(X, "gemm", fake_xgemm)
     monkeypatch.setattr(ops, "num_sms", lambda: 148)
     return rec
 
@@ -140,7 +130,7 @@ def test_training_step_schedule(dry, spec_kw, batch_kw):
     assert len([g for g in gemms if g[0] == "gemm"]) >= 3 * (3 * n_blocks + 4 + 1) - 1
     assert names.count("vtx_cross_entropy") == 2 and names.count("vtx_embed_fwd") == 2
     assert names.count("vtx_attn_fwd") == 2 * 2 * spec.layers == names.count("vtx_attn_bwd")
-    assert "vtx_stem_im2col" in names and not any(g[0] == "gemm_x" for g in gemms)
+    assert "vtx_stem_s2d" in names and "vtx_stem_im2col" not in names
     # layer1's three 64 -> 64 3x3 convs use the halo-reuse wgrad
     assert len([g for g in gemms if g[4] == 4]) == 3
 
@@ -162,15 +152,15 @@ def test_eval_forward_only_and_frozen_backbone(dry):
     assert dry.names().count("vtx_cross_entropy") == 1
 
 
-def test_experimental_stem_branch_schedule(dry, monkeypatch):
-    monkeypatch.setenv("VTX_EXPERIMENTAL", "stem_s2d")
+def test_stem_branch_schedule(dry):
+    """224-class image sizes run the space-to-depth implicit stem conv; sizes the TMA boxes do not tile exactly run
+    the im2col route."""
     spec = O.Spec(**SMALL)
     _run(_model(spec), O.synth_batch(2, seed=8))
     names = dry.names()
     gemms = [c for c in dry.calls if not isinstance(c, str)]
-    assert "vtx_stem_im2col" not in names and "vtx_x_stem_s2d" in names and "vtx_x_stem_w_pack" in names
-    assert [g[4] for g in gemms if g[0] == "gemm_x"] == [5, 6] and "vtx_x_stem_w_unpack_add" in names
-    # an image size whose output is not tiled exactly by the TMA boxes falls back to the validated path
+    assert "vtx_stem_im2col" not in names and "vtx_stem_s2d" in names and "vtx_stem_s2d_w_pack" in names
+    assert [g[4] for g in gemms if g[4] in (5, 6)] == [5, 6] and "vtx_stem_s2d_w_unpack_add" in names
     dry.calls.clear()
     _run(_model(spec), O.synth_batch(2, seed=9, image_size=200))
-    assert "vtx_stem_im2col" in dry.names() and "vtx_x_stem_s2d" not in dry.names()
+    assert "vtx_stem_im2col" in dry.names() and "vtx_stem_s2d" not in dry.names()

@@ -1,0 +1,349 @@
+"""Stand-alone GPU tests of every backbone elementwise / gather kernel and of the dropout sites, each against a plain
+torch fp32 formula of the same op (the library ops the reference calls: torchvision/models/resnet.py:143-163 BatchNorm +
+ReLU + residual, F.max_pool2d, F.unfold/fold for the strided-conv gathers; nn.Dropout for the head).  All calls go
+through the C ABI (virtex_b200.ops.call).  Tolerances: bf16 outputs -> 1 bf16 ulp of the fp32 result (rel 8e-3 on the
+tensor norm, and max-abs 2^-7 relative to the largest magnitude); fp32 reductions -> 1e-4 relative.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+def _need_cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+
+
+def _ops():
+    from virtex_b200 import ops
+    return ops
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def _s():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _pack_mask(keep):
+    """[M, C] bool -> uint8 [M, C/8], bit j of byte g = channel 8g + j (the layout vtx_bn_act writes)."""
+    M, C = keep.shape
+    w = (1 << torch.arange(8, device=keep.device)).to(torch.int32)
+    return (keep.view(M, C // 8, 8).to(torch.int32) * w).sum(-1).to(torch.uint8).contiguous()
+
+
+def _bnp(C, g, dev="cuda"):
+    """[4, C]: mean, invstd, scale = gamma * invstd, shift = beta - mean * scale."""
+    mean = torch.randn(C, generator=g) * 0.5
+    invstd = torch.rand(C, generator=g) + 0.5
+    gamma = torch.rand(C, generator=g) + 0.5
+    beta = torch.randn(C, generator=g) * 0.3
+    sc = gamma * invstd
+    return torch.stack([mean, invstd, sc, beta - mean * sc]).contiguous().to(dev)
+
+
+# ------------------------------------------------------------------------------------------------ BN forward family
+@pytest.mark.parametrize("M,C,mode", [(1000, 64, "plain"), (777, 256, "res"), (513, 512, "res_bn"), (64, 2048, "plain")])
+def test_bn_act_matches_formula(M, C, mode):
+    _need_cuda()
+    ops = _ops()
+    g = torch.Generator().manual_seed(M + C)
+    y = torch.randn(M, C, generator=g).bfloat16().cuda()
+    bnp = _bnp(C, g)
+    res = torch.randn(M, C, generator=g).bfloat16().cuda() if mode != "plain" else None
+    bnp_r = _bnp(C, g) if mode == "res_bn" else None
+    out = torch.empty(M, C, dtype=BF16, device="cuda")
+    mask = torch.full((M, C // 8), 0xAA, dtype=torch.uint8, device="cuda")
+    ops.call("vtx_bn_act", y.data_ptr(), bnp.data_ptr(), ops._p(res), ops._p(bnp_r), out.data_ptr(), mask.data_ptr(), M,
+             C, 1, _s())
+    ref = y.float() * bnp[2] + bnp[3]
+    if mode == "res":
+        ref = ref + res.float()
+    if mode == "res_bn":
+        ref = ref + res.float() * bnp_r[2] + bnp_r[3]
+    pre = ref
+    ref = ref.clamp_min(0)
+    assert rel(out, ref) < 4e-3
+    assert (out.float() - ref).abs().max().item() <= 2 ** -7 * ref.abs().max().item()
+    # the ReLU bit mask is exactly the sign of the stored activation (what backward used to read), up to fp32 contraction
+    # of values within 1e-6 of zero
+    got = mask.view(M, C // 8, 1).bitwise_right_shift(torch.arange(8, device="cuda").to(torch.uint8)).bitwise_and(1)
+    got = got.view(M, C).bool()
+    sure = pre.abs() > 1e-5
+    assert torch.equal(got[sure], (pre > 0)[sure])
+    assert torch.equal(got, out.float() > 0) or (got != (out.float() > 0)).sum().item() <= 2
+
+
+def test_bn_finalize_act_fold_matches_batchnorm():
+    """sum / sumsq -> (mean, invstd, scale, shift), running-statistics update and apply in one launch == F.batch_norm."""
+    _need_cuda()
+    ops = _ops()
+    M, C = 1536, 128
+    g = torch.Generator().manual_seed(1)
+    y = (torch.randn(M, C, generator=g) * 2 + 0.5).bfloat16().cuda()
+    yf = y.float()
+    stats = torch.stack([yf.sum(0), (yf * yf).sum(0)]).contiguous()
+    gamma, beta = (torch.rand(C, generator=g) + 0.5).cuda(), torch.randn(C, generator=g).cuda()
+    rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    nbt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    bnp = torch.empty(4, C, device="cuda")
+    out = torch.empty(M, C, dtype=BF16, device="cuda")
+    ops.call("vtx_bn_finalize_act", stats.data_ptr(), float(M), gamma.data_ptr(), beta.data_ptr(), rm.data_ptr(),
+             rv.data_ptr(), nbt.data_ptr(), 0.1, 1e-5, 1, bnp.data_ptr(), y.data_ptr(), 0, 0, out.data_ptr(), 0, M, C, 1,
+             _s())
+    rm_ref, rv_ref = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    ref = F.relu(F.batch_norm(yf, rm_ref, rv_ref, gamma, beta, True, 0.1, 1e-5))
+    assert rel(out, ref) < 4e-3
+    assert rel(rm, rm_ref) < 1e-4 and rel(rv, rv_ref) < 1e-4
+    assert int(nbt) == 1
+    assert rel(bnp[0], yf.mean(0)) < 1e-4 and rel(bnp[1], (yf.var(0, unbiased=False) + 1e-5).rsqrt()) < 1e-3
+
+
+# ------------------------------------------------------------------------------------------------ BN backward family
+@pytest.mark.parametrize("M,C,mask", [(2000, 64, "from_a"), (1111, 256, "from_y"), (640, 1024, "none")])
+def test_bn_backward_reduce_and_apply_match_autograd(M, C, mask):
+    """dz = dA * relu'(.) ; dy = BN-backward(dz) with batch statistics; dgamma / dbeta accumulate."""
+    _need_cuda()
+    ops = _ops()
+    g = torch.Generator().manual_seed(M)
+    y = (torch.randn(M, C, generator=g) * 1.5).bfloat16().cuda()
+    yf = y.float()
+    gamma, beta = (torch.rand(C, generator=g) + 0.5).cuda(), (torch.randn(C, generator=g) * 0.3).cuda()
+    mean, var = yf.mean(0), yf.var(0, unbiased=False)
+    invstd = (var + 1e-5).rsqrt()
+    bnp = torch.stack([mean, invstd, gamma * invstd, beta - mean * gamma * invstd]).contiguous()
+    dA = (torch.randn(M, C, generator=g) * 0.1).bfloat16().cuda()
+    pre = yf * bnp[2] + bnp[3]
+    a = _pack_mask(pre > 0) if mask == "from_a" else None  # the bit mask vtx_bn_act writes next to the activation
+    if mask == "from_a":
+        keep = (pre > 0).float()
+    elif mask == "from_y":
+        keep = (pre > 0).float()
+    else:
+        keep = torch.ones_like(pre)
+    dz = dA.float() * keep
+    sums = torch.zeros(2, C, device="cuda")
+    ops.call("vtx_bn_bwd_reduce", dA.data_ptr(), ops._p(a), y.data_ptr(), bnp.data_ptr(), 0, 0, sums.data_ptr(), 0, M,
+             C, int(mask == "from_y"), _s())
+    xhat = (yf - mean) * invstd
+    assert rel(sums[0], dz.sum(0)) < 1e-4
+    assert rel(sums[1], (dz * xhat).sum(0)) < 1e-4
+    dgamma, dbeta = torch.full((C,), 0.5, device="cuda"), torch.full((C,), -0.25, device="cuda")
+    dy = torch.empty(M, C, dtype=BF16, device="cuda")
+    dz_out = torch.empty(M, C, dtype=BF16, device="cuda")
+    ops.call("vtx_bn_bwd_finalize_apply", sums.data_ptr(), 0, float(M), dgamma.data_ptr(), dbeta.data_ptr(), 0, 0,
+             dA.data_ptr(), ops._p(a), y.data_ptr(), bnp.data_ptr(), dy.data_ptr(), 0, 0, 0, dz_out.data_ptr(), M, C,
+             int(mask == "from_y"), _s())
+    # autograd reference of y -> batch_norm(train) with upstream gradient dz
+    yr = yf.clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    F.batch_norm(yr, None, None, gr, br, True, 0.0, 1e-5).backward(dz)
+    assert rel(dy, yr.grad) < 6e-3
+    assert rel(dgamma - 0.5, gr.grad) < 1e-3 and rel(dbeta + 0.25, br.grad) < 1e-3
+    assert rel(dz_out, dz) < 1e-6 or mask == "none"  # dz is dA with zeros: exact in bf16
+
+
+def test_bn_backward_two_branch_variant_shares_dz():
+    """bn3 + downsample BN of a transition block: one masked dz feeds both BN backward formulas."""
+    _need_cuda()
+    ops = _ops()
+    M, C = 900, 512
+    g = torch.Generator().manual_seed(9)
+    ys = [(torch.randn(M, C, generator=g) * s).bfloat16().cuda() for s in (1.0, 2.0)]
+    bnps, gammas = [], []
+    for y in ys:
+        yf = y.float()
+        gamma, beta = (torch.rand(C, generator=g) + 0.5).cuda(), (torch.randn(C, generator=g) * 0.3).cuda()
+        mean, invstd = yf.mean(0), (yf.var(0, unbiased=False) + 1e-5).rsqrt()
+        bnps.append(torch.stack([mean, invstd, gamma * invstd, beta - mean * gamma * invstd]).contiguous())
+        gammas.append(gamma)
+    pre = ys[0].float() * bnps[0][2] + bnps[0][3] + ys[1].float() * bnps[1][2] + bnps[1][3]
+    a = _pack_mask(pre > 0)
+    dA = (torch.randn(M, C, generator=g) * 0.1).bfloat16().cuda()
+    dz = dA.float() * (pre > 0).float()
+    s1, s2 = torch.zeros(2, C, device="cuda"), torch.zeros(2, C, device="cuda")
+    ops.call("vtx_bn_bwd_reduce", dA.data_ptr(), a.data_ptr(), ys[0].data_ptr(), bnps[0].data_ptr(), ys[1].data_ptr(),
+             bnps[1].data_ptr(), s1.data_ptr(), s2.data_ptr(), M, C, 0, _s())
+    dg = [torch.zeros(C, device="cuda") for _ in range(4)]
+    dy1, dy2 = torch.empty(M, C, dtype=BF16, device="cuda"), torch.empty(M, C, dtype=BF16, device="cuda")
+    ops.call("vtx_bn_bwd_finalize_apply", s1.data_ptr(), s2.data_ptr(), float(M), dg[0].data_ptr(), dg[1].data_ptr(),
+             dg[2].data_ptr(), dg[3].data_ptr(), dA.data_ptr(), a.data_ptr(), ys[0].data_ptr(), bnps[0].data_ptr(),
+             dy1.data_ptr(), ys[1].data_ptr(), bnps[1].data_ptr(), dy2.data_ptr(), 0, M, C, 0, _s())
+    for y, gamma, dy, dgam, dbet in ((ys[0], gammas[0], dy1, dg[0], dg[1]), (ys[1], gammas[1], dy2, dg[2], dg[3])):
+        yr = y.float().clone().requires_grad_(True)
+        gr = gamma.clone().requires_grad_(True)
+        br = torch.zeros(C, device="cuda", requires_grad=True)
+        F.batch_norm(yr, None, None, gr, br, True, 0.0, 1e-5).backward(dz)
+        assert rel(dy, yr.grad) < 6e-3
+        assert rel(dgam, gr.grad) < 1e-3 and rel(dbet, br.grad) < 1e-3
+
+
+# ------------------------------------------------------------------------------------------------ stem pooling pair
+@pytest.mark.parametrize("N,H,W,C", [(3, 112, 112, 64), (2, 30, 22, 64), (2, 7, 9, 64)])
+def test_bn_relu_maxpool_and_backward_match_torch(N, H, W, C):
+    _need_cuda()
+    ops = _ops()
+    g = torch.Generator().manual_seed(H * W)
+    y = torch.randn(N * H * W, C, generator=g).bfloat16().cuda()
+    bnp = _bnp(C, g)
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    out = torch.empty(N * Ho * Wo, C, dtype=BF16, device="cuda")
+    idx = torch.empty(N * Ho * Wo, C, dtype=torch.uint8, device="cuda")
+    ops.call("vtx_bn_relu_maxpool", y.data_ptr(), bnp.data_ptr(), out.data_ptr(), idx.data_ptr(), N, H, W, C, _s())
+    # the kernel pools the bf16-ROUNDED activation (what a separate bn_act pass would have stored)
+    act = (y.float() * bnp[2] + bnp[3]).clamp_min(0).bfloat16().float()
+    act_nchw = act.view(N, H, W, C).permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    ref = F.max_pool2d(act_nchw, 3, 2, 1)
+    ref_nhwc = ref.permute(0, 2, 3, 1).reshape(N * Ho * Wo, C)
+    assert torch.equal(out.float(), ref_nhwc.detach())
+    dpool = torch.randn(N * Ho * Wo, C, generator=g).bfloat16().cuda()
+    da = torch.empty(N * H * W, C, dtype=BF16, device="cuda")
+    ops.call("vtx_maxpool_bwd", dpool.data_ptr(), idx.data_ptr(), da.data_ptr(), N, H, W, C, _s())
+    # window scan order and the strict `>` comparison are those of ATen's max_pool2d: ties (several zeros after the
+    # ReLU in one window) go to the first element in (kh, kw) order in both, so the gradients agree element-wise
+    ref.backward(dpool.float().view(N, Ho, Wo, C).permute(0, 3, 1, 2))
+    ref_da = act_nchw.grad.permute(0, 2, 3, 1).reshape(N * H * W, C)
+    assert rel(da, ref_da) < 4e-3
+
+
+# ------------------------------------------------------------------------------------------------ strided-conv gathers
+@pytest.mark.parametrize("N,H,W,C,stride", [(2, 14, 14, 128, 2), (3, 9, 11, 64, 2), (2, 8, 8, 64, 1)])
+def test_im2col3x3_col2im3x3_match_unfold_fold(N, H, W, C, stride):
+    _need_cuda()
+    ops = _ops()
+    g = torch.Generator().manual_seed(H + W)
+    x = torch.randn(N, H, W, C, generator=g).bfloat16().cuda()
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    cols = torch.empty(N * Ho * Wo, 9 * C, dtype=BF16, device="cuda")
+    ops.call("vtx_im2col3x3", x.data_ptr(), cols.data_ptr(), N, H, W, C, stride, _s())
+    unf = F.unfold(x.float().permute(0, 3, 1, 2), 3, padding=1, stride=stride)          # [N, C*9, L], k = c*9 + tap
+    ref = unf.view(N, C, 9, Ho * Wo).permute(0, 3, 2, 1).reshape(N * Ho * Wo, 9 * C)     # k = tap*C + c
+    assert torch.equal(cols.float(), ref)
+    dcols = torch.randn(N * Ho * Wo, 9 * C, generator=g).bfloat16().cuda()
+    dx = torch.empty(N, H, W, C, dtype=BF16, device="cuda")
+    ops.call("vtx_col2im3x3", dcols.data_ptr(), dx.data_ptr(), N, H, W, C, stride, _s())
+    d = dcols.float().view(N, Ho * Wo, 9, C).permute(0, 3, 2, 1).reshape(N, C * 9, Ho * Wo)
+    ref_dx = F.fold(d, (H, W), 3, padding=1, stride=stride).permute(0, 2, 3, 1)
+    assert rel(dx, ref_dx) < 4e-3
+
+
+@pytest.mark.parametrize("N,H,W,C", [(2, 14, 14, 256), (3, 7, 9, 64)])
+def test_subsample_upsample_add_match_slicing(N, H, W, C):
+    _need_cuda()
+    ops = _ops()
+    g = torch.Generator().manual_seed(C)
+    x = torch.randn(N, H, W, C, generator=g).bfloat16().cuda()
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    xs = torch.empty(N, Ho, Wo, C, dtype=BF16, device="cuda")
+    ops.call("vtx_subsample", x.data_ptr(), xs.data_ptr(), N, H, W, C, 2, _s())
+    assert torch.equal(xs, x[:, ::2, ::2])
+    dxs = torch.randn(N, Ho, Wo, C, generator=g).bfloat16().cuda()
+    dx = torch.randn(N, H, W, C, generator=g).bfloat16().cuda()
+    ref = dx.float().clone()
+    ref[:, ::2, ::2] += dxs.float()
+    ops.call("vtx_upsample_add", dxs.data_ptr(), dx.data_ptr(), N, H, W, C, 2, _s())
+    assert rel(dx, ref) < 4e-3
+
+
+# ------------------------------------------------------------------------------------------------ dropout sites
+def _seed(v):
+    return torch.tensor([v], dtype=torch.int64, device="cuda")
+
+
+def test_gelu_dropout_keep_rate_scaling_and_mask_agreement():
+    """nn.Dropout semantics (embedding.py:46, transformer.py:1173-1199): keep rate 1-p within 3 sigma, kept values
+    scaled by 1/(1-p) (so E[out] = gelu(u)), and backward applies the SAME mask as forward."""
+    _need_cuda()
+    ops = _ops()
+    n, p = 1 << 20, 0.1
+    g = torch.Generator().manual_seed(0)
+    u = (torch.randn(n, generator=g) + 1.5).bfloat16().cuda()
+    h = torch.empty(n, dtype=BF16, device="cuda")
+    seed = _seed(77)
+    ops.call("vtx_gelu_dropout_fwd", u.data_ptr(), h.data_ptr(), n, p, seed.data_ptr(), 14, _s())
+    gl = F.gelu(u.float())
+    nz = gl.abs() > 1e-3
+    kept = (h.float() != 0) & nz
+    rate = kept.sum().item() / nz.sum().item()
+    sigma = math.sqrt(p * (1 - p) / nz.sum().item())
+    assert abs(rate - (1 - p)) < 3 * sigma + 1e-4, (rate, sigma)
+    assert rel(h.float()[kept], gl[kept] / (1 - p)) < 4e-3
+    assert abs(h.float().mean().item() - gl.mean().item()) < 4 * gl.std().item() * math.sqrt(p / (1 - p) / n) + 2e-3
+    # same seed, same site -> identical mask; different seed -> different mask
+    h2 = torch.empty_like(h)
+    ops.call("vtx_gelu_dropout_fwd", u.data_ptr(), h2.data_ptr(), n, p, seed.data_ptr(), 14, _s())
+    assert torch.equal(h, h2)
+    seed2 = _seed(78)
+    ops.call("vtx_gelu_dropout_fwd", u.data_ptr(), h2.data_ptr(), n, p, seed2.data_ptr(), 14, _s())
+    assert not torch.equal(h, h2)
+    # backward of ones: du = mask/(1-p) * gelu'(u): zero exactly where forward dropped
+    dh = torch.ones(n, dtype=BF16, device="cuda")
+    du = torch.empty(n, dtype=BF16, device="cuda")
+    ops.call("vtx_gelu_dropout_bwd", dh.data_ptr(), u.data_ptr(), du.data_ptr(), n, p, seed.data_ptr(), 14, _s())
+    uf = u.float().requires_grad_(True)
+    F.gelu(uf).sum().backward()
+    mask = (h.float() != 0).float()
+    chk = nz & (uf.grad.abs() > 1e-2)
+    assert torch.equal((du.float() != 0)[chk], mask.bool()[chk])
+    assert rel(du.float()[chk], (uf.grad * mask / (1 - p))[chk]) < 6e-3
+
+
+def test_residual_dropout_layernorm_site_is_unbiased_and_replayed_in_backward():
+    """z = res + dropout(branch) (transformer.py:1131-1143): statistics of the mask, and ln_bwd's d_branch uses it."""
+    _need_cuda()
+    ops = _ops()
+    M, H, p = 2048, 256, 0.1
+    g = torch.Generator().manual_seed(3)
+    res = torch.zeros(M, H, device="cuda")
+    branch = torch.ones(M, H, dtype=BF16, device="cuda")
+    z = torch.empty(M, H, device="cuda")
+    seed = _seed(5)
+    ops.call("vtx_add_ln_fwd", res.data_ptr(), branch.data_ptr(), 0, 0, z.data_ptr(), 0, 0, 0, M, H, 0.0, p,
+             seed.data_ptr(), 21, 0, _s())
+    n = M * H
+    rate = (z != 0).float().mean().item()
+    assert abs(rate - (1 - p)) < 3 * math.sqrt(p * (1 - p) / n) + 1e-4
+    vals = z[z != 0]
+    assert (vals - 1 / (1 - p)).abs().max().item() < 1e-5
+    assert abs(z.mean().item() - 1.0) < 4 * math.sqrt(p / (1 - p) / n) + 1e-4
+    # backward through the same site: d_branch = dy * mask / (1-p)
+    dy = torch.ones(M, H, device="cuda")
+    d_branch = torch.empty(M, H, dtype=BF16, device="cuda")
+    ops.call("vtx_ln_bwd", dy.data_ptr(), 0, 0, 0, 0, 0, 0, d_branch.data_ptr(), 0, 0, M, H, p, seed.data_ptr(), 21, 0,
+             _s())
+    assert rel(d_branch.float(), z) < 4e-3
+    assert torch.equal(d_branch.float() != 0, z != 0)
+
+
+def test_attention_dropout_keeps_rows_normalised_in_expectation():
+    """Attention-probability dropout (functional.py:6608-6682): E[out] equals the p = 0 output."""
+    _need_cuda()
+    ops = _ops()
+    B, A, T = 64, 4, 30
+    H = A * 64
+    g = torch.Generator().manual_seed(2)
+    qkv = (torch.randn(B * T, 3 * H, generator=g) * 0.5).bfloat16().cuda()
+    lengths = torch.full((B,), T, dtype=torch.int64, device="cuda")
+    lse = torch.empty(B * A * 32, device="cuda")
+    outs = []
+    for p, sd in ((0.0, 1), (0.1, 1), (0.1, 2), (0.1, 3), (0.1, 4)):
+        o = torch.empty(B * T, H, dtype=BF16, device="cuda")
+        seed = _seed(sd)
+        ops.call("vtx_attn_fwd", qkv.data_ptr(), 3 * H, qkv.data_ptr() + 2 * H, 3 * H, qkv.data_ptr() + 4 * H, 3 * H,
+                 o.data_ptr(), H, lse.data_ptr(), B, A, T, T, lengths.data_ptr(), 1, p, seed.data_ptr(), 7, _s())
+        outs.append(o.float())
+    base = outs[0]
+    mean_drop = sum(outs[1:]) / 4
+    assert not torch.equal(outs[1], outs[2])
+    # the average over 4 independent masks is closer to the p = 0 output than any single draw, and unbiased overall
+    assert rel(mean_drop, base) < rel(outs[1], base)
+    assert abs((mean_drop - base).mean().item()) < 5e-3

@@ -597,17 +597,7 @@ def test_hub_resnet50_forward():
     assert y.shape == (2, 2048 * 7 * 7) and torch.isfinite(y).all()
 
 
-# ------------------------------------------------------------------------- experimental kernels (opt-in, see header)
-def _need_experimental(feature):
-    """Experimental kernels (include/virtex_b200_x.h) were written without hardware access; their tests run only when
-    VTX_EXPERIMENTAL names the feature:  VTX_EXPERIMENTAL=all python -m pytest tests -m gpu -q"""
-    _need_cuda()
-    from virtex_b200 import experimental as X
-    if not X.enabled(feature):
-        pytest.skip(f"experimental feature {feature} not enabled (set VTX_EXPERIMENTAL={feature})")
-    return X
-
-
+# ------------------------------------------------------------------------------------- space-to-depth stem conv
 def _s2d_ref(x):
     """S[n, i, j, (r*2+q)*3 + c] = x[n, c, 2i + r - 3, 2j + q - 3] (zero padded), [N, H/2+3, W/2+3, 16]."""
     N, _, H, W = x.shape
@@ -632,8 +622,12 @@ def _stem_wpack_ref(w):
 
 
 @pytest.mark.parametrize("N,H,W", [(3, 224, 224), (2, 64, 96)])
-def test_experimental_stem_space_to_depth_conv(N, H, W):
-    X = _need_experimental("stem_s2d")
+def test_stem_space_to_depth_conv(N, H, W):
+    """vtx_stem_s2d + vtx_gemm conv_mode 5 / 6 == F.conv2d(7x7, stride 2, pad 3) and conv2d_weight on the bf16-rounded
+    operands (torchvision resnet.py:197)."""
+    _need_cuda()
+    from virtex_b200 import ops
+    from virtex_b200.ops import call, gemm
     torch.manual_seed(6)
     dev = "cuda"
     s = torch.cuda.current_stream().cuda_stream
@@ -641,16 +635,16 @@ def test_experimental_stem_space_to_depth_conv(N, H, W):
     w = torch.randn(64, 3, 7, 7, device=dev) * 0.05
     Ho, Wo = H // 2, W // 2
     S = torch.full((N, Ho + 3, Wo + 3, 16), 9.0, device=dev, dtype=torch.bfloat16)
-    X.call("vtx_x_stem_s2d", x.data_ptr(), S.data_ptr(), N, H, W, s)
+    call("vtx_stem_s2d", x.data_ptr(), S.data_ptr(), N, H, W, s)
     assert torch.equal(S, _s2d_ref(x).bfloat16())
     wp = torch.empty(64, 256, device=dev, dtype=torch.bfloat16)
-    X.call("vtx_x_stem_w_pack", w.data_ptr(), wp.data_ptr(), 64, s)
+    call("vtx_stem_s2d_w_pack", w.data_ptr(), wp.data_ptr(), 64, s)
     assert torch.equal(wp, _stem_wpack_ref(w).bfloat16())
     # fprop (+ BN statistics) against conv2d on the bf16-rounded operands
     M = N * Ho * Wo
     y = torch.full((M + 64, 64), 7.0, device=dev, dtype=torch.bfloat16)
     st = torch.zeros(2, 64, device=dev)
-    X.gemm(S, wp, y, M, 64, 256, lda=64, ldb=256, stats=st, conv=(N, Ho, Wo, 64), conv_mode=5)
+    gemm(S, wp, y, M, 64, 256, lda=64, ldb=256, stats=st, conv=(N, Ho, Wo, 64), conv_mode=5)
     ref = torch.nn.functional.conv2d(x.bfloat16().float(), w.bfloat16().float(), stride=2, padding=3)
     ref = ref.permute(0, 2, 3, 1).reshape(M, 64)
     assert rel(y[:M], ref) < 4e-3
@@ -659,31 +653,22 @@ def test_experimental_stem_space_to_depth_conv(N, H, W):
     # wgrad
     dy = (torch.randn(N, Ho, Wo, 64, device=dev) * 0.5).bfloat16()
     dwp = torch.zeros(64, 256, device=dev)
-    X.gemm(dy, S, dwp, 64, 256, M, lda=64, ldb=64, atomic=True, out_f32=True, split_k=16, conv=(N, Ho, Wo, 64),
-           conv_mode=6)
+    gemm(dy, S, dwp, 64, 256, M, lda=64, ldb=64, atomic=True, out_f32=True, split_k=16, conv=(N, Ho, Wo, 64),
+         conv_mode=6)
     grad = torch.ones(64, 3, 7, 7, device=dev)
-    X.call("vtx_x_stem_w_unpack_add", dwp.data_ptr(), grad.data_ptr(), 64, s)
+    call("vtx_stem_s2d_w_unpack_add", dwp.data_ptr(), grad.data_ptr(), 64, s)
     gref = torch.nn.grad.conv2d_weight(x.bfloat16().float(), (64, 3, 7, 7), dy.float().permute(0, 3, 1, 2), stride=2,
                                        padding=3)
     assert rel(grad, 1.0 + gref) < 1e-4
 
 
-# ---------------------------------------------------------------- written after round 1's GPU budget ran out (opt-in)
-def _need_unverified():
-    """Tests added after the last GPU run of round 1: they exercise validated kernels on new shapes, but their
-    tolerances have not been seen to pass on hardware yet.  Run with VTX_RUN_UNVERIFIED=1, then drop this gate."""
-    import os
-    _need_cuda()
-    if os.environ.get("VTX_RUN_UNVERIFIED", "") != "1":
-        pytest.skip("not yet run on hardware (set VTX_RUN_UNVERIFIED=1)")
-
-
+# ------------------------------------------------------------------- BASELINE.json configs #4 / #5, resume, edge shapes
 @pytest.mark.parametrize("spec_kw,B,ragged", [
     (dict(layers=4), 2, True),                                              # BASELINE.json config #4: R50-L4-H1024
     (dict(backbone="resnet101", hidden=2048, heads=32, ffn=8192), 2, False),  # config #5: R101-L1-H2048
 ])
 def test_baseline_config_architectures_vs_oracle(spec_kw, B, ragged):
-    _need_unverified()
+    _need_cuda()
     spec = O.Spec(**spec_kw)
     state = O.synth_state(spec, 12, bn3_gain=0.25)
     model = build_model(spec, state)
@@ -707,7 +692,7 @@ def test_baseline_config_architectures_vs_oracle(spec_kw, B, ragged):
 def test_trainer_checkpoint_resume_matches_uninterrupted_run(tmp_path):
     """3 steps -> CheckpointManager.step -> fresh model + Trainer -> load -> 3 more steps == 6 uninterrupted steps
     (Lookahead off: the reference does not serialise its slow weights either)."""
-    _need_unverified()
+    _need_cuda()
     from virtex_b200.checkpointing import CheckpointManager
     from virtex_b200.config import Config
     from virtex_b200.factories import PretrainingModelFactory
@@ -737,89 +722,11 @@ def test_trainer_checkpoint_resume_matches_uninterrupted_run(tmp_path):
         assert abs(a - b) < 2e-3 * abs(a), (losses_a, losses_b)
 
 
-@pytest.mark.parametrize("H,p", [(1024, 0.1), (256, 0.0)])
-def test_experimental_head_x_kernels_match_the_validated_ones(H, p):
-    """A/B: the register-accumulating LayerNorm / embedding backward kernels against the validated kernels of the main
-    library on the same inputs (same arithmetic, different summation order)."""
-    X = _need_experimental("head_x")
-    import ctypes
-    from virtex_b200 import lib as L, ops
-    main = ctypes.CDLL(L.LIB_PATH)
-    xlib = X.load()
-    torch.manual_seed(8)
-    dev = "cuda"
-    B, T = 37, 30
-    M = B * T
-    s = torch.cuda.current_stream().cuda_stream
-    dy_a = torch.randn(M, H, device=dev)
-    dy_b = torch.randn(M, H, device=dev).bfloat16()
-    z = torch.randn(M, H, device=dev) * 2 + 0.5
-    stats = torch.stack([z.mean(1), 1.0 / torch.sqrt(z.var(1, unbiased=False) + 1e-5)], 1).contiguous()
-    gamma = torch.rand(H, device=dev) + 0.5
-    d_skip = torch.randn(M, H, device=dev)
-    seed = torch.full((1,), 1234, dtype=torch.int64, device=dev)
-    outs = []
-    for lib in (main, xlib):
-        fn = lib.vtx_ln_bwd
-        fn.argtypes, fn.restype = ops._PROTOS["vtx_ln_bwd"], ctypes.c_int
-        d_res = torch.zeros(M, H, device=dev)
-        d_branch = torch.zeros(M, H, device=dev, dtype=torch.bfloat16)
-        d_gamma, d_beta = torch.zeros(H, device=dev), torch.zeros(H, device=dev)
-        rc = fn(dy_a.data_ptr(), dy_b.data_ptr(), z.data_ptr(), stats.data_ptr(), gamma.data_ptr(), d_skip.data_ptr(),
-                d_res.data_ptr(), d_branch.data_ptr(), d_gamma.data_ptr(), d_beta.data_ptr(), M, H, p, seed.data_ptr(), 7,
-                1, s)
-        assert rc == 0
-        outs.append((d_res, d_branch.float(), d_gamma, d_beta))
-    for a, b in zip(*outs):
-        assert rel(b, a) < 2e-5
-    # embedding backward
-    tokens = torch.randint(4, 500, (B, T), device=dev)
-    tokens[:, -3:] = 0  # padding
-    outs = []
-    for lib in (main, xlib):
-        fn = lib.vtx_embed_bwd
-        fn.argtypes, fn.restype = ops._PROTOS["vtx_embed_bwd"], ctypes.c_int
-        d_words, d_pos = torch.zeros(500, H, device=dev), torch.zeros(T, H, device=dev)
-        d_gamma, d_beta = torch.zeros(H, device=dev), torch.zeros(H, device=dev)
-        rc = fn(dy_a.data_ptr(), dy_b.data_ptr(), tokens.data_ptr(), z.data_ptr(), stats.data_ptr(), gamma.data_ptr(),
-                d_words.data_ptr(), d_pos.data_ptr(), d_gamma.data_ptr(), d_beta.data_ptr(), M, T, H, 0, p,
-                seed.data_ptr(), 9, s)
-        assert rc == 0
-        outs.append((d_words, d_pos, d_gamma, d_beta))
-    for a, b in zip(*outs):
-        assert rel(b, a) < 2e-5
-    assert torch.all(outs[1][0][0] == 0)  # the padding row of the word table receives nothing
-    # cross-entropy with in-place dlogits (identical arithmetic: expect bit-equal gradients)
-    Bc, Tc, V = 9, 30, 10000
-    logits0 = (torch.randn(Bc * Tc, V, device=dev) * 3).bfloat16()
-    toks = torch.randint(4, V, (Bc, Tc), device=dev)
-    toks[:, 20:] = 0
-    cnt = torch.tensor([float((toks[:, 1:] != 0).sum())], device=dev)
-    res = []
-    for lib in (main, xlib):
-        fn = lib.vtx_cross_entropy
-        fn.argtypes, fn.restype = ops._PROTOS["vtx_cross_entropy"], ctypes.c_int
-        lg, loss = logits0.clone(), torch.zeros(1, device=dev)
-        assert fn(lg.data_ptr(), V, toks.data_ptr(), Bc, Tc, V, 0, cnt.data_ptr(), loss.data_ptr(), 1, s) == 0
-        res.append((lg, loss))
-    assert torch.equal(res[0][0], res[1][0]) and abs(res[0][1].item() - res[1][1].item()) < 1e-5 * res[0][1].item()
-    # bias-gradient column sums (+= semantics), incl. a strided input and a column count that is not a multiple of 256
-    for (Mc, Nc, ldc) in [(7680, 1024, 1024), (7424, 10000, 10000), (870, 128, 384), (100, 3072, 3072)]:
-        Xc = (torch.randn(Mc, ldc, device=dev) * 0.5).bfloat16()
-        ref = Xc[:, :Nc].float().sum(0)
-        for lib in (main, xlib):
-            fn = lib.vtx_colsum
-            fn.argtypes, fn.restype = ops._PROTOS["vtx_colsum"], ctypes.c_int
-            out = torch.ones(Nc, device=dev)
-            assert fn(Xc.data_ptr(), ldc, Mc, Nc, out.data_ptr(), s) == 0
-            assert rel(out, 1.0 + ref) < 1e-5
-
-
 @pytest.mark.parametrize("B,max_len", [(1, 30), (3, 13), (5, 2)])
 def test_edge_batch_shapes_vs_oracle(B, max_len):
     """Batch of one; captions shorter than MAX_CAPTION_LENGTH (the collate pads to the longest caption of the batch,
     virtex/data/datasets/captioning.py:84-100); and the shortest legal caption `[SOS] [EOS]` (one target per row)."""
-    _need_unverified()
+    _need_cuda()
     spec = O.Spec(hidden=128, layers=1, heads=2, ffn=256)
     state = O.synth_state(spec, 13, bn3_gain=0.25)
     model = build_model(spec, state)
@@ -837,66 +744,3 @@ def test_edge_batch_shapes_vs_oracle(B, max_len):
     with torch.no_grad():
         ev = model(to_cuda(batch))
     assert ev["predictions"].shape == (B, max_len)
-
-
-@pytest.mark.parametrize("N,H,W,C", [(3, 112, 112, 64), (2, 30, 22, 64), (2, 7, 9, 16)])
-def test_experimental_backbone_x_maxpool_backward_matches_the_validated_kernel(N, H, W, C):
-    X = _need_experimental("backbone_x")
-    import ctypes
-    from virtex_b200 import lib as L, ops
-    main, xlib = ctypes.CDLL(L.LIB_PATH), X.load()
-    torch.manual_seed(9)
-    dev = "cuda"
-    s = torch.cuda.current_stream().cuda_stream
-    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
-    dpool = torch.randn(N, Ho, Wo, C, device=dev).bfloat16()
-    idx = torch.randint(0, 9, (N, Ho, Wo, C), device=dev, dtype=torch.uint8)
-    outs = []
-    for lib in (main, xlib):
-        fn = lib.vtx_maxpool_bwd
-        fn.argtypes, fn.restype = ops._PROTOS["vtx_maxpool_bwd"], ctypes.c_int
-        da = torch.full((N, H, W, C), 5.0, device=dev, dtype=torch.bfloat16)
-        assert fn(dpool.data_ptr(), idx.data_ptr(), da.data_ptr(), N, H, W, C, s) == 0
-        outs.append(da)
-    assert torch.equal(outs[0], outs[1])
-    # forward: BN + ReLU + 3x3/2 max-pool with argmax slots
-    y = torch.randn(N, H, W, C, device=dev).bfloat16()
-    bnp = torch.cat([torch.zeros(2 * C, device=dev), torch.rand(C, device=dev) + 0.5, torch.randn(C, device=dev) * 0.3])
-    outs = []
-    for lib in (main, xlib):
-        fn = lib.vtx_bn_relu_maxpool
-        fn.argtypes, fn.restype = ops._PROTOS["vtx_bn_relu_maxpool"], ctypes.c_int
-        out = torch.full((N, Ho, Wo, C), 5.0, device=dev, dtype=torch.bfloat16)
-        slot = torch.full((N, Ho, Wo, C), 77, device=dev, dtype=torch.uint8)
-        assert fn(y.data_ptr(), bnp.data_ptr(), out.data_ptr(), slot.data_ptr(), N, H, W, C, s) == 0
-        outs.append((out, slot))
-    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
-    # strided 3x3 gathers with 32-bit index arithmetic
-    for stride in (1, 2):
-        Hs, Ws = (H - 1) // stride + 1, (W - 1) // stride + 1
-        x = torch.randn(N, H, W, C, device=dev).bfloat16()
-        dcols = torch.randn(N * Hs * Ws, 9 * C, device=dev).bfloat16()
-        res = []
-        for lib in (main, xlib):
-            f1, f2 = lib.vtx_im2col3x3, lib.vtx_col2im3x3
-            f1.argtypes, f1.restype = ops._PROTOS["vtx_im2col3x3"], ctypes.c_int
-            f2.argtypes, f2.restype = ops._PROTOS["vtx_col2im3x3"], ctypes.c_int
-            cols = torch.full((N * Hs * Ws, 9 * C), 3.0, device=dev, dtype=torch.bfloat16)
-            dx = torch.full((N, H, W, C), 3.0, device=dev, dtype=torch.bfloat16)
-            assert f1(x.data_ptr(), cols.data_ptr(), N, H, W, C, stride, s) == 0
-            assert f2(dcols.data_ptr(), dx.data_ptr(), N, H, W, C, stride, s) == 0
-            res.append((cols, dx))
-        assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
-        if stride == 2:
-            dxs = torch.randn(N, Hs, Ws, C, device=dev).bfloat16()
-            res = []
-            for lib in (main, xlib):
-                f1, f2 = lib.vtx_subsample, lib.vtx_upsample_add
-                f1.argtypes, f1.restype = ops._PROTOS["vtx_subsample"], ctypes.c_int
-                f2.argtypes, f2.restype = ops._PROTOS["vtx_upsample_add"], ctypes.c_int
-                xs = torch.full((N, Hs, Ws, C), 3.0, device=dev, dtype=torch.bfloat16)
-                dxx = x.clone()
-                assert f1(x.data_ptr(), xs.data_ptr(), N, H, W, C, stride, s) == 0
-                assert f2(dxs.data_ptr(), dxx.data_ptr(), N, H, W, C, stride, s) == 0
-                res.append((xs, dxx))
-            assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])

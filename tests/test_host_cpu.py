@@ -247,41 +247,3 @@ def test_fused_optimizer_state_is_empty_before_the_first_step_and_skips_frozen_p
     assert sd["param_groups"][frozen[0]]["lr"] == pytest.approx(0.1 * 2 / 4)
     with pytest.raises(ValueError):
         view.load_state_dict({"state": {}, "param_groups": sd["param_groups"][:-1]})
-
-
-def test_experimental_library_exports_and_is_off_by_default(monkeypatch):
-    from virtex_b200 import experimental as X
-    hdr = open(os.path.join(ROOT, "include", "virtex_b200_x.h")).read()
-    declared = sorted(set(re.findall(r"\b(vtx_[a-z0-9_]+)\s*\(", hdr)))
-    assert declared == X.exported_symbols()
-    lib = ctypes.CDLL(X.lib_path())
-    for name in declared:
-        assert hasattr(lib, name), name
-    monkeypatch.delenv("VTX_EXPERIMENTAL", raising=False)
-    assert not X.any_enabled()
-    monkeypatch.setenv("VTX_EXPERIMENTAL", "stem_s2d")
-    assert X.enabled("stem_s2d")
-    monkeypatch.setenv("VTX_EXPERIMENTAL", "all")
-    assert X.enabled("stem_s2d")
-
-
-def test_pdl_library_exports_the_same_abi():
-    from virtex_b200 import lib as L, ops
-    assert os.path.exists(L.LIB_PDL_PATH)
-    pdl = ctypes.CDLL(L.LIB_PDL_PATH)
-    for name in ops.exported_symbols():
-        assert hasattr(pdl, name), name
-
-
-def test_routed_entry_points_default_to_the_main_library(monkeypatch):
-    from virtex_b200 import experimental as X, ops
-    xlib = ctypes.CDLL(X.lib_path())
-    for name, feature in X.ROUTED.items():
-        assert feature in X.FEATURES and name in ops._PROTOS and hasattr(xlib, X.routed_symbol(name))
-    monkeypatch.delenv("VTX_EXPERIMENTAL", raising=False)
-    assert all(X.routed_lib(n) is None for n in X.ROUTED)
-    monkeypatch.setenv("VTX_EXPERIMENTAL", "head_x")
-    assert all((X.routed_lib(n) is not None) == (f == "head_x") for n, f in X.ROUTED.items())
-    assert X.routed_lib("vtx_gemm") is None and X.routed_lib("vtx_sumsq") is None
-    monkeypatch.setenv("VTX_EXPERIMENTAL", "gemm_x")
-    assert X.routed_lib("vtx_gemm") is not None and X.routed_symbol("vtx_gemm") == "vtx_gemm_x"

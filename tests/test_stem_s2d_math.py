@@ -1,7 +1,7 @@
-"""CPU checks of the index maps behind the experimental stem path (csrc_x/stem_s2d.cu, vtx_gemm_x conv_mode 5 / 6):
+"""CPU checks of the index maps behind the space-to-depth stem path (csrc/stem_s2d.cu, vtx_gemm conv_mode 5 / 6):
 the space-to-depth formulation IS the 7x7 / stride-2 / pad-3 convolution, and a line-by-line transliteration of the
 packing kernel's index arithmetic reproduces the layout definition.  (The kernels themselves need a GPU: see
-tests/test_gpu_parity.py::test_experimental_stem_space_to_depth_conv.)"""
+tests/test_gpu_parity.py::test_stem_space_to_depth_conv.)"""
 import torch
 
 from tests.test_gpu_parity import _s2d_ref, _stem_wpack_ref

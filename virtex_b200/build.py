@@ -15,14 +15,6 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OBJ_DIR = os.path.join(ROOT, "build", "obj")
 LIB_PATH = os.path.join(HERE, "libvirtex_b200.so")
-# experimental kernels (not on the default path, see include/virtex_b200_x.h) live in a SEPARATE library so that the
-# validated one is bit-for-bit what was tested: csrc_x/*.cu + gemm_tc.cu compiled with -DVTX_GEMM_X + common.cu
-CSRC_X = os.path.join(HERE, "csrc_x")
-LIB_X_PATH = os.path.join(HERE, "libvirtex_b200_x.so")
-# the whole main library once more with -DVTX_PDL (programmatic dependent launch, see csrc/vtx_common.cuh): same
-# exported symbols, loaded INSTEAD of the main library when VTX_EXPERIMENTAL names `pdl`
-LIB_PDL_PATH = os.path.join(HERE, "libvirtex_b200_pdl.so")
-
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -78,20 +70,9 @@ def build(verbose=False, force=False):
     if force:
         for old in os.listdir(OBJ_DIR):
             os.remove(os.path.join(OBJ_DIR, old))
-    jobs = [(s, (), "") for s in srcs]
-    # experimental library: its own sources + the GEMM with runtime tap geometry + its own copy of the error helpers
-    jobs += [(os.path.join(CSRC_X, n), (), "") for n in sorted(os.listdir(CSRC_X)) if n.endswith(".cu")]
-    jobs += [(os.path.join(CSRC, "gemm_tc.cu"), ("-DVTX_GEMM_X",), "_x")]
-    jobs += [(os.path.join(CSRC, "head.cu"), ("-DVTX_HEAD_X",), "_x")]
-    jobs += [(os.path.join(CSRC, "backbone.cu"), ("-DVTX_BACKBONE_X",), "_x")]
-    n_x = len(jobs)
-    jobs += [(s, ("-DVTX_PDL",), "_pdl") for s in srcs]
-    with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
-        objs = list(ex.map(lambda j: _compile_one(j[0], hdr, verbose, j[1], j[2]), jobs))
-    _link(objs[:len(srcs)], LIB_PATH, "link.stamp", verbose)
-    common = [o for o in objs[:len(srcs)] if os.path.basename(o).startswith("common.")]
-    _link(objs[len(srcs):n_x] + common, LIB_X_PATH, "link_x.stamp", verbose)
-    _link(objs[n_x:], LIB_PDL_PATH, "link_pdl.stamp", verbose)
+    with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
+        objs = list(ex.map(lambda src: _compile_one(src, hdr, verbose), srcs))
+    _link(objs, LIB_PATH, "link.stamp", verbose)
     return LIB_PATH
 
 

@@ -128,8 +128,7 @@ __global__ void col2im3x3_kernel(const __nv_bfloat16* __restrict__ dcols, __nv_b
   }
 }
 
-#ifdef VTX_BACKBONE_X
-// EXPERIMENTAL (backbone_x): the two gather kernels above spend most of their time in 64-bit integer division
+// the two gather kernels above spend most of their time in 64-bit integer division
 // (seven div/mod by run-time values per 16-byte copy); when the item count fits 31 bits the same index arithmetic in
 // 32 bits is 4-5x fewer instructions.  Identical results.
 __global__ void im2col3x3_i32_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ cols, int N, int H,
@@ -192,7 +191,6 @@ __global__ void col2im3x3_i32_kernel(const __nv_bfloat16* __restrict__ dcols, __
     *reinterpret_cast<bf16x8*>(dx + (long long)pix * C + g * 8) = pack8(acc);
   }
 }
-#endif
 
 // xs[n,ho,wo,:] = x[n,ho*s,wo*s,:]
 __global__ void subsample_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ xs, int N, int H,
@@ -233,8 +231,7 @@ __global__ void upsample_add_kernel(const __nv_bfloat16* __restrict__ dxs, __nv_
   }
 }
 
-#ifdef VTX_BACKBONE_X
-// EXPERIMENTAL (backbone_x): 32-bit index arithmetic, see im2col3x3_i32_kernel
+// 32-bit index arithmetic, see im2col3x3_i32_kernel
 __global__ void subsample_i32_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ xs, int N, int H,
                                      int W, int C, int Ho, int Wo, int stride) {
   VTX_PDL_TRIGGER();
@@ -272,7 +269,6 @@ __global__ void upsample_add_i32_kernel(const __nv_bfloat16* __restrict__ dxs, _
     *reinterpret_cast<bf16x8*>(p) = pack8(a);
   }
 }
-#endif
 
 // ---------------------------------------------------------------------------------------------- BatchNorm forward
 // stats [2,C] (sum, sumsq over `count` samples)  ->  bnp [4,C] = mean, invstd, scale = gamma*invstd, shift
@@ -304,7 +300,8 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, float count,
   bnp[3 * C + c] = beta[c] - mean * sc;
 }
 
-// a = act( y*scale + shift  [+ res  |  + res*scale2 + shift2] )
+// a = act( y*scale + shift  [+ res  |  + res*scale2 + shift2] );  relu_mask (optional): bit j of byte (m*C/8 + c/8) =
+// [pre-activation of channel 8*(c/8)+j of row m > 0]
 constexpr int kU = 4;  // independent 16-byte loads per tensor in flight per thread (memory-level parallelism)
 
 // Optional fold of bn_finalize into the apply kernel: every thread derives scale/shift of its 8 channels from the raw
@@ -323,7 +320,8 @@ struct BnFwdFold {
 template <bool kFold>
 __global__ void __launch_bounds__(256, 2) bn_act_kernel(const __nv_bfloat16* __restrict__ y, float* __restrict__ bnp,
                               const __nv_bfloat16* __restrict__ res, const float* __restrict__ bnp_res,
-                              __nv_bfloat16* __restrict__ out, long long M, int C, int relu, const BnFwdFold f) {
+                              __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ relu_mask, long long M, int C,
+                              int relu, const BnFwdFold f) {
   VTX_PDL_TRIGGER();
   const int cg = C / 8;
   const long long total = M * cg;
@@ -391,6 +389,13 @@ __global__ void __launch_bounds__(256, 2) bn_act_kernel(const __nv_bfloat16* __r
         for (int j = 0; j < 8; ++j) v[j] += r[j] * sc2[j] + sh2[j];
       }
       if (relu) {
+        // one bit per channel: what backward needs of this activation (its sign), 1/16 of the bytes of `out`
+        if (relu_mask != nullptr) {
+          uint32_t bits = 0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) bits |= (v[j] > 0.f ? 1u : 0u) << j;
+          relu_mask[idx] = (uint8_t)bits;
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
       }
@@ -490,8 +495,7 @@ __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dpool, cons
   }
 }
 
-#ifdef VTX_BACKBONE_X
-// EXPERIMENTAL (backbone_x): same arithmetic as bn_relu_maxpool_kernel; a CTA normalises + activates the 2 * kFP + 1
+// same arithmetic as bn_relu_maxpool_kernel; a CTA normalises + activates the 2 * kFP + 1
 // input rows of kFP pooled rows ONCE into shared memory (the validated kernel re-reads and re-normalises every input
 // element for each of the ~2.25 windows that contain it) and pools from there.
 constexpr int kFP = 2;
@@ -552,7 +556,7 @@ __global__ void __launch_bounds__(256) bn_relu_maxpool_tiled_kernel(const __nv_b
   }
 }
 
-// EXPERIMENTAL (backbone_x): same arithmetic as maxpool_bwd_kernel, but a CTA first stages the kTP + 1 pooled rows
+// same arithmetic as maxpool_bwd_kernel, but a CTA first stages the kTP + 1 pooled rows
 // (gradients + argmax slots) it needs in shared memory with linear coalesced copies and then produces 2 * kTP input
 // rows from them.  The validated kernel gathers every pooled element from L2 up to nine times (1.4 GB of L2 -> SM
 // traffic for 565 MB of algorithmic bytes at batch 256).
@@ -614,13 +618,13 @@ __global__ void __launch_bounds__(256) maxpool_bwd_tiled_kernel(const __nv_bfloa
     *reinterpret_cast<bf16x8*>(da + (((long long)n * H + h) * W + w) * C + c0) = pack8(acc);
   }
 }
-#endif
 
 // ---------------------------------------------------------------------------------------------- BatchNorm backward
-// sums[0,c] = sum_m dz, sums[1,c] = sum_m dz * xhat, with dz = dA * [a > 0] (a == null: no ReLU) and
+// sums[0,c] = sum_m dz, sums[1,c] = sum_m dz * xhat, with dz = dA * [relu_mask bit] (relu_mask == null: no ReLU, or the
+// mask recomputed from y when mask_from_y) and
 // xhat = (y - mean) * invstd.  Optionally the same for a second BN (y2, bnp2) sharing dz (downsample branch).
 template <int kTwo>
-__global__ void __launch_bounds__(256, kTwo ? 1 : 2) bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloat16* __restrict__ a,
+__global__ void __launch_bounds__(256, kTwo ? 1 : 2) bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dA, const uint8_t* __restrict__ a,
                                      const __nv_bfloat16* __restrict__ y, const float* __restrict__ bnp,
                                      const __nv_bfloat16* __restrict__ y2, const float* __restrict__ bnp2,
                                      float* __restrict__ sums, float* __restrict__ sums2, long long M, int C,
@@ -649,7 +653,8 @@ __global__ void __launch_bounds__(256, kTwo ? 1 : 2) bn_bwd_reduce_kernel(const 
   if (rr < rows_par) {
     const long long mstride = (long long)gridDim.x * rows_par;
     for (long long m0 = (long long)blockIdx.x * rows_par + rr; m0 < M; m0 += mstride * kU) {
-      bf16x8 vd[kU], vy[kU], va[kU], vy2[kU];
+      bf16x8 vd[kU], vy[kU], vy2[kU];
+      uint32_t va[kU];
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
         const long long m = m0 + u * mstride;
@@ -657,7 +662,7 @@ __global__ void __launch_bounds__(256, kTwo ? 1 : 2) bn_bwd_reduce_kernel(const 
           const long long off = m * C + c0;
           vd[u] = *reinterpret_cast<const bf16x8*>(dA + off);
           vy[u] = *reinterpret_cast<const bf16x8*>(y + off);
-          if (a != nullptr) va[u] = *reinterpret_cast<const bf16x8*>(a + off);
+          if (a != nullptr) va[u] = a[m * cg + g];
           if (kTwo) vy2[u] = *reinterpret_cast<const bf16x8*>(y2 + off);
         }
       }
@@ -669,10 +674,8 @@ __global__ void __launch_bounds__(256, kTwo ? 1 : 2) bn_bwd_reduce_kernel(const 
         unpack8(vd[u], d);
         unpack8(vy[u], yy);
         if (a != nullptr) {
-          float aa[8];
-          unpack8(va[u], aa);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) d[j] = aa[j] > 0.f ? d[j] : 0.f;
+          for (int j = 0; j < 8; ++j) d[j] = ((va[u] >> j) & 1u) ? d[j] : 0.f;
         } else if (mask_from_y) {  // ReLU mask recomputed from the BN output sign: a = relu(y*scale + shift)
 #pragma unroll
           for (int j = 0; j < 8; ++j) d[j] = (yy[j] * msc[j] + msh[j] > 0.f) ? d[j] : 0.f;
@@ -750,7 +753,7 @@ struct BnBwdFold {
 };
 
 template <int kTwo, bool kFold>
-__global__ void __launch_bounds__(256, kTwo ? 1 : 2) bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloat16* __restrict__ a,
+__global__ void __launch_bounds__(256, kTwo ? 1 : 2) bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dA, const uint8_t* __restrict__ a,
                                     const __nv_bfloat16* __restrict__ y, const float* __restrict__ bnp,
                                     const float* __restrict__ coef, __nv_bfloat16* __restrict__ dy,
                                     const __nv_bfloat16* __restrict__ y2, const float* __restrict__ bnp2,
@@ -812,14 +815,15 @@ __global__ void __launch_bounds__(256, kTwo ? 1 : 2) bn_bwd_apply_kernel(const _
   }
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = i0; i < total; i += stride * kU) {
-    bf16x8 vd[kU], vy[kU], va[kU], vy2[kU];
+    bf16x8 vd[kU], vy[kU], vy2[kU];
+    uint32_t va[kU];
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
       const long long idx = i + u * stride;
       if (idx < total) {
         vd[u] = *reinterpret_cast<const bf16x8*>(dA + idx * 8);
         vy[u] = *reinterpret_cast<const bf16x8*>(y + idx * 8);
-        if (a != nullptr) va[u] = *reinterpret_cast<const bf16x8*>(a + idx * 8);
+        if (a != nullptr) va[u] = a[idx];
         if (kTwo) vy2[u] = *reinterpret_cast<const bf16x8*>(y2 + idx * 8);
       }
     }
@@ -831,10 +835,8 @@ __global__ void __launch_bounds__(256, kTwo ? 1 : 2) bn_bwd_apply_kernel(const _
       unpack8(vd[u], d);
       unpack8(vy[u], yy);
       if (a != nullptr) {
-        float aa[8];
-        unpack8(va[u], aa);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) d[j] = aa[j] > 0.f ? d[j] : 0.f;
+        for (int j = 0; j < 8; ++j) d[j] = ((va[u] >> j) & 1u) ? d[j] : 0.f;
       } else if (mask_from_y) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) d[j] = (yy[j] * msc[j] + msh[j] > 0.f) ? d[j] : 0.f;
@@ -954,13 +956,11 @@ extern "C" int vtx_im2col3x3(const void* x, void* cols, int N, int H, int W, int
   REQ(x && cols && C % 8 == 0 && stride >= 1, "bad arguments");
   const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
   const long long total = (long long)N * Ho * Wo * 9 * (C / 8);
-#ifdef VTX_BACKBONE_X
   if (total < (1LL << 31) - (1LL << 24)) {  // headroom: the grid-stride increment must not overflow either
     im2col3x3_i32_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)cols, N, H, W,
                                                                    C, Ho, Wo, stride);
     return check_launch("im2col3x3_i32");
   }
-#endif
   im2col3x3_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)cols, N, H, W, C,
                                                              Ho, Wo, stride);
   return check_launch("im2col3x3");
@@ -969,13 +969,11 @@ extern "C" int vtx_col2im3x3(const void* dcols, void* dx, int N, int H, int W, i
   REQ(dcols && dx && C % 8 == 0 && stride >= 1, "bad arguments");
   const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
   const long long total = (long long)N * H * W * (C / 8);
-#ifdef VTX_BACKBONE_X
   if (total < (1LL << 31) - (1LL << 24)) {
     col2im3x3_i32_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>((const __nv_bfloat16*)dcols, (__nv_bfloat16*)dx, N, H, W,
                                                                    C, Ho, Wo, stride);
     return check_launch("col2im3x3_i32");
   }
-#endif
   col2im3x3_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>((const __nv_bfloat16*)dcols, (__nv_bfloat16*)dx, N, H, W,
                                                              C, Ho, Wo, stride);
   return check_launch("col2im3x3");
@@ -984,13 +982,11 @@ extern "C" int vtx_subsample(const void* x, void* xs, int N, int H, int W, int C
   REQ(x && xs && C % 8 == 0, "bad arguments");
   const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
   const long long total = (long long)N * Ho * Wo * (C / 8);
-#ifdef VTX_BACKBONE_X
   if (total < (1LL << 31) - (1LL << 24)) {
     subsample_i32_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)xs, N, H, W, C,
                                                                    Ho, Wo, stride);
     return check_launch("subsample_i32");
   }
-#endif
   subsample_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)xs, N, H, W, C,
                                                              Ho, Wo, stride);
   return check_launch("subsample");
@@ -999,13 +995,11 @@ extern "C" int vtx_upsample_add(const void* dxs, void* dx, int N, int H, int W, 
   REQ(dxs && dx && C % 8 == 0, "bad arguments");
   const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
   const long long total = (long long)N * Ho * Wo * (C / 8);
-#ifdef VTX_BACKBONE_X
   if (total < (1LL << 31) - (1LL << 24)) {
     upsample_add_i32_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>((const __nv_bfloat16*)dxs, (__nv_bfloat16*)dx, N, H,
                                                                       W, C, Ho, Wo, stride);
     return check_launch("upsample_add_i32");
   }
-#endif
   upsample_add_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>((const __nv_bfloat16*)dxs, (__nv_bfloat16*)dx, N, H, W,
                                                                 C, Ho, Wo, stride);
   return check_launch("upsample_add");
@@ -1019,34 +1013,33 @@ extern "C" int vtx_bn_finalize(const float* stats, float count, const float* gam
   return check_launch("bn_finalize");
 }
 extern "C" int vtx_bn_act(const void* y, const float* bnp, const void* res, const float* bnp_res, void* out,
-                          int64_t M, int C, int relu, void* stream) {
+                          uint8_t* relu_mask, int64_t M, int C, int relu, void* stream) {
   REQ(y && bnp && out && C % 8 == 0, "bad arguments");
   BnFwdFold f;
   memset(&f, 0, sizeof(f));
   bn_act_kernel<false><<<grid_for((M * (C / 8) + kU - 1) / kU, 256, 2), 256, 0, STREAM>>>(
-      (const __nv_bfloat16*)y, const_cast<float*>(bnp), (const __nv_bfloat16*)res, bnp_res, (__nv_bfloat16*)out, M, C,
-      relu, f);
+      (const __nv_bfloat16*)y, const_cast<float*>(bnp), (const __nv_bfloat16*)res, bnp_res, (__nv_bfloat16*)out,
+      relu_mask, M, C, relu, f);
   return check_launch("bn_act");
 }
 // bn_finalize + bn_act in one launch (the statistics -> scale/shift step runs in every thread's prologue)
 extern "C" int vtx_bn_finalize_act(const float* stats, float count, const float* gamma, const float* beta, float* rmean,
                                    float* rvar, int64_t* nbt, float momentum, float eps, int training, float* bnp,
-                                   const void* y, const void* res, const float* bnp_res, void* out, int64_t M, int C,
-                                   int relu, void* stream) {
+                                   const void* y, const void* res, const float* bnp_res, void* out, uint8_t* relu_mask,
+                                   int64_t M, int C, int relu, void* stream) {
   REQ(y && bnp && out && gamma && beta && rmean && rvar && C % 8 == 0 && C / 8 <= 256 && (stats || !training),
       "bad arguments");
   BnFwdFold f;
   f.stats = stats; f.gamma = gamma; f.beta = beta; f.rmean = rmean; f.rvar = rvar; f.nbt = (long long*)nbt;
   f.count = count; f.momentum = momentum; f.eps = eps; f.training = training;
   bn_act_kernel<true><<<grid_for((M * (C / 8) + kU - 1) / kU, 256, 2), 256, 0, STREAM>>>(
-      (const __nv_bfloat16*)y, bnp, (const __nv_bfloat16*)res, bnp_res, (__nv_bfloat16*)out, M, C, relu, f);
+      (const __nv_bfloat16*)y, bnp, (const __nv_bfloat16*)res, bnp_res, (__nv_bfloat16*)out, relu_mask, M, C, relu, f);
   return check_launch("bn_finalize_act");
 }
 extern "C" int vtx_bn_relu_maxpool(const void* y, const float* bnp, void* out, uint8_t* idx, int N, int H, int W, int C,
                                    void* stream) {
   REQ(y && bnp && out && idx && C % 8 == 0, "bad arguments");
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
-#ifdef VTX_BACKBONE_X
   {
     const size_t smem = (size_t)(2 * kFP + 1) * W * C * 2;
     if (smem <= 100 * 1024) {
@@ -1061,7 +1054,6 @@ extern "C" int vtx_bn_relu_maxpool(const void* y, const float* bnp, void* out, u
       return check_launch("bn_relu_maxpool_tiled");
     }
   }
-#endif
   const long long total = (long long)N * Ho * Wo * (C / 8);
   bn_relu_maxpool_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>((const __nv_bfloat16*)y, bnp, (__nv_bfloat16*)out,
                                                                    idx, N, H, W, C, Ho, Wo);
@@ -1071,7 +1063,6 @@ extern "C" int vtx_maxpool_bwd(const void* dpool, const uint8_t* idx, void* da, 
                                void* stream) {
   REQ(dpool && idx && da && C % 8 == 0, "bad arguments");
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
-#ifdef VTX_BACKBONE_X
   {
     const size_t smem = (size_t)(kTP + 1) * Wo * C * 3;  // bf16 gradients + u8 slots
     if (C % 16 == 0 && smem <= 200 * 1024) {
@@ -1086,13 +1077,12 @@ extern "C" int vtx_maxpool_bwd(const void* dpool, const uint8_t* idx, void* da, 
       return check_launch("maxpool_bwd_tiled");
     }
   }
-#endif
   const long long total = (long long)N * H * W * (C / 8);
   maxpool_bwd_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>((const __nv_bfloat16*)dpool, idx, (__nv_bfloat16*)da, N,
                                                                H, W, C, Ho, Wo);
   return check_launch("maxpool_bwd");
 }
-extern "C" int vtx_bn_bwd_reduce(const void* dA, const void* a, const void* y, const float* bnp, const void* y2,
+extern "C" int vtx_bn_bwd_reduce(const void* dA, const uint8_t* a, const void* y, const float* bnp, const void* y2,
                                  const float* bnp2, float* sums, float* sums2, int64_t M, int C, int mask_from_y,
                                  void* stream) {
   REQ(dA && y && bnp && sums && C % 8 == 0 && C / 8 <= 256, "bad arguments");
@@ -1105,12 +1095,12 @@ extern "C" int vtx_bn_bwd_reduce(const void* dA, const void* a, const void* y, c
   if (blocks > cap) blocks = cap;
   if (two) {
     REQ(bnp2 && sums2, "second BN needs bnp2/sums2");
-    bn_bwd_reduce_kernel<1><<<(int)blocks, threads, smem, STREAM>>>((const __nv_bfloat16*)dA, (const __nv_bfloat16*)a,
+    bn_bwd_reduce_kernel<1><<<(int)blocks, threads, smem, STREAM>>>((const __nv_bfloat16*)dA, (const uint8_t*)a,
                                                                     (const __nv_bfloat16*)y, bnp,
                                                                     (const __nv_bfloat16*)y2, bnp2, sums, sums2, M, C,
                                                                     mask_from_y);
   } else {
-    bn_bwd_reduce_kernel<0><<<(int)blocks, threads, smem, STREAM>>>((const __nv_bfloat16*)dA, (const __nv_bfloat16*)a,
+    bn_bwd_reduce_kernel<0><<<(int)blocks, threads, smem, STREAM>>>((const __nv_bfloat16*)dA, (const uint8_t*)a,
                                                                     (const __nv_bfloat16*)y, bnp, nullptr, nullptr,
                                                                     sums, nullptr, M, C, mask_from_y);
   }
@@ -1122,12 +1112,12 @@ extern "C" int vtx_bn_bwd_finalize(const float* sums, const float* bnp, float co
   bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, STREAM>>>(sums, bnp, count, coef, dgamma, dbeta, C);
   return check_launch("bn_bwd_finalize");
 }
-static int launch_bn_bwd_apply(bool fold, const BnBwdFold& f, const void* dA, const void* a, const void* y,
+static int launch_bn_bwd_apply(bool fold, const BnBwdFold& f, const void* dA, const uint8_t* a, const void* y,
                                const float* bnp, const float* coef, void* dy, const void* y2, const float* bnp2,
                                const float* coef2, void* dy2, void* dz_out, int64_t M, int C, int mask_from_y,
                                cudaStream_t st) {
   const int grid = grid_for((M * (C / 8) + kU - 1) / kU, 256, y2 != nullptr ? 1 : 2);
-#define VTX_APPLY_ARGS (const __nv_bfloat16*)dA, (const __nv_bfloat16*)a, (const __nv_bfloat16*)y, bnp, coef,          \
+#define VTX_APPLY_ARGS (const __nv_bfloat16*)dA, (const uint8_t*)a, (const __nv_bfloat16*)y, bnp, coef,                \
                        (__nv_bfloat16*)dy, (const __nv_bfloat16*)y2, bnp2, coef2, (__nv_bfloat16*)dy2,                  \
                        (__nv_bfloat16*)dz_out, M, C, mask_from_y, f
   if (y2 != nullptr) {
@@ -1140,7 +1130,7 @@ static int launch_bn_bwd_apply(bool fold, const BnBwdFold& f, const void* dA, co
 #undef VTX_APPLY_ARGS
   return check_launch("bn_bwd_apply");
 }
-extern "C" int vtx_bn_bwd_apply(const void* dA, const void* a, const void* y, const float* bnp, const float* coef,
+extern "C" int vtx_bn_bwd_apply(const void* dA, const uint8_t* a, const void* y, const float* bnp, const float* coef,
                                 void* dy, const void* y2, const float* bnp2, const float* coef2, void* dy2,
                                 void* dz_out, int64_t M, int C, int mask_from_y, void* stream) {
   REQ(dA && y && bnp && coef && dy && C % 8 == 0, "bad arguments");
@@ -1151,7 +1141,7 @@ extern "C" int vtx_bn_bwd_apply(const void* dA, const void* a, const void* y, co
 }
 // bn_bwd_finalize + bn_bwd_apply in one launch: sums [2,C] (and sums2) straight from vtx_bn_bwd_reduce
 extern "C" int vtx_bn_bwd_finalize_apply(const float* sums, const float* sums2, float count, float* dgamma, float* dbeta,
-                                         float* dgamma2, float* dbeta2, const void* dA, const void* a, const void* y,
+                                         float* dgamma2, float* dbeta2, const void* dA, const uint8_t* a, const void* y,
                                          const float* bnp, void* dy, const void* y2, const float* bnp2, void* dy2,
                                          void* dz_out, int64_t M, int C, int mask_from_y, void* stream) {
   REQ(sums && dA && y && bnp && dy && C % 8 == 0 && C / 8 <= 256, "bad arguments");

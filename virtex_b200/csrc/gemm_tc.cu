@@ -31,22 +31,12 @@
 #include "vtx_common.cuh"
 #include "../../include/virtex_b200.h"
 
-// Experimental build (-DVTX_GEMM_X, linked into libvirtex_b200_x.so only): the tap geometry of the implicit-conv modes
-// becomes a runtime parameter, which adds conv_mode 5 / 6 -- the 7x7/2 stem conv as a 4-tap implicit GEMM over a
-// space-to-depth view of the image (include/virtex_b200_x.h).  The regular build sees the literal constants below, i.e.
-// exactly the code that was validated on hardware.
-#ifdef VTX_GEMM_X
-#define gemm_tc_kernel gemm_tc_kernel_x
-#define GemmKParams GemmKParamsX
-#define vtx_gemm vtx_gemm_x
+// The tap geometry of the implicit-conv modes 1 / 2 is a runtime parameter (taps per kernel row, zero padding, tap
+// count): 3 x 3 / pad 1 for the bottleneck convs, and 4 x 1 / pad 0 for conv_mode 5 / 6 -- the 7x7/2 stem conv as a
+// 4-tap implicit GEMM over the space-to-depth view of the image (csrc/stem_s2d.cu).
 #define KP_TAPS_W p.taps_w
 #define KP_PAD p.pad
 #define KP_NTAPS p.ntaps
-#else
-#define KP_TAPS_W 3
-#define KP_PAD 1
-#define KP_NTAPS 9
-#endif
 
 namespace vtx {
 
@@ -84,9 +74,7 @@ struct GemmKParams {
   const __nv_bfloat16* residual;
   long long ldr;
   float* stats;
-#ifdef VTX_GEMM_X
   int taps_w, pad, ntaps;    // taps per kernel row / zero padding / number of taps of the implicit conv (3, 1, 9 for 3x3)
-#endif
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
@@ -218,7 +206,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  VTX_PDL_WAIT();  // (PDL build) everything above overlapped the previous kernel's tail; its results are visible from here
+  VTX_PDL_WAIT();  // everything above overlapped the previous kernel's tail; its results are visible from here
 
   const uint32_t b_bytes = (uint32_t)p.bn * kBK * 2;
 
@@ -440,17 +428,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // BN statistics: thread (scg, srg) owns 8 columns x 16 rows of every staged tile and keeps running partial sums in
     // registers across all tiles of this CTA that share the same column block; they are reduced through shared
     // memory and flushed with one atomic per column only when the column block changes (or at the end).
-#ifdef VTX_GEMM_X
-    // experimental: for 64- / 128-wide tiles ALL 256 threads take part (8 / 16 column groups x 32 / 16 row groups of
-    // 4 / 8 rows) instead of only the threads whose column group exists (8 column groups x 8 row groups x 16 rows)
-    const int st_cgs = (p.bn == 64) ? 8 : (p.bn == 128) ? 16 : 32;   // column groups of 8 columns
-    const int st_rgs = 256 / st_cgs;                                   // row groups
-    const int st_rpt = 128 / st_rgs;                                   // rows per thread
-    const int scg = et % st_cgs, srg = et / st_cgs;
-#else
     constexpr int st_rgs = 8, st_rpt = 16;
     const int scg = et & 31, srg = et >> 5;
-#endif
     float st_s[8], st_q[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) st_s[i] = st_q[i] = 0.f;
@@ -796,14 +775,10 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
   p.M = g->M; p.N = g->N; p.K = g->K;
   p.a_mn = g->a_mn; p.b_mn = g->b_mn;
   p.mode = g->conv_mode;
-#ifdef VTX_GEMM_X
   // conv_mode 5 / 6: stem conv over the space-to-depth view = modes 1 / 2 with 4 x 1 taps, no padding
   const bool stem = g->conv_mode == 5 || g->conv_mode == 6;
   p.taps_w = 3; p.pad = 1; p.ntaps = 9;
   if (stem) { p.mode = g->conv_mode == 5 ? 1 : 2; p.taps_w = 1; p.pad = 0; p.ntaps = 4; }
-#else
-  constexpr bool stem = false;
-#endif
   const int ntaps = stem ? 4 : 9;
   if (p.mode == 1) { p.a_mn = 0; p.b_mn = 0; }
   if (p.mode == 2 || p.mode == 4) { p.a_mn = 1; p.b_mn = 1; }
@@ -903,11 +878,9 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
     } else if (p.mode & 1) {
       // A: activation [NI,H,W,C]; M = NI*H*W (tiled as boxes); K = 9*C; B: weights [N, 9*C] K-major
       if (g->M != NI * H * W || g->K != ntaps * C) return set_error(VTX_EINVAL, "vtx_gemm: conv fprop shape mismatch");
-#ifdef VTX_GEMM_X
       // rows of a partial box below the image are real rows of the padded view: they would reach the BN statistics
       if (stem && g->stats && (W % bw != 0 || H % bh != 0))
-        return set_error(VTX_EUNSUPPORTED, "vtx_gemm_x: conv_mode 5 with stats needs an output size tiled exactly by %dx%d", bw, bh);
-#endif
+        return set_error(VTX_EUNSUPPORTED, "vtx_gemm: conv_mode 5 with stats needs an output size tiled exactly by %dx%d", bw, bh);
       p.m_tiles = p.tiles_w * p.tiles_h * tiles_n;
       p.kb_total = halo ? 1 : ntaps * p.cpb;
       uint32_t box[4] = {64, (uint32_t)(halo ? p.halo_w : bw), (uint32_t)(halo ? kHaloH : bh), (uint32_t)bnn};
@@ -988,16 +961,20 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
       }
     }
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
-    if (e != cudaSuccess) return set_error(VTX_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
+  {
+    // the attribute is per device: remember which devices of this process already have it
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+      cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
+      if (e != cudaSuccess) return set_error(VTX_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
   }
   const long total = (long)p.m_tiles * p.n_tiles * p.k_splits;
   const int sms = vtx_num_sms();
   const int grid = (int)(total < sms ? total : sms);
-#ifdef VTX_PDL
   {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -1013,9 +990,6 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
     cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel, tmA, tmB, tmD, tmR, p);
     if (le != cudaSuccess) return set_error(VTX_ECUDA, "gemm_tc_kernel PDL launch: %s", cudaGetErrorString(le));
   }
-#else
-  gemm_tc_kernel<<<grid, kThreads, kSmemTotal, stream>>>(tmA, tmB, tmD, tmR, p);
-#endif
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(VTX_ECUDA, "gemm_tc_kernel launch: %s", cudaGetErrorString(e));
   return VTX_OK;

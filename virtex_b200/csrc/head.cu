@@ -293,10 +293,9 @@ __global__ void ln_bwd_kernel(const float* __restrict__ dy_a, const __nv_bfloat1
   }
 }
 
-#ifdef VTX_HEAD_X
-// ------------------------------------------------------------------------------- EXPERIMENTAL variants (head_x)
-// Compiled only into libvirtex_b200_x.so (-DVTX_HEAD_X) and used only when VTX_EXPERIMENTAL names `head_x`; written
-// without hardware access.  Same arithmetic as ln_bwd_kernel / embed_bwd_kernel above, different data movement:
+// ------------------------------------------------------------------------------- register-accumulating variants
+// Used for H in {128, 256, 512, 1024} (the generic kernels above serve every other width, e.g. H = 2048).  Same
+// arithmetic as ln_bwd_kernel / embed_bwd_kernel, different data movement (validated on B200 in round 2: -1.1 ms/step):
 //   * every lane owns the columns {lane*4 + 128*k}: the upstream gradient and z are read ONCE per row (they were read
 //     twice) and the dgamma / dbeta (/ dposition) partial sums of all rows of a warp stay in REGISTERS; the validated
 //     kernels do two shared-memory read-modify-writes per element, 4-way bank conflicted (ln_bwd) or shared-memory
@@ -487,7 +486,6 @@ embed_bwd_reg_kernel(const float* __restrict__ dy_a, const __nv_bfloat16* __rest
   flush_columns<KB>(acc, dg, d_gamma, H);
   flush_columns<KB>(acc, db, d_beta, H);
 }
-#endif  // VTX_HEAD_X
 
 // ------------------------------------------------------------------------------------------------ attention
 // One warp per (batch b, head h); head_dim = 64; Tq <= 32 queries, Tk <= 64 keys.  The five small matrix products
@@ -555,19 +553,30 @@ __device__ __forceinline__ void frag_b_t(uint32_t* b, const __nv_bfloat16* t, in
   ldsm_x2_t(b, t + (k0 + (lane & 7) + ((lane >> 3) & 1) * 8) * kLd + n0);
 }
 
-// rows x 64 bf16 global -> smem [rows_pad][kLd], zero filling rows >= rows
-__device__ __forceinline__ void stage_rows(__nv_bfloat16* dst, const __nv_bfloat16* src, long long ld, int rows,
-                                           int rows_pad, int lane) {
+// rows x 64 bf16 global -> smem [rows_pad][kLd], zero filling rows >= rows.  Asynchronous 16-byte copies
+// (cp.async.cg, bypassing L1): a warp issues ALL chunks of Q, K and V (and dO) before waiting once, so the unit costs
+// one memory latency instead of one per loop iteration (the synchronous load -> store loop made the kernel latency
+// bound at ~10x its byte roofline).  Rows past `rows` use src-size 0: the hardware writes zeros, the (clamped) source
+// address is never dereferenced.
+__device__ __forceinline__ void stage_rows_async(__nv_bfloat16* dst, const __nv_bfloat16* src, long long ld, int rows,
+                                                 int rows_pad, int lane) {
   for (int e = lane; e < rows_pad * 8; e += 32) {
     const int r = e >> 3, c = (e & 7) * 8;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (r < rows) v = *reinterpret_cast<const uint4*>(src + (long long)r * ld + c);
-    *reinterpret_cast<uint4*>(dst + r * kLd + c) = v;
+    const bool ok = r < rows;
+    const __nv_bfloat16* gp = src + (long long)(ok ? r : 0) * ld + c;
+    const uint32_t sa = static_cast<uint32_t>(__cvta_generic_to_shared(dst + r * kLd + c));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(gp), "r"(ok ? 16 : 0) : "memory");
   }
+}
+__device__ __forceinline__ void stage_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+  __syncwarp();
 }
 
 constexpr int kAttnFwdWarps = 4;
-constexpr int kAttnFwdSmemPerWarp = (32 + 64 + 64) * kLd * 2;  // Q, K, V
+// shared memory per warp: Q [32] + K [Tk16] + V [Tk16] rows of kLd bf16 (self-attention: Tk16 = 32 -> 13.5 KB, twice the
+// resident warps of the cross-attention case Tk16 = 64)
+__host__ __device__ constexpr int attn_fwd_smem_per_warp(int Tk16) { return (32 + 2 * Tk16) * kLd * 2; }
 
 __global__ void __launch_bounds__(32 * kAttnFwdWarps) attn_fwd_kernel(const AttnArgs a, __nv_bfloat16* __restrict__ out,
                                                                         long long ldo, float* __restrict__ lse) {
@@ -578,14 +587,14 @@ __global__ void __launch_bounds__(32 * kAttnFwdWarps) attn_fwd_kernel(const Attn
   const int unit = blockIdx.x * kAttnFwdWarps + warp;
   if (unit >= a.B * a.heads) return;
   const int b = unit / a.heads, h = unit % a.heads;
-  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(sm_raw + (size_t)warp * kAttnFwdSmemPerWarp);
-  __nv_bfloat16* sK = sQ + 32 * kLd;
-  __nv_bfloat16* sV = sK + 64 * kLd;
   const int Tk16 = (a.Tk + 15) & ~15;
-  stage_rows(sQ, a.q + (long long)b * a.Tq * a.ldq + h * kD, a.ldq, a.Tq, 32, lane);
-  stage_rows(sK, a.k + (long long)b * a.Tk * a.ldk + h * kD, a.ldk, a.Tk, Tk16, lane);
-  stage_rows(sV, a.v + (long long)b * a.Tk * a.ldv + h * kD, a.ldv, a.Tk, Tk16, lane);
-  __syncwarp();
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(sm_raw + (size_t)warp * attn_fwd_smem_per_warp(Tk16));
+  __nv_bfloat16* sK = sQ + 32 * kLd;
+  __nv_bfloat16* sV = sK + Tk16 * kLd;
+  stage_rows_async(sQ, a.q + (long long)b * a.Tq * a.ldq + h * kD, a.ldq, a.Tq, 32, lane);
+  stage_rows_async(sK, a.k + (long long)b * a.Tk * a.ldk + h * kD, a.ldk, a.Tk, Tk16, lane);
+  stage_rows_async(sV, a.v + (long long)b * a.Tk * a.ldv + h * kD, a.ldv, a.Tk, Tk16, lane);
+  stage_wait_all();
   const int g = lane >> 2, tq = lane & 3;
   const int len = a.causal ? (int)a.lengths[b] : a.Tk;
   const int nkt = Tk16 >> 3;  // 8-key tiles
@@ -692,7 +701,8 @@ __global__ void __launch_bounds__(32 * kAttnFwdWarps) attn_fwd_kernel(const Attn
 }
 
 constexpr int kAttnBwdWarps = 3;
-constexpr int kAttnBwdSmemPerWarp = (32 + 32 + 64 + 64 + 32 + 32) * kLd * 2;  // Q, dO, K, V, Pd, dS
+// Q, dO, Pd, dS [32 rows each] + K, V [Tk16 rows each]
+__host__ __device__ constexpr int attn_bwd_smem_per_warp(int Tk16) { return (4 * 32 + 2 * Tk16) * kLd * 2; }
 
 __global__ void __launch_bounds__(32 * kAttnBwdWarps) attn_bwd_kernel(const AttnArgs a, const __nv_bfloat16* __restrict__ dout,
                                                                         long long ldo, const float* __restrict__ lse,
@@ -706,18 +716,18 @@ __global__ void __launch_bounds__(32 * kAttnBwdWarps) attn_bwd_kernel(const Attn
   const int unit = blockIdx.x * kAttnBwdWarps + warp;
   if (unit >= a.B * a.heads) return;
   const int b = unit / a.heads, h = unit % a.heads;
-  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(sm_raw + (size_t)warp * kAttnBwdSmemPerWarp);
+  const int Tk16 = (a.Tk + 15) & ~15;
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(sm_raw + (size_t)warp * attn_bwd_smem_per_warp(Tk16));
   __nv_bfloat16* sdO = sQ + 32 * kLd;
   __nv_bfloat16* sK = sdO + 32 * kLd;
-  __nv_bfloat16* sV = sK + 64 * kLd;
-  __nv_bfloat16* sP = sV + 64 * kLd;   // dropped probabilities Pd [query][key]
-  __nv_bfloat16* sdS = sP + 32 * kLd;  // dS [query][key]
-  const int Tk16 = (a.Tk + 15) & ~15;
-  stage_rows(sQ, a.q + (long long)b * a.Tq * a.ldq + h * kD, a.ldq, a.Tq, 32, lane);
-  stage_rows(sdO, dout + (long long)b * a.Tq * ldo + h * kD, ldo, a.Tq, 32, lane);
-  stage_rows(sK, a.k + (long long)b * a.Tk * a.ldk + h * kD, a.ldk, a.Tk, Tk16, lane);
-  stage_rows(sV, a.v + (long long)b * a.Tk * a.ldv + h * kD, a.ldv, a.Tk, Tk16, lane);
-  __syncwarp();
+  __nv_bfloat16* sV = sK + Tk16 * kLd;
+  __nv_bfloat16* sP = sV + Tk16 * kLd;  // dropped probabilities Pd [query][key]
+  __nv_bfloat16* sdS = sP + 32 * kLd;   // dS [query][key]
+  stage_rows_async(sQ, a.q + (long long)b * a.Tq * a.ldq + h * kD, a.ldq, a.Tq, 32, lane);
+  stage_rows_async(sdO, dout + (long long)b * a.Tq * ldo + h * kD, ldo, a.Tq, 32, lane);
+  stage_rows_async(sK, a.k + (long long)b * a.Tk * a.ldk + h * kD, a.ldk, a.Tk, Tk16, lane);
+  stage_rows_async(sV, a.v + (long long)b * a.Tk * a.ldv + h * kD, a.ldv, a.Tk, Tk16, lane);
+  stage_wait_all();
   const int g = lane >> 2, tq = lane & 3;
   const int len = a.causal ? (int)a.lengths[b] : a.Tk;
   const int nkt = Tk16 >> 3;
@@ -989,8 +999,7 @@ __global__ void ce_kernel(__nv_bfloat16* __restrict__ logits, long long ldl, con
   }
 }
 
-#ifdef VTX_HEAD_X
-// EXPERIMENTAL (head_x): same arithmetic as ce_kernel with the row held in registers -- one global read pass with all
+// Same arithmetic as ce_kernel with the row held in registers -- one global read pass with all
 // of a thread's loads in flight (the validated kernel walks the row three times with one dependent load at a time,
 // ~3 x 5 x memory latency per CTA) and exp() evaluated once.  Rows of up to 256 * 8 * IT logits.
 template <int IT>
@@ -1079,7 +1088,6 @@ __global__ void __launch_bounds__(256) ce_reg_kernel(__nv_bfloat16* __restrict__
     }
   }
 }
-#endif
 
 // out[n] += sum_m X[m,n]    X bf16 [M, ld]
 __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ X, long long ld, int M, int N, float* __restrict__ out,
@@ -1116,8 +1124,7 @@ __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ X, long long ld,
     if (g * 8 + j < N) atomicAdd(out + g * 8 + j, acc[j]);
 }
 
-#ifdef VTX_HEAD_X
-// EXPERIMENTAL (head_x): a CTA covers 256 columns x a row slice with 8 row lanes (one per warp) and reduces the lanes in
+// Row-lane variant (M >= 64): a CTA covers 256 columns x a row slice with 8 row lanes (one per warp) and reduces the lanes in
 // shared memory, so the number of atomics per output column drops from (row blocks) = 296 to 296 / (N / 256) -- the
 // validated kernel is bound by those atomics (31 us for a 15.7 MB input).
 __global__ void __launch_bounds__(256) colsum_lanes_kernel(const __nv_bfloat16* __restrict__ X, long long ld, int M, int N,
@@ -1164,7 +1171,6 @@ __global__ void __launch_bounds__(256) colsum_lanes_kernel(const __nv_bfloat16* 
     atomicAdd(out + c, t);
   }
 }
-#endif
 
 // first-index argmax of each fp32 row
 __global__ void argmax_rows_kernel(const float* __restrict__ X, long long ld, int N, long long* __restrict__ out) {
@@ -1222,7 +1228,6 @@ extern "C" int vtx_embed_bwd(const float* dy_a, const void* dy_b, const int64_t*
   int blocks = (M + kWarpsPerBlock - 1) / kWarpsPerBlock;
   const int cap = vtx_num_sms() * 2;
   if (blocks > cap) blocks = cap;
-#ifdef VTX_HEAD_X
   if (H % 128 == 0 && H <= 1024 && (H / 128 == 1 || H / 128 == 2 || H / 128 == 4 || H / 128 == 8) && T > 0 && M % T == 0) {
     int xb = cap;
     if (xb * kWarpsPerBlock < T) xb = (T + kWarpsPerBlock - 1) / kWarpsPerBlock;
@@ -1240,7 +1245,6 @@ extern "C" int vtx_embed_bwd(const float* dy_a, const void* dy_b, const int64_t*
 #undef VTX_EMB_X
     return check_launch("embed_bwd_reg");
   }
-#endif
   embed_bwd_kernel<<<blocks, 32 * kWarpsPerBlock, 2 * H * sizeof(float), STREAM>>>(
       dy_a, (const __nv_bfloat16*)dy_b, (const long long*)tokens, z, stats, gamma, d_words, d_pos, d_gamma, d_beta, M, T,
       H, pad, p, seed_ptr, site);
@@ -1262,7 +1266,6 @@ extern "C" int vtx_ln_bwd(const float* dy_a, const void* dy_b, const float* z, c
   int blocks = (M + kWarpsPerBlock - 1) / kWarpsPerBlock;
   const int cap = vtx_num_sms() * 2;
   if (blocks > cap) blocks = cap;
-#ifdef VTX_HEAD_X
   if (ln && H % 128 == 0 && (H / 128 == 1 || H / 128 == 2 || H / 128 == 4 || H / 128 == 8)) {
     const size_t xs = (size_t)kWarpsPerBlock * H * sizeof(float);
 #define VTX_LN_X(KB)                                                                                                   \
@@ -1278,7 +1281,6 @@ extern "C" int vtx_ln_bwd(const float* dy_a, const void* dy_b, const float* z, c
 #undef VTX_LN_X
     return check_launch("ln_bwd_reg");
   }
-#endif
   const size_t ln_smem = ln ? (size_t)kWarpsPerBlock * 2 * H * sizeof(float) : 0;
   static size_t ln_attr = 0;
   if (ln_smem > 48 * 1024 && ln_smem > ln_attr) {
@@ -1313,12 +1315,10 @@ extern "C" int vtx_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t l
   int rc = fill_attn(&a, q, ldq, k, ldk, v, ldv, B, heads, Tq, Tk, lengths, causal, p, seed_ptr, site);
   if (rc) return rc;
   REQ(out && ldo % 8 == 0, "bad output");
-  const size_t smem = (size_t)kAttnFwdWarps * kAttnFwdSmemPerWarp;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr = true;
-  }
+  const size_t smem = (size_t)kAttnFwdWarps * attn_fwd_smem_per_warp((Tk + 15) & ~15);
+  // per device and cheap: set unconditionally (a process may drive several devices through the module-level API)
+  cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       kAttnFwdWarps * attn_fwd_smem_per_warp(64));
   const int units = B * heads;
   attn_fwd_kernel<<<(units + kAttnFwdWarps - 1) / kAttnFwdWarps, 32 * kAttnFwdWarps, smem, STREAM>>>(
       a, (__nv_bfloat16*)out, ldo, lse);
@@ -1332,12 +1332,9 @@ extern "C" int vtx_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t l
   int rc = fill_attn(&a, q, ldq, k, ldk, v, ldv, B, heads, Tq, Tk, lengths, causal, p, seed_ptr, site);
   if (rc) return rc;
   REQ(dout && lse && dq && dk && dv && ldo % 8 == 0 && lddq % 8 == 0 && lddk % 8 == 0 && lddv % 8 == 0, "bad arguments");
-  const size_t smem = (size_t)kAttnBwdWarps * kAttnBwdSmemPerWarp;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr = true;
-  }
+  const size_t smem = (size_t)kAttnBwdWarps * attn_bwd_smem_per_warp((Tk + 15) & ~15);
+  cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       kAttnBwdWarps * attn_bwd_smem_per_warp(64));
   const int units = B * heads;
   attn_bwd_kernel<<<(units + kAttnBwdWarps - 1) / kAttnBwdWarps, 32 * kAttnBwdWarps, smem, STREAM>>>(
       a, (const __nv_bfloat16*)dout, ldo, lse, (__nv_bfloat16*)dq, lddq, (__nv_bfloat16*)dk, lddk, (__nv_bfloat16*)dv,
@@ -1373,20 +1370,17 @@ extern "C" int vtx_count_valid(const int64_t* tokens, int B, int T, int pad, flo
 extern "C" int vtx_cross_entropy(void* logits, int64_t ldl, const int64_t* tokens, int B, int T, int V, int pad,
                                  const float* count, float* loss, int write_grad, void* stream) {
   REQ(logits && tokens && count && loss && V % 8 == 0 && ldl % 8 == 0, "bad arguments");
-#ifdef VTX_HEAD_X
   if (V / 8 <= 256 * 5) {
     ce_reg_kernel<5><<<B * T, 256, 0, STREAM>>>((__nv_bfloat16*)logits, ldl, (const long long*)tokens, T, V, pad, count,
                                                 loss, write_grad);
     return check_launch("cross_entropy_reg");
   }
-#endif
   ce_kernel<<<B * T, 256, 0, STREAM>>>((__nv_bfloat16*)logits, ldl, (const long long*)tokens, T, V, pad, count, loss,
                                        write_grad);
   return check_launch("cross_entropy");
 }
 extern "C" int vtx_colsum(const void* X, int64_t ld, int M, int N, float* out, void* stream) {
   REQ(X && out && ld % 8 == 0, "bad arguments");
-#ifdef VTX_HEAD_X
   if (N % 8 == 0 && M >= 64) {
     const int by = (N + 255) / 256;
     int bx = (vtx_num_sms() * 2 + by - 1) / by;
@@ -1396,7 +1390,6 @@ extern "C" int vtx_colsum(const void* X, int64_t ld, int M, int N, float* out, v
     colsum_lanes_kernel<<<dim3(bx, by), 256, 0, STREAM>>>((const __nv_bfloat16*)X, ld, M, N, out, rpb);
     return check_launch("colsum_lanes");
   }
-#endif
   const int groups = (N + 7) / 8;
   const int threads = 128;
   const int gy = (groups + threads - 1) / threads;

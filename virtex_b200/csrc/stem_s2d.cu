@@ -1,23 +1,24 @@
-// EXPERIMENTAL (libvirtex_b200_x.so; written without hardware access, to be validated next round):
-// the 7x7 / stride-2 / pad-3 stem convolution as a 4-tap implicit GEMM over a space-to-depth (s2d) view of the image.
+// The 7x7 / stride-2 / pad-3 stem convolution as a 4-tap implicit GEMM over a space-to-depth (s2d) view of the image
+// (validated on B200 in round 2; the im2col route of backbone.cu remains only for image sizes whose stem output is not
+// tiled exactly by the 16 x 8 TMA boxes).
 //
 //   S[n, i, j, (r*2+q)*3 + c] = x[n, c, 2i + r - 3, 2j + q - 3]      (zero outside the image, channels 12..15 zero)
 //   y[n, oh, ow, o] = sum_{a<4} sum_{b<4} sum_{ch<16} S[n, oh + a, ow + b, ch] * Wp[o, a*64 + b*16 + ch]
 //   Wp[o, a*64 + b*16 + (r*2+q)*3 + c] = w[o, c, 2a + r, 2b + q]      (zero where 2a + r = 7 or 2b + q = 7)
 //
 // The four pixels (ow .. ow+3) x 16 channels of a tap row are 64 CONTIGUOUS bf16 in S, so the A operand of k-block `a`
-// is one 4-D TMA box of a tensor map whose W stride is a single pixel (overlapping rows): vtx_gemm_x conv_mode 5 / 6.
+// is one 4-D TMA box of a tensor map whose W stride is a single pixel (overlapping rows): vtx_gemm conv_mode 5 / 6.
 // HBM traffic: 154 MB (fp32 image) + 2 x 108 MB (S write, read) instead of 1 GB written + 1 GB read for the im2col
 // matrix (and once more in the wgrad).  Replaces torchvision resnet.py:197 `self.conv1` fwd / wgrad on this path.
-#include "../csrc/vtx_common.cuh"
+#include "vtx_common.cuh"
 #include "../../include/virtex_b200.h"
-#include "../../include/virtex_b200_x.h"
 
 namespace vtx {
 
 // one CTA per (n, i): the two image rows 2i-3, 2i-2 of the three channels are staged in shared memory
 __global__ void __launch_bounds__(256) stem_s2d_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ S, int N,
                                                       int H, int W, int Hs, int Ws) {
+  VTX_PDL_TRIGGER();
   extern __shared__ float tile[];  // [3][2][Wp], Wp = W + 8: image column x lives at tile column x + 4
   const int Wp = W + 8;
   const int n = blockIdx.x / Hs, i = blockIdx.x % Hs;
@@ -53,6 +54,7 @@ __global__ void __launch_bounds__(256) stem_s2d_kernel(const float* __restrict__
 }
 
 __global__ void stem_w_pack_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp, int O) {
+  VTX_PDL_TRIGGER();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= O * 256) return;
   const int o = t >> 8, k = t & 255;
@@ -67,6 +69,7 @@ __global__ void stem_w_pack_kernel(const float* __restrict__ w, __nv_bfloat16* _
 }
 
 __global__ void stem_w_unpack_add_kernel(const float* __restrict__ dwp, float* __restrict__ grad, int O) {
+  VTX_PDL_TRIGGER();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= O * 147) return;
   const int kw = t % 7, kh = (t / 7) % 7, c = (t / 49) % 3, o = t / 147;
@@ -80,22 +83,22 @@ using namespace vtx;
 
 #define STREAM reinterpret_cast<cudaStream_t>(stream)
 
-extern "C" int vtx_x_stem_s2d(const float* img, void* S, int N, int H, int W, void* stream) {
+extern "C" int vtx_stem_s2d(const float* img, void* S, int N, int H, int W, void* stream) {
   if (!img || !S || N <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 3))
-    return set_error(VTX_EINVAL, "vtx_x_stem_s2d: bad arguments (H must be even, W a multiple of 4)");
+    return set_error(VTX_EINVAL, "vtx_stem_s2d: bad arguments (H must be even, W a multiple of 4)");
   const size_t smem = (size_t)6 * (W + 8) * sizeof(float);
-  if (smem > 48 * 1024) return set_error(VTX_EINVAL, "vtx_x_stem_s2d: image too wide");
+  if (smem > 48 * 1024) return set_error(VTX_EINVAL, "vtx_stem_s2d: image too wide");
   const int Hs = H / 2 + 3, Ws = W / 2 + 3;
   stem_s2d_kernel<<<N * Hs, 256, smem, STREAM>>>(img, (__nv_bfloat16*)S, N, H, W, Hs, Ws);
   return check_launch("stem_s2d");
 }
-extern "C" int vtx_x_stem_w_pack(const float* w, void* wp, int O, void* stream) {
-  if (!w || !wp || O <= 0) return set_error(VTX_EINVAL, "vtx_x_stem_w_pack: bad arguments");
+extern "C" int vtx_stem_s2d_w_pack(const float* w, void* wp, int O, void* stream) {
+  if (!w || !wp || O <= 0) return set_error(VTX_EINVAL, "vtx_stem_s2d_w_pack: bad arguments");
   stem_w_pack_kernel<<<(O * 256 + 255) / 256, 256, 0, STREAM>>>(w, (__nv_bfloat16*)wp, O);
   return check_launch("stem_w_pack");
 }
-extern "C" int vtx_x_stem_w_unpack_add(const float* dwp, float* grad, int O, void* stream) {
-  if (!dwp || !grad || O <= 0) return set_error(VTX_EINVAL, "vtx_x_stem_w_unpack_add: bad arguments");
+extern "C" int vtx_stem_s2d_w_unpack_add(const float* dwp, float* grad, int O, void* stream) {
+  if (!dwp || !grad || O <= 0) return set_error(VTX_EINVAL, "vtx_stem_s2d_w_unpack_add: bad arguments");
   stem_w_unpack_add_kernel<<<(O * 147 + 255) / 256, 256, 0, STREAM>>>(dwp, grad, O);
   return check_launch("stem_w_unpack_add");
 }

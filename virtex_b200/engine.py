@@ -22,7 +22,6 @@ import torch
 from torch import nn
 
 from . import ops
-from . import experimental as X
 from .ops import call, gemm, _p, _stream
 
 BF16, F32 = torch.bfloat16, torch.float32
@@ -150,7 +149,6 @@ class Engine:
         self._packed: Dict[str, torch.Tensor] = {}
         self._tape = None
         self._weights_fresh = False
-        self._x_stem = X.enabled("stem_s2d")  # opt-in experimental stem path (virtex_b200/experimental.py)
         self._build_backbone_plan()
 
     # ------------------------------------------------------------------------------------------------ parameters
@@ -185,9 +183,8 @@ class Engine:
             w = self.P("visual.cnn.conv1.weight")
             pk = self._pack_buf("visual.cnn.conv1.weight", (64, 160))
             call("vtx_conv_w_pack", w.data_ptr(), pk.data_ptr(), 64, 3, 7, 7, 160, s)
-            if self._x_stem:
-                px = self._pack_buf("visual.cnn.conv1.weight#s2d", (64, 256))
-                X.call("vtx_x_stem_w_pack", w.data_ptr(), px.data_ptr(), 64, s)
+            px = self._pack_buf("visual.cnn.conv1.weight#s2d", (64, 256))
+            call("vtx_stem_s2d_w_pack", w.data_ptr(), px.data_ptr(), 64, s)
             for name, blk in self.blocks:
                 w = self.P(name + ".conv2.weight")
                 planes = w.shape[0]
@@ -215,14 +212,15 @@ class Engine:
              bnp.data_ptr(), C, _stream())
         return bnp
 
-    def _bn_act_fwd(self, y, bn_name, M, C, training, stats, out, res=None, bnp_res=None, relu=1):
-        """BN finalize (batch or running statistics -> bnp, running-stat update) + apply + ReLU (+ residual), one launch."""
+    def _bn_act_fwd(self, y, bn_name, M, C, training, stats, out, res=None, bnp_res=None, relu=1, mask=None):
+        """BN finalize (batch or running statistics -> bnp, running-stat update) + apply + ReLU (+ residual), one launch.
+        `mask`: uint8 [M, C/8] ReLU sign bits for backward (block outputs, whose pre-activation includes the shortcut)."""
         bnp = self.ws.get("bnp:" + bn_name, (4, C), F32)
         call("vtx_bn_finalize_act", _p(stats), float(M), self.P(bn_name + ".weight").data_ptr(),
              self.P(bn_name + ".bias").data_ptr(), self.buffers[bn_name + ".running_mean"].data_ptr(),
              self.buffers[bn_name + ".running_var"].data_ptr(),
              self.buffers[bn_name + ".num_batches_tracked"].data_ptr(), 0.1, 1e-5, int(training), bnp.data_ptr(),
-             y.data_ptr(), _p(res), _p(bnp_res), out.data_ptr(), M, C, relu, _stream())
+             y.data_ptr(), _p(res), _p(bnp_res), out.data_ptr(), _p(mask), M, C, relu, _stream())
         return bnp
 
     def _stats_slab(self, training):
@@ -258,13 +256,13 @@ class Engine:
         y0 = ws.get("stem.y", (M0, 64), BF16)
         st = self._slab_take(128) if training else None
         cols = s2d = None
-        if self._x_stem and H % 2 == 0 and W % 4 == 0 and Ho % 8 == 0 and Wo % 16 == 0:  # boxes tile the output exactly
-            # EXPERIMENTAL (VTX_EXPERIMENTAL=stem_s2d): 4-tap implicit GEMM over the space-to-depth view of the image
+        if H % 2 == 0 and W % 4 == 0 and Ho % 8 == 0 and Wo % 16 == 0:  # the 16 x 8 TMA boxes tile the output exactly
+            # 4-tap implicit GEMM over the space-to-depth view of the image (csrc/stem_s2d.cu)
             s2d = ws.get("stem.s2d", (B, H // 2 + 3, W // 2 + 3, 16), BF16)
-            X.call("vtx_x_stem_s2d", image.data_ptr(), s2d.data_ptr(), B, H, W, s)
-            X.gemm(s2d, self._packed["visual.cnn.conv1.weight#s2d"], y0, M0, 64, 256, lda=64, ldb=256, stats=st,
-                   conv=(B, Ho, Wo, 64), conv_mode=5)
-        else:
+            call("vtx_stem_s2d", image.data_ptr(), s2d.data_ptr(), B, H, W, s)
+            gemm(s2d, self._packed["visual.cnn.conv1.weight#s2d"], y0, M0, 64, 256, lda=64, ldb=256, stats=st,
+                 conv=(B, Ho, Wo, 64), conv_mode=5)
+        else:  # other image sizes: im2col + plain GEMM
             cols = ws.get("stem.cols", (M0, 160), BF16)
             call("vtx_stem_im2col", image.data_ptr(), cols.data_ptr(), B, H, W, 160, s)
             gemm(cols, self._packed["visual.cnn.conv1.weight"], y0, M0, 64, 160, stats=st)
@@ -309,6 +307,9 @@ class Engine:
             st3 = self._slab_take(2 * C4) if training else None
             gemm(a2, self.W(name + ".conv3.weight").view(C4, planes), y3, Mout, C4, planes, stats=st3)
             out = ws.get(name + ".out", (Mout, C4), BF16)
+            # backward needs only the SIGN of the block output's pre-activation: one bit per element instead of re-reading
+            # the bf16 output twice (bn_bwd_reduce and bn_bwd_apply)
+            m3 = ws.get(name + ".m3", (Mout, C4 // 8), torch.uint8) if training else None
             if blk.downsample is not None:
                 if stride == 1:
                     xs = x
@@ -319,11 +320,11 @@ class Engine:
                 std = self._slab_take(2 * C4) if training else None
                 gemm(xs, self.W(name + ".downsample.0.weight").view(C4, Cin), yd, Mout, C4, Cin, stats=std)
                 bnpd = self._bn_fwd(yd, name + ".downsample.1", Mout, C4, training, std)
-                bnp3 = self._bn_act_fwd(y3, name + ".bn3", Mout, C4, training, st3, out, res=yd, bnp_res=bnpd)
+                bnp3 = self._bn_act_fwd(y3, name + ".bn3", Mout, C4, training, st3, out, res=yd, bnp_res=bnpd, mask=m3)
                 rec.update(xs=xs, yd=yd, bnpd=bnpd)
             else:
-                bnp3 = self._bn_act_fwd(y3, name + ".bn3", Mout, C4, training, st3, out, res=x)
-            rec.update(y1=y1, bnp1=bnp1, a1=a1, y2=y2, bnp2=bnp2, a2=a2, y3=y3, bnp3=bnp3, out=out)
+                bnp3 = self._bn_act_fwd(y3, name + ".bn3", Mout, C4, training, st3, out, res=x, mask=m3)
+            rec.update(y1=y1, bnp1=bnp1, a1=a1, y2=y2, bnp2=bnp2, a2=a2, y3=y3, bnp3=bnp3, out=out, m3=m3)
             tape["blocks"].append(rec)
             x, Hc, Wc, Cin = out, Hn, Wn, C4
         tape["feat"] = x
@@ -340,7 +341,7 @@ class Engine:
         gemm(dY, X, dW, n_out, k_in, m_rows, a_mn=1, b_mn=1, atomic=True, split_k=sk, ldd=k_in, out_f32=True)
 
     def _bn_bwd(self, dA, a, y, bnp, bn_name, M, C, dy, two=None, dz_out=None, mask_from_y=0):
-        """dA -> dy through (ReLU mask from `a`, or recomputed from y when mask_from_y) + train-mode BN;
+        """dA -> dy through (ReLU from the bit mask `a`, or recomputed from y when mask_from_y) + train-mode BN;
         two = (y2, bnp2, bn2_name, dy2) shares dz."""
         s = _stream()
         sums = self._slab_take(2 * C)
@@ -385,12 +386,12 @@ class Engine:
             dy3 = ws.get("bwd.dy3", (Mout, C4), BF16)
             if rec["has_ds"]:
                 dyd = ws.get("bwd.dyd", (Mout, C4), BF16)
-                self._bn_bwd(dOut, rec["out"], rec["y3"], rec["bnp3"], name + ".bn3", Mout, C4, dy3,
+                self._bn_bwd(dOut, rec["m3"], rec["y3"], rec["bnp3"], name + ".bn3", Mout, C4, dy3,
                              two=(rec["yd"], rec["bnpd"], name + ".downsample.1", dyd))
                 dz = None
             else:
                 dz = ws.get("bwd.dz", (Mout, C4), BF16)
-                self._bn_bwd(dOut, rec["out"], rec["y3"], rec["bnp3"], name + ".bn3", Mout, C4, dy3, dz_out=dz)
+                self._bn_bwd(dOut, rec["m3"], rec["y3"], rec["bnp3"], name + ".bn3", Mout, C4, dy3, dz_out=dz)
             # ---- conv3 (1x1): wgrad + dgrad
             self._wgrad(dy3, rec["a2"], self.G(name + ".conv3.weight"), C4, planes, Mout)
             da2 = ws.get("bwd.da2", (Mout, planes), BF16)
@@ -455,12 +456,12 @@ class Engine:
         call("vtx_maxpool_bwd", dOut.data_ptr(), st["idx"].data_ptr(), da0.data_ptr(), B, st["Ho"], st["Wo"], 64, s)
         dy0 = ws.get("bwd.dy0", (M0, 64), BF16)
         self._bn_bwd(da0, None, st["y"], st["bnp"], "visual.cnn.bn1", M0, 64, dy0, mask_from_y=1)
-        if st["s2d"] is not None:  # EXPERIMENTAL: implicit wgrad over the space-to-depth view
+        if st["s2d"] is not None:  # implicit wgrad over the space-to-depth view
             dwx = ws.get("bwd.dwp0x", (64, 256), F32)
             dwx.zero_()
-            X.gemm(dy0, st["s2d"], dwx, 64, 256, M0, lda=64, ldb=64, atomic=True, out_f32=True,
-                   split_k=ops.split_k_for(1, M0 // 64), conv=(B, st["Ho"], st["Wo"], 64), conv_mode=6)
-            X.call("vtx_x_stem_w_unpack_add", dwx.data_ptr(), self.G("visual.cnn.conv1.weight").data_ptr(), 64, s)
+            gemm(dy0, st["s2d"], dwx, 64, 256, M0, lda=64, ldb=64, atomic=True, out_f32=True,
+                 split_k=ops.split_k_for(1, M0 // 64), conv=(B, st["Ho"], st["Wo"], 64), conv_mode=6)
+            call("vtx_stem_s2d_w_unpack_add", dwx.data_ptr(), self.G("visual.cnn.conv1.weight").data_ptr(), 64, s)
             return
         dwp0 = ws.get("bwd.dwp0", (64, 160), F32)
         dwp0.zero_()

@@ -8,13 +8,6 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvirtex_b200.so")
-# EXPERIMENTAL (off by default, see virtex_b200/experimental.py): the same library compiled with -DVTX_PDL
-LIB_PDL_PATH = os.path.join(_HERE, "libvirtex_b200_pdl.so")
-
-
-def _use_pdl() -> bool:
-    v = os.environ.get("VTX_EXPERIMENTAL", "")
-    return v == "all" or "pdl" in [t.strip() for t in v.split(",")]
 
 c_int = ctypes.c_int
 c_i32 = ctypes.c_int32
@@ -47,7 +40,7 @@ def load():
     """Load (once) and return the shared library; raises VtxError if it has not been built."""
     global _lib
     if _lib is None:
-        path = LIB_PDL_PATH if _use_pdl() else LIB_PATH
+        path = LIB_PATH
         if not os.path.exists(path):
             raise VtxError(
                 f"{path} is missing: run `python -m virtex_b200.build` (there is no fallback path)")

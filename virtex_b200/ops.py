@@ -15,13 +15,16 @@ P, I, I64, F, U32 = c_void_p, c_int, c_int64, c_float, c_uint32
 _PROTOS = {
     "vtx_gemm": [P, P],
     "vtx_stem_im2col": [P, P, I, I, I, I, P],
+    "vtx_stem_s2d": [P, P, I, I, I, P],
+    "vtx_stem_s2d_w_pack": [P, P, I, P],
+    "vtx_stem_s2d_w_unpack_add": [P, P, I, P],
     "vtx_im2col3x3": [P, P, I, I, I, I, I, P],
     "vtx_col2im3x3": [P, P, I, I, I, I, I, P],
     "vtx_subsample": [P, P, I, I, I, I, I, P],
     "vtx_upsample_add": [P, P, I, I, I, I, I, P],
     "vtx_bn_finalize": [P, F, P, P, P, P, P, F, F, I, P, I, P],
-    "vtx_bn_act": [P, P, P, P, P, I64, I, I, P],
-    "vtx_bn_finalize_act": [P, F, P, P, P, P, P, F, F, I, P, P, P, P, P, I64, I, I, P],
+    "vtx_bn_act": [P, P, P, P, P, P, I64, I, I, P],
+    "vtx_bn_finalize_act": [P, F, P, P, P, P, P, F, F, I, P, P, P, P, P, P, I64, I, I, P],
     "vtx_bn_bwd_finalize_apply": [P, P, F, P, P, P, P, P, P, P, P, P, P, P, P, P, I64, I, I, P],
     "vtx_bn_relu_maxpool": [P, P, P, P, I, I, I, I, P],
     "vtx_maxpool_bwd": [P, P, P, I, I, I, I, P],
@@ -46,6 +49,10 @@ _PROTOS = {
     "vtx_cross_entropy": [P, I64, P, I, I, I, I, P, P, I, P],
     "vtx_colsum": [P, I64, I, I, P, P],
     "vtx_argmax_rows": [P, I64, I, I, P, P],
+    "vtx_image_resample": [P, P, P, P, P, P, I, I, P],
+    "vtx_image_gray_sum": [P, P, P, P, I, I, P],
+    "vtx_image_jitter_normalize": [P, P, P, P, P, P, I, I, P],
+    "vtx_collate_tokens": [P, P, P, P, P, I, I, I, I64, P],
     "vtx_sumsq": [P, I64, P, P],
     "vtx_clip_coef": [P, I, F, P, P],
     "vtx_sgd_step": [P, P, P, P, P, P, I, P, P, F, F, P],
@@ -57,9 +64,7 @@ _fn = {}
 def _get(name):
     f = _fn.get(name)
     if f is None:
-        from . import experimental as X  # opt-in re-implementations of a few entry points (off by default)
-        xlib = X.routed_lib(name)
-        f = getattr(xlib, X.routed_symbol(name)) if xlib is not None else getattr(L.load(), name)
+        f = getattr(L.load(), name)
         f.argtypes = _PROTOS[name]
         f.restype = c_int
         _fn[name] = f
