@@ -159,7 +159,8 @@ int vtx_add_ln_fwd(const float* res, const void* branch, const float* gamma, con
 int vtx_ln_bwd(const float* dy_a, const void* dy_b, const float* z, const float* stats, const float* gamma,
                const float* d_skip, float* d_res, void* d_branch, float* d_gamma, float* d_beta, int M, int H, float p,
                const uint64_t* seed, uint32_t site, int ln, void* stream);
-/* attention core, head_dim 64, Tq <= 32, Tk <= 64; causal=1: key j visible to query i iff j <= i and j < lengths[b] */
+/* attention core, head_dim 64, Tq <= 32, Tk <= 64; causal = 1: key j visible to query i iff j <= i and j < lengths[b];
+   causal = 2: iff j < lengths[b] (key-padding mask only: masked language modelling); causal = 0: every key */
 int vtx_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,
                  int64_t ldo, float* lse, int B, int heads, int Tq, int Tk, const int64_t* lengths, int causal,
                  float p, const uint64_t* seed, uint32_t site, void* stream);
@@ -170,9 +171,11 @@ int vtx_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const v
 int vtx_gelu_dropout_fwd(const void* u, void* h, int64_t n, float p, const uint64_t* seed, uint32_t site, void* stream);
 int vtx_gelu_dropout_bwd(const void* dh, const void* u, void* du, int64_t n, float p, const uint64_t* seed,
                          uint32_t site, void* stream);
-int vtx_count_valid(const int64_t* tokens, int B, int T, int pad, float* count, void* stream);
+/* shift = 1: the target of position t is tokens[b, t+1] (captioning.py:111-114); shift = 0: tokens[b, t] is the label of
+   position t itself (masked_labels of virtex/models/masked_lm.py:68-72).  Targets equal to pad are ignored. */
+int vtx_count_valid(const int64_t* tokens, int B, int T, int pad, int shift, float* count, void* stream);
 /* logits bf16 [B*T, ldl]; loss += mean NLL over valid targets; write_grad: logits := dlogits in place */
-int vtx_cross_entropy(void* logits, int64_t ldl, const int64_t* tokens, int B, int T, int V, int pad,
+int vtx_cross_entropy(void* logits, int64_t ldl, const int64_t* tokens, int B, int T, int V, int pad, int shift,
                       const float* count, float* loss, int write_grad, void* stream);
 int vtx_colsum(const void* X, int64_t ld, int M, int N, float* out, void* stream);
 int vtx_argmax_rows(const float* X, int64_t ld, int M, int N, int64_t* out, void* stream);

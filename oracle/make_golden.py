@@ -98,6 +98,46 @@ def run_case(name, spec_kw, batch_kw, seed):
     torch.save(out, os.path.join(GOLDEN_DIR, name + ".pt"))
 
 
+def run_masked_lm_case():
+    """The masked-LM sibling (virtex/models/masked_lm.py:35-86) through the reference's own MaskedLMModel and a head
+    built with mask_future_positions=False: loss, gradient summaries, eval predictions."""
+    from virtex.models import MaskedLMModel
+    from virtex.modules.textual_heads import TransformerDecoderTextualHead
+    from virtex.modules.visual_backbones import TorchvisionVisualBackbone
+    spec_kw = dict(hidden=128, layers=1, heads=2, ffn=256, caption_backward=False, mask_future=False)
+    spec = O.Spec(**spec_kw)
+    state = O.synth_state(spec, 31)
+    batch = O.synth_masked_batch(3, seed=21)
+    out = {"spec": spec_kw, "seed": 31, "batch_seed": 21}
+    for tag, dtype in (("f64", torch.float64), ("f32", torch.float32)):
+        visual = TorchvisionVisualBackbone(spec.backbone, visual_feature_size=spec.visual_feature_size)
+        textual = TransformerDecoderTextualHead(
+            visual_feature_size=spec.visual_feature_size, vocab_size=spec.vocab, hidden_size=spec.hidden,
+            num_layers=spec.layers, attention_heads=spec.heads, feedforward_size=spec.ffn, dropout=0.0,
+            norm_first=False, mask_future_positions=False, max_caption_length=spec.max_len, padding_idx=spec.pad)
+        model = MaskedLMModel(visual, textual)
+        sd = {k: v for k, v in O.to_reference_state_dict(state, spec).items() if not k.startswith("backward_textual.")}
+        model.load_state_dict(sd, strict=True)
+        model = model.to(dtype)
+        b = dict(batch)
+        b["image"] = batch["image"].to(dtype)
+        model.train()
+        res = model(b)
+        res["loss"].backward()
+        named = dict(model.named_parameters())
+        grads = {k: named[k].grad for k in named}
+        rec = {"loss": res["loss"].detach().double(), "grads": grad_summary(grads)}
+        model.load_state_dict({k: (v.to(dtype) if v.is_floating_point() else v) for k, v in sd.items()}, strict=True)
+        model.eval()
+        with torch.no_grad():
+            ev = model(b)
+        rec["eval_loss"] = ev["loss"].double()
+        rec["eval_predictions"] = ev["predictions"].clone()
+        out[tag] = rec
+        print(f"masked_lm [{tag}] loss {rec['loss'].item():.9f} eval {rec['eval_loss'].item():.9f}", flush=True)
+    torch.save(out, os.path.join(GOLDEN_DIR, "masked_lm_r50_l1_h128_b3.pt"))
+
+
 def run_trainer_case():
     """6 optimiser steps (crosses the Lookahead k=5 boundary) through the reference's own factories + loop body."""
     from virtex.config import Config
@@ -149,6 +189,8 @@ def main():
     for name, (spec_kw, batch_kw, seed) in CASES.items():
         if not only or name in only:
             run_case(name, spec_kw, batch_kw, seed)
+    if not only or "masked_lm" in only:
+        run_masked_lm_case()
     if not only or "trainer" in only:
         run_trainer_case()
 

@@ -49,6 +49,7 @@ class Spec:
     pad: int = 0
     visual_feature_size: int = 2048
     caption_backward: bool = True
+    mask_future: bool = True  # False: masked language modelling (virtex/factories.py:395 -> textual_heads.py:255-262)
     blocks: List[int] = field(default_factory=list)
 
     def __post_init__(self):
@@ -354,7 +355,8 @@ def head_forward(P, visual_features, tokens, lengths, spec: Spec, direction: str
     pos = torch.arange(1, T + 1)[None, :]
     kpm = lengths[:, None] < pos  # True = padded key
     bias = torch.zeros(B, 1, T, T, dtype=emb.dtype)
-    bias = bias.masked_fill(torch.triu(torch.ones(T, T, dtype=torch.bool), diagonal=1)[None, None], float("-inf"))
+    if spec.mask_future:
+        bias = bias.masked_fill(torch.triu(torch.ones(T, T, dtype=torch.bool), diagonal=1)[None, None], float("-inf"))
     bias = bias.masked_fill(kpm[:, None, None, :], float("-inf"))
     x = emb
     for l in range(spec.layers):
@@ -387,6 +389,51 @@ def caption_loss(logits, tokens, pad=0):
     picked = z.gather(1, y[:, None]).squeeze(1)
     valid = (y != pad).to(z.dtype)
     return ((lse - picked) * valid).sum() / valid.sum()
+
+
+def masked_lm_loss(logits, labels, pad=0):
+    """CrossEntropyLoss(ignore_index=pad) between every position's logits and its label (virtex/models/masked_lm.py:68-72)."""
+    V = logits.shape[-1]
+    z, y = logits.reshape(-1, V), labels.reshape(-1)
+    lse = torch.logsumexp(z, dim=-1)
+    picked = z.gather(1, y[:, None]).squeeze(1)
+    valid = (y != pad).to(z.dtype)
+    return ((lse - picked) * valid).sum() / valid.sum()
+
+
+def masked_lm_forward(P, batch, spec: Spec, training=True, new_buffers=None, return_logits=False):
+    """virtex/models/masked_lm.py:35-86 (spec.mask_future must be False)."""
+    vf = backbone_forward(P, batch["image"], spec, training, new_buffers)
+    logits = head_forward(P, vf, batch["caption_tokens"], batch["caption_lengths"], spec, "textual")
+    loss = masked_lm_loss(logits, batch["masked_labels"], spec.pad)
+    out = {"loss": loss, "loss_components": {"masked_lm": loss.detach().clone()}}
+    if not training:
+        pred = torch.argmax(logits, dim=-1)
+        pred[batch["masked_labels"] == spec.pad] = spec.pad
+        out["predictions"] = pred
+    if return_logits:
+        out["logits"] = logits
+    return out
+
+
+def synth_masked_batch(batch_size: int, seed: int = 0, max_len: int = 30, vocab: int = 10000, mask_index: int = 3,
+                       mask_prob: float = 0.3, ragged: bool = True):
+    """A captioning batch turned into a masked-LM batch the way virtex/data/datasets/masked_lm.py does in spirit:
+    ~mask_prob of the real tokens (never [SOS]/[EOS]) are replaced by [MASK]; `masked_labels` holds the original id
+    there and the padding id everywhere else (at least one label per caption)."""
+    batch = synth_batch(batch_size, seed=seed, max_len=max_len, vocab=vocab, ragged=ragged)
+    g = torch.Generator().manual_seed(seed + 777)
+    tokens = batch["caption_tokens"].clone()
+    labels = torch.zeros_like(tokens)
+    for b in range(batch_size):
+        n = int(batch["caption_lengths"][b])
+        cand = [t for t in range(1, n - 1) if tokens[b, t] != 0]
+        pick = [t for t in cand if torch.rand(1, generator=g).item() < mask_prob] or cand[:1]
+        for t in pick:
+            labels[b, t] = tokens[b, t]
+            tokens[b, t] = mask_index
+    batch["caption_tokens"], batch["masked_labels"] = tokens, labels
+    return batch
 
 
 def model_forward(P, batch, spec: Spec, training=True, new_buffers=None, return_logits=False):
@@ -426,7 +473,8 @@ def loss_and_grads(state, batch, spec: Spec, dtype=torch.float32):
              else (v.clone().to(dtype) if v.is_floating_point() else v.clone())) for k, v in state.items()}
     batch = _cast_batch(batch, dtype)
     new_buffers: Dict[str, torch.Tensor] = {}
-    out = model_forward(P, batch, spec, training=True, new_buffers=new_buffers, return_logits=True)
+    fwd = masked_lm_forward if "masked_labels" in batch else model_forward
+    out = fwd(P, batch, spec, training=True, new_buffers=new_buffers, return_logits=True)
     out["loss"].backward()
     grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in P.items() if not is_buffer(k)}
     # NB: row `pad` of the tied word matrix still receives the vocabulary-projection gradient (class-0 logit);

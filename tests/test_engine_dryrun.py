@@ -164,3 +164,24 @@ def test_stem_branch_schedule(dry):
     dry.calls.clear()
     _run(_model(spec), O.synth_batch(2, seed=9, image_size=200))
     assert "vtx_stem_im2col" in dry.names() and "vtx_stem_s2d" not in dry.names()
+
+
+def test_masked_lm_schedule(dry):
+    """The masked-LM sibling: one direction, key-padding-only attention mask (mode 2), labels passed to the loss."""
+    from virtex_b200.models import MaskedLMModel
+    from virtex_b200.modules import TorchvisionVisualBackbone, TransformerDecoderTextualHead
+    spec = O.Spec(**SMALL)
+    visual = TorchvisionVisualBackbone(spec.backbone, visual_feature_size=spec.visual_feature_size)
+    textual = TransformerDecoderTextualHead(spec.visual_feature_size, spec.vocab, spec.hidden, spec.layers, spec.heads,
+                                            spec.ffn, dropout=0.1, mask_future_positions=False)
+    model = MaskedLMModel(visual, textual)
+    batch = O.synth_masked_batch(3, seed=5)
+    eng = model.engine
+    eng.forward(batch["image"], batch["caption_tokens"], batch["caption_tokens"], batch["caption_lengths"], training=True,
+                with_grad=True, labels=batch["masked_labels"])
+    eng.backward(zero_grads=True)
+    assert dry.names().count("vtx_cross_entropy") == 1 and dry.names().count("vtx_attn_fwd") == 2
+    assert eng._recs[0]["mask_mode"] == 2
+    with pytest.raises(ValueError):
+        MaskedLMModel(visual, TransformerDecoderTextualHead(spec.visual_feature_size, spec.vocab, spec.hidden, 1,
+                                                            spec.heads, spec.ffn))

@@ -110,3 +110,29 @@ def test_state_dict_key_set():
     nparams = sum(v.numel() for k, v in state.items() if not O.is_buffer(k))
     assert nparams == 69_482_320
     assert sum(1 for k in state if not O.is_buffer(k)) == 202
+
+
+def test_masked_lm_oracle_matches_the_reference(golden_dir):
+    """The masked-LM sibling (virtex/models/masked_lm.py:35-86, head with mask_future_positions=False): float64 oracle ==
+    float64 reference MaskedLMModel -- loss, every gradient's norm and sum, eval loss and masked predictions bit-exact."""
+    g = _load(golden_dir, "masked_lm_r50_l1_h128_b3")
+    spec = O.Spec(**g["spec"])
+    state = O.synth_state(spec, g["seed"])
+    batch = O.synth_masked_batch(3, seed=g["batch_seed"])
+    assert (batch["masked_labels"] != 0).sum() >= 3 and (batch["caption_tokens"] == 3).sum() == (batch["masked_labels"] != 0).sum()
+    out, grads, _ = O.loss_and_grads(state, batch, spec, dtype=torch.float64)
+    ref = g["f64"]
+    assert abs(out["loss"].item() - ref["loss"].item()) < 1e-9
+    # the reference model owns no backward head: compare the parameters it has
+    names = [n for n in ref["grads"]["names"]]
+    mine = {n: grads[n] for n in names}
+    norm = torch.tensor([mine[n].norm().item() for n in names], dtype=torch.float64)
+    ssum = torch.tensor([mine[n].sum().item() for n in names], dtype=torch.float64)
+    assert torch.allclose(norm, ref["grads"]["norm"], rtol=1e-7, atol=1e-12)
+    assert ((ssum - ref["grads"]["sum"]).abs() <= 1e-6 * ref["grads"]["sum"].abs() + 1e-9 * (1 + norm)).all()
+    st64 = O.cast_state(state, torch.float64)
+    b64 = dict(batch, image=batch["image"].double())
+    with torch.no_grad():
+        ev = O.masked_lm_forward(st64, b64, spec, training=False)
+    assert abs(ev["loss"].item() - ref["eval_loss"].item()) < 1e-9
+    assert torch.equal(ev["predictions"], ref["eval_predictions"])

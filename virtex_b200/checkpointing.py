@@ -158,6 +158,9 @@ class FusedSchedulerState:
 
     def load_state_dict(self, state_dict: Dict[str, Any]):
         self._t.iteration = int(state_dict["last_epoch"])
+        sync = getattr(self._t, "sync_dropout_seed", None)
+        if sync is not None:
+            sync()  # dropout stream position follows the iteration
 
     def get_last_lr(self) -> List[float]:
         return self.state_dict()["_last_lr"]

@@ -493,7 +493,9 @@ embed_bwd_reg_kernel(const float* __restrict__ dy_a, const __nv_bfloat16* __rest
 // tiles with fp32 accumulation -- the tiles are 30x30 / 30x49, far below a tcgen05 instruction shape, and the kernel
 // is bound by its q/k/v/o bytes, not by math.  Operands are staged once in shared memory (row stride 72 halves:
 // conflict-free ldmatrix); the causal + key-padding mask comes from caption_lengths and is never materialised.
-// causal != 0: key j allowed for query i iff j <= i and j < lengths[b]; causal == 0: all Tk keys (cross-attention).
+// causal == 1: key j allowed for query i iff j <= i and j < lengths[b] (captioning: future + key-padding mask);
+// causal == 2: iff j < lengths[b] (masked language modelling: key-padding mask only, textual_heads.py:255-262 with
+// mask_future_positions = False); causal == 0: all Tk keys (cross-attention over the visual grid).
 constexpr int kD = 64;
 constexpr int kLd = 72;  // smem row stride in bf16 elements (144 B)
 
@@ -634,7 +636,7 @@ __global__ void __launch_bounds__(32 * kAttnFwdWarps) attn_fwd_kernel(const Attn
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int j = nt * 8 + 2 * tq + e;
-          const bool ok = (j < a.Tk) && (a.causal ? (j <= i && j < len) : true);
+          const bool ok = (j < a.Tk) && (a.causal == 1 ? (j <= i && j < len) : a.causal == 2 ? (j < len) : true);
           const float v = ok ? s[mt][nt][hh * 2 + e] * a.scale : -INFINITY;
           s[mt][nt][hh * 2 + e] = v;
           mx = fmaxf(mx, v);
@@ -774,7 +776,7 @@ __global__ void __launch_bounds__(32 * kAttnBwdWarps) attn_bwd_kernel(const Attn
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int j = nt * 8 + 2 * tq + e;
-          const bool ok = row_ok && (j < a.Tk) && (a.causal ? (j <= i && j < len) : true);
+          const bool ok = row_ok && (j < a.Tk) && (a.causal == 1 ? (j <= i && j < len) : a.causal == 2 ? (j < len) : true);
           const float pr = ok ? __expf(s[mt][nt][hh * 2 + e] * a.scale - L) : 0.f;
           const float mk = dropout_scale(a.p, inv_keep, seed, a.site, ((uint64_t)unit * 32 + i) * 64 + j);
           const float dpr = dp[mt][nt][hh * 2 + e] * mk;  // dP = dPd * mask
@@ -914,27 +916,31 @@ __global__ void gelu_dropout_bwd_kernel(const __nv_bfloat16* __restrict__ dh, co
 }
 
 // ------------------------------------------------------------------------------------------------ cross entropy
-// counts[0] = number of targets tokens[b, t>=1] != pad
-__global__ void count_valid_kernel(const long long* __restrict__ tokens, int B, int T, int pad, float* __restrict__ count) {
+// counts[0] = number of targets != pad: tokens[b, t>=1] (shift = 1: next-token targets) or tokens[b, t] (shift = 0: the
+// tensor already holds one label per position, e.g. masked_labels of virtex/models/masked_lm.py:68-72)
+__global__ void count_valid_kernel(const long long* __restrict__ tokens, int B, int T, int pad, int shift,
+                                   float* __restrict__ count) {
   VTX_PDL_TRIGGER();
   float c = 0.f;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B * T; i += gridDim.x * blockDim.x)
-    if ((i % T) >= 1 && tokens[i] != pad) c += 1.f;
+    if ((i % T) >= shift && tokens[i] != pad) c += 1.f;
   c = warp_sum(c);
   if ((threadIdx.x & 31) == 0 && c != 0.f) atomicAdd(count, c);
 }
 
-// One CTA per row (b,t) of bf16 logits [B*T, ldl].  Target = tokens[b,t+1] for t < T-1 (else ignored); ignored when
+// One CTA per row (b,t) of bf16 logits [B*T, ldl].  Target = tokens[b,t+1] for t < T-1 (else ignored) when shift = 1,
+// tokens[b,t] when shift = 0; ignored when
 // == pad.  loss += nll / count;  if write_grad: logits row overwritten by dlogits = (softmax - onehot)/count (or 0).
 __global__ void ce_kernel(__nv_bfloat16* __restrict__ logits, long long ldl, const long long* __restrict__ tokens, int T,
-                          int V, int pad, const float* __restrict__ count, float* __restrict__ loss, int write_grad) {
+                          int V, int pad, int shift, const float* __restrict__ count, float* __restrict__ loss,
+                          int write_grad) {
   VTX_PDL_TRIGGER();
   __shared__ float red[32];
   __shared__ float bcast;
   const int row = blockIdx.x;
   const int t = row % T;
   __nv_bfloat16* z = logits + (long long)row * ldl;
-  const long long target = (t < T - 1) ? tokens[row + 1] : (long long)pad;
+  const long long target = !shift ? tokens[row] : (t < T - 1) ? tokens[row + 1] : (long long)pad;
   const bool valid = target != pad;
   const int nv = V / 8;
   if (!valid) {
@@ -1005,15 +1011,15 @@ __global__ void ce_kernel(__nv_bfloat16* __restrict__ logits, long long ldl, con
 template <int IT>
 __global__ void __launch_bounds__(256) ce_reg_kernel(__nv_bfloat16* __restrict__ logits, long long ldl,
                                                     const long long* __restrict__ tokens, int T, int V, int pad,
-                                                    const float* __restrict__ count, float* __restrict__ loss,
-                                                    int write_grad) {
+                                                    int shift, const float* __restrict__ count,
+                                                    float* __restrict__ loss, int write_grad) {
   VTX_PDL_TRIGGER();
   __shared__ float red[32];
   __shared__ float bcast;
   const int row = blockIdx.x;
   const int t = row % T;
   __nv_bfloat16* z = logits + (long long)row * ldl;
-  const long long target = (t < T - 1) ? tokens[row + 1] : (long long)pad;
+  const long long target = !shift ? tokens[row] : (t < T - 1) ? tokens[row + 1] : (long long)pad;
   const bool valid = target != pad;
   const int nv = V / 8;
   if (!valid) {
@@ -1296,7 +1302,7 @@ extern "C" int vtx_ln_bwd(const float* dy_a, const void* dy_b, const float* z, c
 static int fill_attn(AttnArgs* a, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                      int B, int heads, int Tq, int Tk, const int64_t* lengths, int causal, float p, const uint64_t* seed_ptr,
                      uint32_t site) {
-  if (!q || !k || !v || Tq < 1 || Tq > 32 || Tk < 1 || Tk > 64 || (causal && !lengths))
+  if (!q || !k || !v || Tq < 1 || Tq > 32 || Tk < 1 || Tk > 64 || causal < 0 || causal > 2 || (causal && !lengths))
     return set_error(VTX_EINVAL, "attention: unsupported shape (Tq<=32, Tk<=64, head_dim 64)");
   if (ldq % 8 || ldk % 8 || ldv % 8) return set_error(VTX_EINVAL, "attention: leading dims must be multiples of 8");
   a->q = (const __nv_bfloat16*)q; a->k = (const __nv_bfloat16*)k; a->v = (const __nv_bfloat16*)v;
@@ -1362,21 +1368,21 @@ extern "C" int vtx_gelu_dropout_bwd(const void* dh, const void* u, void* du, int
                                                            (__nv_bfloat16*)du, n8, p, seed_ptr, site);
   return check_launch("gelu_dropout_bwd");
 }
-extern "C" int vtx_count_valid(const int64_t* tokens, int B, int T, int pad, float* count, void* stream) {
-  REQ(tokens && count, "bad arguments");
-  count_valid_kernel<<<32, 256, 0, STREAM>>>((const long long*)tokens, B, T, pad, count);
+extern "C" int vtx_count_valid(const int64_t* tokens, int B, int T, int pad, int shift, float* count, void* stream) {
+  REQ(tokens && count && (shift == 0 || shift == 1), "bad arguments");
+  count_valid_kernel<<<32, 256, 0, STREAM>>>((const long long*)tokens, B, T, pad, shift, count);
   return check_launch("count_valid");
 }
 extern "C" int vtx_cross_entropy(void* logits, int64_t ldl, const int64_t* tokens, int B, int T, int V, int pad,
-                                 const float* count, float* loss, int write_grad, void* stream) {
-  REQ(logits && tokens && count && loss && V % 8 == 0 && ldl % 8 == 0, "bad arguments");
+                                 int shift, const float* count, float* loss, int write_grad, void* stream) {
+  REQ(logits && tokens && count && loss && V % 8 == 0 && ldl % 8 == 0 && (shift == 0 || shift == 1), "bad arguments");
   if (V / 8 <= 256 * 5) {
-    ce_reg_kernel<5><<<B * T, 256, 0, STREAM>>>((__nv_bfloat16*)logits, ldl, (const long long*)tokens, T, V, pad, count,
-                                                loss, write_grad);
+    ce_reg_kernel<5><<<B * T, 256, 0, STREAM>>>((__nv_bfloat16*)logits, ldl, (const long long*)tokens, T, V, pad, shift,
+                                                count, loss, write_grad);
     return check_launch("cross_entropy_reg");
   }
-  ce_kernel<<<B * T, 256, 0, STREAM>>>((__nv_bfloat16*)logits, ldl, (const long long*)tokens, T, V, pad, count, loss,
-                                       write_grad);
+  ce_kernel<<<B * T, 256, 0, STREAM>>>((__nv_bfloat16*)logits, ldl, (const long long*)tokens, T, V, pad, shift, count,
+                                       loss, write_grad);
   return check_launch("cross_entropy");
 }
 extern "C" int vtx_colsum(const void* X, int64_t ld, int M, int N, float* out, void* stream) {

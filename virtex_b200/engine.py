@@ -148,6 +148,7 @@ class Engine:
         self.count = torch.zeros(2, dtype=F32, device=dev)      # per-direction number of valid targets
         self._packed: Dict[str, torch.Tensor] = {}
         self._tape = None
+        self.generation = 0  # bumped by every forward(): a backward must match the forward that filled the tape
         self._weights_fresh = False
         self._build_backbone_plan()
 
@@ -243,8 +244,6 @@ class Engine:
         """image fp32 NCHW [B,3,H,W] -> NHWC bf16 feature matrix [B*h*w, 2048]; fills the tape used by backward."""
         if not self._weights_fresh:
             self.prepare_weights()
-        if self.visual is not None and getattr(self.visual, "frozen", False):
-            training = False
         B, _, H, W = image.shape
         s = _stream()
         ws = self.ws
@@ -366,8 +365,10 @@ class Engine:
         """dfeat bf16 [B*h*w, C]: gradient w.r.t. the backbone output.  Accumulates into the gradient arena.
         `bucket_cb(tag)` is called when every gradient of 'layer4' / 'layer3' / 'layer2' has been enqueued."""
         tape = self._tape
+        if getattr(self.visual, "frozen", False):
+            return  # frozen backbone: no parameter gradients, nothing below the visual projection
         if not tape["training"]:
-            return  # frozen backbone
+            raise RuntimeError("backward through eval-mode BatchNorm (running statistics) is not implemented")
         B = tape["B"]
         s = _stream()
         ws = self.ws
@@ -490,11 +491,14 @@ class Engine:
         p = float(mod.dropout) if training else 0.0
         d = direction
         di = 0 if d == "textual" else 1
+        # self-attention mask: 1 = future + key padding (captioning), 2 = key padding only (masked language modelling)
+        self._mask_mode = mm = 1 if mod.mask_future_positions else 2
         s = _stream()
         ws = self.ws
         seed = self.seed.data_ptr()
         site = di * 1000
-        rec = dict(direction=d, B=B, T=T, M=M, S=S, Sk=Sk, p=p, layers=[], tokens=tokens, lengths=lengths, mem=mem)
+        rec = dict(direction=d, B=B, T=T, M=M, S=S, Sk=Sk, p=p, layers=[], tokens=tokens, lengths=lengths, mem=mem,
+                   mask_mode=mm)
         emb = "textual.embedding."
         z0 = ws.get(d + ".z0", (M, H), F32)
         st0 = ws.get(d + ".st0", (M, 2), F32)
@@ -520,7 +524,7 @@ class Engine:
             lse_s = ws.get(k + "lse_s", (B * A * 32,), F32)
             e = qkv.element_size()
             call("vtx_attn_fwd", qkv.data_ptr(), 3 * H, qkv.data_ptr() + H * e, 3 * H, qkv.data_ptr() + 2 * H * e,
-                 3 * H, o_s.data_ptr(), H, lse_s.data_ptr(), B, A, T, T, lengths.data_ptr(), 1, p, seed, sb + 0, s)
+                 3 * H, o_s.data_ptr(), H, lse_s.data_ptr(), B, A, T, T, lengths.data_ptr(), mm, p, seed, sb + 0, s)
             pr = ws.get(k + "proj", (M, H), BF16)
             gemm(o_s, self.W(q + "self_attn.out_proj.weight"), pr, M, H, H, bias=self.P(q + "self_attn.out_proj.bias"))
             z1, st1 = ws.get(k + "z1", (M, H), F32), ws.get(k + "st1", (M, 2), F32)
@@ -609,7 +613,7 @@ class Engine:
         o_s = ws.get(k + "o_s", (M, H), BF16)
         lse_s = ws.get(k + "lse_s", (B * A * 32,), F32)
         call("vtx_attn_fwd", qkv.data_ptr(), 3 * H, qkv.data_ptr() + H * e, 3 * H, qkv.data_ptr() + 2 * H * e, 3 * H,
-             o_s.data_ptr(), H, lse_s.data_ptr(), B, A, T, T, lengths.data_ptr(), 1, p, seed, sb + 0, s)
+             o_s.data_ptr(), H, lse_s.data_ptr(), B, A, T, T, lengths.data_ptr(), rec["mask_mode"], p, seed, sb + 0, s)
         gemm(o_s, self.W(q + "self_attn.out_proj.weight"), pr, M, H, H, bias=self.P(q + "self_attn.out_proj.bias"))
         x1 = residual(x, pr, "1", sb + 1)
         # cross attention
@@ -687,17 +691,21 @@ class Engine:
         qkv = lr["qkv"]
         call("vtx_attn_bwd", qkv.data_ptr(), 3 * H, qkv.data_ptr() + H * e, 3 * H, qkv.data_ptr() + 2 * H * e, 3 * H,
              do.data_ptr(), H, lr["lse_s"].data_ptr(), dqkv.data_ptr(), 3 * H, dqkv.data_ptr() + H * e, 3 * H,
-             dqkv.data_ptr() + 2 * H * e, 3 * H, B, A, T, T, rec["lengths"].data_ptr(), 1, p, seed, sb + 0, s)
+             dqkv.data_ptr() + 2 * H * e, 3 * H, B, A, T, T, rec["lengths"].data_ptr(), rec["mask_mode"], p, seed, sb + 0,
+             s)
         self._linear_bwd(dqkv, lr["n1b"], q + "self_attn.in_proj_weight", q + "self_attn.in_proj_bias", dxb, M, 3 * H, H)
         norm_bwd("norm1", lr["z1"], lr["st1"], dxb)
 
-    def head_loss(self, rec, write_grad):
+    def head_loss(self, rec, write_grad, labels=None):
+        """Token-mean cross entropy (ignore_index = pad).  labels None: next-token targets tokens[:, 1:] against
+        logits[:, :-1] (captioning.py:111-114); labels [B,T]: one label per position (masked_lm.py:68-72)."""
         di = 0 if rec["direction"] == "textual" else 1
         s = _stream()
         V = rec["logits"].shape[1]
-        call("vtx_count_valid", rec["tokens"].data_ptr(), rec["B"], rec["T"], self.pad, self.count[di:].data_ptr(), s)
-        call("vtx_cross_entropy", rec["logits"].data_ptr(), V, rec["tokens"].data_ptr(), rec["B"], rec["T"], V,
-             self.pad, self.count[di:].data_ptr(), self.loss[di:].data_ptr(), int(write_grad), s)
+        tgt, shift = (rec["tokens"], 1) if labels is None else (labels, 0)
+        call("vtx_count_valid", tgt.data_ptr(), rec["B"], rec["T"], self.pad, shift, self.count[di:].data_ptr(), s)
+        call("vtx_cross_entropy", rec["logits"].data_ptr(), V, tgt.data_ptr(), rec["B"], rec["T"], V, self.pad, shift,
+             self.count[di:].data_ptr(), self.loss[di:].data_ptr(), int(write_grad), s)
 
     def _linear_bwd(self, dY, X, wname, bname, dX, M, n_out, k_in, w_rows=None, residual=None):
         """Backward of Y = X W^T + b for W [n_out, k_in] (optionally the row slice `w_rows` of a packed weight)."""
@@ -778,7 +786,8 @@ class Engine:
             qkv = lr["qkv"]
             call("vtx_attn_bwd", qkv.data_ptr(), 3 * H, qkv.data_ptr() + H * e, 3 * H, qkv.data_ptr() + 2 * H * e,
                  3 * H, do.data_ptr(), H, lr["lse_s"].data_ptr(), dqkv.data_ptr(), 3 * H, dqkv.data_ptr() + H * e,
-                 3 * H, dqkv.data_ptr() + 2 * H * e, 3 * H, B, A, T, T, rec["lengths"].data_ptr(), 1, p, seed, sb + 0, s)
+                 3 * H, dqkv.data_ptr() + 2 * H * e, 3 * H, B, A, T, T, rec["lengths"].data_ptr(), rec["mask_mode"], p, seed,
+                 sb + 0, s)
             self._linear_bwd(dqkv, lr["x_inb"], q + "self_attn.in_proj_weight", q + "self_attn.in_proj_bias", dxb, M,
                              3 * H, H)
             dy_a, dy_b = dres_a, dxb
@@ -792,18 +801,23 @@ class Engine:
         return dmem_started
 
     # ------------------------------------------------------------------------------------------------ full model
-    def forward(self, image, tokens, noitpac, lengths, training=True, with_grad=True):
-        """Loss of the bicaptioning model.  Leaves dlogits in the logits buffers when `with_grad`."""
+    def forward(self, image, tokens, noitpac, lengths, training=True, with_grad=True, labels=None):
+        """Loss of the bicaptioning model (labels None) or of the masked-LM sibling (labels = masked_labels [B,T], single
+        direction).  Leaves dlogits in the logits buffers when `with_grad`."""
         if not self.arena.intact():
             raise RuntimeError("model parameters were moved after the engine adopted them; rebuild the engine")
+        self.generation += 1
         self.loss.zero_()
         self.count.zero_()
-        feat, h, w = self.backbone_forward(image, training)
+        # BatchNorm follows the backbone's OWN mode flag, like the reference's nn.BatchNorm2d: `model.train()` puts a
+        # frozen backbone's BN back into batch-statistics mode (visual_backbones.py:48-52 only calls .eval() once)
+        bn_training = bool(self.visual.cnn.training) if self.visual is not None else training
+        feat, h, w = self.backbone_forward(image, bn_training)
         B = image.shape[0]
         S = B * h * w
         mem = self.visual_projection_forward(feat, S)
         recs = [self.head_forward("textual", mem, tokens, lengths, training, want_logits_f32=not training)]
-        self.head_loss(recs[0], with_grad)
+        self.head_loss(recs[0], with_grad, labels)
         if self.backward_textual is not None:
             recs.append(self.head_forward("backward_textual", mem, noitpac, lengths, training))
             self.head_loss(recs[1], with_grad)

@@ -104,6 +104,7 @@ class PretrainingModelFactory(Factory):
         "virtex": vmodels.VirTexModel,
         "bicaptioning": vmodels.BidirectionalCaptioningModel,
         "captioning": vmodels.ForwardCaptioningModel,
+        "masked_lm": vmodels.MaskedLMModel,
     }
 
     @classmethod

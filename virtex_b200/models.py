@@ -21,10 +21,12 @@ class _StepFunction(torch.autograd.Function):
     """Whole-model forward/backward as one autograd node; the kernels are scheduled by `Engine`."""
 
     @staticmethod
-    def forward(ctx, model, image, tokens, noitpac, lengths, *params):
+    def forward(ctx, model, image, tokens, noitpac, lengths, labels, *params):
         eng = model.engine
-        loss = eng.forward(image, tokens, noitpac, lengths, training=model.training, with_grad=True)
+        eng.seed.add_(1)  # fresh dropout masks every training forward (nn.Dropout draws from an advancing RNG stream)
+        loss = eng.forward(image, tokens, noitpac, lengths, training=model.training, with_grad=True, labels=labels)
         ctx.model = model
+        ctx.generation = eng.generation
         ctx.n_params = len(params)
         out = loss.clone()
         return out[0], out[1]
@@ -33,20 +35,27 @@ class _StepFunction(torch.autograd.Function):
     def backward(ctx, g_fwd, g_bwd):
         model = ctx.model
         eng = model.engine
+        if eng.generation != ctx.generation:
+            raise RuntimeError(
+                "the engine ran another forward since this loss was computed (a validation forward, or a second "
+                "micro-batch): its single activation tape was overwritten; call backward() before the next forward")
+        # d(loss_f + loss_b): both components enter the total with weight 1 (captioning.py:133).  A common factor (a loss
+        # scaler) is applied to every gradient; DIFFERENT weights per direction are not representable after the fused
+        # cross-entropy has written dlogits, so they are rejected instead of being silently ignored.
+        if g_bwd is not g_fwd and getattr(model, "caption_backward", False) and not torch.equal(g_fwd, g_bwd):
+            raise NotImplementedError("the two captioning directions must enter the loss with the same weight")
         eng.backward(zero_grads=True)
-        # d(loss_f + loss_b): both components enter the total with weight 1 (captioning.py:133); honour other weights
-        # (e.g. a loss scaler) when they agree, which is the only case the reference loop produces.
-        grads = []
-        scale = g_fwd
         arena = eng.arena
+        scaled = arena.grads * g_fwd  # ONE fused scale over the flat arena; parameter gradients are views of the result
         by_id = model._engine_param_names
+        grads = []
         for p in model._engine_params:
             name = by_id.get(id(p))
             if name is None or not p.requires_grad:
                 grads.append(None)
             else:
-                grads.append(arena.g(name) * scale)
-        return (None, None, None, None, None, *grads)
+                grads.append(arena.view(scaled, name))
+        return (None, None, None, None, None, None, *grads)
 
 
 class CaptioningModel(nn.Module):
@@ -109,7 +118,7 @@ class CaptioningModel(nn.Module):
         eng = self.engine
         eng.mark_weights_dirty()  # parameters may have been updated by any optimiser since the last call
         if self.training and torch.is_grad_enabled():
-            loss_f, loss_b = _StepFunction.apply(self, image, tokens, noitpac, lengths, *self._engine_params)
+            loss_f, loss_b = _StepFunction.apply(self, image, tokens, noitpac, lengths, None, *self._engine_params)
         else:
             loss = eng.forward(image, tokens, noitpac, lengths, training=self.training, with_grad=False).clone()
             loss_f, loss_b = loss[0], loss[1]
@@ -138,3 +147,37 @@ class BidirectionalCaptioningModel(CaptioningModel):
 
 
 VirTexModel = BidirectionalCaptioningModel
+
+
+class MaskedLMModel(CaptioningModel):
+    """Drop-in for virtex/models/masked_lm.py:11-86 on the same engine: one textual head whose self-attention masks
+    padded keys only (`mask_future_positions=False`, textual_heads.py:255-262), cross entropy between the logits of
+    EVERY position and `batch["masked_labels"]` (ignore_index = padding), and in eval mode the argmax predictions with
+    the positions that carry no label set to the padding index (masked_lm.py:78-84)."""
+
+    def __init__(self, visual: VisualBackbone, textual: TextualHead):
+        super().__init__(visual, textual, caption_backward=False)
+        if getattr(textual, "mask_future_positions", False):
+            raise ValueError("masked language modelling needs a textual head built with mask_future_positions=False")
+
+    def forward(self, batch: Dict[str, torch.Tensor]) -> Dict[str, Any]:
+        image = batch["image"]
+        if image.device.type != "cuda":
+            raise RuntimeError("virtex_b200 has no CPU path: the batch must live on the model's CUDA device")
+        image = image.contiguous().float()
+        tokens = batch["caption_tokens"].contiguous()
+        lengths = batch["caption_lengths"].contiguous()
+        labels = batch["masked_labels"].contiguous()
+        eng = self.engine
+        eng.mark_weights_dirty()
+        if self.training and torch.is_grad_enabled():
+            loss, _ = _StepFunction.apply(self, image, tokens, tokens, lengths, labels, *self._engine_params)
+        else:
+            loss = eng.forward(image, tokens, tokens, lengths, training=self.training, with_grad=False,
+                               labels=labels).clone()[0]
+        output: Dict[str, Any] = {"loss": loss, "loss_components": {"masked_lm": loss.detach().clone()}}
+        if not self.training:
+            predictions = eng.predictions().clone()
+            predictions[labels == self.padding_idx] = self.padding_idx
+            output["predictions"] = predictions
+        return output

@@ -171,8 +171,6 @@ class TransformerDecoderTextualHead(TextualHead):
         super().__init__(visual_feature_size, vocab_size, hidden_size)
         if hidden_size != 64 * attention_heads:
             raise ValueError("the B200 attention kernel is specialised for head_dim 64 (A = H/64 in every VirTex config)")
-        if not mask_future_positions:
-            raise NotImplementedError("bidirectional (masked-LM) attention is outside the bicaptioning hot path")
         self.num_layers = num_layers
         self.attention_heads = attention_heads
         self.feedforward_size = feedforward_size

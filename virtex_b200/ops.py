@@ -45,8 +45,8 @@ _PROTOS = {
     "vtx_attn_bwd": [P, I64, P, I64, P, I64, P, I64, P, P, I64, P, I64, P, I64, I, I, I, I, P, I, F, P, U32, P],
     "vtx_gelu_dropout_fwd": [P, P, I64, F, P, U32, P],
     "vtx_gelu_dropout_bwd": [P, P, P, I64, F, P, U32, P],
-    "vtx_count_valid": [P, I, I, I, P, P],
-    "vtx_cross_entropy": [P, I64, P, I, I, I, I, P, P, I, P],
+    "vtx_count_valid": [P, I, I, I, I, P, P],
+    "vtx_cross_entropy": [P, I64, P, I, I, I, I, I, P, P, I, P],
     "vtx_colsum": [P, I64, I, I, P, P],
     "vtx_argmax_rows": [P, I64, I, I, P, P],
     "vtx_image_resample": [P, P, P, P, P, P, I, I, P],

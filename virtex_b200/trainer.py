@@ -88,6 +88,10 @@ class Trainer:
         self.iteration = 0
         self._k_counter = 0
         self.momentum_ready = False  # torch.optim.SGD: the first step with a gradient initialises the buffer to it
+        # dropout seed of step i = base + i (restored from the iteration on resume); ranks get decorrelated streams
+        rank = dist.get_rank(process_group) if dist.is_initialized() else 0
+        self._seed_base = (int(config.RANDOM_SEED) << 24) + rank * 1000003
+        eng.seed.fill_(self._seed_base)
         self.comm_stream = torch.cuda.Stream(device=dev) if self.world > 1 else None
         self._pending = []
         self._ranges = self._bucket_ranges()
@@ -117,6 +121,9 @@ class Trainer:
     def step(self, batch) -> torch.Tensor:
         """One optimisation step on a device-resident batch dict; returns the per-direction losses (device, [2])."""
         eng = self.engine
+        if self.model.engine is not eng:
+            raise RuntimeError("the model rebuilt its engine (model.to() / .cuda() after Trainer construction): "
+                               "create a new Trainer, this one would update a stale parameter arena")
         eng.seed.add_(1)
         m = self.model
         loss = eng.forward(batch["image"], batch["caption_tokens"],
@@ -150,6 +157,18 @@ class Trainer:
         eng.prepare_weights(mirror=False)  # the step kernel refreshed the bf16 mirror; re-pack the k>1 conv weights
         self.momentum_ready = True
         self.iteration += 1
+
+    def sync_dropout_seed(self):
+        """Dropout stream position as a function of the iteration (called after a checkpoint load)."""
+        self.engine.seed.fill_(self._seed_base + self.iteration)
+
+    def broadcast_buffers(self):
+        """BN running statistics of rank 0 everywhere -- what DistributedDataParallel(broadcast_buffers=True) does at
+        every forward; here on demand (before an evaluation or a checkpoint written by a non-master rank), since
+        training itself never reads them."""
+        if self.world > 1:
+            for b in self.engine.buffers.values():
+                dist.broadcast(b, src=0, group=self.group)
 
     # ------------------------------------------------------------------------------------------- checkpoint views
     def reset_lookahead(self):
