@@ -137,6 +137,18 @@ int vtx_conv_w_pack_dgrad(const float* w, void* out, int O, int I, void* stream)
 int vtx_conv_w_unpack_add(const float* dwp, float* grad, int O, int I, int KH, int KW, int ldk, void* stream);
 /* same for the transposed [(tap, I), O] weight-gradient layout written by vtx_gemm conv_mode 4 */
 int vtx_conv_w_unpack_add_t(const float* dwt, float* grad, int O, int I, int KH, int KW, void* stream);
+/* Batched form of the six weight-layout kernels above (and of vtx_stem_s2d_w_pack / _unpack_add): one launch executes a
+   DEVICE-resident table of jobs.  kind: 0 pack, 1 pack_dgrad, 2 unpack_add, 3 unpack_add_t, 4 stem s2d pack,
+   5 stem s2d unpack_add; total = number of output elements of the job; block0 = first thread block of the job (jobs are
+   sorted by block0, every block handles vtx_weight_job_block_elems() consecutive elements). */
+typedef struct VtxWeightJob {
+  const void* src;
+  void* dst;
+  int64_t total;
+  int32_t O, I, KH, KW, ldk, kind, block0, reserved;
+} VtxWeightJob;
+int vtx_conv_w_jobs(const VtxWeightJob* jobs, int njobs, int total_blocks, void* stream);
+int vtx_weight_job_block_elems(void);
 int vtx_cast_bf16(const float* in, void* out, int64_t n, void* stream);
 int vtx_nhwc_to_nchw_f32(const void* in, float* out, int N, int HW, int C, void* stream);
 

@@ -6,7 +6,8 @@ set -u
 cd "$(dirname "$0")/.."
 T=$1; S=$2; G=${3:-1}
 rm -rf .stage && mkdir .stage
-rsync -a --exclude .git --exclude .stage --exclude gpurun_out --exclude build --exclude .pytest_cache --exclude __pycache__ ./ .stage/
+tar -c --exclude=./.git --exclude=./.stage --exclude=./gpurun_out --exclude=./build --exclude=./.pytest_cache --exclude=__pycache__ . | tar -x -C .stage
+[ -f ".stage/$S" ] || { echo "staging failed: .stage/$S missing"; exit 1; }
 CMD="cd .stage && mkdir -p gpurun_out && bash $S > gpurun_out/$(basename $S .sh).log 2>&1; mkdir -p ../gpurun_out && cp -r gpurun_out/. ../gpurun_out/; tail -3 gpurun_out/$(basename $S .sh).log"
 GF=""; [ "$G" != "1" ] && GF="--gpus $G"
 for i in $(seq 1 60); do

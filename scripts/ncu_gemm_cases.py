@@ -39,5 +39,15 @@ for _ in range(2):
         D = torch.zeros(576, 64, device=dev)
         ops.gemm(dy, x, D, 576, 64, 256 * 3136, lda=64, ldb=64, ldd=64, atomic=True, out_f32=True,
                  conv=(256, 56, 56, 64), conv_mode=4)
+    if "l2wgrad" in cases:  # layer2 3x3 implicit wgrad (conv_mode 2), 128 -> 128 channels at 28 x 28
+        x, dy = bf(256, 28, 28, 128), bf(256, 28, 28, 128)
+        D = torch.zeros(128, 1152, device=dev)
+        ops.gemm(dy, x, D, 128, 1152, 256 * 784, lda=128, ldb=128, atomic=True, out_f32=True,
+                 split_k=ops.split_k_for(5, 256 * 784 // 64), conv=(256, 28, 28, 128), conv_mode=2)
+    if "l3conv" in cases:  # layer3 3x3 implicit fprop 256 -> 256 at 14 x 14 with BN statistics: tensor bound
+        x, w = bf(256, 14, 14, 256), bf(256, 2304)
+        D = torch.empty(256 * 196, 256, device=dev, dtype=torch.bfloat16)
+        st = torch.zeros(2, 256, device=dev)
+        ops.gemm(x, w, D, 256 * 196, 256, 2304, lda=256, stats=st, conv=(256, 14, 14, 256), conv_mode=1)
     torch.cuda.synchronize()
 print("done")

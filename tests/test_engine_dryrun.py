@@ -159,8 +159,10 @@ def test_stem_branch_schedule(dry):
     _run(_model(spec), O.synth_batch(2, seed=8))
     names = dry.names()
     gemms = [c for c in dry.calls if not isinstance(c, str)]
-    assert "vtx_stem_im2col" not in names and "vtx_stem_s2d" in names and "vtx_stem_s2d_w_pack" in names
-    assert [g[4] for g in gemms if g[4] in (5, 6)] == [5, 6] and "vtx_stem_s2d_w_unpack_add" in names
+    assert "vtx_stem_im2col" not in names and "vtx_stem_s2d" in names
+    assert [g[4] for g in gemms if g[4] in (5, 6)] == [5, 6]
+    # weight layouts: one batched pack launch + one batched unpack launch per gradient bucket (layer4/3/2, layer1+stem)
+    assert names.count("vtx_conv_w_jobs") == 1 + 4 and "vtx_conv_w_pack" not in names
     dry.calls.clear()
     _run(_model(spec), O.synth_batch(2, seed=9, image_size=200))
     assert "vtx_stem_im2col" in dry.names() and "vtx_stem_s2d" not in dry.names()

@@ -347,3 +347,51 @@ def test_attention_dropout_keeps_rows_normalised_in_expectation():
     # the average over 4 independent masks is closer to the p = 0 output than any single draw, and unbiased overall
     assert rel(mean_drop, base) < rel(outs[1], base)
     assert abs((mean_drop - base).mean().item()) < 5e-3
+
+
+# ------------------------------------------------------------------------------------------------ weight-layout jobs
+def test_batched_weight_jobs_match_the_per_tensor_kernels():
+    """vtx_conv_w_jobs (one launch, device job table) == vtx_conv_w_pack / _pack_dgrad / _unpack_add / _unpack_add_t /
+    vtx_stem_s2d_w_pack / _unpack_add, bit for bit, including the OIHW <-> [O, (kh,kw,I)] index maps vs torch.permute."""
+    _need_cuda()
+    import struct
+    ops = _ops()
+    g = torch.Generator().manual_seed(5)
+    dev = "cuda"
+    w3 = torch.randn(128, 128, 3, 3, generator=g).to(dev)
+    w7 = torch.randn(64, 3, 7, 7, generator=g).to(dev)
+    dwp3 = torch.randn(128, 1152, generator=g).to(dev)
+    dwt3 = torch.randn(1152, 128, generator=g).to(dev)
+    dw7 = torch.randn(64, 256, generator=g).to(dev)
+    dw7c = torch.randn(64, 160, generator=g).to(dev)
+    outs = {k: torch.full(shape, 3.0, dtype=dt, device=dev) for k, (shape, dt) in {
+        "p3": ((128, 1152), BF16), "pd3": ((128, 1152), BF16), "p7": ((64, 160), BF16), "ps2d": ((64, 256), BF16),
+        "g3": ((128, 128, 3, 3), F32), "g3t": ((128, 128, 3, 3), F32), "g7": ((64, 3, 7, 7), F32),
+        "g7c": ((64, 3, 7, 7), F32)}.items()}
+    rows = [(w3, outs["p3"], 128 * 1152, 128, 128, 3, 3, 1152, 0), (w3, outs["pd3"], 128 * 1152, 128, 128, 3, 3, 1152, 1),
+            (w7, outs["p7"], 64 * 160, 64, 3, 7, 7, 160, 0), (w7, outs["ps2d"], 64 * 256, 64, 3, 7, 7, 256, 4),
+            (dwp3, outs["g3"], 128 * 1152, 128, 128, 3, 3, 1152, 2), (dwt3, outs["g3t"], 128 * 1152, 128, 128, 3, 3, 1152, 3),
+            (dw7, outs["g7"], 64 * 147, 64, 3, 7, 7, 256, 5), (dw7c, outs["g7c"], 64 * 147, 64, 3, 7, 7, 160, 2)]
+    blk = ops.L.load().vtx_weight_job_block_elems()
+    blob, b0 = b"", 0
+    for src, dst, total, O, I, KH, KW, ldk, kind in rows:
+        blob += struct.pack("<QQq8i", src.data_ptr(), dst.data_ptr(), total, O, I, KH, KW, ldk, kind, b0, 0)
+        b0 += (total + blk - 1) // blk
+    table = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(dev)
+    ops.call("vtx_conv_w_jobs", table.data_ptr(), len(rows), b0, _s())
+    # references: torch index maps
+    assert torch.equal(outs["p3"], w3.permute(0, 2, 3, 1).reshape(128, 1152).bfloat16())
+    assert torch.equal(outs["pd3"], w3.flip(2, 3).permute(1, 2, 3, 0).reshape(128, 1152).bfloat16())
+    ref7 = torch.zeros(64, 160, device=dev)
+    ref7[:, :147] = w7.permute(0, 2, 3, 1).reshape(64, 147)
+    assert torch.equal(outs["p7"], ref7.bfloat16())
+    assert torch.equal(outs["g3"], 3.0 + dwp3.view(128, 3, 3, 128).permute(0, 3, 1, 2))
+    assert torch.equal(outs["g3t"], 3.0 + dwt3.view(3, 3, 128, 128).permute(3, 2, 0, 1))
+    assert torch.equal(outs["g7c"], 3.0 + dw7c[:, :147].reshape(64, 7, 7, 3).permute(0, 3, 1, 2))
+    # stem s2d maps: against the per-tensor kernels of csrc/stem_s2d.cu
+    ps = torch.empty(64, 256, dtype=BF16, device=dev)
+    ops.call("vtx_stem_s2d_w_pack", w7.data_ptr(), ps.data_ptr(), 64, _s())
+    assert torch.equal(outs["ps2d"], ps)
+    g7 = torch.full((64, 3, 7, 7), 3.0, device=dev)
+    ops.call("vtx_stem_s2d_w_unpack_add", dw7.data_ptr(), g7.data_ptr(), 64, _s())
+    assert torch.equal(outs["g7"], g7)

@@ -16,6 +16,7 @@ decoder residual stream fp32 with bf16 shadows feeding the GEMMs, logits bf16 (f
 from __future__ import annotations
 
 import math
+import struct
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -167,6 +168,7 @@ class Engine:
 
     def _build_backbone_plan(self):
         self.blocks = []
+        self._jobs: Dict[str, tuple] = {}
         if self.visual is None:
             return
         cnn = self.visual.cnn
@@ -174,26 +176,75 @@ class Engine:
             layer = getattr(cnn, f"layer{li}")
             for bi, blk in enumerate(layer):
                 self.blocks.append((f"visual.cnn.layer{li}.{bi}", blk))
+        # fp32 weight-gradient scratch of every k > 1 convolution (GEMM output layout), one flat buffer zeroed once per
+        # backward; the batched unpack jobs fold it into the OIHW gradient arena per all-reduce bucket
+        sizes = [("visual.cnn.conv1", 64 * 256)]
+        sizes += [(name + ".conv2", 9 * blk.conv2.weight.shape[0] ** 2) for name, blk in self.blocks]
+        total = sum(_round_up(n, _ALIGN) for _, n in sizes)
+        self._dwp_flat = torch.zeros(total, dtype=F32, device=self.device)
+        self._dwp, off = {}, 0
+        for key, n in sizes:
+            self._dwp[key] = self._dwp_flat[off:off + n]
+            off += _round_up(n, _ALIGN)
+
+    # ------------------------------------------------------------------------------------ batched weight-layout jobs
+    def _job_table(self, key, make):
+        """Device-resident VtxWeightJob table, built once per key: (src, dst, total, O, I, KH, KW, ldk, kind) rows."""
+        tab = self._jobs.get(key)
+        if tab is None:
+            rows = make()
+            blk = ops.L.load().vtx_weight_job_block_elems()
+            blob, b0 = b"", 0
+            for src, dst, total, O, I, KH, KW, ldk, kind in rows:
+                blob += struct.pack("<QQq8i", src.data_ptr(), dst.data_ptr(), total, O, I, KH, KW, ldk, kind, b0, 0)
+                b0 += (total + blk - 1) // blk
+            dev = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(self.device) if rows else None
+            tab = self._jobs[key] = (dev, len(rows), b0)
+        return tab
+
+    def _run_jobs(self, key, make):
+        dev, n, blocks = self._job_table(key, make)
+        if n:
+            call("vtx_conv_w_jobs", dev.data_ptr(), n, blocks, _stream())
+
+    def _pack_rows(self):
+        w = self.P("visual.cnn.conv1.weight")
+        rows = [(w, self._pack_buf("visual.cnn.conv1.weight", (64, 160)), 64 * 160, 64, 3, 7, 7, 160, 0),
+                (w, self._pack_buf("visual.cnn.conv1.weight#s2d", (64, 256)), 64 * 256, 64, 3, 7, 7, 256, 4)]
+        for name, blk in self.blocks:
+            w = self.P(name + ".conv2.weight")
+            pl = w.shape[0]
+            rows.append((w, self._pack_buf(name + ".conv2.weight", (pl, 9 * pl)), 9 * pl * pl, pl, pl, 3, 3, 9 * pl, 0))
+            if blk.stride == 1:
+                rows.append((w, self._pack_buf(name + ".conv2.weight#dgrad", (pl, 9 * pl)), 9 * pl * pl, pl, pl, 3, 3,
+                             9 * pl, 1))
+        return rows
+
+    def _unpack_rows(self, layer, stem_s2d):
+        """Unpack-accumulate jobs of one gradient bucket: 'layer4' / 'layer3' / 'layer2' / 'rest' (layer1 + stem)."""
+        rows = []
+        want = "layer1" if layer == "rest" else layer
+        for name, blk in self.blocks:
+            if name.split(".")[2] != want:
+                continue
+            pl = blk.conv2.weight.shape[0]
+            transposed = blk.stride == 1 and pl == 64  # halo-reuse wgrad writes [(tap, cin), cout]
+            rows.append((self._dwp[name + ".conv2"], self.G(name + ".conv2.weight"), 9 * pl * pl, pl, pl, 3, 3, 9 * pl,
+                         3 if transposed else 2))
+        if layer == "rest":
+            g = self.G("visual.cnn.conv1.weight")
+            if stem_s2d:
+                rows.append((self._dwp["visual.cnn.conv1"], g, 64 * 147, 64, 3, 7, 7, 256, 5))
+            else:
+                rows.append((self._dwp["visual.cnn.conv1"], g, 64 * 147, 64, 3, 7, 7, 160, 2))
+        return rows
 
     def prepare_weights(self, mirror=True):
         """bf16 mirror of all parameters + packed GEMM layouts of the k>1 convolution weights."""
         if mirror:
             self.arena.refresh_mirror()
         if self.visual is not None:
-            s = _stream()
-            w = self.P("visual.cnn.conv1.weight")
-            pk = self._pack_buf("visual.cnn.conv1.weight", (64, 160))
-            call("vtx_conv_w_pack", w.data_ptr(), pk.data_ptr(), 64, 3, 7, 7, 160, s)
-            px = self._pack_buf("visual.cnn.conv1.weight#s2d", (64, 256))
-            call("vtx_stem_s2d_w_pack", w.data_ptr(), px.data_ptr(), 64, s)
-            for name, blk in self.blocks:
-                w = self.P(name + ".conv2.weight")
-                planes = w.shape[0]
-                pk = self._pack_buf(name + ".conv2.weight", (planes, 9 * planes))
-                call("vtx_conv_w_pack", w.data_ptr(), pk.data_ptr(), planes, planes, 3, 3, 9 * planes, s)
-                if blk.stride == 1:
-                    pd = self._pack_buf(name + ".conv2.weight#dgrad", (planes, 9 * planes))
-                    call("vtx_conv_w_pack_dgrad", w.data_ptr(), pd.data_ptr(), planes, planes, s)
+            self._run_jobs("pack", self._pack_rows)  # every packed conv-weight layout in one launch
         self._weights_fresh = True
 
     def _pack_buf(self, key, shape):
@@ -375,11 +426,15 @@ class Engine:
         dOut = dfeat
         scratch_i = 0
         prev_layer = None
+        self._dwp_flat.zero_()
+        stem_s2d = tape["stem"]["s2d"] is not None
         for rec in reversed(tape["blocks"]):
             name, planes, Cin, stride = rec["name"], rec["planes"], rec["Cin"], rec["stride"]
             layer = name.split(".")[2]
-            if bucket_cb is not None and prev_layer is not None and layer != prev_layer:
-                bucket_cb(prev_layer)
+            if prev_layer is not None and layer != prev_layer:
+                self._run_jobs("unpack:" + prev_layer, lambda: self._unpack_rows(prev_layer, stem_s2d))
+                if bucket_cb is not None:
+                    bucket_cb(prev_layer)
             prev_layer = layer
             Min, Mout, C4 = rec["Min"], rec["Mout"], 4 * rec["planes"]
             Hc, Wc, Hn, Wn = rec["Hin"], rec["Win"], rec["Hout"], rec["Wout"]
@@ -401,16 +456,13 @@ class Engine:
             dy2 = ws.get("bwd.dy2", (Mout, planes), BF16)
             self._bn_bwd(da2, None, rec["y2"], rec["bnp2"], name + ".bn2", Mout, planes, dy2, mask_from_y=1)
             # ---- conv2 (3x3): wgrad + dgrad
-            dwp = ws.get("bwd.dwp", (planes, 9 * planes), F32)
-            dwp.zero_()
+            dwp = self._dwp[name + ".conv2"].view(planes, 9 * planes)
             da1 = ws.get("bwd.da1", (Min, planes), BF16)
-            transposed = False
             if rec["cols2"] is None:
                 if planes == 64:
                     # halo-reuse wgrad: D[(tap, cin), cout], accumulated in TMEM over all spatial tiles of a CTA
                     gemm(dy2, rec["a1"], dwp, 9 * planes, planes, Mout, atomic=True, lda=planes, ldb=planes, ldd=planes,
                          conv=(B, Hc, Wc, planes), conv_mode=4, out_f32=True)
-                    transposed = True
                 else:
                     tiles = ((planes + 127) // 128) * ((9 * planes + 255) // 256)
                     sk = ops.split_k_for(tiles, (Mout + 63) // 64)
@@ -423,12 +475,6 @@ class Engine:
                 dcols = ws.get("bwd.dcols", (Mout, 9 * planes), BF16)
                 gemm(dy2, self._packed[name + ".conv2.weight"], dcols, Mout, 9 * planes, planes, b_mn=1)
                 call("vtx_col2im3x3", dcols.data_ptr(), da1.data_ptr(), B, Hc, Wc, planes, stride, s)
-            if transposed:
-                call("vtx_conv_w_unpack_add_t", dwp.data_ptr(), self.G(name + ".conv2.weight").data_ptr(), planes,
-                     planes, 3, 3, s)
-            else:
-                call("vtx_conv_w_unpack_add", dwp.data_ptr(), self.G(name + ".conv2.weight").data_ptr(), planes, planes,
-                     3, 3, 9 * planes, s)
             # ---- bn1 + ReLU backward
             dy1 = ws.get("bwd.dy1", (Min, planes), BF16)
             self._bn_bwd(da1, None, rec["y1"], rec["bnp1"], name + ".bn1", Min, planes, dy1, mask_from_y=1)
@@ -457,17 +503,15 @@ class Engine:
         call("vtx_maxpool_bwd", dOut.data_ptr(), st["idx"].data_ptr(), da0.data_ptr(), B, st["Ho"], st["Wo"], 64, s)
         dy0 = ws.get("bwd.dy0", (M0, 64), BF16)
         self._bn_bwd(da0, None, st["y"], st["bnp"], "visual.cnn.bn1", M0, 64, dy0, mask_from_y=1)
-        if st["s2d"] is not None:  # implicit wgrad over the space-to-depth view
-            dwx = ws.get("bwd.dwp0x", (64, 256), F32)
-            dwx.zero_()
+        if stem_s2d:  # implicit wgrad over the space-to-depth view
+            dwx = self._dwp["visual.cnn.conv1"].view(64, 256)
             gemm(dy0, st["s2d"], dwx, 64, 256, M0, lda=64, ldb=64, atomic=True, out_f32=True,
                  split_k=ops.split_k_for(1, M0 // 64), conv=(B, st["Ho"], st["Wo"], 64), conv_mode=6)
-            call("vtx_stem_s2d_w_unpack_add", dwx.data_ptr(), self.G("visual.cnn.conv1.weight").data_ptr(), 64, s)
-            return
-        dwp0 = ws.get("bwd.dwp0", (64, 160), F32)
-        dwp0.zero_()
-        self._wgrad(dy0, st["cols"], dwp0, 64, 160, M0)
-        call("vtx_conv_w_unpack_add", dwp0.data_ptr(), self.G("visual.cnn.conv1.weight").data_ptr(), 64, 3, 7, 7, 160, s)
+        else:
+            dwp0 = self._dwp["visual.cnn.conv1"][:64 * 160].view(64, 160)
+            self._wgrad(dy0, st["cols"], dwp0, 64, 160, M0)
+        # layer1's 3x3 weight gradients + the stem's, in one launch (the 'rest' all-reduce bucket follows)
+        self._run_jobs("unpack:rest:" + ("s2d" if stem_s2d else "cols"), lambda: self._unpack_rows("rest", stem_s2d))
 
     # ------------------------------------------------------------------------------------------------ head
     def _head_modules(self, direction):
@@ -826,7 +870,7 @@ class Engine:
 
     def backward(self, zero_grads=True, bucket_cb=None):
         """Gradients of (loss_fwd + loss_bwd) w.r.t. every parameter into the flat gradient arena.
-        `bucket_cb(tag)`, tag in {'head','layer4','layer3','layer2','rest'}, fires as gradient ranges complete (in
+        `bucket_cb(tag)`, tag in {'head_b','head','layer4','layer3','layer2','rest'}, fires as gradient ranges complete (in
         backward order) so a data-parallel all-reduce can overlap the remaining backward."""
         if zero_grads:
             self.arena.grads.zero_()
@@ -836,6 +880,8 @@ class Engine:
         started = False
         for rec in reversed(self._recs):
             started = self.head_backward(rec, dmem, started)
+            if bucket_cb is not None and rec["direction"] == "backward_textual":
+                bucket_cb("head_b")  # only this direction writes the backward_textual.* gradients
         Cv = feat.shape[1]
         dfeat = self.ws.get("hb.dfeat", (S, Cv), BF16)
         frozen = getattr(self.visual, "frozen", False)

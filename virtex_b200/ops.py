@@ -35,6 +35,7 @@ _PROTOS = {
     "vtx_conv_w_pack_dgrad": [P, P, I, I, P],
     "vtx_conv_w_unpack_add": [P, P, I, I, I, I, I, P],
     "vtx_conv_w_unpack_add_t": [P, P, I, I, I, I, P],
+    "vtx_conv_w_jobs": [P, I, I, P],
     "vtx_cast_bf16": [P, P, I64, P],
     "vtx_nhwc_to_nchw_f32": [P, P, I, I, I, P],
     "vtx_embed_fwd": [P, P, P, P, P, P, P, P, P, I, I, I, I, F, F, P, U32, P],
@@ -73,7 +74,7 @@ def _get(name):
 
 def exported_symbols():
     """All C-ABI entry points this module binds (used by the CPU test that checks the library exports them)."""
-    return sorted(_PROTOS) + ["vtx_last_error", "vtx_version", "vtx_num_sms"]
+    return sorted(_PROTOS) + ["vtx_last_error", "vtx_version", "vtx_num_sms", "vtx_weight_job_block_elems"]
 
 
 def _stream():

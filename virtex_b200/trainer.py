@@ -6,7 +6,8 @@
 The optimiser tail runs as fused kernels over the flat arenas (virtex_b200/csrc/optim.cu) with the arithmetic of
 torch.optim.SGD + virtex/optim/lookahead.py + virtex/optim/lr_scheduler.py; bf16 needs no GradScaler.
 Gradient all-reduce: NCCL over NVLink on a side stream, one bucket per completed gradient range in backward order
-(both heads; layer4; layer3; layer2; the rest), SUM on the wire and the 1/world_size folded into the clip coefficient,
+(backward-direction decoder; forward-direction decoder + shared embedding / projection; layer4; layer3; layer2; the
+rest), SUM on the wire and the 1/world_size folded into the clip coefficient,
 so averaged gradients equal the mean of per-rank gradients like DistributedDataParallel's.
 """
 import struct
@@ -22,7 +23,9 @@ from .ops import _stream, call
 from .optim import lr_multiplier_fn
 
 _CHUNK = 65536
-BUCKET_ORDER = ("head", "layer4", "layer3", "layer2", "rest")  # completion order of gradient ranges in backward
+# completion order of gradient ranges in backward: the backward-direction decoder finishes first (its gradients are the
+# last contiguous range of the arena), then everything shared / forward-direction of the head, then the backbone layers
+BUCKET_ORDER = ("head_b", "head", "layer4", "layer3", "layer2", "rest")
 
 
 def bucket_ranges(names, offsets, numels) -> Dict[str, Optional[tuple]]:
@@ -34,7 +37,8 @@ def bucket_ranges(names, offsets, numels) -> Dict[str, Optional[tuple]]:
             return None
         return offsets[sel[0]], offsets[sel[-1]] + numels[sel[-1]]
 
-    out = {"head": rng(lambda n: not n.startswith("visual."))}
+    out = {"head_b": rng(lambda n: n.startswith("backward_textual.")),
+           "head": rng(lambda n: not n.startswith("visual.") and not n.startswith("backward_textual."))}
     for l in ("layer4", "layer3", "layer2"):
         out[l] = rng(lambda n, l=l: n.startswith(f"visual.cnn.{l}."))
     out["rest"] = rng(lambda n: n.startswith("visual.cnn.") and (".layer1." in n or ".layer" not in n))
