@@ -74,6 +74,10 @@ typedef struct VtxGemm {
                             x 16 channels), B = packed weights [64, 256] (vtx_stem_s2d_w_pack), D [n*h*w, 64] NHWC
                             (torchvision resnet.py:197 conv1 forward, BN statistics through `stats`),
                         6 = stem wgrad: A = dy [conv_n, conv_h, conv_w, 64], B = S; D [64, 256] fp32 += (atomic) */
+  const uint8_t* residual_mask; /* optional (plain bf16 GEMMs, N % 32 == 0): bit (m, n) of a [M, N/8] bit mask in the layout
+                                   vtx_bn_act writes; residual[m, n] is added only where the bit is set.  This is the
+                                   shortcut gradient dz = dOut * [block output > 0] of a bottleneck without dz ever being
+                                   written to memory (torchvision resnet.py:160-161 backward). */
 } VtxGemm;
 
 int vtx_gemm(const VtxGemm* g, void* stream);

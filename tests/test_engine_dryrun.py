@@ -20,7 +20,7 @@ class Recorder:
 
 
 def _check_gemm(A, B, D, M, N, K, lda=None, ldb=None, ldd=None, a_mn=0, b_mn=0, bias=None, act=0, residual=None, ldr=0,
-                stats=None, atomic=False, split_k=1, tile_n=0, conv=None, conv_mode=0, out_f32=None):
+                stats=None, atomic=False, split_k=1, tile_n=0, conv=None, conv_mode=0, out_f32=None, residual_mask=None):
     assert A.dtype == BF16 and B.dtype == BF16, (A.dtype, B.dtype)
     f32 = (D.dtype == F32) if out_f32 is None else bool(out_f32)
     assert D.dtype == (F32 if f32 else BF16)
@@ -60,6 +60,9 @@ def _check_gemm(A, B, D, M, N, K, lda=None, ldb=None, ldd=None, a_mn=0, b_mn=0, 
         assert bias.dtype == F32 and bias.numel() >= N
     if residual is not None:
         assert residual.dtype == BF16 and residual.numel() >= M * N
+    if residual_mask is not None:
+        assert residual is not None and residual_mask.dtype == torch.uint8 and residual_mask.numel() >= M * N // 8
+        assert N % 32 == 0 and conv_mode == 0 and not f32
 
 
 @pytest.fixture

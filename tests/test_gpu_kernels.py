@@ -395,3 +395,25 @@ def test_batched_weight_jobs_match_the_per_tensor_kernels():
     g7 = torch.full((64, 3, 7, 7), 3.0, device=dev)
     ops.call("vtx_stem_s2d_w_unpack_add", dw7.data_ptr(), g7.data_ptr(), 64, _s())
     assert torch.equal(outs["g7"], g7)
+
+
+def test_gemm_masked_residual_epilogue():
+    """D = A.B^T + residual * [mask bit]: the shortcut gradient of a bottleneck (dz = dOut * [out > 0]) added by the
+    conv1-dgrad epilogue without dz ever being materialised; TMA-staged and direct residual paths."""
+    _need_cuda()
+    ops = _ops()
+    g = torch.Generator().manual_seed(11)
+    for M, N, K, b_mn in ((1000, 256, 64, 1), (777, 64, 256, 1), (300, 1024, 256, 0)):
+        A = (torch.randn(M, K, generator=g) * 0.5).bfloat16().cuda()
+        B = (torch.randn(K, N, generator=g) * 0.5).bfloat16().cuda() if b_mn else \
+            (torch.randn(N, K, generator=g) * 0.5).bfloat16().cuda()
+        R = torch.randn(M, N, generator=g).bfloat16().cuda()
+        keep = (torch.rand(M, N, generator=g) > 0.4).cuda()
+        mask = _pack_mask(keep)
+        D = torch.empty(M, N, dtype=BF16, device="cuda")
+        ops.gemm(A, B, D, M, N, K, b_mn=b_mn, residual=R, residual_mask=mask)
+        ref = A.float() @ (B.float() if b_mn else B.float().t()) + R.float() * keep.float()
+        assert rel(D, ref) < 4e-3, (M, N, K)
+        D2 = torch.empty(M, N, dtype=BF16, device="cuda")
+        ops.gemm(A, B, D2, M, N, K, b_mn=b_mn, residual=R)  # no mask: plain residual add, unchanged
+        assert rel(D2, A.float() @ (B.float() if b_mn else B.float().t()) + R.float()) < 4e-3

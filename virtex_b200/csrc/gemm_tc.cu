@@ -73,6 +73,7 @@ struct GemmKParams {
   const float* bias;
   const __nv_bfloat16* residual;
   long long ldr;
+  const uint8_t* res_mask;   // optional bit mask [M, N/8]: the residual of (row, col) is added only where its bit is set
   float* stats;
   int taps_w, pad, ntaps;    // taps per kernel row / zero padding / number of taps of the implicit conv (3, 1, 9 for 3x3)
 };
@@ -105,6 +106,8 @@ __device__ __forceinline__ void epi_math(float* v, const GemmKParams& p, long lo
   }
   if (p.residual != nullptr && !p.res_tma && grow >= 0) {
     const __nv_bfloat16* rp = p.residual + grow * p.ldr + col0;
+    // res_mask requires N % 32 == 0 (checked on the host), so a masked chunk is always full
+    const uint32_t mb = p.res_mask ? *reinterpret_cast<const uint32_t*>(p.res_mask + (grow * p.N + col0) / 8) : 0xffffffffu;
     if (full) {
 #pragma unroll
       for (int i = 0; i < 32; i += 8) {
@@ -113,8 +116,8 @@ __device__ __forceinline__ void epi_math(float* v, const GemmKParams& p, long lo
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float2 f = __bfloat1622float2(h2[j]);
-          v[i + 2 * j] += f.x;
-          v[i + 2 * j + 1] += f.y;
+          v[i + 2 * j] += ((mb >> (i + 2 * j)) & 1u) ? f.x : 0.f;
+          v[i + 2 * j + 1] += ((mb >> (i + 2 * j + 1)) & 1u) ? f.y : 0.f;
         }
       }
     } else {
@@ -541,7 +544,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int w = (tw << 3) + (r_in_tile & 7), h = (th << 4) + (r_in_tile >> 3);
         row_dead = (w >= p.cW) || (h >= p.cH);
       }
-      if (!staged || (p.residual != nullptr && !p.res_tma)) {
+      if (!staged || (p.residual != nullptr && !p.res_tma) || p.res_mask != nullptr) {
         if (p.mode & 1) {
           const int dw = r_in_tile & ((1 << p.lbw) - 1);
           const int dh = (r_in_tile >> p.lbw) & ((1 << p.lbh) - 1);
@@ -572,13 +575,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t sp = srow + (j >> 1) * 16384;
           const int cb = (j & 1) * 4;
           if (p.res_tma) {
+            // optional bit mask of the residual (dz = dOut * [block output > 0], never materialised): one 32-bit
+            // word per row and 32-column chunk
+            const uint32_t mb = (p.res_mask != nullptr && grow >= 0)
+                                    ? *reinterpret_cast<const uint32_t*>(p.res_mask + (grow * p.N + col0) / 8)
+                                    : 0xffffffffu;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const uint4 raw = lds128(sp + (((cb + i) ^ sw) << 4));
               float f[8];
               unpack8(*reinterpret_cast<const bf16x8*>(&raw), f);
 #pragma unroll
-              for (int e2 = 0; e2 < 8; ++e2) va[8 * i + e2] += f[e2];
+              for (int e2 = 0; e2 < 8; ++e2) va[8 * i + e2] += ((mb >> (8 * i + e2)) & 1u) ? f[e2] : 0.f;
             }
           }
           epi_math(va, p, grow, col0, full);
@@ -607,13 +615,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t sp = srow + ((j + 2) >> 1) * 16384;
           const int cb = ((j + 2) & 1) * 4;
           if (p.res_tma) {
+            // optional bit mask of the residual (dz = dOut * [block output > 0], never materialised): one 32-bit
+            // word per row and 32-column chunk
+            const uint32_t mb = (p.res_mask != nullptr && grow >= 0)
+                                    ? *reinterpret_cast<const uint32_t*>(p.res_mask + (grow * p.N + col0) / 8)
+                                    : 0xffffffffu;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const uint4 raw = lds128(sp + (((cb + i) ^ sw) << 4));
               float f[8];
               unpack8(*reinterpret_cast<const bf16x8*>(&raw), f);
 #pragma unroll
-              for (int e2 = 0; e2 < 8; ++e2) vb[8 * i + e2] += f[e2];
+              for (int e2 = 0; e2 < 8; ++e2) vb[8 * i + e2] += ((mb >> (8 * i + e2)) & 1u) ? f[e2] : 0.f;
             }
           }
           epi_math(vb, p, grow, col0, full);
@@ -811,6 +824,10 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
   p.bias = g->bias;
   p.residual = reinterpret_cast<const __nv_bfloat16*>(g->residual);
   p.ldr = g->ldr;
+  p.res_mask = reinterpret_cast<const uint8_t*>(g->residual_mask);
+  if (p.res_mask != nullptr && (g->residual == nullptr || g->N % 32 != 0 || g->conv_mode != 0 || g->out_f32 ||
+                                (reinterpret_cast<uintptr_t>(g->residual_mask) & 3) != 0))
+    return set_error(VTX_EINVAL, "vtx_gemm: residual_mask needs a residual, a plain bf16 GEMM and N %% 32 == 0");
   p.stats = g->stats;
 
   CUtensorMap tmA, tmB;

@@ -446,8 +446,10 @@ class Engine:
                              two=(rec["yd"], rec["bnpd"], name + ".downsample.1", dyd))
                 dz = None
             else:
-                dz = ws.get("bwd.dz", (Mout, C4), BF16)
-                self._bn_bwd(dOut, rec["m3"], rec["y3"], rec["bnp3"], name + ".bn3", Mout, C4, dy3, dz_out=dz)
+                # the shortcut gradient dz = dOut * [block output > 0] is never written: conv1's dgrad epilogue adds
+                # dOut under the same bit mask (VtxGemm.residual_mask)
+                dz = None
+                self._bn_bwd(dOut, rec["m3"], rec["y3"], rec["bnp3"], name + ".bn3", Mout, C4, dy3)
             # ---- conv3 (1x1): wgrad + dgrad
             self._wgrad(dy3, rec["a2"], self.G(name + ".conv3.weight"), C4, planes, Mout)
             da2 = ws.get("bwd.da2", (Mout, planes), BF16)
@@ -494,7 +496,7 @@ class Engine:
                     gemm(dyd, wd, dxs, Mout, Cin, C4, b_mn=1)
                     call("vtx_upsample_add", dxs.data_ptr(), dx.data_ptr(), B, Hc, Wc, Cin, stride, s)
             else:
-                gemm(dy1, w1, dx, Min, Cin, planes, b_mn=1, residual=dz)
+                gemm(dy1, w1, dx, Min, Cin, planes, b_mn=1, residual=dOut, residual_mask=rec["m3"])
             dOut = dx
         # ---- stem: maxpool bwd -> ReLU/BN bwd -> wgrad
         st = tape["stem"]

@@ -120,11 +120,12 @@ _gemm_struct = L.VtxGemm()
 
 
 def gemm(A, B, D, M, N, K, *, lda=None, ldb=None, ldd=None, a_mn=0, b_mn=0, bias=None, act=0, residual=None,
-         ldr=0, stats=None, atomic=False, split_k=1, tile_n=0, conv=None, conv_mode=0, out_f32=None):
+         ldr=0, stats=None, atomic=False, split_k=1, tile_n=0, conv=None, conv_mode=0, out_f32=None, residual_mask=None):
     """D[M,N] = epilogue(A . B^T) through the tcgen05 kernel; see include/virtex_b200.h (VtxGemm)."""
     g = _gemm_struct
     g.A, g.B, g.D = A.data_ptr(), B.data_ptr(), D.data_ptr()
     g.bias, g.residual, g.stats = _p(bias), _p(residual), _p(stats)
+    g.residual_mask = _p(residual_mask)
     g.lda = A.stride(0) if lda is None else lda
     g.ldb = B.stride(0) if ldb is None else ldb
     g.ldd = D.stride(0) if ldd is None else ldd
