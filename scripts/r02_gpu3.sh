@@ -4,6 +4,7 @@ set -u
 mkdir -p gpurun_out
 run() { echo "=== $*"; timeout -k 5 "${T:-420}" "$@" 2>&1 | tail -${TAIL:-6}; echo "--- exit ${PIPESTATUS[0]}"; }
 T=900 TAIL=60 run python -m pytest tests -m gpu -q
+T=300 TAIL=30 run python scripts/debug/dbg_bias_h2048.py
 T=500 TAIL=1 run python bench.py --steps 20 --warmup 5 --dump-gemm-profile gpurun_out/r02_gemm_launches.json
 cp gpurun_out/r02_gemm_launches.json gpurun_out/r02_gemm_launches_c2.json 2>/dev/null
 T=500 TAIL=1 run python bench.py --skip-cpu --steps 10 --warmup 3 --config depth_ablations/bicaptioning_R_50_L4_H1024.yaml --dump-gemm-profile gpurun_out/r02_gemm_launches_c4.json

@@ -749,10 +749,22 @@ def test_baseline_config_architectures_vs_oracle(spec_kw, B, ragged):
     out["loss"].backward()
     named = dict(model.named_parameters())
     bad = []
+    n_valid = float((batch["caption_tokens"][:, 1:] != 0).sum())
     for name, gref in grads.items():
         if name.startswith("visual."):
             continue
         r, c = rel(named[name].grad, gref), cos(named[name].grad, gref)
+        if name == "textual.output.bias":
+            # sum over rows of (softmax - onehot)/count.  With H = 2048 this synthetic model predicts its INPUT token with
+            # p ~ 0.998, so each direction's sum telescopes to e_SOS - e_EOS and the two directions cancel: the true
+            # gradient is ~150x smaller than the per-row terms (checked on the oracle, scripts/debug/dbg_bias_h2048.py).
+            # dlogits are bf16 here exactly as under the reference's autocast (the gradient of a bf16 linear output is
+            # bf16), so the error is bounded relative to the per-row scale, not to the cancelled sum.
+            scale = sum((torch.softmax(ref[k].detach().float(), -1) / n_valid).norm().item()
+                        for k in ("logits", "backward_logits"))
+            if (named[name].grad.float().cpu() - gref).norm().item() > 1e-2 * scale:
+                bad.append((name, r, c, scale))
+            continue
         if not (c > 0.998 and r < 5e-2):
             bad.append((name, r, c))
     assert not bad, bad

@@ -303,6 +303,8 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, float count,
 // a = act( y*scale + shift  [+ res  |  + res*scale2 + shift2] );  relu_mask (optional): bit j of byte (m*C/8 + c/8) =
 // [pre-activation of channel 8*(c/8)+j of row m > 0]
 constexpr int kU = 4;  // independent 16-byte loads per tensor in flight per thread (memory-level parallelism)
+constexpr int kUbwd = 6;  // single-BN backward apply (two input streams): 96 KB in flight per SM
+constexpr int kUred = 5;  // single-BN backward reduce (one more load would spill at 128 registers)
 
 // Optional fold of bn_finalize into the apply kernel: every thread derives scale/shift of its 8 channels from the raw
 // batch sums (or the running statistics in eval mode); block 0 also publishes bnp and updates the running buffers.
@@ -317,7 +319,10 @@ struct BnFwdFold {
   int training;
 };
 
-template <bool kFold>
+// kUa = independent 16-byte loads per tensor in flight per thread.  Measured on B200 (r02_bn_attn.ncu-rep): ~32 KB in
+// flight per SM (one input tensor at kUa = 4) caps the kernel at ~3.9 TB/s, ~64 KB reaches ~5.9 TB/s -- so the
+// single-input variants (no residual operand) run 8 loads deep.
+template <bool kFold, int kUa>
 __global__ void __launch_bounds__(256, 2) bn_act_kernel(const __nv_bfloat16* __restrict__ y, float* __restrict__ bnp,
                               const __nv_bfloat16* __restrict__ res, const float* __restrict__ bnp_res,
                               __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ relu_mask, long long M, int C,
@@ -364,10 +369,10 @@ __global__ void __launch_bounds__(256, 2) bn_act_kernel(const __nv_bfloat16* __r
     sh2[j] = bnp_res ? bnp_res[3 * C + c] : 0.f;
   }
   if (kFold && blockIdx.x == 0 && threadIdx.x == 0 && f.training && f.nbt != nullptr) *f.nbt += 1;
-  for (long long i = i0; i < total; i += stride * kU) {
-    bf16x8 vy[kU], vr[kU];
+  for (long long i = i0; i < total; i += stride * kUa) {
+    bf16x8 vy[kUa], vr[kUa];
 #pragma unroll
-    for (int u = 0; u < kU; ++u) {
+    for (int u = 0; u < kUa; ++u) {
       const long long idx = i + u * stride;
       if (idx < total) {
         vy[u] = *reinterpret_cast<const bf16x8*>(y + idx * 8);
@@ -375,7 +380,7 @@ __global__ void __launch_bounds__(256, 2) bn_act_kernel(const __nv_bfloat16* __r
       }
     }
 #pragma unroll
-    for (int u = 0; u < kU; ++u) {
+    for (int u = 0; u < kUa; ++u) {
       const long long idx = i + u * stride;
       if (idx >= total) break;
       float v[8];
@@ -623,7 +628,7 @@ __global__ void __launch_bounds__(256) maxpool_bwd_tiled_kernel(const __nv_bfloa
 // sums[0,c] = sum_m dz, sums[1,c] = sum_m dz * xhat, with dz = dA * [relu_mask bit] (relu_mask == null: no ReLU, or the
 // mask recomputed from y when mask_from_y) and
 // xhat = (y - mean) * invstd.  Optionally the same for a second BN (y2, bnp2) sharing dz (downsample branch).
-template <int kTwo>
+template <int kTwo, int kUb>
 __global__ void __launch_bounds__(256, kTwo ? 1 : 2) bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dA, const uint8_t* __restrict__ a,
                                      const __nv_bfloat16* __restrict__ y, const float* __restrict__ bnp,
                                      const __nv_bfloat16* __restrict__ y2, const float* __restrict__ bnp2,
@@ -652,11 +657,11 @@ __global__ void __launch_bounds__(256, kTwo ? 1 : 2) bn_bwd_reduce_kernel(const 
   }
   if (rr < rows_par) {
     const long long mstride = (long long)gridDim.x * rows_par;
-    for (long long m0 = (long long)blockIdx.x * rows_par + rr; m0 < M; m0 += mstride * kU) {
-      bf16x8 vd[kU], vy[kU], vy2[kU];
-      uint32_t va[kU];
+    for (long long m0 = (long long)blockIdx.x * rows_par + rr; m0 < M; m0 += mstride * kUb) {
+      bf16x8 vd[kUb], vy[kUb], vy2[kUb];
+      uint32_t va[kUb];
 #pragma unroll
-      for (int u = 0; u < kU; ++u) {
+      for (int u = 0; u < kUb; ++u) {
         const long long m = m0 + u * mstride;
         if (m < M) {
           const long long off = m * C + c0;
@@ -667,7 +672,7 @@ __global__ void __launch_bounds__(256, kTwo ? 1 : 2) bn_bwd_reduce_kernel(const 
         }
       }
 #pragma unroll
-      for (int u = 0; u < kU; ++u) {
+      for (int u = 0; u < kUb; ++u) {
         const long long m = m0 + u * mstride;
         if (m >= M) break;
         float d[8], yy[8];
@@ -752,7 +757,7 @@ struct BnBwdFold {
   float count;
 };
 
-template <int kTwo, bool kFold>
+template <int kTwo, bool kFold, int kUb>
 __global__ void __launch_bounds__(256, kTwo ? 1 : 2) bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dA, const uint8_t* __restrict__ a,
                                     const __nv_bfloat16* __restrict__ y, const float* __restrict__ bnp,
                                     const float* __restrict__ coef, __nv_bfloat16* __restrict__ dy,
@@ -814,11 +819,11 @@ __global__ void __launch_bounds__(256, kTwo ? 1 : 2) bn_bwd_apply_kernel(const _
     }
   }
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = i0; i < total; i += stride * kU) {
-    bf16x8 vd[kU], vy[kU], vy2[kU];
-    uint32_t va[kU];
+  for (long long i = i0; i < total; i += stride * kUb) {
+    bf16x8 vd[kUb], vy[kUb], vy2[kUb];
+    uint32_t va[kUb];
 #pragma unroll
-    for (int u = 0; u < kU; ++u) {
+    for (int u = 0; u < kUb; ++u) {
       const long long idx = i + u * stride;
       if (idx < total) {
         vd[u] = *reinterpret_cast<const bf16x8*>(dA + idx * 8);
@@ -828,7 +833,7 @@ __global__ void __launch_bounds__(256, kTwo ? 1 : 2) bn_bwd_apply_kernel(const _
       }
     }
 #pragma unroll
-    for (int u = 0; u < kU; ++u) {
+    for (int u = 0; u < kUb; ++u) {
       const long long idx = i + u * stride;
       if (idx >= total) break;
       float d[8], yy[8], o[8];
@@ -1081,9 +1086,13 @@ extern "C" int vtx_bn_act(const void* y, const float* bnp, const void* res, cons
   REQ(y && bnp && out && C % 8 == 0, "bad arguments");
   BnFwdFold f;
   memset(&f, 0, sizeof(f));
-  bn_act_kernel<false><<<grid_for((M * (C / 8) + kU - 1) / kU, 256, 2), 256, 0, STREAM>>>(
-      (const __nv_bfloat16*)y, const_cast<float*>(bnp), (const __nv_bfloat16*)res, bnp_res, (__nv_bfloat16*)out,
-      relu_mask, M, C, relu, f);
+  if (res == nullptr)
+    bn_act_kernel<false, 8><<<grid_for((M * (C / 8) + 7) / 8, 256, 2), 256, 0, STREAM>>>(
+        (const __nv_bfloat16*)y, const_cast<float*>(bnp), nullptr, bnp_res, (__nv_bfloat16*)out, relu_mask, M, C, relu, f);
+  else
+    bn_act_kernel<false, kU><<<grid_for((M * (C / 8) + kU - 1) / kU, 256, 2), 256, 0, STREAM>>>(
+        (const __nv_bfloat16*)y, const_cast<float*>(bnp), (const __nv_bfloat16*)res, bnp_res, (__nv_bfloat16*)out,
+        relu_mask, M, C, relu, f);
   return check_launch("bn_act");
 }
 // bn_finalize + bn_act in one launch (the statistics -> scale/shift step runs in every thread's prologue)
@@ -1096,8 +1105,12 @@ extern "C" int vtx_bn_finalize_act(const float* stats, float count, const float*
   BnFwdFold f;
   f.stats = stats; f.gamma = gamma; f.beta = beta; f.rmean = rmean; f.rvar = rvar; f.nbt = (long long*)nbt;
   f.count = count; f.momentum = momentum; f.eps = eps; f.training = training;
-  bn_act_kernel<true><<<grid_for((M * (C / 8) + kU - 1) / kU, 256, 2), 256, 0, STREAM>>>(
-      (const __nv_bfloat16*)y, bnp, (const __nv_bfloat16*)res, bnp_res, (__nv_bfloat16*)out, relu_mask, M, C, relu, f);
+  if (res == nullptr)
+    bn_act_kernel<true, 8><<<grid_for((M * (C / 8) + 7) / 8, 256, 2), 256, 0, STREAM>>>(
+        (const __nv_bfloat16*)y, bnp, nullptr, bnp_res, (__nv_bfloat16*)out, relu_mask, M, C, relu, f);
+  else
+    bn_act_kernel<true, kU><<<grid_for((M * (C / 8) + kU - 1) / kU, 256, 2), 256, 0, STREAM>>>(
+        (const __nv_bfloat16*)y, bnp, (const __nv_bfloat16*)res, bnp_res, (__nv_bfloat16*)out, relu_mask, M, C, relu, f);
   return check_launch("bn_finalize_act");
 }
 extern "C" int vtx_bn_relu_maxpool(const void* y, const float* bnp, void* out, uint8_t* idx, int N, int H, int W, int C,
@@ -1154,17 +1167,18 @@ extern "C" int vtx_bn_bwd_reduce(const void* dA, const uint8_t* a, const void* y
   const int rows_par = threads / (C / 8);
   const bool two = (y2 != nullptr);
   const size_t smem = (size_t)rows_par * C * (two ? 4 : 2) * sizeof(float);
-  long long blocks = (M + (long long)rows_par * kU - 1) / ((long long)rows_par * kU);
+  const int ku = y2 != nullptr ? kU : kUred;
+  long long blocks = (M + (long long)rows_par * ku - 1) / ((long long)rows_par * ku);
   const long long cap = (long long)vtx_num_sms() * (two ? 1 : 2);
   if (blocks > cap) blocks = cap;
   if (two) {
     REQ(bnp2 && sums2, "second BN needs bnp2/sums2");
-    bn_bwd_reduce_kernel<1><<<(int)blocks, threads, smem, STREAM>>>((const __nv_bfloat16*)dA, (const uint8_t*)a,
+    bn_bwd_reduce_kernel<1, kU><<<(int)blocks, threads, smem, STREAM>>>((const __nv_bfloat16*)dA, (const uint8_t*)a,
                                                                     (const __nv_bfloat16*)y, bnp,
                                                                     (const __nv_bfloat16*)y2, bnp2, sums, sums2, M, C,
                                                                     mask_from_y);
   } else {
-    bn_bwd_reduce_kernel<0><<<(int)blocks, threads, smem, STREAM>>>((const __nv_bfloat16*)dA, (const uint8_t*)a,
+    bn_bwd_reduce_kernel<0, kUred><<<(int)blocks, threads, smem, STREAM>>>((const __nv_bfloat16*)dA, (const uint8_t*)a,
                                                                     (const __nv_bfloat16*)y, bnp, nullptr, nullptr,
                                                                     sums, nullptr, M, C, mask_from_y);
   }
@@ -1180,16 +1194,17 @@ static int launch_bn_bwd_apply(bool fold, const BnBwdFold& f, const void* dA, co
                                const float* bnp, const float* coef, void* dy, const void* y2, const float* bnp2,
                                const float* coef2, void* dy2, void* dz_out, int64_t M, int C, int mask_from_y,
                                cudaStream_t st) {
-  const int grid = grid_for((M * (C / 8) + kU - 1) / kU, 256, y2 != nullptr ? 1 : 2);
+  const int ku = y2 != nullptr ? kU : kUbwd;
+  const int grid = grid_for((M * (C / 8) + ku - 1) / ku, 256, y2 != nullptr ? 1 : 2);
 #define VTX_APPLY_ARGS (const __nv_bfloat16*)dA, (const uint8_t*)a, (const __nv_bfloat16*)y, bnp, coef,                \
                        (__nv_bfloat16*)dy, (const __nv_bfloat16*)y2, bnp2, coef2, (__nv_bfloat16*)dy2,                  \
                        (__nv_bfloat16*)dz_out, M, C, mask_from_y, f
   if (y2 != nullptr) {
-    if (fold) bn_bwd_apply_kernel<1, true><<<grid, 256, 0, st>>>(VTX_APPLY_ARGS);
-    else bn_bwd_apply_kernel<1, false><<<grid, 256, 0, st>>>(VTX_APPLY_ARGS);
+    if (fold) bn_bwd_apply_kernel<1, true, kU><<<grid, 256, 0, st>>>(VTX_APPLY_ARGS);
+    else bn_bwd_apply_kernel<1, false, kU><<<grid, 256, 0, st>>>(VTX_APPLY_ARGS);
   } else {
-    if (fold) bn_bwd_apply_kernel<0, true><<<grid, 256, 0, st>>>(VTX_APPLY_ARGS);
-    else bn_bwd_apply_kernel<0, false><<<grid, 256, 0, st>>>(VTX_APPLY_ARGS);
+    if (fold) bn_bwd_apply_kernel<0, true, kUbwd><<<grid, 256, 0, st>>>(VTX_APPLY_ARGS);
+    else bn_bwd_apply_kernel<0, false, kU><<<grid, 256, 0, st>>>(VTX_APPLY_ARGS);
   }
 #undef VTX_APPLY_ARGS
   return check_launch("bn_bwd_apply");

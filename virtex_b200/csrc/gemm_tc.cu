@@ -50,6 +50,28 @@ constexpr int kThreads = 384;
 constexpr int kEpiThreads = 256;
 constexpr int kHaloH = 18, kHaloW = 10;  // modes 3/4: halo of an 8 (w) x 16 (h) tile = 18 lines x 10 pixels x 64 ch (bf16)
 
+// x / d for 0 <= x < 2^31 and the launch-invariant divisor d: (umulhi(x, mul) >> shr), d == 1 handled apart
+struct FastDiv {
+  uint32_t mul, shr;  // mul == 0 encodes d == 1
+};
+__device__ __forceinline__ int fdiv(int x, const FastDiv& f) {
+  return f.mul == 0u ? x : (int)(__umulhi((uint32_t)x, f.mul) >> f.shr);
+}
+static FastDiv make_fastdiv(int d) {
+  FastDiv f;
+  f.mul = 0;
+  f.shr = 0;
+  if (d > 1) {
+    int l = 0;
+    while ((1u << l) < (uint32_t)d) ++l;  // ceil(log2 d)
+    const int pw = 31 + l;
+    const unsigned long long m = ((1ull << pw) + (uint32_t)d - 1) / (uint32_t)d;  // 2^31 < m < 2^32: never 0
+    f.mul = (uint32_t)m;
+    f.shr = (uint32_t)(pw - 32);
+  }
+  return f;
+}
+
 struct GemmKParams {
   int M, N, K;
   int bn;
@@ -76,6 +98,9 @@ struct GemmKParams {
   const uint8_t* res_mask;   // optional bit mask [M, N/8]: the residual of (row, col) is added only where its bit is set
   float* stats;
   int taps_w, pad, ntaps;    // taps per kernel row / zero padding / number of taps of the implicit conv (3, 1, 9 for 3x3)
+  // division by the launch-invariant tile-schedule extents as multiply-high + shift (a runtime integer division costs
+  // ~25 dependent instructions; the schedule decode was ~13 % of the epilogue's instructions on the short-K convs)
+  FastDiv d_mn, d_nt, d_tw, d_twh, d_cpb, d_taps;
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
@@ -223,9 +248,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_arrive_expect_tx(bst_bar, 9u * (uint32_t)p.bn * 128u);
         for (int tap = 0; tap < 9; ++tap) tma_load_2d(bstat + tap * p.bn * 128, &tmB, bst_bar, tap * 64, 0);
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-          const int tw = t % p.tiles_w;
-          const int th = (t / p.tiles_w) % p.tiles_h;
-          const int tn = t / (p.tiles_w * p.tiles_h);
+          const int tn = fdiv(t, p.d_twh);
+          const int r_wh = t - tn * (p.tiles_w * p.tiles_h);
+          const int th = fdiv(r_wh, p.d_tw);
+          const int tw = r_wh - th * p.tiles_w;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(p.halo_w * kHaloH * 128));
           tma_load_4d(smem + stage * p.stage_bytes, &tmA, &full_bar[stage], 0, (tw << 3) - 1, (th << 4) - 1, tn);
@@ -237,9 +263,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // and ONE output-gradient tile; all nine taps are row-shifted views of the halo tile
         const uint32_t halo_bytes = (uint32_t)(p.halo_w * kHaloH * 128);
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-          const int tw = t % p.tiles_w;
-          const int th = (t / p.tiles_w) % p.tiles_h;
-          const int tn = t / (p.tiles_w * p.tiles_h);
+          const int tn = fdiv(t, p.d_twh);
+          const int r_wh = t - tn * (p.tiles_w * p.tiles_h);
+          const int th = fdiv(r_wh, p.d_tw);
+          const int tw = r_wh - th * p.tiles_w;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sX = smem + stage * p.stage_bytes;
           mbar_arrive_expect_tx(&full_bar[stage], halo_bytes + 16384u);
@@ -249,17 +276,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
       for (int t = blockIdx.x; t < total_tiles && p.mode < 3; t += gridDim.x) {
-        const int ks = t / (p.m_tiles * p.n_tiles);
+        const int ks = fdiv(t, p.d_mn);
         const int rem = t - ks * (p.m_tiles * p.n_tiles);
-        const int mt = rem / p.n_tiles;
+        const int mt = fdiv(rem, p.d_nt);
         const int nt = rem - mt * p.n_tiles;
         const int kb0 = ks * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         int w0 = 0, h0 = 0, n0 = 0;
         if (p.mode == 1) {
-          const int tw = mt % p.tiles_w;
-          const int th = (mt / p.tiles_w) % p.tiles_h;
-          const int tn = mt / (p.tiles_w * p.tiles_h);
+          const int tn = fdiv(mt, p.d_twh);
+          const int r_wh = mt - tn * (p.tiles_w * p.tiles_h);
+          const int th = fdiv(r_wh, p.d_tw);
+          const int tw = r_wh - th * p.tiles_w;
           w0 = tw << p.lbw; h0 = th << p.lbh; n0 = tn << p.lbn;
         }
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -284,24 +312,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tma_load_2d(sB + j * 8192, &tmB, &full_bar[stage], nt * p.bn + 64 * j, kb * kBK);
             }
           } else if (p.mode == 1) {
-            const int tap = kb / p.cpb;
+            const int tap = fdiv(kb, p.d_cpb);
             const int cb = kb - tap * p.cpb;
-            const int kh = tap / KP_TAPS_W, kw = tap - kh * KP_TAPS_W;
+            const int kh = fdiv(tap, p.d_taps), kw = tap - kh * KP_TAPS_W;
             tma_load_4d(sA, &tmA, &full_bar[stage], cb * 64, w0 + kw - KP_PAD, h0 + kh - KP_PAD, n0);
             tma_load_2d(sB, &tmB, &full_bar[stage], kb * kBK, nt * p.bn);
           } else {
             // wgrad: reduction block kb is a spatial box of 64 output positions
-            const int tw = kb % p.tiles_w;
-            const int th = (kb / p.tiles_w) % p.tiles_h;
-            const int tn = kb / (p.tiles_w * p.tiles_h);
+            const int tn = fdiv(kb, p.d_twh);
+            const int r_wh = kb - tn * (p.tiles_w * p.tiles_h);
+            const int th = fdiv(r_wh, p.d_tw);
+            const int tw = r_wh - th * p.tiles_w;
             const int bw0 = tw << p.lbw, bh0 = th << p.lbh, bn0 = tn << p.lbn;
             tma_load_4d(sA, &tmA, &full_bar[stage], mt * kBM, bw0, bh0, bn0);
             if (!half_a) tma_load_4d(sA + 8192, &tmA, &full_bar[stage], mt * kBM + 64, bw0, bh0, bn0);
             for (int j = 0; j < (p.bn >> 6); ++j) {
               const int atom = nt * (p.bn >> 6) + j;
-              const int tap = atom / p.cpb;
+              const int tap = fdiv(atom, p.d_cpb);
               const int cb = atom - tap * p.cpb;
-              const int kh = tap / KP_TAPS_W, kw = tap - kh * KP_TAPS_W;
+              const int kh = fdiv(tap, p.d_taps), kw = tap - kh * KP_TAPS_W;
               // atoms past the 9 taps are loaded fully out of bounds (zero fill) to keep the tx count fixed
               const int nn = tap < KP_NTAPS ? bn0 : p.cN + 1;
               tma_load_4d(sB + j * 8192, &tmB, &full_bar[stage], cb * 64, bw0 + kw - KP_PAD, bh0 + kh - KP_PAD, nn);
@@ -396,7 +425,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         umma_commit_ws(&tfull_bar[0]);
       }
       for (int t = blockIdx.x; t < total_tiles && p.mode < 3; t += gridDim.x, ++it) {
-        const int ks = t / (p.m_tiles * p.n_tiles);
+        const int ks = fdiv(t, p.d_mn);
         const int kb0 = ks * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         const int as = it & 1;
@@ -428,33 +457,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int et = threadIdx.x - 128; // 0..255 within the epilogue group
     const bool staged = p.cbytes != 0;
     const int nchunks = (p.bn + 31) >> 5;
-    // BN statistics: thread (scg, srg) owns 8 columns x 16 rows of every staged tile and keeps running partial sums in
-    // registers across all tiles of this CTA that share the same column block; they are reduced through shared
-    // memory and flushed with one atomic per column only when the column block changes (or at the end).
-    constexpr int st_rgs = 8, st_rpt = 16;
-    const int scg = et & 31, srg = et >> 5;
-    float st_s[8], st_q[8];
+    // BN statistics: thread (scg, srg) owns 8 columns x st_rpt rows of every staged tile and keeps running partial sums
+    // in registers (packed fp32x2: FADD2 / FFMA2) across all tiles of this CTA that share the same column block; they
+    // are reduced through shared memory and flushed with one atomic per column only when the column block changes (or
+    // at the end).  All 256 threads take part for the three tile widths the BN'd convs use: 64 / 128 / 256 columns =
+    // 8 / 16 / 32 column groups x 32 / 16 / 8 row groups of 4 / 8 / 16 rows (with the fixed 32 x 8 x 16 mapping a
+    // 64-wide tile kept 3/4 of the lanes idle while every warp still executed all 16 rows' instructions).
+    const int st_lg = (p.bn == 64) ? 3 : (p.bn == 128) ? 4 : 5;  // log2(column groups)
+    const int st_rgs = 256 >> st_lg, st_rpt = 128 >> (8 - st_lg);
+    const int scg = et & ((1 << st_lg) - 1), srg = et >> st_lg;
+    float2 st_s[4], st_q[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) st_s[i] = st_q[i] = 0.f;
+    for (int i = 0; i < 4; ++i) st_s[i] = st_q[i] = make_float2(0.f, 0.f);
     int st_nt = -1;
     auto flush_stats = [&](uint8_t* scratch) {
       // `scratch` is a staging buffer no TMA store is reading and nobody is writing (callers guarantee it)
       float* scr = reinterpret_cast<float*>(scratch);
       if (scg * 8 < p.bn) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          scr[(srg * p.bn + scg * 8 + i) * 2] = st_s[i];
-          scr[(srg * p.bn + scg * 8 + i) * 2 + 1] = st_q[i];
-          st_s[i] = st_q[i] = 0.f;
+        for (int i = 0; i < 4; ++i) {
+          *reinterpret_cast<float4*>(scr + (srg * p.bn + scg * 8 + 2 * i) * 2) =
+              make_float4(st_s[i].x, st_q[i].x, st_s[i].y, st_q[i].y);
+          st_s[i] = st_q[i] = make_float2(0.f, 0.f);
         }
       }
       epi_bar();
       if (et < p.bn && st_nt * p.bn + et < p.N) {
         float a = 0.f, b = 0.f;
-#pragma unroll
         for (int g = 0; g < st_rgs; ++g) {
-          a += scr[(g * p.bn + et) * 2];
-          b += scr[(g * p.bn + et) * 2 + 1];
+          const float2 v = *reinterpret_cast<const float2*>(scr + (g * p.bn + et) * 2);
+          a += v.x;
+          b += v.y;
         }
         atomicAdd(p.stats + st_nt * p.bn + et, a);
         atomicAdd(p.stats + p.N + st_nt * p.bn + et, b);
@@ -464,15 +497,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // asynchronous, coalesced TMA load of the residual tile of schedule slot `t_` into staging buffer `bi_`
     // (called by ONE thread, only once the TMA store that last read that buffer has finished reading it)
     auto issue_residual = [&](int t_, int bi_) {
-      const int rem_ = t_ % (p.m_tiles * p.n_tiles);
-      const int mt_ = rem_ / p.n_tiles;
+      const int rem_ = t_ - fdiv(t_, p.d_mn) * (p.m_tiles * p.n_tiles);
+      const int mt_ = fdiv(rem_, p.d_nt);
       const int nb_ = (rem_ - mt_ * p.n_tiles) * p.bn;
       uint8_t* buf_ = cstage0 + (size_t)bi_ * p.cbytes;
       const int slabs = (min(p.bn, p.N - nb_) + 63) >> 6;
       mbar_arrive_expect_tx(&res_bar[bi_], (uint32_t)slabs * 16384u);
       for (int sl = 0; sl < slabs; ++sl) {
         if (p.mode & 1) {
-          const int tw_ = mt_ % p.tiles_w, th_ = (mt_ / p.tiles_w) % p.tiles_h, tn_ = mt_ / (p.tiles_w * p.tiles_h);
+          const int tn_ = fdiv(mt_, p.d_twh);
+          const int rwh_ = mt_ - tn_ * (p.tiles_w * p.tiles_h);
+          const int th_ = fdiv(rwh_, p.d_tw), tw_ = rwh_ - th_ * p.tiles_w;
           tma_load_4d(buf_ + sl * 16384, &tmR, &res_bar[bi_], nb_ + sl * 64, tw_ << p.lbw, th_ << p.lbh, tn_ << p.lbn);
         } else {
           tma_load_2d(buf_ + sl * 16384, &tmR, &res_bar[bi_], nb_ + sl * 64, mt_ * kBM);
@@ -501,32 +536,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
     for (int t = blockIdx.x; t < total_tiles && p.mode != 4; t += gridDim.x, ++it) {
-      const int rem = t % (p.m_tiles * p.n_tiles);
-      const int mt = rem / p.n_tiles;
+      const int rem = t - fdiv(t, p.d_mn) * (p.m_tiles * p.n_tiles);
+      const int mt = fdiv(rem, p.d_nt);
       const int nt = rem - mt * p.n_tiles;
       const int as = it & 1;
       const int n_base = nt * p.bn;
       int tw = 0, th = 0, tn = 0;
       if (p.mode & 1) {
-        tw = mt % p.tiles_w;
-        th = (mt / p.tiles_w) % p.tiles_h;
-        tn = mt / (p.tiles_w * p.tiles_h);
+        tn = fdiv(mt, p.d_twh);
+        const int r_wh = mt - tn * (p.tiles_w * p.tiles_h);
+        th = fdiv(r_wh, p.d_tw);
+        tw = r_wh - th * p.tiles_w;
       }
       uint8_t* cbuf = cstage0 + (size_t)(p.nbuf > 1 ? (it & 1) : 0) * p.cbytes;
       if (staged) {
         // the TMA store that last read this staging buffer must have finished reading it
         if (et == 0) {
-          if (p.nbuf > 1) tma_store_wait_read<1>();
-          else tma_store_wait_read<0>();
+          if (p.res_tma && p.nbuf > 1) {
+            // Residual prefetch ONE FULL TILE ahead: this tile's residual was requested at the top of the previous
+            // iteration; the next tile's goes into the other buffer now.  That buffer was last read by the store issued
+            // at the end of the previous iteration, so it has to drain first (wait_read<0>, a few hundred cycles for a
+            // 64 KB tile) -- the round-2 profile (r02_gemm_cases.ncu-rep, launch 1) showed 25 % of all warp samples of
+            // the dgrad+shortcut GEMMs waiting on a residual requested less than a stats-pass before its use.
+            tma_store_wait_read<0>();
+            if (it == 0) issue_residual(t, 0);
+            if (t + (int)gridDim.x < total_tiles) issue_residual(t + gridDim.x, (it + 1) & 1);
+          } else {
+            if (p.nbuf > 1) tma_store_wait_read<1>();
+            else tma_store_wait_read<0>();
+            if (p.res_tma) issue_residual(t, 0);  // single staging buffer: requested now that the buffer is free
+          }
         }
         epi_bar();
         if (p.stats != nullptr && st_nt != nt) {
           if (st_nt >= 0) flush_stats(cbuf);
           st_nt = nt;
         }
-        // with two staging buffers the residual of this tile was prefetched one tile ago (see below); otherwise, and
-        // for the CTA's first tile, it is requested now that the buffer is free
-        if (p.res_tma && et == 0 && (p.nbuf == 1 || it == 0)) issue_residual(t, p.nbuf > 1 ? (it & 1) : 0);
       }
       mbar_wait(&tfull_bar[as], (it >> 1) & 1);
       tc_fence_after();
@@ -663,27 +708,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               tma_store_2d(&tmD, cbuf + sl * 16384, n_base + sl * 64, mt * kBM);
           }
           tma_store_commit();
-          if (p.res_tma && p.nbuf > 1 && t + (int)gridDim.x < total_tiles) {
-            // prefetch the next tile's residual into the other buffer as soon as its previous store has been read
-            tma_store_wait_read<1>();
-            issue_residual(t + gridDim.x, (it + 1) & 1);
-          }
         }
         // ---------------- BN statistics of the staged (bf16-rounded) tile, accumulated in registers.
         // Rows outside the problem are exact zeros (TMA zero fill; stats forbids bias/residual): no masking needed.
         if (p.stats != nullptr && scg * 8 < p.bn) {
-          const int r0 = srg * st_rpt;  // first row of this thread (a multiple of 8 in the regular build)
+          const int r0 = srg * st_rpt;  // first row of this thread (a multiple of 4)
           const uint32_t cp = smem_u32(cbuf) + (scg >> 3) * 16384 + r0 * 128;
           const int c8 = scg & 7;
-#pragma unroll 4
-          for (int r = 0; r < st_rpt; ++r) {
-            float f[8];
-            const uint4 raw = lds128(cp + r * 128 + ((c8 ^ ((r0 + r) & 7)) << 4));
-            unpack8(*reinterpret_cast<const bf16x8*>(&raw), f);
+          for (int rb = 0; rb < st_rpt; rb += 4) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              st_s[i] += f[i];
-              st_q[i] += f[i] * f[i];
+            for (int r4 = 0; r4 < 4; ++r4) {
+              const int r = rb + r4;
+              const uint4 raw = lds128(cp + r * 128 + ((c8 ^ ((r0 + r) & 7)) << 4));
+              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 f = __bfloat1622float2(h2[i]);
+                st_s[i] = __fadd2_rn(st_s[i], f);
+                st_q[i] = __ffma2_rn(f, f, st_q[i]);
+              }
             }
           }
         }
@@ -989,6 +1032,12 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
       if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
   }
+  p.d_mn = make_fastdiv(p.m_tiles * p.n_tiles);
+  p.d_nt = make_fastdiv(p.n_tiles);
+  p.d_tw = make_fastdiv(p.tiles_w);
+  p.d_twh = make_fastdiv(p.tiles_w * p.tiles_h);
+  p.d_cpb = make_fastdiv(p.cpb);
+  p.d_taps = make_fastdiv(p.taps_w);
   const long total = (long)p.m_tiles * p.n_tiles * p.k_splits;
   const int sms = vtx_num_sms();
   const int grid = (int)(total < sms ? total : sms);
