@@ -500,67 +500,8 @@ __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dpool, cons
   }
 }
 
-// same arithmetic as bn_relu_maxpool_kernel; a CTA normalises + activates the 2 * kFP + 1
-// input rows of kFP pooled rows ONCE into shared memory (the validated kernel re-reads and re-normalises every input
-// element for each of the ~2.25 windows that contain it) and pools from there.
-constexpr int kFP = 2;
-__global__ void __launch_bounds__(256) bn_relu_maxpool_tiled_kernel(const __nv_bfloat16* __restrict__ y,
-                                                                   const float* __restrict__ bnp,
-                                                                   __nv_bfloat16* __restrict__ out,
-                                                                   uint8_t* __restrict__ idx, int N, int H, int W, int C,
-                                                                   int Ho, int Wo) {
-  VTX_PDL_TRIGGER();
-  extern __shared__ __align__(16) uint8_t pool_smem[];
-  __nv_bfloat16* sa = reinterpret_cast<__nv_bfloat16*>(pool_smem);  // [2 * kFP + 1][W][C] activated rows
-  const int tiles = (Ho + kFP - 1) / kFP;
-  const int n = blockIdx.x / tiles, ph0 = (blockIdx.x % tiles) * kFP;
-  const int cg = C / 8;
-  const int hs = 2 * ph0 - 1;  // input row held in shared-memory row 0
-  for (int it = threadIdx.x; it < (2 * kFP + 1) * W * cg; it += blockDim.x) {
-    const int g = it % cg, w = (it / cg) % W, r = it / (cg * W);
-    const int h = hs + r;
-    if (h < 0 || h >= H) continue;
-    const int c0 = g * 8;
-    float v[8];
-    unpack8(*reinterpret_cast<const bf16x8*>(y + (((long long)n * H + h) * W + w) * C + c0), v);
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      v[j] = fmaxf(v[j] * __ldg(bnp + 2 * C + c0 + j) + __ldg(bnp + 3 * C + c0 + j), 0.f);
-    *reinterpret_cast<bf16x8*>(sa + ((long long)r * W + w) * C + c0) = pack8(v);  // bf16 rounding as in the reference
-  }
-  __syncthreads();
-  const int p1 = min(Ho, ph0 + kFP);
-  for (int it = threadIdx.x; it < (p1 - ph0) * Wo * cg; it += blockDim.x) {
-    const int g = it % cg, pw = (it / cg) % Wo, ph = ph0 + it / (cg * Wo);
-    const int c0 = g * 8;
-    float best[8];
-    int bi[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bi[j] = 0; }
-#pragma unroll
-    for (int kh = 0; kh < 3; ++kh) {
-      const int h = ph * 2 - 1 + kh;
-      if (h < 0 || h >= H) continue;
-#pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
-        const int w = pw * 2 - 1 + kw;
-        if (w < 0 || w >= W) continue;
-        float a[8];
-        unpack8(*reinterpret_cast<const bf16x8*>(sa + ((long long)(h - hs) * W + w) * C + c0), a);
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (a[j] > best[j]) { best[j] = a[j]; bi[j] = kh * 3 + kw; }
-      }
-    }
-    const long long pos = ((long long)n * Ho + ph) * Wo + pw;
-    *reinterpret_cast<bf16x8*>(out + pos * C + c0) = pack8(best);
-    uint8_t b[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) b[j] = (uint8_t)bi[j];
-    *reinterpret_cast<uint2*>(idx + pos * C + c0) = *reinterpret_cast<uint2*>(b);
-  }
-}
-
+// (A shared-memory tiled variant of the FORWARD pool was measured in round 2 and deleted: 0.42 ms against 0.28 ms for
+// the direct kernel above -- the ~2.25x re-normalisation it saved is cheaper than its staging pass.)
 // same arithmetic as maxpool_bwd_kernel, but a CTA first stages the kTP + 1 pooled rows
 // (gradients + argmax slots) it needs in shared memory with linear coalesced copies and then produces 2 * kTP input
 // rows from them.  The validated kernel gathers every pooled element from L2 up to nine times (1.4 GB of L2 -> SM
@@ -1117,20 +1058,6 @@ extern "C" int vtx_bn_relu_maxpool(const void* y, const float* bnp, void* out, u
                                    void* stream) {
   REQ(y && bnp && out && idx && C % 8 == 0, "bad arguments");
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
-  {
-    const size_t smem = (size_t)(2 * kFP + 1) * W * C * 2;
-    if (smem <= 100 * 1024) {
-      static size_t attr = 0;
-      if (smem > 48 * 1024 && smem > attr) {
-        cudaFuncSetAttribute(bn_relu_maxpool_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr = smem;
-      }
-      const int tiles = (Ho + kFP - 1) / kFP;
-      bn_relu_maxpool_tiled_kernel<<<N * tiles, 256, smem, STREAM>>>((const __nv_bfloat16*)y, bnp, (__nv_bfloat16*)out,
-                                                                     idx, N, H, W, C, Ho, Wo);
-      return check_launch("bn_relu_maxpool_tiled");
-    }
-  }
   const long long total = (long long)N * Ho * Wo * (C / 8);
   bn_relu_maxpool_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>((const __nv_bfloat16*)y, bnp, (__nv_bfloat16*)out,
                                                                    idx, N, H, W, C, Ho, Wo);

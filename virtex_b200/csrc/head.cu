@@ -65,8 +65,9 @@ __global__ void embed_fwd_kernel(const long long* __restrict__ tokens, const flo
     const float4 b = *reinterpret_cast<const float4*>(beta + i);
     float o[4] = {(v.x - mean) * rstd * g.x + b.x, (v.y - mean) * rstd * g.y + b.y, (v.z - mean) * rstd * g.z + b.z,
                   (v.w - mean) * rstd * g.w + b.w};
+    const Drop4 dr = drop4(p, inv_keep, seed, site, ((uint64_t)row * H + i) >> 2);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) o[j] *= keep * dropout_scale(p, inv_keep, seed, site, (uint64_t)row * H + i + j);
+    for (int j = 0; j < 4; ++j) o[j] *= keep * dr.scale(j);
     *reinterpret_cast<float4*>(out + (long long)row * H + i) = make_float4(o[0], o[1], o[2], o[3]);
     __nv_bfloat162 h0 = __floats2bfloat162_rn(o[0], o[1]), h1 = __floats2bfloat162_rn(o[2], o[3]);
     uint2 u;
@@ -149,11 +150,11 @@ __global__ void add_ln_fwd_kernel(const float* __restrict__ res, const __nv_bflo
       const uint2 u = *reinterpret_cast<const uint2*>(branch + (long long)row * H + i);
       const float2 b0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
       const float2 b1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
-      const uint64_t e = (uint64_t)row * H + i;
-      r.x += b0.x * dropout_scale(p, inv_keep, seed, site, e);
-      r.y += b0.y * dropout_scale(p, inv_keep, seed, site, e + 1);
-      r.z += b1.x * dropout_scale(p, inv_keep, seed, site, e + 2);
-      r.w += b1.y * dropout_scale(p, inv_keep, seed, site, e + 3);
+      const Drop4 dr = drop4(p, inv_keep, seed, site, ((uint64_t)row * H + i) >> 2);
+      r.x += b0.x * dr.scale(0);
+      r.y += b0.y * dr.scale(1);
+      r.z += b1.x * dr.scale(2);
+      r.w += b1.y * dr.scale(3);
     }
     *reinterpret_cast<float4*>(zr + i) = r;
   }
@@ -265,7 +266,9 @@ __global__ void ln_bwd_kernel(const float* __restrict__ dy_a, const __nv_bfloat1
       if (d_branch) {
         float t[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) t[j] = dz[j] * dropout_scale(p, inv_keep, seed, site, (uint64_t)base + i + j);
+        const Drop4 dr = drop4(p, inv_keep, seed, site, ((uint64_t)base + i) >> 2);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) t[j] = dz[j] * dr.scale(j);
         __nv_bfloat162 h0 = __floats2bfloat162_rn(t[0], t[1]), h1 = __floats2bfloat162_rn(t[2], t[3]);
         uint2 u;
         u.x = *reinterpret_cast<uint32_t*>(&h0);
@@ -390,7 +393,9 @@ ln_bwd_reg_kernel(const float* __restrict__ dy_a, const __nv_bfloat16* __restric
       if (d_branch) {
         float t[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) t[j] = dz[j] * dropout_scale(p, inv_keep, seed, site, (uint64_t)base + i + j);
+        const Drop4 dr = drop4(p, inv_keep, seed, site, ((uint64_t)base + i) >> 2);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) t[j] = dz[j] * dr.scale(j);
         __nv_bfloat162 h0 = __floats2bfloat162_rn(t[0], t[1]), h1 = __floats2bfloat162_rn(t[2], t[3]);
         uint2 u;
         u.x = *reinterpret_cast<uint32_t*>(&h0);
@@ -449,9 +454,10 @@ embed_bwd_reg_kernel(const float* __restrict__ dy_a, const __nv_bfloat16* __rest
         const float4 gm = *reinterpret_cast<const float4*>(gamma + i);
         const float zv[4] = {zz.x, zz.y, zz.z, zz.w};
         const float gwv[4] = {gm.x, gm.y, gm.z, gm.w};
+        const Drop4 dr = drop4(p, inv_keep, seed, site, ((uint64_t)base + i) >> 2);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float gj = g[4 * k + j] * dropout_scale(p, inv_keep, seed, site, (uint64_t)base + i + j);
+          const float gj = g[4 * k + j] * dr.scale(j);
           const float x = (zv[j] - mean) * rstd;
           g[4 * k + j] = gj;
           xh[4 * k + j] = x;
@@ -645,16 +651,18 @@ __global__ void __launch_bounds__(32 * kAttnFwdWarps) attn_fwd_kernel(const Attn
       mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
       float sum = 0.f;
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt)
+      for (int nt = 0; nt < 8; ++nt) {
+        // keys (j, j + 1) of this lane share one hash: element index ((unit*32 + i)*64 + j), j even
+        const Drop4 dr = drop4(a.p, inv_keep, seed, a.site, (((uint64_t)unit * 32 + i) * 64 + nt * 8 + 2 * tq) >> 2);
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          const int j = nt * 8 + 2 * tq + e;
           const float v = s[mt][nt][hh * 2 + e];
           float pr = (v == -INFINITY) ? 0.f : __expf(v - mx);
           sum += pr;
-          pr *= dropout_scale(a.p, inv_keep, seed, a.site, ((uint64_t)unit * 32 + i) * 64 + j);
+          pr *= dr.scale(((2 * tq) & 3) + e);
           s[mt][nt][hh * 2 + e] = pr;
         }
+      }
       sum += __shfl_xor_sync(0xffffffffu, sum, 1);
       sum += __shfl_xor_sync(0xffffffffu, sum, 2);
       rsum[mt][hh] = sum;
@@ -772,13 +780,14 @@ __global__ void __launch_bounds__(32 * kAttnBwdWarps) attn_bwd_kernel(const Attn
       const float L = row_ok ? lse[(long long)unit * 32 + i] : 0.f;
       float Di = 0.f;
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt)
+      for (int nt = 0; nt < 8; ++nt) {
+        const Drop4 dr = drop4(a.p, inv_keep, seed, a.site, (((uint64_t)unit * 32 + i) * 64 + nt * 8 + 2 * tq) >> 2);
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int j = nt * 8 + 2 * tq + e;
           const bool ok = row_ok && (j < a.Tk) && (a.causal == 1 ? (j <= i && j < len) : a.causal == 2 ? (j < len) : true);
           const float pr = ok ? __expf(s[mt][nt][hh * 2 + e] * a.scale - L) : 0.f;
-          const float mk = dropout_scale(a.p, inv_keep, seed, a.site, ((uint64_t)unit * 32 + i) * 64 + j);
+          const float mk = dr.scale(((2 * tq) & 3) + e);
           const float dpr = dp[mt][nt][hh * 2 + e] * mk;  // dP = dPd * mask
           Di += pr * dpr;
           s[mt][nt][hh * 2 + e] = pr;
@@ -786,6 +795,7 @@ __global__ void __launch_bounds__(32 * kAttnBwdWarps) attn_bwd_kernel(const Attn
           // Pd is consumed by dV only
           sP[i * kLd + j] = f2bf(pr * mk);
         }
+      }
       Di += __shfl_xor_sync(0xffffffffu, Di, 1);
       Di += __shfl_xor_sync(0xffffffffu, Di, 2);
 #pragma unroll
@@ -885,11 +895,12 @@ __global__ void gelu_dropout_fwd_kernel(const __nv_bfloat16* __restrict__ u, __n
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
     float f[8];
     unpack8(*reinterpret_cast<const bf16x8*>(u + i * 8), f);
+    const Drop4 d0 = drop4(p, inv_keep, seed, site, (uint64_t)i * 2), d1 = drop4(p, inv_keep, seed, site, (uint64_t)i * 2 + 1);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       // the reference evaluates GELU on the bf16 tensor and rounds the result to bf16 before dropout
       const float g = bf2f(f2bf(0.5f * f[j] * (1.0f + erff(f[j] * 0.70710678118654752f))));
-      f[j] = g * dropout_scale(p, inv_keep, seed, site, (uint64_t)i * 8 + j);
+      f[j] = g * (j < 4 ? d0.scale(j) : d1.scale(j - 4));
     }
     *reinterpret_cast<bf16x8*>(h + i * 8) = pack8(f);
   }
@@ -905,11 +916,12 @@ __global__ void gelu_dropout_bwd_kernel(const __nv_bfloat16* __restrict__ dh, co
     float d[8], x[8];
     unpack8(*reinterpret_cast<const bf16x8*>(dh + i * 8), d);
     unpack8(*reinterpret_cast<const bf16x8*>(u + i * 8), x);
+    const Drop4 d0 = drop4(p, inv_keep, seed, site, (uint64_t)i * 2), d1 = drop4(p, inv_keep, seed, site, (uint64_t)i * 2 + 1);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float cdf = 0.5f * (1.0f + erff(x[j] * 0.70710678118654752f));
       const float pdf = 0.3989422804014327f * __expf(-0.5f * x[j] * x[j]);
-      d[j] = d[j] * dropout_scale(p, inv_keep, seed, site, (uint64_t)i * 8 + j) * (cdf + x[j] * pdf);
+      d[j] = d[j] * (j < 4 ? d0.scale(j) : d1.scale(j - 4)) * (cdf + x[j] * pdf);
     }
     *reinterpret_cast<bf16x8*>(du + i * 8) = pack8(d);
   }

@@ -49,20 +49,37 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-// Counter-based RNG for dropout: keep-decision for element `idx` of dropout site `site` at step seed `seed`.
-// (murmur3-style finaliser over a 64-bit counter; masks are recomputed in backward, never stored.)
-__device__ __forceinline__ uint32_t hash_u32(uint64_t seed, uint32_t site, uint64_t idx) {
-  uint64_t x = seed ^ (0x9E3779B97F4A7C15ull * (uint64_t)(site + 1)) ^ (idx * 0xD6E8FEB86659FD93ull);
+// Counter-based RNG for dropout (masks are recomputed in backward, never stored).  One 64-bit hash (murmur3-style
+// finaliser) of (step seed, dropout site, element index / 4) serves FOUR consecutive elements, 16 bits each: the round-2
+// launch list showed the per-element hash (three 64-bit multiplies) dominating the attention and GELU kernels.
+// Drop probability = round(p * 65536) / 65536 (p = 0.1: 0.100006), kept elements are scaled by 1 / (1 - p).
+__device__ __forceinline__ uint64_t hash_u64(uint64_t seed, uint32_t site, uint64_t ctr) {
+  uint64_t x = seed ^ (0x9E3779B97F4A7C15ull * (uint64_t)(site + 1)) ^ (ctr * 0xD6E8FEB86659FD93ull);
   x ^= x >> 32; x *= 0xD6E8FEB86659FD93ull;
   x ^= x >> 32; x *= 0xD6E8FEB86659FD93ull;
   x ^= x >> 32;
-  return (uint32_t)x;
+  return x;
 }
-// returns scale to multiply by: 0 if dropped, 1/(1-p) if kept.  p == 0 -> always 1.
+struct Drop4 {
+  uint64_t h;
+  uint32_t thr;
+  float inv_keep;
+  // scale of element `lane` (0..3) of the group: 0 if dropped, 1/(1-p) if kept; p == 0 -> thr == 0 -> always 1
+  __device__ __forceinline__ float scale(int lane) const {
+    return (((uint32_t)(h >> (16 * lane)) & 0xffffu) < thr) ? 0.f : inv_keep;
+  }
+};
+// idx4 = (index of the group's first element) / 4; the group's elements are 4*idx4 .. 4*idx4 + 3
+__device__ __forceinline__ Drop4 drop4(float p, float inv_keep, uint64_t seed, uint32_t site, uint64_t idx4) {
+  Drop4 d;
+  d.thr = p > 0.f ? (uint32_t)(p * 65536.f + 0.5f) : 0u;
+  d.inv_keep = p > 0.f ? inv_keep : 1.f;
+  d.h = p > 0.f ? hash_u64(seed, site, idx4) : 0ull;
+  return d;
+}
+// single-element form (same mask as the grouped form for the same element index)
 __device__ __forceinline__ float dropout_scale(float p, float inv_keep, uint64_t seed, uint32_t site, uint64_t idx) {
   if (p <= 0.f) return 1.f;
-  const uint32_t h = hash_u32(seed, site, idx);
-  const float u = (float)(h >> 8) * (1.0f / 16777216.0f);
-  return u < p ? 0.f : inv_keep;
+  return drop4(p, inv_keep, seed, site, idx >> 2).scale((int)(idx & 3));
 }
 }  // namespace vtx
