@@ -265,7 +265,6 @@ __global__ void ln_bwd_kernel(const float* __restrict__ dy_a, const __nv_bfloat1
       }
       if (d_branch) {
         float t[4];
-#pragma unroll
         const Drop4 dr = drop4(p, inv_keep, seed, site, ((uint64_t)base + i) >> 2);
 #pragma unroll
         for (int j = 0; j < 4; ++j) t[j] = dz[j] * dr.scale(j);
@@ -392,7 +391,6 @@ ln_bwd_reg_kernel(const float* __restrict__ dy_a, const __nv_bfloat16* __restric
       for (int j = 0; j < 4; ++j) dz[j] = rstd * (g[4 * k + j] * gw[j] - s1 - xh[4 * k + j] * s2);
       if (d_branch) {
         float t[4];
-#pragma unroll
         const Drop4 dr = drop4(p, inv_keep, seed, site, ((uint64_t)base + i) >> 2);
 #pragma unroll
         for (int j = 0; j < 4; ++j) t[j] = dz[j] * dr.scale(j);
