@@ -194,8 +194,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* empty_bar = bars + kMaxStages;       // [kMaxStages]
   uint64_t* tfull_bar = bars + 2 * kMaxStages;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;          // [2]
-  uint64_t* res_bar = tempty_bar + 2;            // [2] residual tile landed in staging buffer b
-  uint64_t* bst_bar = res_bar + 2;               // [1] stationary weights landed (mode 3)
+  uint64_t* res_bar = tempty_bar + 2;            // [3] residual tile landed in staging buffer b
+  uint64_t* bst_bar = res_bar + 3;               // [1] stationary weights landed (mode 3)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bst_bar + 1);
   uint8_t* smem = base + kCtrlBytes;                       // stage ring (1024-aligned)
   uint8_t* bstat = smem + p.stages * p.stage_bytes;        // mode 3: stationary weights [9 taps][bn rows][128 B]
@@ -223,6 +223,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&tempty_bar[i], kEpiThreads);
       mbar_init(&res_bar[i], 1);
     }
+    mbar_init(&res_bar[2], 1);
     mbar_init(bst_bar, 1);
     fence_mbar_init();
   }
@@ -458,27 +459,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool staged = p.cbytes != 0;
     const int nchunks = (p.bn + 31) >> 5;
     // BN statistics: thread (scg, srg) owns 8 columns x st_rpt rows of every staged tile and keeps running partial sums
-    // in registers (packed fp32x2: FADD2 / FFMA2) across all tiles of this CTA that share the same column block; they
-    // are reduced through shared memory and flushed with one atomic per column only when the column block changes (or
+    // in registers across all tiles of this CTA that share the same column block (scalar FADD / FFMA: the packed
+    // fp32x2 forms measured 5-9 % SLOWER on the 256-wide tiles in round 2); they are reduced through shared memory and flushed with one atomic per column only when the column block changes (or
     // at the end).  All 256 threads take part for the three tile widths the BN'd convs use: 64 / 128 / 256 columns =
     // 8 / 16 / 32 column groups x 32 / 16 / 8 row groups of 4 / 8 / 16 rows (with the fixed 32 x 8 x 16 mapping a
     // 64-wide tile kept 3/4 of the lanes idle while every warp still executed all 16 rows' instructions).
     const int st_lg = (p.bn == 64) ? 3 : (p.bn == 128) ? 4 : 5;  // log2(column groups)
     const int st_rgs = 256 >> st_lg, st_rpt = 128 >> (8 - st_lg);
     const int scg = et & ((1 << st_lg) - 1), srg = et >> st_lg;
-    float2 st_s[4], st_q[4];
+    float st_s[8], st_q[8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) st_s[i] = st_q[i] = make_float2(0.f, 0.f);
+    for (int i = 0; i < 8; ++i) st_s[i] = st_q[i] = 0.f;
     int st_nt = -1;
     auto flush_stats = [&](uint8_t* scratch) {
       // `scratch` is a staging buffer no TMA store is reading and nobody is writing (callers guarantee it)
       float* scr = reinterpret_cast<float*>(scratch);
       if (scg * 8 < p.bn) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          *reinterpret_cast<float4*>(scr + (srg * p.bn + scg * 8 + 2 * i) * 2) =
-              make_float4(st_s[i].x, st_q[i].x, st_s[i].y, st_q[i].y);
-          st_s[i] = st_q[i] = make_float2(0.f, 0.f);
+        for (int i = 0; i < 8; i += 2) {
+          *reinterpret_cast<float4*>(scr + (srg * p.bn + scg * 8 + i) * 2) =
+              make_float4(st_s[i], st_q[i], st_s[i + 1], st_q[i + 1]);
+          st_s[i] = st_q[i] = st_s[i + 1] = st_q[i + 1] = 0.f;
         }
       }
       epi_bar();
@@ -535,7 +536,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_before();
       }
     }
-    for (int t = blockIdx.x; t < total_tiles && p.mode != 4; t += gridDim.x, ++it) {
+    int cb3 = 0, cwrap = 0;  // three-buffer residual pipeline: buffer index it % 3 and its use count it / 3
+    for (int t = blockIdx.x; t < total_tiles && p.mode != 4; t += gridDim.x, ++it, cwrap += (cb3 == 2), cb3 = (cb3 == 2) ? 0 : cb3 + 1) {
       const int rem = t - fdiv(t, p.d_mn) * (p.m_tiles * p.n_tiles);
       const int mt = fdiv(rem, p.d_nt);
       const int nt = rem - mt * p.n_tiles;
@@ -548,11 +550,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         th = fdiv(r_wh, p.d_tw);
         tw = r_wh - th * p.tiles_w;
       }
-      uint8_t* cbuf = cstage0 + (size_t)(p.nbuf > 1 ? (it & 1) : 0) * p.cbytes;
+      const int cbi = p.nbuf == 3 ? cb3 : (p.nbuf > 1 ? (it & 1) : 0);
+      uint8_t* cbuf = cstage0 + (size_t)cbi * p.cbytes;
       if (staged) {
         // the TMA store that last read this staging buffer must have finished reading it
         if (et == 0) {
-          if (p.res_tma && p.nbuf > 1) {
+          if (p.res_tma && p.nbuf == 3) {
+            // Three staging buffers (128-wide tiles): the store of tile it-1 keeps draining in the background while
+            // the residual of tile it+1 goes into the buffer store it-2 has left -- a full tile of prefetch distance
+            // and no drain stall (with two buffers the wait below serialised every store with the next epilogue:
+            // 16 % of the warp samples in r02b_gemm_cases.ncu-rep, launch 1).
+            tma_store_wait_read<1>();
+            if (it == 0) issue_residual(t, 0);
+            if (t + (int)gridDim.x < total_tiles) issue_residual(t + gridDim.x, cb3 == 2 ? 0 : cb3 + 1);
+          } else if (p.res_tma && p.nbuf > 1) {
             // Residual prefetch ONE FULL TILE ahead: this tile's residual was requested at the top of the previous
             // iteration; the next tile's goes into the other buffer now.  That buffer was last read by the store issued
             // at the end of the previous iteration, so it has to drain first (wait_read<0>, a few hundred cycles for a
@@ -576,9 +587,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(&tfull_bar[as], (it >> 1) & 1);
       tc_fence_after();
       if (p.res_tma) {
-        const int bi = p.nbuf > 1 ? (it & 1) : 0;
-        const int uses = p.nbuf > 1 ? (it >> 1) : it;
-        mbar_wait(&res_bar[bi], uses & 1);
+        const int uses = p.nbuf == 3 ? cwrap : (p.nbuf > 1 ? (it >> 1) : it);
+        mbar_wait(&res_bar[cbi], uses & 1);
       }
 
       // ---------------- phase 1: TMEM -> registers -> fp32 epilogue math -> swizzled bf16 staging (or fp32 global)
@@ -720,12 +730,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int r4 = 0; r4 < 4; ++r4) {
               const int r = rb + r4;
               const uint4 raw = lds128(cp + r * 128 + ((c8 ^ ((r0 + r) & 7)) << 4));
-              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+              float f[8];
+              unpack8(*reinterpret_cast<const bf16x8*>(&raw), f);
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float2 f = __bfloat1622float2(h2[i]);
-                st_s[i] = __fadd2_rn(st_s[i], f);
-                st_q[i] = __ffma2_rn(f, f, st_q[i]);
+              for (int i = 0; i < 8; ++i) {
+                st_s[i] += f[i];
+                st_q[i] += f[i] * f[i];
               }
             }
           }
@@ -857,6 +867,10 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
       if (t256 < 100) bn = 128;
     }
   }
+  // dgrad + shortcut GEMMs (bf16 output, TMA-loadable residual): 128-wide tiles leave room for THREE staging buffers
+  const bool res_tma_ok = !g->out_f32 && g->residual != nullptr && g->ldr % 8 == 0 &&
+                          (reinterpret_cast<uintptr_t>(g->residual) & 15) == 0;
+  if (g->tile_n == 0 && res_tma_ok && bn == 256 && g->N % 128 == 0) bn = 128;
   if (bn < 16 || bn > 256 || bn % 16 != 0 || (p.b_mn && bn % 64 != 0))
     return set_error(VTX_EINVAL, "vtx_gemm: bad tile_n %d", bn);
   p.bn = bn;
@@ -989,6 +1003,8 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
     if (p.cbytes) {
       const int st2 = (budget - 2 * p.cbytes) / p.stage_bytes;
       if (st2 >= 4 || (st2 >= 2 && st2 >= kb_tile)) { p.nbuf = 2; st = st2; }
+      const int st3 = (budget - 3 * p.cbytes) / p.stage_bytes;
+      if (res_tma_ok && p.nbuf == 2 && st3 >= 3) { p.nbuf = 3; st = st3; }
     }
     if (st == 0) st = (budget - p.nbuf * p.cbytes) / p.stage_bytes;
     if (st > kMaxStages) st = kMaxStages;
