@@ -194,8 +194,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* empty_bar = bars + kMaxStages;       // [kMaxStages]
   uint64_t* tfull_bar = bars + 2 * kMaxStages;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;          // [2]
-  uint64_t* res_bar = tempty_bar + 2;            // [3] residual tile landed in staging buffer b
-  uint64_t* bst_bar = res_bar + 3;               // [1] stationary weights landed (mode 3)
+  uint64_t* res_bar = tempty_bar + 2;            // [2] residual tile landed in staging buffer b
+  uint64_t* bst_bar = res_bar + 2;               // [1] stationary weights landed (mode 3)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bst_bar + 1);
   uint8_t* smem = base + kCtrlBytes;                       // stage ring (1024-aligned)
   uint8_t* bstat = smem + p.stages * p.stage_bytes;        // mode 3: stationary weights [9 taps][bn rows][128 B]
@@ -223,7 +223,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&tempty_bar[i], kEpiThreads);
       mbar_init(&res_bar[i], 1);
     }
-    mbar_init(&res_bar[2], 1);
     mbar_init(bst_bar, 1);
     fence_mbar_init();
   }
@@ -536,8 +535,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_before();
       }
     }
-    int cb3 = 0, cwrap = 0;  // three-buffer residual pipeline: buffer index it % 3 and its use count it / 3
-    for (int t = blockIdx.x; t < total_tiles && p.mode != 4; t += gridDim.x, ++it, cwrap += (cb3 == 2), cb3 = (cb3 == 2) ? 0 : cb3 + 1) {
+    for (int t = blockIdx.x; t < total_tiles && p.mode != 4; t += gridDim.x, ++it) {
       const int rem = t - fdiv(t, p.d_mn) * (p.m_tiles * p.n_tiles);
       const int mt = fdiv(rem, p.d_nt);
       const int nt = rem - mt * p.n_tiles;
@@ -550,25 +548,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         th = fdiv(r_wh, p.d_tw);
         tw = r_wh - th * p.tiles_w;
       }
-      const int cbi = p.nbuf == 3 ? cb3 : (p.nbuf > 1 ? (it & 1) : 0);
+      const int cbi = p.nbuf > 1 ? (it & 1) : 0;
       uint8_t* cbuf = cstage0 + (size_t)cbi * p.cbytes;
       if (staged) {
         // the TMA store that last read this staging buffer must have finished reading it
         if (et == 0) {
-          if (p.res_tma && p.nbuf == 3) {
-            // Three staging buffers (128-wide tiles): the store of tile it-1 keeps draining in the background while
-            // the residual of tile it+1 goes into the buffer store it-2 has left -- a full tile of prefetch distance
-            // and no drain stall (with two buffers the wait below serialised every store with the next epilogue:
-            // 16 % of the warp samples in r02b_gemm_cases.ncu-rep, launch 1).
-            tma_store_wait_read<1>();
-            if (it == 0) issue_residual(t, 0);
-            if (t + (int)gridDim.x < total_tiles) issue_residual(t + gridDim.x, cb3 == 2 ? 0 : cb3 + 1);
-          } else if (p.res_tma && p.nbuf > 1) {
+          if (p.res_tma && p.nbuf > 1) {
             // Residual prefetch ONE FULL TILE ahead: this tile's residual was requested at the top of the previous
             // iteration; the next tile's goes into the other buffer now.  That buffer was last read by the store issued
             // at the end of the previous iteration, so it has to drain first (wait_read<0>, a few hundred cycles for a
             // 64 KB tile) -- the round-2 profile (r02_gemm_cases.ncu-rep, launch 1) showed 25 % of all warp samples of
-            // the dgrad+shortcut GEMMs waiting on a residual requested less than a stats-pass before its use.
+            // the dgrad+shortcut GEMMs waiting on a residual requested less than a stats-pass before its use.  (A third
+            // staging buffer on 128-wide tiles, which removes the drain wait too, measured SLOWER: 305 vs 256 us.)
             tma_store_wait_read<0>();
             if (it == 0) issue_residual(t, 0);
             if (t + (int)gridDim.x < total_tiles) issue_residual(t + gridDim.x, (it + 1) & 1);
@@ -587,7 +578,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(&tfull_bar[as], (it >> 1) & 1);
       tc_fence_after();
       if (p.res_tma) {
-        const int uses = p.nbuf == 3 ? cwrap : (p.nbuf > 1 ? (it >> 1) : it);
+        const int uses = p.nbuf > 1 ? (it >> 1) : it;
         mbar_wait(&res_bar[cbi], uses & 1);
       }
 
@@ -854,23 +845,30 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
     const int gran = p.b_mn ? 64 : 16;
     if (g->N >= 256) bn = 256;
     else bn = ((g->N + gran - 1) / gran) * gran;
-    if (p.b_mn && bn == 256 && g->N % 256 != 0) {
-      // MN-major B is fetched in 64-column atoms: a 192-wide tile wastes nothing on N = 576 / 1152 (3x3 wgrads)
-      if (g->N % 192 == 0) bn = 192;
-      else if (g->N % 128 == 0) bn = 128;
-    }
-    // prefer 128-wide tiles when that fills the machine noticeably better
-    if (bn == 256) {
+    // Heuristics from the round-2 sweep (scripts/tune_gemm.py, profiles/r02c_tune_gemm.txt):
+    //  * N = 1152 weight gradients (3x3, 128 channels) run 256-wide tiles even though the fifth tile is half empty:
+    //    every N-tile re-reads the dy operand, and 5 tiles beat 6 (72 vs 109 us for the implicit wgrad);
+    //  * problems with few tiles pick the width that minimises  rounds x (width + per-tile overhead): N = 512 with 98
+    //    M-tiles (layer4 at batch 256) runs 192-wide tiles -- 294 tiles = two full rounds -- instead of 196 256-wide ones;
+    //  * tiny problems (under ~100 tiles of 256) use 128-wide tiles to fill the machine.
+    if (bn == 256 && split_k == 1) {
       const long mt = (g->M + kBM - 1) / kBM;
-      const long t256 = mt * ((g->N + 255) / 256) * split_k;
-      if (t256 < 148 && g->N % 256 != 0 && g->N <= 2048) bn = 128;
-      if (t256 < 100) bn = 128;
+      const long t256 = mt * ((g->N + 255) / 256);
+      const int sms = vtx_num_sms();
+      if (t256 < 100 || (t256 < sms && g->N % 256 != 0 && g->N <= 2048)) {
+        bn = 128;
+      } else if (t256 < 3L * sms && p.mode <= 1) {
+        long best_cost = 0;
+        int best_bn = 256;
+        for (int cand = 256; cand >= 128; cand -= 64) {
+          const long tiles = mt * ((g->N + cand - 1) / cand);
+          const long cost = ((tiles + sms - 1) / sms) * (cand + 64);
+          if (best_cost == 0 || cost < best_cost) { best_cost = cost; best_bn = cand; }
+        }
+        bn = best_bn;
+      }
     }
   }
-  // dgrad + shortcut GEMMs (bf16 output, TMA-loadable residual): 128-wide tiles leave room for THREE staging buffers
-  const bool res_tma_ok = !g->out_f32 && g->residual != nullptr && g->ldr % 8 == 0 &&
-                          (reinterpret_cast<uintptr_t>(g->residual) & 15) == 0;
-  if (g->tile_n == 0 && res_tma_ok && bn == 256 && g->N % 128 == 0) bn = 128;
   if (bn < 16 || bn > 256 || bn % 16 != 0 || (p.b_mn && bn % 64 != 0))
     return set_error(VTX_EINVAL, "vtx_gemm: bad tile_n %d", bn);
   p.bn = bn;
@@ -1003,8 +1001,6 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
     if (p.cbytes) {
       const int st2 = (budget - 2 * p.cbytes) / p.stage_bytes;
       if (st2 >= 4 || (st2 >= 2 && st2 >= kb_tile)) { p.nbuf = 2; st = st2; }
-      const int st3 = (budget - 3 * p.cbytes) / p.stage_bytes;
-      if (res_tma_ok && p.nbuf == 2 && st3 >= 3) { p.nbuf = 3; st = st3; }
     }
     if (st == 0) st = (budget - p.nbuf * p.cbytes) / p.stage_bytes;
     if (st > kMaxStages) st = kMaxStages;

@@ -151,9 +151,15 @@ def gemm(A, B, D, M, N, K, *, lda=None, ldb=None, ldd=None, a_mn=0, b_mn=0, bias
 
 
 def split_k_for(m_tiles_x_n_tiles, k_blocks, sms=None):
-    """Split-K factor that fills the machine for reduction-heavy (wgrad) GEMMs."""
+    """Split-K factor for reduction-heavy (wgrad) GEMMs; thresholds from the round-2 sweep (scripts/tune_gemm.py)."""
     sms = sms or num_sms()
-    if m_tiles_x_n_tiles >= sms:
-        return 1
+    t = m_tiles_x_n_tiles
+    if t >= sms:
+        # one to three rounds of long-K tiles (vocabulary wgrad: 316 tiles x 120 k-blocks): two splits balance the tail
+        return 2 if (t < 3 * sms and k_blocks >= 64) else 1
+    if sms // t == 1:
+        # 75..147 tiles: a single under-filled round; four splits measured best at 96 tiles (3H x H wgrad: 98 -> 60 us),
+        # none at 128 tiles (FFN wgrads)
+        return 4 if (t <= 0.7 * sms and k_blocks >= 16) else 1
     # about one wave of tiles: every extra split multiplies the fp32 atomic traffic of the epilogue
-    return max(1, min(max(1, k_blocks // 4), sms // m_tiles_x_n_tiles))
+    return max(1, min(max(1, k_blocks // 4), sms // t))
