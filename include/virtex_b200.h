@@ -74,6 +74,10 @@ typedef struct VtxGemm {
                             x 16 channels), B = packed weights [64, 256] (vtx_stem_s2d_w_pack), D [n*h*w, 64] NHWC
                             (torchvision resnet.py:197 conv1 forward, BN statistics through `stats`),
                         6 = stem wgrad: A = dy [conv_n, conv_h, conv_w, 64], B = S; D [64, 256] fp32 += (atomic) */
+  int32_t conv_stride;          /* conv_mode 1 / 2 only: 0 or 1 = unit stride; 2 = stride-2 convolution -- conv_h / conv_w
+                                   are the INPUT extent, outputs (M, K of the wgrad) run over (h-1)/2+1 x (w-1)/2+1; the
+                                   gather uses TMA traversal strides (torchvision resnet.py:133-138, 239-243) */
+  int32_t conv_taps;            /* 0 or 9 = 3x3 / pad 1 taps; 1 = a single tap (1x1 / pad 0: the strided downsample) */
   const uint8_t* residual_mask; /* optional (plain bf16 GEMMs, N % 32 == 0): bit (m, n) of a [M, N/8] bit mask in the layout
                                    vtx_bn_act writes; residual[m, n] is added only where the bit is set.  This is the
                                    shortcut gradient dz = dOut * [block output > 0] of a bottleneck without dz ever being

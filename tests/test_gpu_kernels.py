@@ -421,3 +421,55 @@ def test_gemm_masked_residual_epilogue():
         D2 = torch.empty(M, N, dtype=BF16, device="cuda")
         ops.gemm(A, B, D2, M, N, K, b_mn=b_mn, residual=R)  # no mask: plain residual add, unchanged
         assert rel(D2, A.float() @ (B.float() if b_mn else B.float().t()) + R.float()) < 4e-3
+
+
+# ------------------------------------------------------------------------------------------------ strided implicit convs
+@pytest.mark.parametrize("NI,H,W,C,Cout", [(8, 28, 28, 128, 128), (4, 14, 14, 256, 256), (6, 13, 15, 64, 128)])
+def test_strided_implicit_conv3x3_fprop_and_wgrad(NI, H, W, C, Cout):
+    """3x3 / stride 2 / pad 1 (torchvision resnet.py:133-138, first block of layers 2-4) as implicit GEMMs whose gather
+    uses TMA traversal strides: fprop (+ BN statistics) vs F.conv2d, weight gradient vs conv2d_weight."""
+    _need_cuda()
+    ops = _ops()
+    g = torch.Generator().manual_seed(H * W + C)
+    x = (torch.randn(NI, H, W, C, generator=g) * 0.5).bfloat16().cuda()
+    w = (torch.randn(Cout, C, 3, 3, generator=g) * 0.05).bfloat16().cuda()
+    wp = w.permute(0, 2, 3, 1).reshape(Cout, 9 * C).contiguous()
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    M = NI * Ho * Wo
+    y = torch.full((M + 16, Cout), 7.0, dtype=BF16, device="cuda")
+    st = torch.zeros(2, Cout, device="cuda")
+    ops.gemm(x, wp, y, M, Cout, 9 * C, lda=C, stats=st, conv=(NI, H, W, C), conv_mode=1, conv_stride=2)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), stride=2, padding=1).permute(0, 2, 3, 1).reshape(M, Cout)
+    assert rel(y[:M], ref) < 4e-3
+    assert torch.all(y[M:] == 7.0)
+    assert rel(st[0], y[:M].float().sum(0)) < 2e-3 and rel(st[1], (y[:M].float() ** 2).sum(0)) < 2e-3
+    dy = (torch.randn(NI, Ho, Wo, Cout, generator=g) * 0.5).bfloat16().cuda()
+    dw = torch.zeros(Cout, 9 * C, device="cuda")
+    ops.gemm(dy, x, dw, Cout, 9 * C, M, lda=Cout, ldb=C, atomic=True, out_f32=True, split_k=4, conv=(NI, H, W, C),
+             conv_mode=2, conv_stride=2)
+    gref = torch.nn.grad.conv2d_weight(x.float().permute(0, 3, 1, 2), (Cout, C, 3, 3), dy.float().permute(0, 3, 1, 2),
+                                       stride=2, padding=1)
+    assert rel(dw.view(Cout, 3, 3, C).permute(0, 3, 1, 2), gref) < 2e-3
+
+
+@pytest.mark.parametrize("NI,H,W,C,Cout", [(8, 28, 28, 256, 512), (5, 7, 9, 64, 128)])
+def test_strided_downsample_one_tap_fprop_and_wgrad(NI, H, W, C, Cout):
+    """1x1 / stride 2 downsample (resnet.py:239-243) as a one-tap implicit GEMM over the strided view of x."""
+    _need_cuda()
+    ops = _ops()
+    g = torch.Generator().manual_seed(C + H)
+    x = (torch.randn(NI, H, W, C, generator=g) * 0.5).bfloat16().cuda()
+    w = (torch.randn(Cout, C, generator=g) * 0.05).bfloat16().cuda()
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    M = NI * Ho * Wo
+    y = torch.empty(M, Cout, dtype=BF16, device="cuda")
+    st = torch.zeros(2, Cout, device="cuda")
+    ops.gemm(x, w, y, M, Cout, C, lda=C, stats=st, conv=(NI, H, W, C), conv_mode=1, conv_stride=2, conv_taps=1)
+    xs = x[:, ::2, ::2].reshape(M, C).float()
+    assert rel(y, xs @ w.float().t()) < 4e-3
+    assert rel(st[0], y.float().sum(0)) < 2e-3
+    dy = (torch.randn(M, Cout, generator=g) * 0.5).bfloat16().cuda()
+    dw = torch.zeros(Cout, C, device="cuda")
+    ops.gemm(dy, x, dw, Cout, C, M, lda=Cout, ldb=C, atomic=True, out_f32=True, split_k=2, conv=(NI, H, W, C),
+             conv_mode=2, conv_stride=2, conv_taps=1)
+    assert rel(dw, dy.float().t() @ xs) < 2e-3

@@ -98,6 +98,7 @@ struct GemmKParams {
   const uint8_t* res_mask;   // optional bit mask [M, N/8]: the residual of (row, col) is added only where its bit is set
   float* stats;
   int taps_w, pad, ntaps;    // taps per kernel row / zero padding / number of taps of the implicit conv (3, 1, 9 for 3x3)
+  int cstride;               // spatial stride of the implicit conv (1 or 2): output position w reads input cstride*w + kw - pad
   // division by the launch-invariant tile-schedule extents as multiply-high + shift (a runtime integer division costs
   // ~25 dependent instructions; the schedule decode was ~13 % of the epilogue's instructions on the short-K convs)
   FastDiv d_mn, d_nt, d_tw, d_twh, d_cpb, d_taps;
@@ -315,7 +316,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int tap = fdiv(kb, p.d_cpb);
             const int cb = kb - tap * p.cpb;
             const int kh = fdiv(tap, p.d_taps), kw = tap - kh * KP_TAPS_W;
-            tma_load_4d(sA, &tmA, &full_bar[stage], cb * 64, w0 + kw - KP_PAD, h0 + kh - KP_PAD, n0);
+            tma_load_4d(sA, &tmA, &full_bar[stage], cb * 64, p.cstride * w0 + kw - KP_PAD, p.cstride * h0 + kh - KP_PAD, n0);
             tma_load_2d(sB, &tmB, &full_bar[stage], kb * kBK, nt * p.bn);
           } else {
             // wgrad: reduction block kb is a spatial box of 64 output positions
@@ -333,7 +334,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const int kh = fdiv(tap, p.d_taps), kw = tap - kh * KP_TAPS_W;
               // atoms past the 9 taps are loaded fully out of bounds (zero fill) to keep the tx count fixed
               const int nn = tap < KP_NTAPS ? bn0 : p.cN + 1;
-              tma_load_4d(sB + j * 8192, &tmB, &full_bar[stage], cb * 64, bw0 + kw - KP_PAD, bh0 + kh - KP_PAD, nn);
+              tma_load_4d(sB + j * 8192, &tmB, &full_bar[stage], cb * 64, p.cstride * bw0 + kw - KP_PAD,
+                          p.cstride * bh0 + kh - KP_PAD, nn);
             }
           }
           if (++stage == nstages) { stage = 0; phase ^= 1; }
@@ -766,8 +768,10 @@ static PFN_encodeTiled get_encode() {
 }
 
 // bf16 tensor map of rank 2 or 4; dims[0] is the contiguous dimension; strides in elements for dims 1..rank-1.
+// estr (optional): TMA traversal strides per dimension (1..8): the box then covers box[i] elements of the tensor and
+// delivers every estr[i]-th of them, i.e. ceil(box[i] / estr[i]) elements land in shared memory (strided convolutions).
 static int make_tmap(CUtensorMap* tm, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_elems,
-                     const uint32_t* box) {
+                     const uint32_t* box, const uint32_t* estr = nullptr) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) return set_error(VTX_ECUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t gdim[5];
@@ -777,7 +781,7 @@ static int make_tmap(CUtensorMap* tm, const void* ptr, int rank, const uint64_t*
   for (int i = 0; i < rank; ++i) {
     gdim[i] = dims[i];
     bx[i] = box[i];
-    es[i] = 1;
+    es[i] = estr ? estr[i] : 1;
   }
   for (int i = 0; i < rank - 1; ++i) gstr[i] = strides_elems[i] * 2;
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return set_error(VTX_EINVAL, "TMA base pointer not 16B aligned");
@@ -836,7 +840,15 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
   const bool stem = g->conv_mode == 5 || g->conv_mode == 6;
   p.taps_w = 3; p.pad = 1; p.ntaps = 9;
   if (stem) { p.mode = g->conv_mode == 5 ? 1 : 2; p.taps_w = 1; p.pad = 0; p.ntaps = 4; }
-  const int ntaps = stem ? 4 : 9;
+  // conv_taps = 1: a 1x1 convolution through the gather path (only useful with conv_stride = 2: the strided downsample)
+  const bool one_tap = !stem && g->conv_taps == 1;
+  if (one_tap) { p.taps_w = 1; p.pad = 0; p.ntaps = 1; }
+  const int cstride = (g->conv_stride == 2 && (p.mode == 1 || p.mode == 2) && !stem) ? 2 : 1;
+  if (g->conv_stride != 0 && g->conv_stride != 1 && cstride != 2)
+    return set_error(VTX_EINVAL, "vtx_gemm: conv_stride 2 is supported for conv_mode 1 / 2 only");
+  if (g->conv_taps != 0 && g->conv_taps != 1 && g->conv_taps != 9) return set_error(VTX_EINVAL, "vtx_gemm: conv_taps must be 0, 1 or 9");
+  p.cstride = cstride;
+  const int ntaps = stem ? 4 : one_tap ? 1 : 9;
   if (p.mode == 1) { p.a_mn = 0; p.b_mn = 0; }
   if (p.mode == 2 || p.mode == 4) { p.a_mn = 1; p.b_mn = 1; }
   // ---- tile_n
@@ -907,18 +919,21 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
       if ((rc = make_tmap(&tmB, g->B, 2, dims, str, box)) != VTX_OK) return rc;
     }
   } else {
-    const int C = g->conv_c, H = g->conv_h, W = g->conv_w, NI = g->conv_n;
+    // conv_h / conv_w are the INPUT extent of the activation operand; with stride 2 the tile schedule, the output tensor
+    // map and the row masks run over the OUTPUT extent (H - 1) / 2 + 1 (3x3 / pad 1 and 1x1 / pad 0 alike)
+    const int C = g->conv_c, Hin = g->conv_h, Win = g->conv_w, NI = g->conv_n;
+    const int H = (Hin - 1) / cstride + 1, W = (Win - 1) / cstride + 1;
     if (C <= 0 || C % 64 != 0) return set_error(VTX_EINVAL, "vtx_gemm: implicit conv needs channels %% 64 == 0");
     p.cH = H; p.cW = W; p.cN = NI; p.cpb = C / 64;
     // halo-reuse variant (mode 3): C = 64 -> 64 convs whose 9 weight taps (72 KB) stay resident in shared memory and
     // whose input is fetched ONCE per 8 x 16 output tile as an 18 x 16 halo tile (instead of once per tap)
-    const bool halo = p.mode == 1 && !stem && C == 64 && g->N == 64 && bn == 64 && !g->out_f32 &&
-                      g->residual == nullptr && getenv("VTX_GEMM_NO_HALO") == nullptr;
+    const bool halo = p.mode == 1 && !stem && !one_tap && cstride == 1 && C == 64 && g->N == 64 && bn == 64 &&
+                      !g->out_f32 && g->residual == nullptr && getenv("VTX_GEMM_NO_HALO") == nullptr;
     // the activation operand of the implicit convs: [NI, H, W, C] NHWC; for the stem view [NI, H + 3, W + 3, 16] whose
     // "channel" extent is 4 pixels x 16 channels and whose W stride is ONE pixel (overlapping rows, legal for TMA)
-    const uint64_t xdims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)(stem ? H + 3 : H), (uint64_t)NI};
-    const uint64_t xstr[3] = {(uint64_t)(stem ? 16 : C), stem ? (uint64_t)(W + 3) * 16 : (uint64_t)W * C,
-                              stem ? (uint64_t)(H + 3) * (W + 3) * 16 : (uint64_t)H * W * C};
+    const uint64_t xdims[4] = {(uint64_t)C, (uint64_t)Win, (uint64_t)(stem ? Hin + 3 : Hin), (uint64_t)NI};
+    const uint64_t xstr[3] = {(uint64_t)(stem ? 16 : C), stem ? (uint64_t)(Win + 3) * 16 : (uint64_t)Win * C,
+                              stem ? (uint64_t)(Hin + 3) * (Win + 3) * 16 : (uint64_t)Hin * Win * C};
     int bw, bh, bnn;
     choose_box(H, W, p.mode == 1 ? 128 : 64, &bw, &bh, &bnn);
     if (halo) {
@@ -955,8 +970,10 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
         return set_error(VTX_EUNSUPPORTED, "vtx_gemm: conv_mode 5 with stats needs an output size tiled exactly by %dx%d", bw, bh);
       p.m_tiles = p.tiles_w * p.tiles_h * tiles_n;
       p.kb_total = halo ? 1 : ntaps * p.cpb;
-      uint32_t box[4] = {64, (uint32_t)(halo ? p.halo_w : bw), (uint32_t)(halo ? kHaloH : bh), (uint32_t)bnn};
-      if ((rc = make_tmap(&tmA, g->A, 4, xdims, xstr, box)) != VTX_OK) return rc;
+      uint32_t box[4] = {64, (uint32_t)(halo ? p.halo_w : bw * cstride), (uint32_t)(halo ? kHaloH : bh * cstride),
+                         (uint32_t)bnn};
+      const uint32_t es[4] = {1, (uint32_t)cstride, (uint32_t)cstride, 1};
+      if ((rc = make_tmap(&tmA, g->A, 4, xdims, xstr, box, cstride > 1 ? es : nullptr)) != VTX_OK) return rc;
       uint64_t bd[2] = {(uint64_t)g->K, (uint64_t)g->N};
       uint64_t bs[1] = {(uint64_t)g->ldb};
       uint32_t bb[2] = {64, (uint32_t)bn};
@@ -973,7 +990,9 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
       uint64_t as[3] = {(uint64_t)Cout, (uint64_t)W * Cout, (uint64_t)H * W * Cout};
       uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bh, (uint32_t)bnn};
       if ((rc = make_tmap(&tmA, g->A, 4, ad, as, box)) != VTX_OK) return rc;
-      if ((rc = make_tmap(&tmB, g->B, 4, xdims, xstr, box)) != VTX_OK) return rc;
+      uint32_t xbox[4] = {64, (uint32_t)(bw * cstride), (uint32_t)(bh * cstride), (uint32_t)bnn};
+      const uint32_t es[4] = {1, (uint32_t)cstride, (uint32_t)cstride, 1};
+      if ((rc = make_tmap(&tmB, g->B, 4, xdims, xstr, xbox, cstride > 1 ? es : nullptr)) != VTX_OK) return rc;
     }
   }
   p.k_splits = split_k;
@@ -1014,12 +1033,12 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
                (reinterpret_cast<uintptr_t>(g->residual) & 15) == 0) ? 1 : 0;
   if (p.cbytes) {
     if (p.mode & 1) {
-      uint64_t dd[4] = {(uint64_t)g->N, (uint64_t)g->conv_w, (uint64_t)g->conv_h, (uint64_t)g->conv_n};
-      uint64_t ds[3] = {(uint64_t)g->ldd, (uint64_t)g->conv_w * g->ldd, (uint64_t)g->conv_h * g->conv_w * g->ldd};
+      uint64_t dd[4] = {(uint64_t)g->N, (uint64_t)p.cW, (uint64_t)p.cH, (uint64_t)g->conv_n};
+      uint64_t ds[3] = {(uint64_t)g->ldd, (uint64_t)p.cW * g->ldd, (uint64_t)p.cH * p.cW * g->ldd};
       uint32_t db[4] = {64, 1u << p.lbw, 1u << p.lbh, 1u << p.lbn};
       if ((rc = make_tmap(&tmD, g->D, 4, dd, ds, db)) != VTX_OK) return rc;
       if (p.res_tma) {
-        uint64_t rs[3] = {(uint64_t)g->ldr, (uint64_t)g->conv_w * g->ldr, (uint64_t)g->conv_h * g->conv_w * g->ldr};
+        uint64_t rs[3] = {(uint64_t)g->ldr, (uint64_t)p.cW * g->ldr, (uint64_t)p.cH * p.cW * g->ldr};
         if ((rc = make_tmap(&tmR, g->residual, 4, dd, rs, db)) != VTX_OK) return rc;
       }
     } else {

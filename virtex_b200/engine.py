@@ -341,8 +341,10 @@ class Engine:
             y2 = ws.get(name + ".y2", (Mout, planes), BF16)
             st2 = self._slab_take(2 * planes) if training else None
             w2 = self._packed[name + ".conv2.weight"]
-            if stride == 1 and planes % 64 == 0:
-                gemm(a1, w2, y2, Mout, planes, 9 * planes, lda=planes, stats=st2, conv=(B, Hc, Wc, planes), conv_mode=1)
+            if planes % 64 == 0:
+                # implicit GEMM: 4-D TMA boxes gather the taps (zero fill = padding); stride 2 through TMA traversal strides
+                gemm(a1, w2, y2, Mout, planes, 9 * planes, lda=planes, stats=st2, conv=(B, Hc, Wc, planes), conv_mode=1,
+                     conv_stride=stride)
                 rec["cols2"] = None
             else:
                 cols2 = ws.get(name + ".cols2", (Mout, 9 * planes), BF16)
@@ -361,14 +363,20 @@ class Engine:
             # the bf16 output twice (bn_bwd_reduce and bn_bwd_apply)
             m3 = ws.get(name + ".m3", (Mout, C4 // 8), torch.uint8) if training else None
             if blk.downsample is not None:
+                yd = ws.get(name + ".yd", (Mout, C4), BF16)
+                std = self._slab_take(2 * C4) if training else None
+                wd = self.W(name + ".downsample.0.weight").view(C4, Cin)
                 if stride == 1:
                     xs = x
+                    gemm(xs, wd, yd, Mout, C4, Cin, stats=std)
+                elif Cin % 64 == 0:
+                    xs = None  # strided 1x1 conv = one-tap implicit GEMM over x (no subsampled copy)
+                    gemm(x, wd, yd, Mout, C4, Cin, lda=Cin, stats=std, conv=(B, Hc, Wc, Cin), conv_mode=1,
+                         conv_stride=stride, conv_taps=1)
                 else:
                     xs = ws.get(name + ".xs", (Mout, Cin), BF16)
                     call("vtx_subsample", x.data_ptr(), xs.data_ptr(), B, Hc, Wc, Cin, stride, s)
-                yd = ws.get(name + ".yd", (Mout, C4), BF16)
-                std = self._slab_take(2 * C4) if training else None
-                gemm(xs, self.W(name + ".downsample.0.weight").view(C4, Cin), yd, Mout, C4, Cin, stats=std)
+                    gemm(xs, wd, yd, Mout, C4, Cin, stats=std)
                 bnpd = self._bn_fwd(yd, name + ".downsample.1", Mout, C4, training, std)
                 bnp3 = self._bn_act_fwd(y3, name + ".bn3", Mout, C4, training, st3, out, res=yd, bnp_res=bnpd, mask=m3)
                 rec.update(xs=xs, yd=yd, bnpd=bnpd)
@@ -461,7 +469,7 @@ class Engine:
             dwp = self._dwp[name + ".conv2"].view(planes, 9 * planes)
             da1 = ws.get("bwd.da1", (Min, planes), BF16)
             if rec["cols2"] is None:
-                if planes == 64:
+                if planes == 64 and stride == 1:
                     # halo-reuse wgrad: D[(tap, cin), cout], accumulated in TMEM over all spatial tiles of a CTA
                     gemm(dy2, rec["a1"], dwp, 9 * planes, planes, Mout, atomic=True, lda=planes, ldb=planes, ldd=planes,
                          conv=(B, Hc, Wc, planes), conv_mode=4, out_f32=True)
@@ -469,9 +477,14 @@ class Engine:
                     tiles = ((planes + 127) // 128) * ((9 * planes + 255) // 256)
                     sk = ops.split_k_for(tiles, (Mout + 63) // 64)
                     gemm(dy2, rec["a1"], dwp, planes, 9 * planes, Mout, atomic=True, split_k=sk, lda=planes,
-                         ldb=planes, conv=(B, Hc, Wc, planes), conv_mode=2, out_f32=True)
-                gemm(dy2, self._packed[name + ".conv2.weight#dgrad"], da1, Min, planes, 9 * planes, lda=planes,
-                     conv=(B, Hc, Wc, planes), conv_mode=1)
+                         ldb=planes, conv=(B, Hc, Wc, planes), conv_mode=2, out_f32=True, conv_stride=stride)
+                if stride == 1:
+                    gemm(dy2, self._packed[name + ".conv2.weight#dgrad"], da1, Min, planes, 9 * planes, lda=planes,
+                         conv=(B, Hc, Wc, planes), conv_mode=1)
+                else:  # strided dgrad: per-tap gradients by a plain GEMM, scattered back by col2im
+                    dcols = ws.get("bwd.dcols", (Mout, 9 * planes), BF16)
+                    gemm(dy2, self._packed[name + ".conv2.weight"], dcols, Mout, 9 * planes, planes, b_mn=1)
+                    call("vtx_col2im3x3", dcols.data_ptr(), da1.data_ptr(), B, Hc, Wc, planes, stride, s)
             else:
                 self._wgrad(dy2, rec["cols2"], dwp, planes, 9 * planes, Mout)
                 dcols = ws.get("bwd.dcols", (Mout, 9 * planes), BF16)
@@ -487,7 +500,13 @@ class Engine:
             w1 = self.W(name + ".conv1.weight").view(planes, Cin)
             if rec["has_ds"]:
                 wd = self.W(name + ".downsample.0.weight").view(C4, Cin)
-                self._wgrad(dyd, rec["xs"], self.G(name + ".downsample.0.weight"), C4, Cin, Mout)
+                if rec["xs"] is not None:
+                    self._wgrad(dyd, rec["xs"], self.G(name + ".downsample.0.weight"), C4, Cin, Mout)
+                else:  # one-tap implicit wgrad over the strided view of x, straight into the [C4, Cin, 1, 1] gradient
+                    tiles = ((C4 + 127) // 128) * ((Cin + 255) // 256)
+                    gemm(dyd, rec["x"], self.G(name + ".downsample.0.weight").view(C4, Cin), C4, Cin, Mout, atomic=True,
+                         split_k=ops.split_k_for(tiles, (Mout + 63) // 64), lda=C4, ldb=Cin, conv=(B, Hc, Wc, Cin),
+                         conv_mode=2, conv_stride=stride, conv_taps=1, out_f32=True)
                 gemm(dy1, w1, dx, Min, Cin, planes, b_mn=1)
                 if stride == 1:
                     gemm(dyd, wd, dx, Min, Cin, C4, b_mn=1, residual=dx)

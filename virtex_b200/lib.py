@@ -30,6 +30,7 @@ class VtxGemm(ctypes.Structure):
         ("out_f32", c_i32), ("atomic", c_i32), ("act", c_i32), ("split_k", c_i32), ("tile_n", c_i32),
         ("alpha", c_f32),
         ("conv_n", c_i32), ("conv_h", c_i32), ("conv_w", c_i32), ("conv_c", c_i32), ("conv_mode", c_i32),
+        ("conv_stride", c_i32), ("conv_taps", c_i32),
         ("residual_mask", c_void_p),
     ]
 

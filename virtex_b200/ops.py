@@ -120,7 +120,8 @@ _gemm_struct = L.VtxGemm()
 
 
 def gemm(A, B, D, M, N, K, *, lda=None, ldb=None, ldd=None, a_mn=0, b_mn=0, bias=None, act=0, residual=None,
-         ldr=0, stats=None, atomic=False, split_k=1, tile_n=0, conv=None, conv_mode=0, out_f32=None, residual_mask=None):
+         ldr=0, stats=None, atomic=False, split_k=1, tile_n=0, conv=None, conv_mode=0, out_f32=None, residual_mask=None,
+         conv_stride=1, conv_taps=0):
     """D[M,N] = epilogue(A . B^T) through the tcgen05 kernel; see include/virtex_b200.h (VtxGemm)."""
     g = _gemm_struct
     g.A, g.B, g.D = A.data_ptr(), B.data_ptr(), D.data_ptr()
@@ -140,6 +141,7 @@ def gemm(A, B, D, M, N, K, *, lda=None, ldb=None, ldd=None, a_mn=0, b_mn=0, bias
     else:
         g.conv_n = g.conv_h = g.conv_w = g.conv_c = 0
     g.conv_mode = conv_mode
+    g.conv_stride, g.conv_taps = conv_stride, conv_taps
     if _gemm_profile is None:
         call("vtx_gemm", ctypes.addressof(g), _stream())
     else:
