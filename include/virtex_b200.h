@@ -78,6 +78,14 @@ typedef struct VtxGemm {
                                    are the INPUT extent, outputs (M, K of the wgrad) run over (h-1)/2+1 x (w-1)/2+1; the
                                    gather uses TMA traversal strides (torchvision resnet.py:133-138, 239-243) */
   int32_t conv_taps;            /* 0 or 9 = 3x3 / pad 1 taps; 1 = a single tap (1x1 / pad 0: the strided downsample) */
+  /* conv_mode 1, explicit tap grid (conv_taps_h > 0): conv_taps_h x conv_taps_w taps, tap (a, b) reads (h + a - conv_pad,
+     w + b - conv_pad); K = taps * conv_c.  With the output view below this is one parity class of a stride-2 dgrad. */
+  int32_t conv_taps_h, conv_taps_w, conv_pad;
+  /* conv_mode 1, output view (conv_out_w > 0): D is the strided sub-grid [conv_n, conv_out_h, conv_out_w, N] of a larger
+     NHWC tensor with element strides ldd_n / ldd_h / ldd_w (D points at its first element); rows of the conv_h x conv_w
+     tile grid that fall outside the view are clipped. */
+  int32_t conv_out_h, conv_out_w;
+  int64_t ldd_w, ldd_h, ldd_n;
   const uint8_t* residual_mask; /* optional (plain bf16 GEMMs, N % 32 == 0): bit (m, n) of a [M, N/8] bit mask in the layout
                                    vtx_bn_act writes; residual[m, n] is added only where the bit is set.  This is the
                                    shortcut gradient dz = dOut * [block output > 0] of a bottleneck without dz ever being
@@ -85,6 +93,8 @@ typedef struct VtxGemm {
 } VtxGemm;
 
 int vtx_gemm(const VtxGemm* g, void* stream);
+/* sizeof(VtxGemm) of the built library (a binding compares it with its own struct definition) */
+int vtx_sizeof_gemm(void);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Backbone auxiliaries (NHWC bf16 activations).  Replace cuDNN BatchNorm / ATen elementwise + pooling kernels called by
@@ -147,7 +157,7 @@ int vtx_conv_w_unpack_add(const float* dwp, float* grad, int O, int I, int KH, i
 int vtx_conv_w_unpack_add_t(const float* dwt, float* grad, int O, int I, int KH, int KW, void* stream);
 /* Batched form of the six weight-layout kernels above (and of vtx_stem_s2d_w_pack / _unpack_add): one launch executes a
    DEVICE-resident table of jobs.  kind: 0 pack, 1 pack_dgrad, 2 unpack_add, 3 unpack_add_t, 4 stem s2d pack,
-   5 stem s2d unpack_add; total = number of output elements of the job; block0 = first thread block of the job (jobs are
+   5 stem s2d unpack_add, 6 pack for parity class (KH, KW) of a stride-2 3x3 dgrad ([I, taps*O], see backbone.cu), 7 transpose of a 1x1 weight ([O, I] -> bf16 [I, O]); total = number of output elements of the job; block0 = first thread block of the job (jobs are
    sorted by block0, every block handles vtx_weight_job_block_elems() consecutive elements). */
 typedef struct VtxWeightJob {
   const void* src;

@@ -21,7 +21,7 @@ class Recorder:
 
 def _check_gemm(A, B, D, M, N, K, lda=None, ldb=None, ldd=None, a_mn=0, b_mn=0, bias=None, act=0, residual=None, ldr=0,
                 stats=None, atomic=False, split_k=1, tile_n=0, conv=None, conv_mode=0, out_f32=None, residual_mask=None,
-                conv_stride=1, conv_taps=0):
+                conv_stride=1, conv_taps=0, tap_grid=None, out_view=None, d_ptr=None):
     assert A.dtype == BF16 and B.dtype == BF16, (A.dtype, B.dtype)
     f32 = (D.dtype == F32) if out_f32 is None else bool(out_f32)
     assert D.dtype == (F32 if f32 else BF16)
@@ -38,11 +38,14 @@ def _check_gemm(A, B, D, M, N, K, lda=None, ldb=None, ldd=None, a_mn=0, b_mn=0, 
     else:
         NI, H, W, C = conv
         assert C % 64 == 0
-        taps = 1 if conv_taps == 1 else 9
+        taps = 1 if conv_taps == 1 else (tap_grid[0] * tap_grid[1] if tap_grid is not None else 9)
+        if out_view is not None:
+            assert conv_mode == 1 and residual is None and d_ptr is not None and all(v % 8 == 0 for v in out_view[2:])
+            assert D.data_ptr() <= d_ptr < D.data_ptr() + D.numel() * D.element_size()
         Ho, Wo = (H - 1) // conv_stride + 1, (W - 1) // conv_stride + 1   # conv = INPUT extent; outputs follow the stride
         if conv_mode == 1:
             assert M == NI * Ho * Wo and K == taps * C and A.numel() >= NI * H * W * C and B.numel() >= N * K
-            assert D.numel() >= (M - 1) * ldd + N
+            assert out_view is not None or D.numel() >= (M - 1) * ldd + N
         elif conv_mode == 2:
             assert N == taps * C and K == NI * Ho * Wo and A.numel() >= K * M and B.numel() >= NI * H * W * C and f32 and atomic
             assert D.numel() >= (M - 1) * ldd + N

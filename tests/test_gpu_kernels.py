@@ -473,3 +473,55 @@ def test_strided_downsample_one_tap_fprop_and_wgrad(NI, H, W, C, Cout):
     ops.gemm(dy, x, dw, Cout, C, M, lda=Cout, ldb=C, atomic=True, out_f32=True, split_k=2, conv=(NI, H, W, C),
              conv_mode=2, conv_stride=2, conv_taps=1)
     assert rel(dw, dy.float().t() @ xs) < 2e-3
+
+
+@pytest.mark.parametrize("NI,H,W,C,Cout", [(8, 28, 28, 128, 128), (4, 14, 14, 256, 256), (3, 13, 15, 64, 128)])
+def test_strided_dgrad_by_parity_classes(NI, H, W, C, Cout):
+    """Input gradient of a 3x3 / stride 2 / pad 1 convolution as four implicit GEMMs (one per parity class of the input
+    position, explicit tap grids 1x1 / 1x2 / 2x1 / 2x2 over dy, each writing its own strided sub-grid of dx) against
+    autograd of F.conv2d."""
+    _need_cuda()
+    ops = _ops()
+    g = torch.Generator().manual_seed(H + W + C)
+    w = (torch.randn(Cout, C, 3, 3, generator=g) * 0.05).bfloat16().cuda()
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    dy = (torch.randn(NI, Ho, Wo, Cout, generator=g) * 0.5).bfloat16().cuda()
+    dx = torch.full((NI, H, W, C), 9.0, dtype=BF16, device="cuda")
+    for ph in (0, 1):
+        for pw in (0, 1):
+            th, tw = 1 + ph, 1 + pw
+            taps = []
+            for a in range(th):
+                for b in range(tw):
+                    taps.append(w.float()[:, :, ph + 1 - 2 * a, pw + 1 - 2 * b].t())   # [C(in), Cout]
+            wc = torch.cat(taps, dim=1).bfloat16().contiguous()                          # [C, taps*Cout], k = tap*Cout + co
+            Hs, Ws = (H - ph + 1) // 2, (W - pw + 1) // 2
+            ops.gemm(dy, wc, dx, NI * Ho * Wo, C, th * tw * Cout, lda=Cout, conv=(NI, Ho, Wo, Cout), conv_mode=1,
+                     tap_grid=(th, tw, 0), d_ptr=dx.data_ptr() + (ph * W + pw) * C * 2,
+                     out_view=(Hs, Ws, 2 * C, 2 * W * C, H * W * C))
+    x = torch.zeros(NI, C, H, W, device="cuda", requires_grad=True)
+    F.conv2d(x, w.float(), stride=2, padding=1).backward(dy.float().permute(0, 3, 1, 2))
+    assert rel(dx, x.grad.permute(0, 2, 3, 1)) < 4e-3   # every element written exactly once (no 9.0 left), values match
+
+
+@pytest.mark.parametrize("NI,H,W,Cin,C4", [(8, 28, 28, 256, 512), (3, 13, 15, 64, 128)])
+def test_strided_downsample_dgrad_accumulates_in_place(NI, H, W, Cin, C4):
+    """dx[:, ::2, ::2] += dyd . Wd (input gradient of the 1x1 / stride-2 downsample added to the conv1 dgrad already in
+    dx): one-tap implicit GEMM whose output AND residual are the even-position sub-grid of dx."""
+    _need_cuda()
+    ops = _ops()
+    g = torch.Generator().manual_seed(Cin + H)
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    dyd = (torch.randn(NI, Ho, Wo, C4, generator=g) * 0.5).bfloat16().cuda()
+    wd = (torch.randn(C4, Cin, generator=g) * 0.05).bfloat16().cuda()
+    wt = wd.t().contiguous()                                   # [Cin, C4]: K-major B operand
+    dx0 = torch.randn(NI, H, W, Cin, generator=g).bfloat16().cuda()
+    dx = dx0.clone()
+    ops.gemm(dyd, wt, dx, NI * Ho * Wo, Cin, C4, lda=C4, conv=(NI, Ho, Wo, C4), conv_mode=1, conv_taps=1, residual=dx,
+             d_ptr=dx.data_ptr(), out_view=((H + 1) // 2, (W + 1) // 2, 2 * Cin, 2 * W * Cin, H * W * Cin))
+    ref = dx0.float().clone()
+    ref[:, ::2, ::2] += (dyd.float().reshape(-1, C4) @ wd.float()).view(NI, Ho, Wo, Cin)
+    assert rel(dx, ref) < 4e-3
+    odd = torch.ones(H, W, dtype=torch.bool)
+    odd[::2, ::2] = False
+    assert torch.equal(dx[:, odd], dx0[:, odd])   # positions outside the sub-grid are untouched

@@ -864,6 +864,10 @@ __global__ void conv_w_unpack_add_t_kernel(const float* __restrict__ dwt, float*
 //   kind 3: unpack-add (T) grad OIHW += dwt [(tap, i), O]          (halo-reuse wgrad layout, conv_mode 4)
 //   kind 4: stem s2d pack  fp32 [O,3,7,7] -> bf16 [O, 256]         (index map of csrc/stem_s2d.cu)
 //   kind 5: stem s2d unpack-add  grad [O,3,7,7] += dwp [O, 256]
+//   kind 6: pack (stride-2 dgrad, parity class (ph, pw) = (KH, KW) of the input gradient):
+//           fp32 OIHW [O,I,3,3] -> bf16 [I, ntaps*O], k = (a*tw + b)*O + o with (th, tw) = (1+ph, 1+pw) taps and
+//           (kh, kw) = (ph + 1 - 2a, pw + 1 - 2b): input row 2i+ph receives dy row i+a through kernel row kh
+//   kind 7: transpose      fp32 [O, I] (1x1 weight) -> bf16 [I, O]   (K-major B operand of the strided downsample's dgrad)
 constexpr int kJobElemsPerBlock = 2048;
 __global__ void __launch_bounds__(256) conv_w_jobs_kernel(const VtxWeightJob* __restrict__ jobs, int njobs) {
   VTX_PDL_TRIGGER();
@@ -907,6 +911,19 @@ __global__ void __launch_bounds__(256) conv_w_jobs_kernel(const VtxWeightJob* __
           if (kh < 7 && kw < 7) f = fs[((o * 3 + c) * 7 + kh) * 7 + kw];
         }
         reinterpret_cast<__nv_bfloat16*>(jb.dst)[t] = f2bf(f);
+        break;
+      }
+      case 6: {
+        const int ph = KH, pw = KW, tw = 1 + pw, nt = (1 + ph) * tw;
+        const int o = (int)(t % O), tap = (int)((t / O) % nt), i = (int)(t / ((long long)nt * O));
+        const int a = tap / tw, b = tap - a * tw;
+        const int kh = ph + 1 - 2 * a, kw = pw + 1 - 2 * b;
+        reinterpret_cast<__nv_bfloat16*>(jb.dst)[t] = f2bf(fs[((long long)o * I + i) * 9 + kh * 3 + kw]);
+        break;
+      }
+      case 7: {  // transpose of a 1x1 weight: fp32 [O, I] -> bf16 [I, O]
+        const int o = (int)(t % O), i = (int)(t / O);
+        reinterpret_cast<__nv_bfloat16*>(jb.dst)[t] = f2bf(fs[(long long)o * I + i]);
         break;
       }
       default: {

@@ -22,7 +22,9 @@ int check_launch(const char* what) {
 }  // namespace vtx
 
 extern "C" const char* vtx_last_error(void) { return vtx::g_err; }
-extern "C" int vtx_version(void) { return 100; }
+extern "C" int vtx_version(void) { return 200; }
+/* sizeof(VtxGemm) as this library was compiled: bindings check their own struct against it */
+extern "C" int vtx_sizeof_gemm(void) { return (int)sizeof(VtxGemm); }
 extern "C" int vtx_num_sms(void) {
   static int sms[64] = {0};
   int dev = 0;

@@ -843,12 +843,20 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
   // conv_taps = 1: a 1x1 convolution through the gather path (only useful with conv_stride = 2: the strided downsample)
   const bool one_tap = !stem && g->conv_taps == 1;
   if (one_tap) { p.taps_w = 1; p.pad = 0; p.ntaps = 1; }
+  // explicit tap grid (conv_mode 1): conv_taps_h x conv_taps_w taps, tap (a, b) reads position (h + a - pad, w + b - pad).
+  // Used by the four parity classes of a stride-2 dgrad (1x1, 1x2, 2x1, 2x2 taps, pad 0).
+  const bool tap_grid = !stem && !one_tap && g->conv_taps_h > 0;
+  if (tap_grid) {
+    if (p.mode != 1 || g->conv_taps_w <= 0 || g->conv_taps_h > 3 || g->conv_taps_w > 3 || g->conv_pad < 0 || g->conv_pad > 1)
+      return set_error(VTX_EINVAL, "vtx_gemm: bad explicit tap grid");
+    p.taps_w = g->conv_taps_w; p.pad = g->conv_pad; p.ntaps = g->conv_taps_h * g->conv_taps_w;
+  }
   const int cstride = (g->conv_stride == 2 && (p.mode == 1 || p.mode == 2) && !stem) ? 2 : 1;
   if (g->conv_stride != 0 && g->conv_stride != 1 && cstride != 2)
     return set_error(VTX_EINVAL, "vtx_gemm: conv_stride 2 is supported for conv_mode 1 / 2 only");
   if (g->conv_taps != 0 && g->conv_taps != 1 && g->conv_taps != 9) return set_error(VTX_EINVAL, "vtx_gemm: conv_taps must be 0, 1 or 9");
   p.cstride = cstride;
-  const int ntaps = stem ? 4 : one_tap ? 1 : 9;
+  const int ntaps = stem ? 4 : one_tap ? 1 : tap_grid ? p.ntaps : 9;
   if (p.mode == 1) { p.a_mn = 0; p.b_mn = 0; }
   if (p.mode == 2 || p.mode == 4) { p.a_mn = 1; p.b_mn = 1; }
   // ---- tile_n
@@ -927,7 +935,7 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
     p.cH = H; p.cW = W; p.cN = NI; p.cpb = C / 64;
     // halo-reuse variant (mode 3): C = 64 -> 64 convs whose 9 weight taps (72 KB) stay resident in shared memory and
     // whose input is fetched ONCE per 8 x 16 output tile as an 18 x 16 halo tile (instead of once per tap)
-    const bool halo = p.mode == 1 && !stem && !one_tap && cstride == 1 && C == 64 && g->N == 64 && bn == 64 &&
+    const bool halo = p.mode == 1 && !stem && !one_tap && !tap_grid && cstride == 1 && C == 64 && g->N == 64 && bn == 64 &&
                       !g->out_f32 && g->residual == nullptr && getenv("VTX_GEMM_NO_HALO") == nullptr;
     // the activation operand of the implicit convs: [NI, H, W, C] NHWC; for the stem view [NI, H + 3, W + 3, 16] whose
     // "channel" extent is 4 pixels x 16 channels and whose W stride is ONE pixel (overlapping rows, legal for TMA)
@@ -1035,10 +1043,21 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
     if (p.mode & 1) {
       uint64_t dd[4] = {(uint64_t)g->N, (uint64_t)p.cW, (uint64_t)p.cH, (uint64_t)g->conv_n};
       uint64_t ds[3] = {(uint64_t)g->ldd, (uint64_t)p.cW * g->ldd, (uint64_t)p.cH * p.cW * g->ldd};
+      if (g->conv_out_w > 0) {
+        // output VIEW override: D is a strided sub-grid [conv_n, conv_out_h, conv_out_w, N] of a larger NHWC tensor
+        // (element strides ldd_n / ldd_h / ldd_w); tiles still run over the conv_h x conv_w grid of the A operand and
+        // rows beyond the view are clipped by the TMA store.  (stride-2 dgrad: one parity class of the input gradient)
+        if (g->conv_out_h <= 0 || g->ldd_w % 8 || g->ldd_h % 8 || g->ldd_n % 8 || (g->residual != nullptr && !p.res_tma))
+          return set_error(VTX_EINVAL, "vtx_gemm: bad output view");
+        dd[1] = (uint64_t)g->conv_out_w; dd[2] = (uint64_t)g->conv_out_h;
+        ds[0] = (uint64_t)g->ldd_w; ds[1] = (uint64_t)g->ldd_h; ds[2] = (uint64_t)g->ldd_n;
+      }
       uint32_t db[4] = {64, 1u << p.lbw, 1u << p.lbh, 1u << p.lbn};
       if ((rc = make_tmap(&tmD, g->D, 4, dd, ds, db)) != VTX_OK) return rc;
       if (p.res_tma) {
+        // a residual of a view GEMM is a view with the SAME strides (in-place accumulation into the strided sub-grid)
         uint64_t rs[3] = {(uint64_t)g->ldr, (uint64_t)p.cW * g->ldr, (uint64_t)p.cH * p.cW * g->ldr};
+        if (g->conv_out_w > 0) { rs[0] = ds[0]; rs[1] = ds[1]; rs[2] = ds[2]; }
         if ((rc = make_tmap(&tmR, g->residual, 4, dd, rs, db)) != VTX_OK) return rc;
       }
     } else {

@@ -218,6 +218,18 @@ class Engine:
             if blk.stride == 1:
                 rows.append((w, self._pack_buf(name + ".conv2.weight#dgrad", (pl, 9 * pl)), 9 * pl * pl, pl, pl, 3, 3,
                              9 * pl, 1))
+            if blk.stride == 2 and blk.downsample is not None:
+                wdn = self.P(name + ".downsample.0.weight")
+                C4, Cin = wdn.shape[0], wdn.shape[1]
+                if Cin % 64 == 0:  # transposed copy: K-major B operand of the downsample's (implicit, strided-store) dgrad
+                    rows.append((wdn, self._pack_buf(name + ".downsample.0.weight#t", (Cin, C4)), C4 * Cin, C4, Cin, 1, 1,
+                                 C4, 7))
+            if blk.stride != 1:  # stride-2 dgrad: one weight slice per parity class (ph, pw) of the input gradient
+                for ph in (0, 1):
+                    for pw in (0, 1):
+                        nt = (1 + ph) * (1 + pw)
+                        rows.append((w, self._pack_buf(f"{name}.conv2.weight#dgrad_s2_{ph}{pw}", (pl, nt * pl)),
+                                     nt * pl * pl, pl, pl, ph, pw, nt * pl, 6))
         return rows
 
     def _unpack_rows(self, layer, stem_s2d):
@@ -481,7 +493,22 @@ class Engine:
                 if stride == 1:
                     gemm(dy2, self._packed[name + ".conv2.weight#dgrad"], da1, Min, planes, 9 * planes, lda=planes,
                          conv=(B, Hc, Wc, planes), conv_mode=1)
-                else:  # strided dgrad: per-tap gradients by a plain GEMM, scattered back by col2im
+                elif stride == 2:
+                    # strided dgrad as four implicit GEMMs, one per parity class (ph, pw) of the input position: row
+                    # 2i+ph of da1 gathers dy rows i+a, a < 1+ph, through kernel rows ph+1-2a (same along w); each class
+                    # writes its own strided sub-grid of da1, so every element is written exactly once -- no per-tap
+                    # gradient matrix, no col2im scatter
+                    for ph in (0, 1):
+                        for pw in (0, 1):
+                            th, tw = 1 + ph, 1 + pw
+                            Hs, Ws = (Hc - ph + 1) // 2, (Wc - pw + 1) // 2
+                            if Hs <= 0 or Ws <= 0:
+                                continue
+                            gemm(dy2, self._packed[f"{name}.conv2.weight#dgrad_s2_{ph}{pw}"], da1, Mout, planes,
+                                 th * tw * planes, lda=planes, conv=(B, Hn, Wn, planes), conv_mode=1, tap_grid=(th, tw, 0),
+                                 d_ptr=da1.data_ptr() + (ph * Wc + pw) * planes * 2,
+                                 out_view=(Hs, Ws, 2 * planes, 2 * Wc * planes, Hc * Wc * planes))
+                else:  # other strides: per-tap gradients by a plain GEMM, scattered back by col2im
                     dcols = ws.get("bwd.dcols", (Mout, 9 * planes), BF16)
                     gemm(dy2, self._packed[name + ".conv2.weight"], dcols, Mout, 9 * planes, planes, b_mn=1)
                     call("vtx_col2im3x3", dcols.data_ptr(), da1.data_ptr(), B, Hc, Wc, planes, stride, s)
@@ -510,6 +537,12 @@ class Engine:
                 gemm(dy1, w1, dx, Min, Cin, planes, b_mn=1)
                 if stride == 1:
                     gemm(dyd, wd, dx, Min, Cin, C4, b_mn=1, residual=dx)
+                elif stride == 2 and rec["xs"] is None:
+                    # dx[:, ::2, ::2] += dyd . Wd: one-tap implicit GEMM over the dyd grid whose output (and residual) is
+                    # the even-position sub-grid of dx -- in-place accumulation, no dxs buffer, no upsample_add pass
+                    gemm(dyd, self._packed[name + ".downsample.0.weight#t"], dx, Mout, Cin, C4, lda=C4,
+                         conv=(B, Hn, Wn, C4), conv_mode=1, conv_taps=1, residual=dx, d_ptr=dx.data_ptr(),
+                         out_view=((Hc + 1) // 2, (Wc + 1) // 2, 2 * Cin, 2 * Wc * Cin, Hc * Wc * Cin))
                 else:
                     dxs = ws.get("bwd.dxs", (Mout, Cin), BF16)
                     gemm(dyd, wd, dxs, Mout, Cin, C4, b_mn=1)

@@ -31,6 +31,9 @@ class VtxGemm(ctypes.Structure):
         ("alpha", c_f32),
         ("conv_n", c_i32), ("conv_h", c_i32), ("conv_w", c_i32), ("conv_c", c_i32), ("conv_mode", c_i32),
         ("conv_stride", c_i32), ("conv_taps", c_i32),
+        ("conv_taps_h", c_i32), ("conv_taps_w", c_i32), ("conv_pad", c_i32),
+        ("conv_out_h", c_i32), ("conv_out_w", c_i32),
+        ("ldd_w", c_i64), ("ldd_h", c_i64), ("ldd_n", c_i64),
         ("residual_mask", c_void_p),
     ]
 
@@ -48,6 +51,9 @@ def load():
                 f"{path} is missing: run `python -m virtex_b200.build` (there is no fallback path)")
         lib = ctypes.CDLL(path)
         lib.vtx_last_error.restype = ctypes.c_char_p
+        if lib.vtx_sizeof_gemm() != ctypes.sizeof(VtxGemm):
+            raise VtxError(f"{path} was built from another include/virtex_b200.h (VtxGemm is {lib.vtx_sizeof_gemm()} bytes "
+                           f"there, {ctypes.sizeof(VtxGemm)} here): run `python -m virtex_b200.build`")
         _lib = lib
     return _lib
 

@@ -74,7 +74,7 @@ def _get(name):
 
 def exported_symbols():
     """All C-ABI entry points this module binds (used by the CPU test that checks the library exports them)."""
-    return sorted(_PROTOS) + ["vtx_last_error", "vtx_version", "vtx_num_sms", "vtx_weight_job_block_elems"]
+    return sorted(_PROTOS) + ["vtx_last_error", "vtx_version", "vtx_num_sms", "vtx_weight_job_block_elems", "vtx_sizeof_gemm"]
 
 
 def _stream():
@@ -121,10 +121,10 @@ _gemm_struct = L.VtxGemm()
 
 def gemm(A, B, D, M, N, K, *, lda=None, ldb=None, ldd=None, a_mn=0, b_mn=0, bias=None, act=0, residual=None,
          ldr=0, stats=None, atomic=False, split_k=1, tile_n=0, conv=None, conv_mode=0, out_f32=None, residual_mask=None,
-         conv_stride=1, conv_taps=0):
+         conv_stride=1, conv_taps=0, tap_grid=None, out_view=None, d_ptr=None):
     """D[M,N] = epilogue(A . B^T) through the tcgen05 kernel; see include/virtex_b200.h (VtxGemm)."""
     g = _gemm_struct
-    g.A, g.B, g.D = A.data_ptr(), B.data_ptr(), D.data_ptr()
+    g.A, g.B, g.D = A.data_ptr(), B.data_ptr(), (D.data_ptr() if d_ptr is None else d_ptr)
     g.bias, g.residual, g.stats = _p(bias), _p(residual), _p(stats)
     g.residual_mask = _p(residual_mask)
     g.lda = A.stride(0) if lda is None else lda
@@ -142,6 +142,9 @@ def gemm(A, B, D, M, N, K, *, lda=None, ldb=None, ldd=None, a_mn=0, b_mn=0, bias
         g.conv_n = g.conv_h = g.conv_w = g.conv_c = 0
     g.conv_mode = conv_mode
     g.conv_stride, g.conv_taps = conv_stride, conv_taps
+    g.conv_taps_h, g.conv_taps_w, g.conv_pad = tap_grid if tap_grid is not None else (0, 0, 0)
+    # out_view = (out_h, out_w, ldd_w, ldd_h, ldd_n): D (at d_ptr) is a strided sub-grid of a larger NHWC tensor
+    g.conv_out_h, g.conv_out_w, g.ldd_w, g.ldd_h, g.ldd_n = out_view if out_view is not None else (0, 0, 0, 0, 0)
     if _gemm_profile is None:
         call("vtx_gemm", ctypes.addressof(g), _stream())
     else:
