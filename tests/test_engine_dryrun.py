@@ -40,7 +40,8 @@ def _check_gemm(A, B, D, M, N, K, lda=None, ldb=None, ldd=None, a_mn=0, b_mn=0, 
         assert C % 64 == 0
         taps = 1 if conv_taps == 1 else (tap_grid[0] * tap_grid[1] if tap_grid is not None else 9)
         if out_view is not None:
-            assert conv_mode == 1 and residual is None and d_ptr is not None and all(v % 8 == 0 for v in out_view[2:])
+            assert conv_mode == 1 and d_ptr is not None and all(v % 8 == 0 for v in out_view[2:])
+            assert residual is None or residual.data_ptr() == d_ptr  # a view GEMM accumulates in place or not at all
             assert D.data_ptr() <= d_ptr < D.data_ptr() + D.numel() * D.element_size()
         Ho, Wo = (H - 1) // conv_stride + 1, (W - 1) // conv_stride + 1   # conv = INPUT extent; outputs follow the stride
         if conv_mode == 1:
