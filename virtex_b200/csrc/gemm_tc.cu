@@ -111,6 +111,50 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
+// acc pair -> bf16x2, + (optionally masked) bf16x2 residual word in ONE packed add (the rounding torch's own bf16 graph
+// applies: conv output rounded to bf16, then the bf16 sum rounded again)
+__device__ __forceinline__ uint32_t add_res_bf16x2(float lo, float hi, uint32_t res) {
+  const __nv_bfloat162 a = __floats2bfloat162_rn(lo, hi);
+  const __nv_bfloat162 r = *reinterpret_cast<const __nv_bfloat162*>(&res);
+  const __nv_bfloat162 o = __hadd2(a, r);
+  return *reinterpret_cast<const uint32_t*>(&o);
+}
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+// One 32-column chunk of one row: staged residual (4 x 16 B, swizzled) + accumulators -> staged output, in place.
+// The ReLU bit mask (bit c of `mb` <-> column c) becomes a per-pair AND mask with ONE byte-permute per pair: prmt's
+// sign-replicate mode turns the top bit of a byte into 0x00 / 0xff, and the 8 shifted copies mb << s put every mask
+// bit at the top of some byte.  ~2 instructions per element where unpack + select + fp32 add + repack took ~4.5.
+template <bool kMask>
+__device__ __forceinline__ void residual_chunk_packed(const float* v, uint32_t sp, int cb, int sw, uint32_t mb, bool dead) {
+  uint32_t xs[8];
+  if (kMask) {
+#pragma unroll
+    for (int s_ = 0; s_ < 8; ++s_) xs[s_] = mb << s_;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t addr = sp + (((cb + i) ^ sw) << 4);
+    const uint4 raw = lds128(addr);
+    const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      uint32_t r = rw[k];
+      if (kMask) {
+        // columns 8i + 2k (bit 2k of byte i) and 8i + 2k + 1
+        const uint32_t sel = ((0xCu + i) << 12) | ((0xCu + i) << 8) | ((0x8u + i) << 4) | (0x8u + i);
+        r &= prmt(xs[7 - 2 * k], xs[6 - 2 * k], sel);
+      }
+      o[k] = dead ? 0u : add_res_bf16x2(v[8 * i + 2 * k], v[8 * i + 2 * k + 1], r);
+    }
+    sts128(addr, o[0], o[1], o[2], o[3]);
+  }
+}
+
 // fp32 epilogue math on one 32-column chunk of one accumulator row
 __device__ __forceinline__ void epi_math(float* v, const GemmKParams& p, long long grow, int col0, bool full) {
   if (p.alpha != 1.0f) {
@@ -461,7 +505,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int nchunks = (p.bn + 31) >> 5;
     // BN statistics: thread (scg, srg) owns 8 columns x st_rpt rows of every staged tile and keeps running partial sums
     // in registers across all tiles of this CTA that share the same column block (scalar FADD / FFMA: the packed
-    // fp32x2 forms measured 5-9 % SLOWER on the 256-wide tiles in round 2); they are reduced through shared memory and flushed with one atomic per column only when the column block changes (or
+    // fp32x2 forms measured 5-9 % SLOWER on the 256-wide tiles in round 2, and moving the sums to the warp-level
+    // tensor path -- ones x Y and diag(Y^T x Y) with mma.sync.m16n8k16 fed by ldmatrix.trans from the staging tile, 14
+    // instructions per 16 x 32 elements -- measured 30-50 % slower per launch: 512 legacy HMMAs per tile cost more
+    // than the ~1200 scalar instructions they replace, profiles/r02g_gemm_launches.json vs r02f); they are reduced through shared memory and flushed with one atomic per column only when the column block changes (or
     // at the end).  All 256 threads take part for the three tile widths the BN'd convs use: 64 / 128 / 256 columns =
     // 8 / 16 / 32 column groups x 32 / 16 / 8 row groups of 4 / 8 / 16 rows (with the fixed 32 x 8 x 16 mapping a
     // 64-wide tile kept 3/4 of the lanes idle while every warp still executed all 16 rows' instructions).
@@ -623,34 +670,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t sp = srow + (j >> 1) * 16384;
           const int cb = (j & 1) * 4;
           if (p.res_tma) {
-            // optional bit mask of the residual (dz = dOut * [block output > 0], never materialised): one 32-bit
-            // word per row and 32-column chunk
-            const uint32_t mb = (p.res_mask != nullptr && grow >= 0)
-                                    ? *reinterpret_cast<const uint32_t*>(p.res_mask + (grow * p.N + col0) / 8)
-                                    : 0xffffffffu;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const uint4 raw = lds128(sp + (((cb + i) ^ sw) << 4));
-              float f[8];
-              unpack8(*reinterpret_cast<const bf16x8*>(&raw), f);
-#pragma unroll
-              for (int e2 = 0; e2 < 8; ++e2) va[8 * i + e2] += ((mb >> (8 * i + e2)) & 1u) ? f[e2] : 0.f;
+            // residual (+ optional ReLU bit mask: dz = dOut * [block output > 0], never materialised; one 32-bit word
+            // per row and 32-column chunk) added in packed bf16 -- host guarantees alpha == 1, no bias, no activation
+            if (p.res_mask != nullptr) {
+              const uint32_t mb = grow >= 0 ? *reinterpret_cast<const uint32_t*>(p.res_mask + (grow * p.N + col0) / 8) : 0u;
+              residual_chunk_packed<true>(va, sp, cb, sw, mb, row_dead);
+            } else {
+              residual_chunk_packed<false>(va, sp, cb, sw, 0u, row_dead);
             }
-          }
-          epi_math(va, p, grow, col0, full);
-          if (row_dead) {
+          } else {
+            epi_math(va, p, grow, col0, full);
+            if (row_dead) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) va[i] = 0.f;
-          }
-          if (staged) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const bf16x8 pk = pack8(va + 8 * i);
-              const uint32_t* w = reinterpret_cast<const uint32_t*>(&pk);
-              sts128(sp + (((cb + i) ^ sw) << 4), w[0], w[1], w[2], w[3]);
+              for (int i = 0; i < 32; ++i) va[i] = 0.f;
             }
-          } else if (grow >= 0) {
-            epi_store_f32(va, p, grow, col0, full);
+            if (staged) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const bf16x8 pk = pack8(va + 8 * i);
+                const uint32_t* w = reinterpret_cast<const uint32_t*>(&pk);
+                sts128(sp + (((cb + i) ^ sw) << 4), w[0], w[1], w[2], w[3]);
+              }
+            } else if (grow >= 0) {
+              epi_store_f32(va, p, grow, col0, full);
+            }
           }
         }
         if (!have1) break;
@@ -663,34 +706,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t sp = srow + ((j + 2) >> 1) * 16384;
           const int cb = ((j + 2) & 1) * 4;
           if (p.res_tma) {
-            // optional bit mask of the residual (dz = dOut * [block output > 0], never materialised): one 32-bit
-            // word per row and 32-column chunk
-            const uint32_t mb = (p.res_mask != nullptr && grow >= 0)
-                                    ? *reinterpret_cast<const uint32_t*>(p.res_mask + (grow * p.N + col0) / 8)
-                                    : 0xffffffffu;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const uint4 raw = lds128(sp + (((cb + i) ^ sw) << 4));
-              float f[8];
-              unpack8(*reinterpret_cast<const bf16x8*>(&raw), f);
-#pragma unroll
-              for (int e2 = 0; e2 < 8; ++e2) vb[8 * i + e2] += ((mb >> (8 * i + e2)) & 1u) ? f[e2] : 0.f;
+            // residual (+ optional ReLU bit mask: dz = dOut * [block output > 0], never materialised; one 32-bit word
+            // per row and 32-column chunk) added in packed bf16 -- host guarantees alpha == 1, no bias, no activation
+            if (p.res_mask != nullptr) {
+              const uint32_t mb = grow >= 0 ? *reinterpret_cast<const uint32_t*>(p.res_mask + (grow * p.N + col0) / 8) : 0u;
+              residual_chunk_packed<true>(vb, sp, cb, sw, mb, row_dead);
+            } else {
+              residual_chunk_packed<false>(vb, sp, cb, sw, 0u, row_dead);
             }
-          }
-          epi_math(vb, p, grow, col0, full);
-          if (row_dead) {
+          } else {
+            epi_math(vb, p, grow, col0, full);
+            if (row_dead) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) vb[i] = 0.f;
-          }
-          if (staged) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const bf16x8 pk = pack8(vb + 8 * i);
-              const uint32_t* w = reinterpret_cast<const uint32_t*>(&pk);
-              sts128(sp + (((cb + i) ^ sw) << 4), w[0], w[1], w[2], w[3]);
+              for (int i = 0; i < 32; ++i) vb[i] = 0.f;
             }
-          } else if (grow >= 0) {
-            epi_store_f32(vb, p, grow, col0, full);
+            if (staged) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const bf16x8 pk = pack8(vb + 8 * i);
+                const uint32_t* w = reinterpret_cast<const uint32_t*>(&pk);
+                sts128(sp + (((cb + i) ^ sw) << 4), w[0], w[1], w[2], w[3]);
+              }
+            } else if (grow >= 0) {
+              epi_store_f32(vb, p, grow, col0, full);
+            }
           }
         }
       }
@@ -1037,8 +1076,11 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
   CUtensorMap tmD, tmR;
   memset(&tmD, 0, sizeof(tmD));
   memset(&tmR, 0, sizeof(tmR));
+  // the TMA-staged residual is added in packed bf16 AFTER the accumulator is rounded, which is only the documented
+  // order (alpha * acc + bias + residual, then the activation) when there is nothing else in the epilogue
   p.res_tma = (p.cbytes && g->residual != nullptr && g->ldr % 8 == 0 &&
-               (reinterpret_cast<uintptr_t>(g->residual) & 15) == 0) ? 1 : 0;
+               (reinterpret_cast<uintptr_t>(g->residual) & 15) == 0 && p.alpha == 1.0f && g->bias == nullptr &&
+               g->act == 0) ? 1 : 0;
   if (p.cbytes) {
     if (p.mode & 1) {
       uint64_t dd[4] = {(uint64_t)g->N, (uint64_t)p.cW, (uint64_t)p.cH, (uint64_t)g->conv_n};
