@@ -423,6 +423,46 @@ def test_gemm_masked_residual_epilogue():
         assert rel(D2, A.float() @ (B.float() if b_mn else B.float().t()) + R.float()) < 4e-3
 
 
+@pytest.mark.parametrize("M,N,K,tile_n", [
+    (60000, 64, 64, 0),      # 64-wide tiles: two independent 8-warp epilogue groups on alternate tiles, 3+ tiles per CTA
+    (19077, 64, 192, 0),     # same, ragged last M tile, odd tile count per CTA
+    (150, 64, 64, 0),        # two tiles in the whole launch: second group idle on most CTAs
+    (60000, 128, 64, 0),     # 128-wide: 16 epilogue warps, one chunk each
+    (40000, 256, 128, 0),    # 256-wide: 16 epilogue warps, two chunks each
+    (30011, 96, 64, 0),      # width that is not a multiple of 64
+    (20000, 200, 64, 0),     # partial last column tile
+    (30000, 256, 64, 128),   # forced 128-wide tiles over two column blocks (statistics flushed on block changes)
+])
+def test_gemm_epilogue_configurations_many_tiles(M, N, K, tile_n):
+    """Every epilogue configuration of gemm_tc_kernel (active warps / groups / staging buffers depend on the tile width)
+    on launches with several tiles per CTA: output, BN statistics of the bf16-rounded output, and the packed residual path."""
+    _need_cuda()
+    ops = _ops()
+    g = torch.Generator().manual_seed(M + N)
+    A = (torch.randn(M, K, generator=g) * 0.5).bfloat16().cuda()
+    B = (torch.randn(N, K, generator=g) * 0.5).bfloat16().cuda()
+    ref = A.float() @ B.float().t()
+    D = torch.full((M + 8, N), 7.0, dtype=BF16, device="cuda")
+    st = torch.zeros(2, N, device="cuda")
+    ops.gemm(A, B, D, M, N, K, stats=st, tile_n=tile_n)
+    out = D[:M]
+    assert rel(out, ref) < 4e-3
+    assert torch.all(D[M:] == 7.0)
+    assert rel(st[0], out.double().sum(0)) < 1e-4 and rel(st[1], (out.double() ** 2).sum(0)) < 1e-4
+    ops.gemm(A, B, D, M, N, K, bias=torch.ones(N, device="cuda"), act=1, tile_n=tile_n)   # fp32 epilogue math path
+    assert rel(D[:M], torch.relu(ref + 1.0)) < 4e-3
+    R = torch.randn(M, N, generator=g).bfloat16().cuda()
+    ops.gemm(A, B, D, M, N, K, residual=R, tile_n=tile_n)
+    assert rel(D[:M], ref + R.float()) < 4e-3
+    if N % 32 == 0:
+        keep = (torch.rand(M, N, generator=g) > 0.5).cuda()
+        ops.gemm(A, B, D, M, N, K, residual=R, residual_mask=_pack_mask(keep), tile_n=tile_n)
+        assert rel(D[:M], ref + R.float() * keep.float()) < 4e-3
+    Df = torch.zeros(M, N, device="cuda")
+    ops.gemm(A, B, Df, M, N, K, out_f32=True, tile_n=tile_n)                                # unstaged fp32 output
+    assert rel(Df, ref) < 1e-5
+
+
 # ------------------------------------------------------------------------------------------------ strided implicit convs
 @pytest.mark.parametrize("NI,H,W,C,Cout", [(8, 28, 28, 128, 128), (4, 14, 14, 256, 256), (6, 13, 15, 64, 128)])
 def test_strided_implicit_conv3x3_fprop_and_wgrad(NI, H, W, C, Cout):

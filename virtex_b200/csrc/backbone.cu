@@ -5,6 +5,8 @@
 // (SURVEY.md Appendix C.2): biased variance for normalisation, unbiased for running_var, momentum 0.1, eps 1e-5.
 // All kernels are HBM-bound: 16-byte vector accesses along the contiguous channel dimension, grid-stride loops
 // sized to a multiple of the SM count.
+#include <algorithm>
+
 #include "vtx_common.cuh"
 #include "../../include/virtex_b200.h"
 
@@ -16,6 +18,15 @@ static inline int grid_for(long long work_items, int threads, int per_sm = 16) {
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return (int)blocks;
+}
+
+// threads = (C/8) x the largest divisor of `extent` that keeps the block <= 256 threads: a row of `extent` positions is
+// then walked in whole passes (56 pooled columns x 8 channel groups -> 224 threads, 2 passes, no idle tail)
+static inline int row_threads(int cg, int extent) {
+  int best = 1;
+  for (int d = 1; d * cg <= 256 && d <= extent; ++d)
+    if (extent % d == 0) best = d;
+  return best * cg;
 }
 
 // ---------------------------------------------------------------------------------------------- stem im2col
@@ -410,6 +421,64 @@ __global__ void __launch_bounds__(256, 2) bn_act_kernel(const __nv_bfloat16* __r
 }
 
 // stem: pooled[n,ph,pw,:] = max over the 3x3/stride 2/pad 1 window of relu(y*scale+shift); idx = window slot of the max
+// Row-per-block form of the kernel below for C/8 dividing 256 (every ResNet stem): one CTA walks pooled rows (n, ph);
+// a thread keeps its channel group and BN coefficients for the whole launch and steps pw by blockDim / (C/8), so the loop has
+// no division at all (the flat-index form spent ~400 of its ~900 instructions per item on five 64-bit div / mod:
+// 0.284 ms for 0.54 GB, profiles/r02f_launches_step.csv).
+__global__ void __launch_bounds__(256) bn_relu_maxpool_rows_kernel(const __nv_bfloat16* __restrict__ y,
+                                                                   const float* __restrict__ bnp,
+                                                                   __nv_bfloat16* __restrict__ out,
+                                                                   uint8_t* __restrict__ idx, int N, int H, int W, int C,
+                                                                   int Ho, int Wo) {
+  VTX_PDL_TRIGGER();
+  const int cg = C / 8;
+  const int g = threadIdx.x % cg, pw0 = threadIdx.x / cg, pstep = blockDim.x / cg;
+  const int c0 = g * 8;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = __ldg(bnp + 2 * C + c0 + j);
+    sh[j] = __ldg(bnp + 3 * C + c0 + j);
+  }
+  for (int row = blockIdx.x; row < N * Ho; row += gridDim.x) {
+    const int n = row / Ho, ph = row - n * Ho;
+    const __nv_bfloat16* yn = y + (long long)n * H * W * C + c0;
+    for (int pw = pw0; pw < Wo; pw += pstep) {
+      float best[8];
+      int bi[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        best[j] = -INFINITY;
+        bi[j] = 0;
+      }
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const int h = ph * 2 - 1 + kh;
+        if (h < 0 || h >= H) continue;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int w = pw * 2 - 1 + kw;
+          if (w < 0 || w >= W) continue;
+          float v[8];
+          unpack8(*reinterpret_cast<const bf16x8*>(yn + (h * W + w) * C), v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            // the reference rounds the BN output and the ReLU output to bf16 before pooling
+            const float a = bf2f(f2bf(fmaxf(v[j] * sc[j] + sh[j], 0.f)));
+            if (a > best[j]) { best[j] = a; bi[j] = kh * 3 + kw; }
+          }
+        }
+      }
+      const long long o = ((long long)row * Wo + pw) * C + c0;
+      *reinterpret_cast<bf16x8*>(out + o) = pack8(best);
+      uint8_t b[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) b[j] = (uint8_t)bi[j];
+      *reinterpret_cast<uint2*>(idx + o) = *reinterpret_cast<uint2*>(b);
+    }
+  }
+}
+
 __global__ void bn_relu_maxpool_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ bnp,
                                        __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ idx, int N, int H, int W,
                                        int C, int Ho, int Wo) {
@@ -530,38 +599,47 @@ __global__ void __launch_bounds__(256) maxpool_bwd_tiled_kernel(const __nv_bfloa
   __syncthreads();
   const int cg = C / 8;
   const int h0 = 2 * ph0, h1 = min(H, 2 * (ph0 + kTP));
-  const int items = (h1 - h0) * W * cg;
-  for (int it = threadIdx.x; it < items; it += blockDim.x) {
-    const int g = it % cg;
-    const int w = (it / cg) % W;
-    const int h = h0 + it / (cg * W);
-    const int c0 = g * 8;
-    float acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-#pragma unroll
-    for (int kh = 0; kh < 3; ++kh) {
-      const int hn = h + 1 - kh;
-      if (hn < 0 || (hn & 1)) continue;
-      const int ph = hn >> 1;
-      if (ph >= Ho) continue;
-#pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
-        const int wn = w + 1 - kw;
-        if (wn < 0 || (wn & 1)) continue;
-        const int pw = wn >> 1;
-        if (pw >= Wo) continue;
-        const int off = ((ph - ph0) * Wo + pw) * C + c0;
-        const uint2 raw = *reinterpret_cast<const uint2*>(si + off);
-        const uint8_t* b = reinterpret_cast<const uint8_t*>(&raw);
-        float d[8];
-        unpack8(*reinterpret_cast<const bf16x8*>(sd + off), d);
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (b[j] == kh * 3 + kw) acc[j] += d[j];
-      }
+  // thread-fixed channel group, w stepping by blockDim / cg (the launcher guarantees cg | blockDim): no division in the loops, and
+  // the 1 or 2 pooled columns / rows that can point at (h, w) depend only on the parity of w / h
+  const int c0 = (threadIdx.x % cg) * 8;
+  for (int w = threadIdx.x / cg; w < W; w += blockDim.x / cg) {
+    int kws[2], pws[2], nw = 0;
+    if (w & 1) {
+      if (((w + 1) >> 1) < Wo) { kws[nw] = 0; pws[nw++] = (w + 1) >> 1; }
+      kws[nw] = 2; pws[nw++] = (w - 1) >> 1;
+    } else {
+      kws[0] = 1; pws[0] = w >> 1; nw = 1;
     }
-    *reinterpret_cast<bf16x8*>(da + (((long long)n * H + h) * W + w) * C + c0) = pack8(acc);
+    for (int h = h0; h < h1; ++h) {
+      int khs[2], phs[2], nh = 0;
+      if (h & 1) {
+        if (((h + 1) >> 1) < Ho) { khs[nh] = 0; phs[nh++] = (h + 1) >> 1; }
+        khs[nh] = 2; phs[nh++] = (h - 1) >> 1;
+      } else {
+        khs[0] = 1; phs[0] = h >> 1; nh = 1;
+      }
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        if (a >= nh) continue;
+#pragma unroll
+        for (int b2 = 0; b2 < 2; ++b2) {
+          if (b2 >= nw) continue;
+          const int off = ((phs[a] - ph0) * Wo + pws[b2]) * C + c0;
+          const int slot = khs[a] * 3 + kws[b2];
+          const uint2 raw = *reinterpret_cast<const uint2*>(si + off);
+          const uint8_t* b = reinterpret_cast<const uint8_t*>(&raw);
+          float d[8];
+          unpack8(*reinterpret_cast<const bf16x8*>(sd + off), d);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (b[j] == slot) acc[j] += d[j];
+        }
+      }
+      *reinterpret_cast<bf16x8*>(da + (((long long)n * H + h) * W + w) * C + c0) = pack8(acc);
+    }
   }
 }
 
@@ -1076,6 +1154,12 @@ extern "C" int vtx_bn_relu_maxpool(const void* y, const float* bnp, void* out, u
   REQ(y && bnp && out && idx && C % 8 == 0, "bad arguments");
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   const long long total = (long long)N * Ho * Wo * (C / 8);
+  if (C / 8 <= 256 && (long long)H * W * C < (1LL << 31)) {
+    bn_relu_maxpool_rows_kernel<<<(int)std::min<long long>((long long)N * Ho, (long long)vtx_num_sms() * 16),
+                                  row_threads(C / 8, Wo), 0, STREAM>>>(
+        (const __nv_bfloat16*)y, bnp, (__nv_bfloat16*)out, idx, N, H, W, C, Ho, Wo);
+    return check_launch("bn_relu_maxpool_rows");
+  }
   bn_relu_maxpool_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>((const __nv_bfloat16*)y, bnp, (__nv_bfloat16*)out,
                                                                    idx, N, H, W, C, Ho, Wo);
   return check_launch("bn_relu_maxpool");
@@ -1086,14 +1170,14 @@ extern "C" int vtx_maxpool_bwd(const void* dpool, const uint8_t* idx, void* da, 
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   {
     const size_t smem = (size_t)(kTP + 1) * Wo * C * 3;  // bf16 gradients + u8 slots
-    if (C % 16 == 0 && smem <= 200 * 1024) {
+    if (C % 16 == 0 && C / 8 <= 256 && smem <= 200 * 1024) {
       static size_t attr = 0;
       if (smem > 48 * 1024 && smem > attr) {
         cudaFuncSetAttribute(maxpool_bwd_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr = smem;
       }
       const int tiles = (Ho + kTP - 1) / kTP;
-      maxpool_bwd_tiled_kernel<<<N * tiles, 256, smem, STREAM>>>((const __nv_bfloat16*)dpool, idx, (__nv_bfloat16*)da, N,
+      maxpool_bwd_tiled_kernel<<<N * tiles, row_threads(C / 8, W), smem, STREAM>>>((const __nv_bfloat16*)dpool, idx, (__nv_bfloat16*)da, N,
                                                                  H, W, C, Ho, Wo);
       return check_launch("maxpool_bwd_tiled");
     }

@@ -46,8 +46,13 @@ constexpr int kMaxStages = 8;
 constexpr int kABytes = kBM * kBK * 2;        // 16384
 constexpr int kSmemTotal = 232448;            // 227 KB: the per-CTA maximum on sm_100
 constexpr int kCtrlBytes = 1024;              // barriers + TMEM slot, placed right after the 1024-aligned base
-constexpr int kThreads = 384;
-constexpr int kEpiThreads = 256;
+// Up to 16 epilogue warps (4 TMEM lane quadrants x up to 4 column-chunk groups) at 96 registers each.  The round-2
+// profile showed the 8-warp / 168-register epilogue LATENCY bound on the short-K convs (issue slots 40 % busy, DRAM
+// 40 %, two warps per scheduler): with four warps per scheduler the 256- and 128-wide tiles run 8-12 % faster.  Tiles
+// narrower than 128 columns have only two chunks, so those launches keep 8 active warps (p.epi_warps; the idle ones
+// only cost barrier width: 64-wide tiles measured 10 % SLOWER with all 16 in the barriers).
+constexpr int kEpiWarps = 16;
+constexpr int kThreads = 128 + 32 * kEpiWarps;
 constexpr int kHaloH = 18, kHaloW = 10;  // modes 3/4: halo of an 8 (w) x 16 (h) tile = 18 lines x 10 pixels x 64 ch (bf16)
 
 // x / d for 0 <= x < 2^31 and the launch-invariant divisor d: (umulhi(x, mul) >> shr), d == 1 handled apart
@@ -85,6 +90,7 @@ struct GemmKParams {
   int out_f32, atomic, act;
   int stages, stage_bytes;   // smem ring depth / bytes per stage
   int cbytes, nbuf;          // bytes of one bf16 staging buffer (0: no staging) / number of staging buffers
+  int epi_warps, epi_groups; // active epilogue warps (8 or 16) / independent groups they form (2 for staged 64-wide tiles)
   int res_tma;               // residual tile is TMA-loaded into the staging buffer and added there
   int bstat_bytes;           // mode 3: bytes of the stationary weight region (0 otherwise)
   int halo_w;                // modes 3/4: pixels per halo line in shared memory
@@ -109,7 +115,9 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
 
 // acc pair -> bf16x2, + (optionally masked) bf16x2 residual word in ONE packed add (the rounding torch's own bf16 graph
 // applies: conv output rounded to bf16, then the bf16 sum rounded again)
@@ -265,7 +273,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], kEpiThreads);
+      mbar_init(&tempty_bar[i], p.epi_warps * 32 / p.epi_groups);
       mbar_init(&res_bar[i], 1);
     }
     mbar_init(bst_bar, 1);
@@ -496,11 +504,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
     __syncwarp();
-  } else if (warp >= 4) {
-    // ===================================================== epilogue (8 warps)
+  } else if (warp >= 4 && warp < 4 + p.epi_warps) {
+    // ===================================================== epilogue (p.epi_warps of the kEpiWarps warps)
     const int ew = warp & 3;          // TMEM lane quadrant: lanes [32*ew, 32*ew+32)
-    const int hf = (warp - 4) >> 2;   // chunk parity handled by this warp (chunks of 32 columns)
-    const int et = threadIdx.x - 128; // 0..255 within the epilogue group
+    // 64-wide tiles run TWO independent 8-warp groups on alternate tiles (group g owns accumulator stage g, staging
+    // buffer g and named barrier 1 + g): a narrow tile is two chunks of work per row behind a fixed chain of waits,
+    // barriers and fences, and two such chains in flight overlap each other's latencies.
+    const int ngrp = p.epi_groups;
+    const int epi_threads = p.epi_warps * 32 / ngrp;  // threads of one group
+    const int grp = (threadIdx.x - 128) / epi_threads;
+    const int bar_id = 1 + grp;
+    const int nhf = epi_threads >> 7;                 // column-chunk groups of 4 warps each
+    const int hf = ((warp - 4) >> 2) % nhf;           // this warp handles the 32-column chunks j = hf (mod nhf)
+    const int et = threadIdx.x - 128 - grp * epi_threads;  // 0..epi_threads-1 within the group
     const bool staged = p.cbytes != 0;
     const int nchunks = (p.bn + 31) >> 5;
     // BN statistics: thread (scg, srg) owns 8 columns x st_rpt rows of every staged tile and keeps running partial sums
@@ -513,8 +529,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // 8 / 16 / 32 column groups x 32 / 16 / 8 row groups of 4 / 8 / 16 rows (with the fixed 32 x 8 x 16 mapping a
     // 64-wide tile kept 3/4 of the lanes idle while every warp still executed all 16 rows' instructions).
     const int st_lg = (p.bn == 64) ? 3 : (p.bn == 128) ? 4 : 5;  // log2(column groups)
-    const int st_rgs = 256 >> st_lg, st_rpt = 128 >> (8 - st_lg);
+    const int st_rgs = min(epi_threads >> st_lg, 32), st_rpt = 128 / st_rgs;  // <= 32 row groups: the flush scratch is one staging buffer
     const int scg = et & ((1 << st_lg) - 1), srg = et >> st_lg;
+    const bool st_on = (scg * 8 < p.bn) && (srg < st_rgs);
     float st_s[8], st_q[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) st_s[i] = st_q[i] = 0.f;
@@ -522,7 +539,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     auto flush_stats = [&](uint8_t* scratch) {
       // `scratch` is a staging buffer no TMA store is reading and nobody is writing (callers guarantee it)
       float* scr = reinterpret_cast<float*>(scratch);
-      if (scg * 8 < p.bn) {
+      if (st_on) {
 #pragma unroll
         for (int i = 0; i < 8; i += 2) {
           *reinterpret_cast<float4*>(scr + (srg * p.bn + scg * 8 + i) * 2) =
@@ -530,7 +547,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           st_s[i] = st_q[i] = st_s[i + 1] = st_q[i + 1] = 0.f;
         }
       }
-      epi_bar();
+      epi_bar(bar_id, epi_threads);
       if (et < p.bn && st_nt * p.bn + et < p.N) {
         float a = 0.f, b = 0.f;
         for (int g = 0; g < st_rgs; ++g) {
@@ -541,7 +558,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         atomicAdd(p.stats + st_nt * p.bn + et, a);
         atomicAdd(p.stats + p.N + st_nt * p.bn + et, b);
       }
-      epi_bar();
+      epi_bar(bar_id, epi_threads);
     };
     // asynchronous, coalesced TMA load of the residual tile of schedule slot `t_` into staging buffer `bi_`
     // (called by ONE thread, only once the TMA store that last read that buffer has finished reading it)
@@ -563,20 +580,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     };
-    int it = 0;
+    int it = grp;
     if (p.mode == 4) {
       // one epilogue for the whole CTA: 5 M-tiles x 64 fp32 columns -> red.add into D[(tap,cin), cout]
       if (blockIdx.x < total_tiles) {
         mbar_wait(&tfull_bar[0], 0);
         tc_fence_after();
         float* D = reinterpret_cast<float*>(p.D);
-        for (int j = 0; j < 5; ++j) {
+        for (int u = hf; u < 10; u += nhf) {  // 5 M-tiles x 2 chunks of 32 columns
+          const int j = u >> 1, half = u & 1;
           float v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(j * 64 + hf * 32), v);
+          tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(j * 64 + half * 32), v);
           tmem_ld_wait();
           const int row = j * 128 + ew * 32 + lane;
           if (row < p.M) {
-            float* op = D + (long long)row * p.ldd + hf * 32;
+            float* op = D + (long long)row * p.ldd + half * 32;
 #pragma unroll
             for (int i = 0; i < 32; i += 4) red_add_v4(op + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
           }
@@ -584,7 +602,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_before();
       }
     }
-    for (int t = blockIdx.x; t < total_tiles && p.mode != 4; t += gridDim.x, ++it) {
+    for (int t = blockIdx.x + grp * gridDim.x; t < total_tiles && p.mode != 4; t += ngrp * gridDim.x, it += ngrp) {
       const int rem = t - fdiv(t, p.d_mn) * (p.m_tiles * p.n_tiles);
       const int mt = fdiv(rem, p.d_nt);
       const int nt = rem - mt * p.n_tiles;
@@ -613,12 +631,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (it == 0) issue_residual(t, 0);
             if (t + (int)gridDim.x < total_tiles) issue_residual(t + gridDim.x, (it + 1) & 1);
           } else {
-            if (p.nbuf > 1) tma_store_wait_read<1>();
+            // (two groups: this leader's bulk groups are all stores from ITS buffer, so the latest one must be done)
+            if (p.nbuf > 1 && ngrp == 1) tma_store_wait_read<1>();
             else tma_store_wait_read<0>();
             if (p.res_tma) issue_residual(t, 0);  // single staging buffer: requested now that the buffer is free
           }
         }
-        epi_bar();
+        epi_bar(bar_id, epi_threads);
         if (p.stats != nullptr && st_nt != nt) {
           if (st_nt >= 0) flush_stats(cbuf);
           st_nt = nt;
@@ -654,83 +673,46 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)as * 256u;
       const uint32_t srow = smem_u32(cbuf) + r_in_tile * 128;
       const int sw = r_in_tile & 7;
-      float va[32], vb[32];
-      int j = hf;
-      if (j < nchunks && n_base + 32 * j < p.N) tmem_ld32(t_row + 32 * j, va);
-      for (; j < nchunks; j += 4) {
-        const int c0 = 32 * j, c1 = 32 * (j + 2);
-        const bool have0 = n_base + c0 < p.N;
-        const bool have1 = (j + 2 < nchunks) && (n_base + c1 < p.N);
-        if (!have0) break;
-        tmem_ld_wait();
-        if (have1) tmem_ld32(t_row + c1, vb);
-        {
-          const int col0 = n_base + c0;
-          const bool full = col0 + 32 <= p.N;
-          const uint32_t sp = srow + (j >> 1) * 16384;
-          const int cb = (j & 1) * 4;
-          if (p.res_tma) {
-            // residual (+ optional ReLU bit mask: dz = dOut * [block output > 0], never materialised; one 32-bit word
-            // per row and 32-column chunk) added in packed bf16 -- host guarantees alpha == 1, no bias, no activation
-            if (p.res_mask != nullptr) {
-              const uint32_t mb = grow >= 0 ? *reinterpret_cast<const uint32_t*>(p.res_mask + (grow * p.N + col0) / 8) : 0u;
-              residual_chunk_packed<true>(va, sp, cb, sw, mb, row_dead);
-            } else {
-              residual_chunk_packed<false>(va, sp, cb, sw, 0u, row_dead);
-            }
+      // one 32-column chunk j of this thread's row: v (fp32 accumulators) -> staging / global
+      auto do_chunk = [&](float* v, int j_) {
+        const int col0 = n_base + 32 * j_;
+        const bool full = col0 + 32 <= p.N;
+        const uint32_t sp = srow + (j_ >> 1) * 16384;
+        const int cb = (j_ & 1) * 4;
+        if (p.res_tma) {
+          // residual (+ optional ReLU bit mask: dz = dOut * [block output > 0], never materialised; one 32-bit word
+          // per row and 32-column chunk) added in packed bf16 -- host guarantees alpha == 1, no bias, no activation
+          if (p.res_mask != nullptr) {
+            const uint32_t mb = grow >= 0 ? *reinterpret_cast<const uint32_t*>(p.res_mask + (grow * p.N + col0) / 8) : 0u;
+            residual_chunk_packed<true>(v, sp, cb, sw, mb, row_dead);
           } else {
-            epi_math(va, p, grow, col0, full);
-            if (row_dead) {
+            residual_chunk_packed<false>(v, sp, cb, sw, 0u, row_dead);
+          }
+        } else {
+          epi_math(v, p, grow, col0, full);
+          if (row_dead) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) va[i] = 0.f;
-            }
-            if (staged) {
+            for (int i = 0; i < 32; ++i) v[i] = 0.f;
+          }
+          if (staged) {
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const bf16x8 pk = pack8(va + 8 * i);
-                const uint32_t* w = reinterpret_cast<const uint32_t*>(&pk);
-                sts128(sp + (((cb + i) ^ sw) << 4), w[0], w[1], w[2], w[3]);
-              }
-            } else if (grow >= 0) {
-              epi_store_f32(va, p, grow, col0, full);
+            for (int i = 0; i < 4; ++i) {
+              const bf16x8 pk = pack8(v + 8 * i);
+              const uint32_t* w = reinterpret_cast<const uint32_t*>(&pk);
+              sts128(sp + (((cb + i) ^ sw) << 4), w[0], w[1], w[2], w[3]);
             }
+          } else if (grow >= 0) {
+            epi_store_f32(v, p, grow, col0, full);
           }
         }
-        if (!have1) break;
-        tmem_ld_wait();
-        const int c2 = 32 * (j + 4);
-        if (j + 4 < nchunks && n_base + c2 < p.N) tmem_ld32(t_row + c2, va);
-        {
-          const int col0 = n_base + c1;
-          const bool full = col0 + 32 <= p.N;
-          const uint32_t sp = srow + ((j + 2) >> 1) * 16384;
-          const int cb = ((j + 2) & 1) * 4;
-          if (p.res_tma) {
-            // residual (+ optional ReLU bit mask: dz = dOut * [block output > 0], never materialised; one 32-bit word
-            // per row and 32-column chunk) added in packed bf16 -- host guarantees alpha == 1, no bias, no activation
-            if (p.res_mask != nullptr) {
-              const uint32_t mb = grow >= 0 ? *reinterpret_cast<const uint32_t*>(p.res_mask + (grow * p.N + col0) / 8) : 0u;
-              residual_chunk_packed<true>(vb, sp, cb, sw, mb, row_dead);
-            } else {
-              residual_chunk_packed<false>(vb, sp, cb, sw, 0u, row_dead);
-            }
-          } else {
-            epi_math(vb, p, grow, col0, full);
-            if (row_dead) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) vb[i] = 0.f;
-            }
-            if (staged) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const bf16x8 pk = pack8(vb + 8 * i);
-                const uint32_t* w = reinterpret_cast<const uint32_t*>(&pk);
-                sts128(sp + (((cb + i) ^ sw) << 4), w[0], w[1], w[2], w[3]);
-              }
-            } else if (grow >= 0) {
-              epi_store_f32(vb, p, grow, col0, full);
-            }
-          }
+      };
+      {
+        // one register buffer: up to four epilogue warps per scheduler hide the tcgen05.ld latency
+        float va[32];
+        for (int j = hf; j < nchunks && n_base + 32 * j < p.N; j += nhf) {
+          tmem_ld32(t_row + 32 * j, va);
+          tmem_ld_wait();
+          do_chunk(va, j);
         }
       }
       tmem_ld_wait();
@@ -739,7 +721,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
       if (staged) {
         fence_proxy_async();  // make this thread's staging writes visible to the TMA (async proxy)
-        epi_bar();
+        epi_bar(bar_id, epi_threads);
         // ---------------- TMA store of the staged tile: one 64-column slab per instruction
         if (et == 0) {
           const int slabs = (min(p.bn, p.N - n_base) + 63) >> 6;
@@ -753,7 +735,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         // ---------------- BN statistics of the staged (bf16-rounded) tile, accumulated in registers.
         // Rows outside the problem are exact zeros (TMA zero fill; stats forbids bias/residual): no masking needed.
-        if (p.stats != nullptr && scg * 8 < p.bn) {
+        if (p.stats != nullptr && st_on) {
           const int r0 = srg * st_rpt;  // first row of this thread (a multiple of 4)
           const uint32_t cp = smem_u32(cbuf) + (scg >> 3) * 16384 + r0 * 128;
           const int c8 = scg & 7;
@@ -776,8 +758,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     if (staged) {
       if (et == 0) tma_store_wait_read<0>();
-      epi_bar();
-      if (p.stats != nullptr && st_nt >= 0) flush_stats(cstage0);
+      epi_bar(bar_id, epi_threads);
+      if (p.stats != nullptr && st_nt >= 0) flush_stats(cstage0 + (size_t)grp * p.cbytes);
     }
   }
 
@@ -1074,6 +1056,8 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
     p.stages = st;
   }
   CUtensorMap tmD, tmR;
+  p.epi_warps = (bn >= 128 && p.mode != 4) ? kEpiWarps : 8;
+  p.epi_groups = 1;
   memset(&tmD, 0, sizeof(tmD));
   memset(&tmR, 0, sizeof(tmR));
   // the TMA-staged residual is added in packed bf16 AFTER the accumulator is rounded, which is only the documented
@@ -1081,6 +1065,11 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
   p.res_tma = (p.cbytes && g->residual != nullptr && g->ldr % 8 == 0 &&
                (reinterpret_cast<uintptr_t>(g->residual) & 15) == 0 && p.alpha == 1.0f && g->bias == nullptr &&
                g->act == 0) ? 1 : 0;
+#define VTX_DUAL_EPI 1
+  if (VTX_DUAL_EPI && bn < 128 && p.mode != 4 && p.cbytes && p.nbuf == 2 && !p.res_tma) {
+    p.epi_groups = 2;
+    p.epi_warps = 16;
+  }
   if (p.cbytes) {
     if (p.mode & 1) {
       uint64_t dd[4] = {(uint64_t)g->N, (uint64_t)p.cW, (uint64_t)p.cH, (uint64_t)g->conv_n};

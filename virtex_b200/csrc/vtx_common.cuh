@@ -26,9 +26,11 @@ struct alignas(16) bf16x8 { __nv_bfloat162 h[4]; };
 __device__ __forceinline__ void unpack8(const bf16x8& u, float* f) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const float2 t = __bfloat1622float2(u.h[j]);
-    f[2 * j] = t.x;
-    f[2 * j + 1] = t.y;
+    // bf16 -> fp32 is a 16-bit shift: one shift + one mask per pair (cuda_bf16's __bfloat1622float2 compiles to a
+    // shift plus permute + shift, 3 instructions per pair; the GEMM's statistics pass is instruction-bound)
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(&u.h[j]);
+    f[2 * j] = __uint_as_float(w << 16);
+    f[2 * j + 1] = __uint_as_float(w & 0xffff0000u);
   }
 }
 __device__ __forceinline__ bf16x8 pack8(const float* f) {
