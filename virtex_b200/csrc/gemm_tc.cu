@@ -620,7 +620,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (staged) {
         // the TMA store that last read this staging buffer must have finished reading it
         if (et == 0) {
-          if (p.res_tma && p.nbuf > 1) {
+          if (p.res_tma && p.nbuf > 1 && ngrp == 1) {
             // Residual prefetch ONE FULL TILE ahead: this tile's residual was requested at the top of the previous
             // iteration; the next tile's goes into the other buffer now.  That buffer was last read by the store issued
             // at the end of the previous iteration, so it has to drain first (wait_read<0>, a few hundred cycles for a
@@ -634,7 +634,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // (two groups: this leader's bulk groups are all stores from ITS buffer, so the latest one must be done)
             if (p.nbuf > 1 && ngrp == 1) tma_store_wait_read<1>();
             else tma_store_wait_read<0>();
-            if (p.res_tma) issue_residual(t, 0);  // single staging buffer: requested now that the buffer is free
+            if (p.res_tma) issue_residual(t, cbi);  // requested now that this (group's) buffer is free
           }
         }
         epi_bar(bar_id, epi_threads);
@@ -1065,8 +1065,8 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
   p.res_tma = (p.cbytes && g->residual != nullptr && g->ldr % 8 == 0 &&
                (reinterpret_cast<uintptr_t>(g->residual) & 15) == 0 && p.alpha == 1.0f && g->bias == nullptr &&
                g->act == 0) ? 1 : 0;
-#define VTX_DUAL_EPI 1
-  if (VTX_DUAL_EPI && bn < 128 && p.mode != 4 && p.cbytes && p.nbuf == 2 && !p.res_tma) {
+#define VTX_DUAL_EPI 2
+  if (p.mode != 4 && p.cbytes && p.nbuf == 2 && ((VTX_DUAL_EPI >= 1 && bn < 128 && !p.res_tma) || VTX_DUAL_EPI >= 2)) {
     p.epi_groups = 2;
     p.epi_warps = 16;
   }
