@@ -315,19 +315,24 @@ def main_ours(args, rank, world, local):
         if args.dump_gemm_profile:
             os.makedirs(os.path.dirname(os.path.abspath(args.dump_gemm_profile)), exist_ok=True)
             with open(args.dump_gemm_profile, "w") as f:
-                json.dump([dict(ms=p[0], flops=p[1], M=p[2], N=p[3], K=p[4], conv_mode=p[5], a_mn=p[6], b_mn=p[7])
+                json.dump([dict(ms=p[0], flops=p[1], M=p[2], N=p[3], K=p[4], conv_mode=p[5], a_mn=p[6], b_mn=p[7],
+                                extra_bytes=p[8])
                            for p in prof[len(prof) // 2:]], f)
         peak_tf, peak_bw, peak_src = measured_peaks()
         half = prof[len(prof) // 2:]  # the launches of the second profiled step
         g_ms = sum(p[0] for p in prof) / 2
         g_fl = sum(p[1] for p in prof) / 2
 
-        def min_bytes(ms, fl, M, N, K, mode, a_mn, b_mn):
-            if mode == 1:
-                return 2 * (M * K // 9 + N * K) + 2 * M * N
-            if mode == 2:
-                return 2 * (K * M + K * N // 9) + 4 * M * N
-            return 2 * (M * K + N * K) + (4 if (a_mn and b_mn) else 2) * M * N
+        def min_bytes(ms, fl, M, N, K, mode, a_mn, b_mn, extra):
+            # operands read once + output written once (im2col-free for the implicit convs: the activation is counted
+            # once, not once per tap) + what the epilogue reads besides (residual tile, ReLU bit mask)
+            if mode in (1, 3, 5):
+                return 2 * (M * K // (9 if mode != 5 else 16) + N * K) + 2 * M * N + extra
+            if mode in (2, 6):
+                return 2 * (K * M + K * N // (9 if mode != 6 else 16)) + 4 * M * N + extra
+            if mode == 4:
+                return 2 * (K * N + K * 64) + 4 * M * N + extra
+            return 2 * (M * K + N * K) + (4 if (a_mn and b_mn) else 2) * M * N + extra
 
         g_by = sum(min_bytes(*p) for p in half)
         t_min = sum(max(p[1] / (peak_tf * 1e12), min_bytes(*p) / (peak_bw * 1e9)) for p in half) * 1e3  # ms

@@ -76,7 +76,11 @@ def launches(src, dst):
     print(f"{len(rows)} launches, {tot_ns / 1e6:.2f} ms, {tot_b / 1e9:.1f} GB -> {dst}")
 
 
-def min_bytes(M, N, K, mode, a_mn, b_mn):
+def min_bytes(M, N, K, mode, a_mn, b_mn, extra=0):
+    return _min_bytes(M, N, K, mode, a_mn, b_mn) + extra
+
+
+def _min_bytes(M, N, K, mode, a_mn, b_mn):
     if mode in (1, 3, 5):
         return 2 * (M * K // (9 if mode != 5 else 16) + N * K) + 2 * M * N
     if mode in (2, 6):
@@ -91,24 +95,25 @@ def gemm(src, dst):
     data = json.load(open(src))
     cls = OrderedDict()
     for d in data:
-        key = (d["M"], d["N"], d["K"], d["conv_mode"], d["a_mn"], d["b_mn"])
+        key = (d["M"], d["N"], d["K"], d["conv_mode"], d["a_mn"], d["b_mn"], d.get("extra_bytes", 0))
         c = cls.setdefault(key, [0, 0.0])
         c[0] += 1
         c[1] += d["ms"]
     tot = sum(c[1] for c in cls.values())
     tmin_all = 0.0
     rows = []
-    for (M, N, K, mode, a, b), (n, ms) in cls.items():
+    for (M, N, K, mode, a, b, extra), (n, ms) in cls.items():
         fl = 2.0 * M * N * K
-        by = min_bytes(M, N, K, mode, a, b)
+        by = min_bytes(M, N, K, mode, a, b, extra)
         tmin = max(fl / (peak_tf * 1e12), by / (peak_bw * 1e9)) * 1e3  # ms per launch
         tmin_all += tmin * n
-        rows.append((ms - tmin * n, M, N, K, mode, a, b, n, ms, ms / n * 1e3, fl * n / ms / 1e9, by * n / ms / 1e6, tmin * n / ms))
+        rows.append((ms - tmin * n, M, N, K, mode + (0.5 if extra else 0), a, b, n, ms, ms / n * 1e3, fl * n / ms / 1e9, by * n / ms / 1e6, tmin * n / ms))
     with open(dst, "w") as f:
         f.write(f"# tcgen05 GEMM launches of one step, grouped by shape (CUDA events around every launch) at commit {commit()}\n\n")
         f.write(f"Total {tot:.2f} ms over {len(data)} launches; per-launch roofline (max(flops / {peak_tf:.0f} TFLOP/s, minimal bytes / "
                 f"{peak_bw:.0f} GB/s)) sums to {tmin_all:.2f} ms -> {tmin_all / tot:.3f}. mode: 0 plain, 1 implicit 3x3 fprop/dgrad "
-                "(64->64 shapes run the halo variant), 2 implicit 3x3 wgrad, 4 halo-reuse wgrad, 5/6 stem fprop/wgrad; a/b = operand "
+                "(64->64 shapes run the halo variant), 2 implicit 3x3 wgrad, 4 halo-reuse wgrad, 5/6 stem fprop/wgrad, +.5: the epilogue "
+                "also reads a residual tile (and ReLU bit mask), counted in the minimal bytes; a/b = operand "
                 "MN-major flags. Sorted by time lost against the class's own roofline.\n\n")
         f.write("| M | N | K | mode | a | b | launches | ms total | us/launch | TFLOP/s | min-bytes GB/s | frac of own roofline | ms lost |\n"
                 "|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|\n")

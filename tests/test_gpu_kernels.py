@@ -432,6 +432,8 @@ def test_gemm_masked_residual_epilogue():
     (30011, 96, 64, 0),      # width that is not a multiple of 64
     (20000, 200, 64, 0),     # partial last column tile
     (30000, 256, 64, 128),   # forced 128-wide tiles over two column blocks (statistics flushed on block changes)
+    (20000, 1024, 128, 0),   # four column blocks with statistics: the schedule runs over the row tiles first (nt_major)
+    (9000, 2048, 64, 0),     # eight column blocks, 568 tiles: the tile counter hands most CTAs three or four tiles
 ])
 def test_gemm_epilogue_configurations_many_tiles(M, N, K, tile_n):
     """Every epilogue configuration of gemm_tc_kernel (active warps / groups / staging buffers depend on the tile width)
@@ -461,6 +463,31 @@ def test_gemm_epilogue_configurations_many_tiles(M, N, K, tile_n):
     Df = torch.zeros(M, N, device="cuda")
     ops.gemm(A, B, Df, M, N, K, out_f32=True, tile_n=tile_n)                                # unstaged fp32 output
     assert rel(Df, ref) < 1e-5
+
+
+def test_gemm_tile_counter_slots_are_rearmed():
+    """The dynamic tile scheduler takes its counter from a ring of 4096 slots that the last CTA of a launch re-arms:
+    more launches than slots (of alternating sizes, so that a stale counter would skip or repeat tiles) stay exact."""
+    _need_cuda()
+    ops = _ops()
+    g = torch.Generator().manual_seed(3)
+    shapes = [(700, 64, 64), (40000, 64, 64), (3000, 256, 128)]
+    data = []
+    for M, N, K in shapes:
+        A = (torch.randn(M, K, generator=g) * 0.5).bfloat16().cuda()
+        B = (torch.randn(N, K, generator=g) * 0.5).bfloat16().cuda()
+        data.append((A, B, torch.empty(M, N, dtype=BF16, device="cuda"), A.float() @ B.float().t()))
+    for i in range(4400):
+        A, B, D, _ = data[i % 3]
+        ops.gemm(A, B, D, A.shape[0], B.shape[0], A.shape[1])
+        if i % 1100 == 1099:
+            for A, B, D, ref in data:
+                assert rel(D, ref) < 4e-3, i
+            for _, _, D, _ in data:
+                D.zero_()
+    for j, (A, B, D, ref) in enumerate(data):
+        ops.gemm(A, B, D, A.shape[0], B.shape[0], A.shape[1])
+        assert rel(D, ref) < 4e-3, j
 
 
 # ------------------------------------------------------------------------------------------------ strided implicit convs

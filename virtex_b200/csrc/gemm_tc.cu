@@ -107,7 +107,14 @@ struct GemmKParams {
   int cstride;               // spatial stride of the implicit conv (1 or 2): output position w reads input cstride*w + kw - pad
   // division by the launch-invariant tile-schedule extents as multiply-high + shift (a runtime integer division costs
   // ~25 dependent instructions; the schedule decode was ~13 % of the epilogue's instructions on the short-K convs)
-  FastDiv d_mn, d_nt, d_tw, d_twh, d_cpb, d_taps;
+  FastDiv d_mn, d_nt, d_mt, d_tw, d_twh, d_cpb, d_taps;
+  // Dynamic tile scheduler: sched[0] is this launch's tile counter (every tile index a CTA processes comes from one
+  // atomicAdd on it), sched[1] counts finished CTAs (the last one resets both words for the slot's next user).  With a
+  // static round-robin schedule an SM that is held by somebody else's CTA (NCCL's all-reduce kernels during the
+  // overlapped gradient exchange) delays ITS fixed share of tiles to the end of every GEMM issued meanwhile; here the
+  // CTAs that do run drain the counter and a late CTA finds nothing left.  nullptr: static schedule (mode 4, debugging).
+  unsigned int* sched;
+  int nt_major;              // tile index runs over row tiles first (BN statistics: a CTA's column block changes rarely)
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
@@ -118,6 +125,20 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 __device__ __forceinline__ void epi_bar(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
+
+// schedule index -> (split, row tile, column tile)
+__device__ __forceinline__ void decode_tile(const GemmKParams& p, int t, int& ks, int& mt, int& nt) {
+  ks = fdiv(t, p.d_mn);
+  const int rem = t - ks * (p.m_tiles * p.n_tiles);
+  if (p.nt_major) {
+    nt = fdiv(rem, p.d_mt);
+    mt = rem - nt * p.m_tiles;
+  } else {
+    mt = fdiv(rem, p.d_nt);
+    nt = rem - mt * p.n_tiles;
+  }
+}
+constexpr int kSched = 8;  // depth of the tile-index ring between the producer (who fetches) and the MMA / epilogue roles
 
 // acc pair -> bf16x2, + (optionally masked) bf16x2 residual word in ONE packed add (the rounding torch's own bf16 graph
 // applies: conv output rounded to bf16, then the bf16 sum rounded again)
@@ -249,7 +270,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tempty_bar = tfull_bar + 2;          // [2]
   uint64_t* res_bar = tempty_bar + 2;            // [2] residual tile landed in staging buffer b
   uint64_t* bst_bar = res_bar + 2;               // [1] stationary weights landed (mode 3)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bst_bar + 1);
+  uint64_t* sch_full = bst_bar + 1;              // [kSched] tile index published
+  uint64_t* sch_empty = sch_full + kSched;       // [kSched] tile index read by the MMA warp and the epilogue group that owns the slot
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sch_empty + kSched);
+  volatile int* sch_tile = reinterpret_cast<volatile int*>(tmem_slot + 2);  // [kSched]
   uint8_t* smem = base + kCtrlBytes;                       // stage ring (1024-aligned)
   uint8_t* bstat = smem + p.stages * p.stage_bytes;        // mode 3: stationary weights [9 taps][bn rows][128 B]
   uint8_t* cstage0 = bstat + p.bstat_bytes;                // bf16 staging: nbuf x [bn/64 slabs][128 rows][128 B], SW128
@@ -260,7 +284,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int total_tiles = p.m_tiles * p.n_tiles * p.k_splits;
   const int nstages = p.stages;
 
+  // the producer thread's first tile: requested before anything else (the counter belongs to this launch alone, so it
+  // need not wait for the previous kernel) and consumed after the prologue
+  int t_first = (int)blockIdx.x;
   if (warp == 0 && lane == 0) {
+    if (p.sched != nullptr) t_first = (int)atomicAdd(p.sched, 1u);
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (p.cbytes) tma_prefetch_desc(&tmD);
@@ -277,6 +305,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&res_bar[i], 1);
     }
     mbar_init(bst_bar, 1);
+    for (int i = 0; i < kSched; ++i) {
+      mbar_init(&sch_full[i], 1);
+      mbar_init(&sch_empty[i], 1 + p.epi_warps * 32 / p.epi_groups);
+    }
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -296,11 +328,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      // modes 0-3: every tile index goes through the ring, whether it came from the counter or from the static schedule;
+      // two end markers (>= total_tiles) close it, one per epilogue group
+      int t = t_first, sit = 0, ends = 0;
+      auto publish = [&]() {
+        const int slot = sit & (kSched - 1);
+        mbar_wait(&sch_empty[slot], ((sit / kSched) & 1) ^ 1);
+        sch_tile[slot] = t;
+        mbar_arrive(&sch_full[slot]);
+        ++sit;
+      };
       if (p.mode == 3) {
         // halo-reuse 3x3 conv: weights are loaded once and stay resident; every tile needs ONE halo'd input tile
-        mbar_arrive_expect_tx(bst_bar, 9u * (uint32_t)p.bn * 128u);
-        for (int tap = 0; tap < 9; ++tap) tma_load_2d(bstat + tap * p.bn * 128, &tmB, bst_bar, tap * 64, 0);
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        if (t < total_tiles) {
+          mbar_arrive_expect_tx(bst_bar, 9u * (uint32_t)p.bn * 128u);
+          for (int tap = 0; tap < 9; ++tap) tma_load_2d(bstat + tap * p.bn * 128, &tmB, bst_bar, tap * 64, 0);
+        }
+        for (;;) {
+          publish();
+          if (t >= total_tiles) {
+            if (++ends == 2) break;
+            continue;
+          }
+          // the next index is requested now and needed only after this tile's loads are queued
+          const int t_next = p.sched != nullptr ? (int)atomicAdd(p.sched, 1u) : t + (int)gridDim.x;
           const int tn = fdiv(t, p.d_twh);
           const int r_wh = t - tn * (p.tiles_w * p.tiles_h);
           const int th = fdiv(r_wh, p.d_tw);
@@ -309,6 +360,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(p.halo_w * kHaloH * 128));
           tma_load_4d(smem + stage * p.stage_bytes, &tmA, &full_bar[stage], 0, (tw << 3) - 1, (th << 4) - 1, tn);
           if (++stage == nstages) { stage = 0; phase ^= 1; }
+          t = t_next;
         }
       }
       if (p.mode == 4) {
@@ -328,11 +380,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
       }
-      for (int t = blockIdx.x; t < total_tiles && p.mode < 3; t += gridDim.x) {
-        const int ks = fdiv(t, p.d_mn);
-        const int rem = t - ks * (p.m_tiles * p.n_tiles);
-        const int mt = fdiv(rem, p.d_nt);
-        const int nt = rem - mt * p.n_tiles;
+      for (; p.mode < 3;) {
+        publish();
+        if (t >= total_tiles) {
+          if (++ends == 2) break;
+          continue;
+        }
+        const int t_next = p.sched != nullptr ? (int)atomicAdd(p.sched, 1u) : t + (int)gridDim.x;
+        int ks, mt, nt;
+        decode_tile(p, t, ks, mt, nt);
         const int kb0 = ks * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         int w0 = 0, h0 = 0, n0 = 0;
@@ -392,6 +448,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
+        t = t_next;
       }
     }
     __syncwarp();
@@ -413,10 +470,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      // tile index of schedule slot `it_` (warp-uniform), released to the producer once the whole warp has it
+      auto next_tile = [&](int it_) -> int {
+        const int slot = it_ & (kSched - 1);
+        mbar_wait(&sch_full[slot], (it_ / kSched) & 1);
+        const int t_ = __shfl_sync(0xffffffffu, sch_tile[slot], 0);
+        if (lane == 0) mbar_arrive(&sch_empty[slot]);
+        return t_;
+      };
       if (p.mode == 3) {
-        mbar_wait(bst_bar, 0);
         const uint64_t bd0 = make_smem_desc(smem_u32(bstat), 16, 1024);  // mode 3 always runs bn = 64
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+        for (;; ++it) {
+          const int t = next_tile(it);
+          if (t >= total_tiles) break;
+          if (it == 0) mbar_wait(bst_bar, 0);
           const int as = it & 1;
           mbar_wait(&tempty_bar[as], ((it >> 1) & 1) ^ 1);
           tc_fence_after();
@@ -478,7 +545,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         umma_commit_ws(&tfull_bar[0]);
       }
-      for (int t = blockIdx.x; t < total_tiles && p.mode < 3; t += gridDim.x, ++it) {
+      for (; p.mode < 3; ++it) {
+        const int t = next_tile(it);
+        if (t >= total_tiles) break;
         const int ks = fdiv(t, p.d_mn);
         const int kb0 = ks * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
@@ -563,9 +632,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // asynchronous, coalesced TMA load of the residual tile of schedule slot `t_` into staging buffer `bi_`
     // (called by ONE thread, only once the TMA store that last read that buffer has finished reading it)
     auto issue_residual = [&](int t_, int bi_) {
-      const int rem_ = t_ - fdiv(t_, p.d_mn) * (p.m_tiles * p.n_tiles);
-      const int mt_ = fdiv(rem_, p.d_nt);
-      const int nb_ = (rem_ - mt_ * p.n_tiles) * p.bn;
+      int ks_, mt_, nt_;
+      decode_tile(p, t_, ks_, mt_, nt_);
+      const int nb_ = nt_ * p.bn;
       uint8_t* buf_ = cstage0 + (size_t)bi_ * p.cbytes;
       const int slabs = (min(p.bn, p.N - nb_) + 63) >> 6;
       mbar_arrive_expect_tx(&res_bar[bi_], (uint32_t)slabs * 16384u);
@@ -602,10 +671,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_before();
       }
     }
-    for (int t = blockIdx.x + grp * gridDim.x; t < total_tiles && p.mode != 4; t += ngrp * gridDim.x, it += ngrp) {
-      const int rem = t - fdiv(t, p.d_mn) * (p.m_tiles * p.n_tiles);
-      const int mt = fdiv(rem, p.d_nt);
-      const int nt = rem - mt * p.n_tiles;
+    for (; p.mode != 4; it += ngrp) {
+      // schedule slot `it` belongs to this group (ring depth is even): read it, hand the slot back
+      const int slot = it & (kSched - 1);
+      mbar_wait(&sch_full[slot], (it / kSched) & 1);
+      const int t = sch_tile[slot];
+      mbar_arrive(&sch_empty[slot]);
+      if (t >= total_tiles) break;
+      int ks, mt, nt;
+      decode_tile(p, t, ks, mt, nt);
       const int as = it & 1;
       const int n_base = nt * p.bn;
       int tw = 0, th = 0, tn = 0;
@@ -620,22 +694,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (staged) {
         // the TMA store that last read this staging buffer must have finished reading it
         if (et == 0) {
-          if (p.res_tma && p.nbuf > 1 && ngrp == 1) {
-            // Residual prefetch ONE FULL TILE ahead: this tile's residual was requested at the top of the previous
-            // iteration; the next tile's goes into the other buffer now.  That buffer was last read by the store issued
-            // at the end of the previous iteration, so it has to drain first (wait_read<0>, a few hundred cycles for a
-            // 64 KB tile) -- the round-2 profile (r02_gemm_cases.ncu-rep, launch 1) showed 25 % of all warp samples of
-            // the dgrad+shortcut GEMMs waiting on a residual requested less than a stats-pass before its use.  (A third
-            // staging buffer on 128-wide tiles, which removes the drain wait too, measured SLOWER: 305 vs 256 us.)
-            tma_store_wait_read<0>();
-            if (it == 0) issue_residual(t, 0);
-            if (t + (int)gridDim.x < total_tiles) issue_residual(t + gridDim.x, (it + 1) & 1);
-          } else {
-            // (two groups: this leader's bulk groups are all stores from ITS buffer, so the latest one must be done)
-            if (p.nbuf > 1 && ngrp == 1) tma_store_wait_read<1>();
-            else tma_store_wait_read<0>();
-            if (p.res_tma) issue_residual(t, cbi);  // requested now that this (group's) buffer is free
-          }
+          // (two groups: this leader's bulk groups are all stores from ITS buffer, so the latest one must be done.
+          // Round 2 also tried requesting the residual one full tile ahead -- it removed the wait for the residual,
+          // 25 % of the warp samples of the dgrad + shortcut GEMMs, but exposed the drain of the previous store -- and a
+          // third staging buffer, 305 vs 256 us; the two independent groups below made both moot.)
+          if (p.nbuf > 1 && ngrp == 1) tma_store_wait_read<1>();
+          else tma_store_wait_read<0>();
+          if (p.res_tma) issue_residual(t, cbi);  // requested now that this (group's) buffer is free
         }
         epi_bar(bar_id, epi_threads);
         if (p.stats != nullptr && st_nt != nt) {
@@ -769,6 +834,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+  if (threadIdx.x == 0 && p.sched != nullptr) {
+    // every fetch of this CTA has returned; the last CTA to get here re-arms the slot for the launch that reuses it
+    __threadfence();
+    if (atomicAdd(p.sched + 1, 1u) == gridDim.x - 1) {
+      p.sched[0] = 0u;
+      p.sched[1] = 0u;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -813,6 +886,28 @@ static int make_tmap(CUtensorMap* tm, const void* ptr, int rank, const uint64_t*
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(VTX_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
   return VTX_OK;
+}
+
+// Tile-counter slots of the dynamic scheduler: {next tile, finished CTAs} pairs, zero when idle.  Launch i of a device
+// uses slot i mod kSchedSlots; its last CTA zeroes the pair again, and the launch that reuses the slot is thousands of
+// launches later on the same stream order, so no host-side reset is ever needed (graph replays included).
+constexpr int kSchedSlots = 4096;
+static unsigned int* sched_slot() {
+  static unsigned int* ring[64] = {nullptr};
+  static unsigned int next[64] = {0};
+  static const bool off = getenv("VTX_GEMM_STATIC") != nullptr;  // debugging / A-B knob: the static round-robin schedule
+  if (off) return nullptr;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return nullptr;
+  if (ring[dev] == nullptr) {
+    unsigned int* ptr = nullptr;
+    if (cudaMalloc(&ptr, sizeof(unsigned int) * 2 * kSchedSlots) != cudaSuccess) return nullptr;
+    cudaMemset(ptr, 0, sizeof(unsigned int) * 2 * kSchedSlots);
+    cudaDeviceSynchronize();
+    ring[dev] = ptr;
+  }
+  return ring[dev] + 2 * (next[dev]++ % kSchedSlots);
 }
 
 static int ilog2(int x) {
@@ -1115,6 +1210,12 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
   }
   p.d_mn = make_fastdiv(p.m_tiles * p.n_tiles);
   p.d_nt = make_fastdiv(p.n_tiles);
+  p.d_mt = make_fastdiv(p.m_tiles);
+  // BN statistics are kept in registers per column block: run over the row tiles first, so that a CTA's column block
+  // changes at most n_tiles - 1 times whatever order the tiles are handed out in (the activation operand of every conv
+  // with more than one column tile fits the L2, so the extra passes over it do not reach DRAM)
+  p.nt_major = (p.stats != nullptr && p.n_tiles > 1 && p.mode < 3) ? 1 : 0;
+  p.sched = p.mode == 4 ? nullptr : sched_slot();
   p.d_tw = make_fastdiv(p.tiles_w);
   p.d_twh = make_fastdiv(p.tiles_w * p.tiles_h);
   p.d_cpb = make_fastdiv(p.cpb);

@@ -103,7 +103,8 @@ def start_gemm_profile():
 
 
 def stop_gemm_profile():
-    """Returns [(milliseconds, flops, M, N, K, conv_mode, a_mn, b_mn)] for every GEMM launched since start."""
+    """Returns [(milliseconds, flops, M, N, K, conv_mode, a_mn, b_mn, extra_bytes)] for every GEMM launched since start;
+    extra_bytes = what the epilogue reads besides A and B (residual tile, ReLU bit mask)."""
     global _gemm_profile
     torch.cuda.synchronize()
     out = [(a.elapsed_time(b),) + tuple(rest) for (a, b, *rest) in _gemm_profile]
@@ -152,7 +153,8 @@ def gemm(A, B, D, M, N, K, *, lda=None, ldb=None, ldd=None, a_mn=0, b_mn=0, bias
         e0.record()
         call("vtx_gemm", ctypes.addressof(g), _stream())
         e1.record()
-        _gemm_profile.append((e0, e1, 2.0 * M * N * K, M, N, K, conv_mode, a_mn, b_mn))
+        extra = (2 * M * N if residual is not None else 0) + (M * N // 8 if residual_mask is not None else 0)
+        _gemm_profile.append((e0, e1, 2.0 * M * N * K, M, N, K, conv_mode, a_mn, b_mn, extra))
 
 
 def split_k_for(m_tiles_x_n_tiles, k_blocks, sms=None):
