@@ -90,9 +90,27 @@ typedef struct VtxGemm {
                                    vtx_bn_act writes; residual[m, n] is added only where the bit is set.  This is the
                                    shortcut gradient dz = dOut * [block output > 0] of a bottleneck without dz ever being
                                    written to memory (torchvision resnet.py:160-161 backward). */
+  /* BatchNorm-backward reduction fused into the epilogue (bnr_y != NULL; bf16 output, N % 8 == 0, no bias / activation /
+     stats): D is the gradient w.r.t. the output of a train-mode BN (+ReLU) whose pre-BN input is bnr_y (same geometry as
+     D: leading dimension bnr_ldy, or D's view strides for conv_mode 1 output views) and whose forward parameters are
+     bnr_bnp [4, N] = mean, invstd, scale, shift (vtx_bn_finalize).  With dz = D * mask, mask = bit (m, n) of bnr_mask
+     (layout of vtx_bn_act's mask, plain GEMMs only) or, when bnr_mask is NULL, [bnr_y * scale + shift > 0],
+         bnr_sums[0, n] += sum_m dz[m, n],    bnr_sums[1, n] += sum_m dz[m, n] * (bnr_y[m, n] - mean[n]) * invstd[n]
+     -- exactly what vtx_bn_bwd_reduce computes in a separate pass over D and y (torch batch_norm backward, first half);
+     D itself is stored unmasked, vtx_bn_bwd_finalize_apply consumes the sums. */
+  const void* bnr_y;
+  const float* bnr_bnp;
+  float* bnr_sums;
+  const uint8_t* bnr_mask;
+  int64_t bnr_ldy;
 } VtxGemm;
 
 int vtx_gemm(const VtxGemm* g, void* stream);
+/* Tile schedule of the persistent GEMM.  0 (default): static round robin, tile t of CTA c = c + i * #CTAs -- the fastest
+   when the GEMM has the GPU to itself.  1: every CTA takes its tiles from a per-launch atomic counter, so that an SM held
+   by another stream's kernel (NCCL's all-reduce CTAs during the overlapped gradient exchange of the data-parallel step,
+   scripts/pretrain_virtex.py:121-123) does not own a fixed share of every GEMM issued meanwhile.  Process-wide. */
+int vtx_gemm_set_dynamic_schedule(int on);
 /* sizeof(VtxGemm) of the built library (a binding compares it with its own struct definition) */
 int vtx_sizeof_gemm(void);
 

@@ -21,7 +21,7 @@ class Recorder:
 
 def _check_gemm(A, B, D, M, N, K, lda=None, ldb=None, ldd=None, a_mn=0, b_mn=0, bias=None, act=0, residual=None, ldr=0,
                 stats=None, atomic=False, split_k=1, tile_n=0, conv=None, conv_mode=0, out_f32=None, residual_mask=None,
-                conv_stride=1, conv_taps=0, tap_grid=None, out_view=None, d_ptr=None):
+                conv_stride=1, conv_taps=0, tap_grid=None, out_view=None, d_ptr=None, bnr=None):
     assert A.dtype == BF16 and B.dtype == BF16, (A.dtype, B.dtype)
     f32 = (D.dtype == F32) if out_f32 is None else bool(out_f32)
     assert D.dtype == (F32 if f32 else BF16)
@@ -70,6 +70,16 @@ def _check_gemm(A, B, D, M, N, K, lda=None, ldb=None, ldd=None, a_mn=0, b_mn=0, 
     if residual_mask is not None:
         assert residual is not None and residual_mask.dtype == torch.uint8 and residual_mask.numel() >= M * N // 8
         assert N % 32 == 0 and conv_mode == 0 and not f32
+    if bnr is not None:   # BN-backward sums accumulated by the epilogue: (y, bnp, sums, bit mask or None[, y view pointer])
+        y, bnp, sums, mbits = bnr[:4]
+        assert not f32 and stats is None and bias is None and act == 0 and split_k == 1 and conv_mode in (0, 1) and N % 8 == 0
+        assert y.dtype == BF16 and bnp.dtype == F32 and bnp.numel() == 4 * N and sums.dtype == F32 and sums.numel() == 2 * N
+        if out_view is not None:   # y is addressed through the same strided view as D
+            assert len(bnr) == 5 and bnr[4] - y.data_ptr() == d_ptr - D.data_ptr() and y.numel() == D.numel()
+        else:
+            assert len(bnr) == 4 and y.numel() >= M * N
+        if mbits is not None:
+            assert conv_mode == 0 and mbits.dtype == torch.uint8 and mbits.numel() >= M * N // 8
 
 
 @pytest.fixture
@@ -84,7 +94,7 @@ def dry(monkeypatch):
 
     def fake_gemm(A, B, D, M, N, K, **kw):
         _check_gemm(A, B, D, M, N, K, **kw)
-        rec.calls.append(("gemm", M, N, K, kw.get("conv_mode", 0)))
+        rec.calls.append(("gemm", M, N, K, kw.get("conv_mode", 0), kw.get("bnr") is not None))
 
     monkeypatch.setattr(E, "call", fake_call)
     monkeypatch.setattr(E, "gemm", fake_gemm)
@@ -143,6 +153,13 @@ def test_training_step_schedule(dry, spec_kw, batch_kw):
     assert "vtx_stem_s2d" in names and "vtx_stem_im2col" not in names
     # layer1's three 64 -> 64 3x3 convs use the halo-reuse wgrad
     assert len([g for g in gemms if g[4] == 4]) == 3
+    # BN-backward reductions: bn1 / bn2 of every block and bn3 of every block that is followed by an identity block and
+    # has no downsample branch are accumulated by GEMM epilogues (a stride-2 conv2 dgrad is four GEMMs); stand-alone
+    # reduce launches remain for the stem BN, the four two-branch blocks, the last block of every layer
+    fused_bn3 = n_blocks - 4 - 4
+    assert len([g for g in gemms if g[5]]) == 2 * n_blocks + 3 * 3 + fused_bn3
+    assert names.count("vtx_bn_bwd_reduce") == 1 + 4 + 4
+    assert names.count("vtx_bn_bwd_finalize_apply") == 1 + 3 * n_blocks
 
 
 def test_eval_forward_only_and_frozen_backbone(dry):

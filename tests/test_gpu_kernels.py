@@ -34,6 +34,16 @@ def _s():
     return torch.cuda.current_stream().cuda_stream
 
 
+@pytest.fixture(params=["static", "dynamic"])
+def schedule(request):
+    """Both tile schedules of the persistent GEMM (round robin / per-launch atomic tile counter)."""
+    _need_cuda()
+    ops = _ops()
+    ops.set_dynamic_gemm_schedule(request.param == "dynamic")
+    yield request.param
+    ops.set_dynamic_gemm_schedule(False)
+
+
 def _pack_mask(keep):
     """[M, C] bool -> uint8 [M, C/8], bit j of byte g = channel 8g + j (the layout vtx_bn_act writes)."""
     M, C = keep.shape
@@ -435,7 +445,7 @@ def test_gemm_masked_residual_epilogue():
     (20000, 1024, 128, 0),   # four column blocks with statistics: the schedule runs over the row tiles first (nt_major)
     (9000, 2048, 64, 0),     # eight column blocks, 568 tiles: the tile counter hands most CTAs three or four tiles
 ])
-def test_gemm_epilogue_configurations_many_tiles(M, N, K, tile_n):
+def test_gemm_epilogue_configurations_many_tiles(M, N, K, tile_n, schedule):
     """Every epilogue configuration of gemm_tc_kernel (active warps / groups / staging buffers depend on the tile width)
     on launches with several tiles per CTA: output, BN statistics of the bf16-rounded output, and the packed residual path."""
     _need_cuda()
@@ -465,20 +475,133 @@ def test_gemm_epilogue_configurations_many_tiles(M, N, K, tile_n):
     assert rel(Df, ref) < 1e-5
 
 
-def test_gemm_tile_counter_slots_are_rearmed():
-    """The dynamic tile scheduler takes its counter from a ring of 4096 slots that the last CTA of a launch re-arms:
-    more launches than slots (of alternating sizes, so that a stale counter would skip or repeat tiles) stay exact."""
+def _bn_reduce_ref(ops, D, y, bnp, mask_bits):
+    """The stand-alone reduction (vtx_bn_bwd_reduce) and the torch formula over the SAME bf16 gradient D."""
+    M, C = D.shape
+    sums = torch.zeros(2, C, device="cuda")
+    ops.call("vtx_bn_bwd_reduce", D.data_ptr(), ops._p(mask_bits), y.data_ptr(), bnp.data_ptr(), 0, 0, sums.data_ptr(), 0,
+             M, C, int(mask_bits is None), _s())
+    return sums
+
+
+def _check_bnr(ops, D, y, bnp, sums, mask_bits, keep):
+    ref = _bn_reduce_ref(ops, D, y, bnp, mask_bits)
+    dz = D.double() * keep.double()
+    xhat = (y.double() - bnp[0].double()) * bnp[1].double()
+    assert rel(sums[0], dz.sum(0)) < 1e-4 and rel(sums[1], (dz * xhat).sum(0)) < 1e-4
+    assert rel(sums, ref) < 1e-4
+
+
+@pytest.mark.parametrize("M,N,K", [(5000, 64, 256), (5001, 128, 512), (20000, 256, 64), (3000, 512, 128), (700, 2048, 64)])
+def test_gemm_fused_bn_backward_reduce_plain(M, N, K, schedule):
+    """VtxGemm.bnr_*: the dgrad epilogue accumulates sum dz / sum dz * xhat of its own output (conv3 dgrad -> bn2: ReLU
+    mask recomputed from y; conv1 dgrad + shortcut gradient -> previous block's bn3: ReLU bit mask), D itself unchanged;
+    against vtx_bn_bwd_reduce over the same D and the torch formula."""
     _need_cuda()
     ops = _ops()
+    g = torch.Generator().manual_seed(M + N + K)
+    A = (torch.randn(M, K, generator=g) * 0.5).bfloat16().cuda()
+    B = (torch.randn(K, N, generator=g) * 0.2).bfloat16().cuda()
+    y = (torch.randn(M, N, generator=g) * 1.5).bfloat16().cuda()
+    bnp = _bnp(N, g)
+    # --- mask recomputed from y
+    D0 = torch.empty(M, N, dtype=BF16, device="cuda")
+    ops.gemm(A, B, D0, M, N, K, b_mn=1)
+    D = torch.empty(M, N, dtype=BF16, device="cuda")
+    sums = torch.zeros(2, N, device="cuda")
+    ops.gemm(A, B, D, M, N, K, b_mn=1, bnr=(y, bnp, sums, None))
+    assert torch.equal(D, D0)
+    keep = (y.float() * bnp[2] + bnp[3]) > 0
+    _check_bnr(ops, D, y, bnp, sums, None, keep)
+    # --- bit mask, on top of the masked-residual epilogue (the shape of the conv1 dgrad of an identity block)
+    if N % 32 == 0:
+        R = torch.randn(M, N, generator=g).bfloat16().cuda()
+        rkeep = (torch.rand(M, N, generator=g) > 0.5).cuda()
+        bkeep = (torch.rand(M, N, generator=g) > 0.45).cuda()
+        rbits, bbits = _pack_mask(rkeep), _pack_mask(bkeep)
+        ops.gemm(A, B, D0, M, N, K, b_mn=1, residual=R, residual_mask=rbits)
+        sums.zero_()
+        ops.gemm(A, B, D, M, N, K, b_mn=1, residual=R, residual_mask=rbits, bnr=(y, bnp, sums, bbits))
+        assert torch.equal(D, D0)
+        _check_bnr(ops, D, y, bnp, sums, bbits, bkeep)
+
+
+@pytest.mark.parametrize("NI,H,W,C", [(4, 14, 14, 128), (3, 56, 56, 64), (2, 30, 22, 64), (6, 7, 7, 256)])
+def test_gemm_fused_bn_backward_reduce_conv_dgrad(NI, H, W, C, schedule):
+    """The same through the implicit 3x3 dgrad (conv2 dgrad -> bn1), including the halo-reuse variant (C = 64) whose
+    partial spatial tiles have rows outside the image."""
+    _need_cuda()
+    ops = _ops()
+    g = torch.Generator().manual_seed(H * W + C)
+    M = NI * H * W
+    dy = (torch.randn(NI, H, W, C, generator=g) * 0.5).bfloat16().cuda()
+    wq = (torch.randn(C, 9 * C, generator=g) * 0.05).bfloat16().cuda()
+    y = (torch.randn(M, C, generator=g) * 1.5).bfloat16().cuda()
+    bnp = _bnp(C, g)
+    D0 = torch.empty(M, C, dtype=BF16, device="cuda")
+    ops.gemm(dy, wq, D0, M, C, 9 * C, lda=C, conv=(NI, H, W, C), conv_mode=1)
+    D = torch.empty(M, C, dtype=BF16, device="cuda")
+    sums = torch.zeros(2, C, device="cuda")
+    ops.gemm(dy, wq, D, M, C, 9 * C, lda=C, conv=(NI, H, W, C), conv_mode=1, bnr=(y, bnp, sums, None))
+    assert torch.equal(D, D0)
+    _check_bnr(ops, D, y, bnp, sums, None, (y.float() * bnp[2] + bnp[3]) > 0)
+
+
+@pytest.mark.parametrize("NI,H,W,C,Cout", [(8, 28, 28, 128, 128), (3, 13, 15, 64, 128)])
+def test_gemm_fused_bn_backward_reduce_strided_parity_classes(NI, H, W, C, Cout):
+    """Stride-2 dgrad as four parity-class GEMMs writing strided sub-grids of dx: each accumulates the sums of ITS
+    sub-grid (y addressed through the same view), together the reduction over all of dx."""
+    _need_cuda()
+    ops = _ops()
+    g = torch.Generator().manual_seed(H + W + C + 1)
+    w = (torch.randn(Cout, C, 3, 3, generator=g) * 0.05).bfloat16().cuda()
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    dy = (torch.randn(NI, Ho, Wo, Cout, generator=g) * 0.5).bfloat16().cuda()
+    y = (torch.randn(NI * H * W, C, generator=g) * 1.5).bfloat16().cuda()
+    bnp = _bnp(C, g)
+    outs = []
+    for fused in (False, True):
+        dx = torch.full((NI, H, W, C), 9.0, dtype=BF16, device="cuda")
+        sums = torch.zeros(2, C, device="cuda")
+        for ph in (0, 1):
+            for pw in (0, 1):
+                th, tw = 1 + ph, 1 + pw
+                taps = [w.float()[:, :, ph + 1 - 2 * a, pw + 1 - 2 * b].t() for a in range(th) for b in range(tw)]
+                wc = torch.cat(taps, dim=1).bfloat16().contiguous()
+                Hs, Ws = (H - ph + 1) // 2, (W - pw + 1) // 2
+                voff = (ph * W + pw) * C * 2
+                ops.gemm(dy, wc, dx, NI * Ho * Wo, C, th * tw * Cout, lda=Cout, conv=(NI, Ho, Wo, Cout), conv_mode=1,
+                         tap_grid=(th, tw, 0), d_ptr=dx.data_ptr() + voff, out_view=(Hs, Ws, 2 * C, 2 * W * C, H * W * C),
+                         bnr=(y, bnp, sums, None, y.data_ptr() + voff) if fused else None)
+        outs.append((dx, sums))
+    assert torch.equal(outs[0][0], outs[1][0])
+    D = outs[1][0].view(-1, C)
+    _check_bnr(ops, D, y, bnp, outs[1][1], None, (y.float() * bnp[2] + bnp[3]) > 0)
+
+
+def test_gemm_tile_counter_windows_stay_in_step():
+    """The dynamic tile scheduler takes its tiles from a ring of 4096 ever-growing counters whose per-launch windows the
+    host keeps track of: more launches than counters (of alternating sizes and chunk widths, so that a window that is
+    off by one fetch would skip or repeat tiles) stay exact."""
+    _need_cuda()
+    ops = _ops()
+    ops.set_dynamic_gemm_schedule(True)
+    try:
+        _tile_counter_windows(ops)
+    finally:
+        ops.set_dynamic_gemm_schedule(False)
+
+
+def _tile_counter_windows(ops):
     g = torch.Generator().manual_seed(3)
-    shapes = [(700, 64, 64), (40000, 64, 64), (3000, 256, 128)]
+    shapes = [(700, 64, 64), (40000, 64, 64), (3000, 256, 128), (700000, 64, 64), (250000, 64, 64)]  # chunks of 1, 4, 2 tiles
     data = []
     for M, N, K in shapes:
         A = (torch.randn(M, K, generator=g) * 0.5).bfloat16().cuda()
         B = (torch.randn(N, K, generator=g) * 0.5).bfloat16().cuda()
         data.append((A, B, torch.empty(M, N, dtype=BF16, device="cuda"), A.float() @ B.float().t()))
     for i in range(4400):
-        A, B, D, _ = data[i % 3]
+        A, B, D, _ = data[i % 3] if i % 40 else data[3 + (i // 40) % 2]
         ops.gemm(A, B, D, A.shape[0], B.shape[0], A.shape[1])
         if i % 1100 == 1099:
             for A, B, D, ref in data:

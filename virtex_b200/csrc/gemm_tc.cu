@@ -108,13 +108,24 @@ struct GemmKParams {
   // division by the launch-invariant tile-schedule extents as multiply-high + shift (a runtime integer division costs
   // ~25 dependent instructions; the schedule decode was ~13 % of the epilogue's instructions on the short-K convs)
   FastDiv d_mn, d_nt, d_mt, d_tw, d_twh, d_cpb, d_taps;
-  // Dynamic tile scheduler: sched[0] is this launch's tile counter (every tile index a CTA processes comes from one
-  // atomicAdd on it), sched[1] counts finished CTAs (the last one resets both words for the slot's next user).  With a
-  // static round-robin schedule an SM that is held by somebody else's CTA (NCCL's all-reduce kernels during the
-  // overlapped gradient exchange) delays ITS fixed share of tiles to the end of every GEMM issued meanwhile; here the
-  // CTAs that do run drain the counter and a late CTA finds nothing left.  nullptr: static schedule (mode 4, debugging).
+  // Dynamic tile scheduler: *sched is a counter that only ever grows; this launch owns the values [sched_base,
+  // sched_base + chunks + gridDim.x) of it (the host knows how many fetches a launch performs: one per chunk of
+  // sched_chunk consecutive tiles plus exactly one end marker per CTA), so nothing is reset and no CTA has to wait for an
+  // atomic on its way out.  With a static round-robin schedule an SM that is held by somebody else's CTA (NCCL's
+  // all-reduce kernels during the overlapped gradient exchange) delays ITS fixed share of tiles to the end of every GEMM
+  // issued meanwhile; here the CTAs that do run drain the counter and a late CTA finds nothing left.
+  // nullptr: static schedule (mode 4, single-GPU default -- see vtx_gemm_set_dynamic_schedule).
   unsigned int* sched;
-  int nt_major;              // tile index runs over row tiles first (BN statistics: a CTA's column block changes rarely)
+  unsigned int sched_base;
+  int sched_chunk;
+  int nt_major;
+  // BN-backward reduction fused into the epilogue (kBnr kernel; `stats` then holds the [2, N] sums of dz and dz * xhat):
+  // y has the geometry of D -- row stride bnr_ldy for plain GEMMs, (w, h, n) strides for implicit-conv outputs and views
+  const __nv_bfloat16* bnr_y;
+  const float* bnr_bnp;      // [4, N]: mean, invstd, scale, shift of the BN whose output gradient D is
+  const uint8_t* bnr_mask;   // optional ReLU bit mask [M, N/8] (plain GEMMs); nullptr: mask recomputed from y
+  long long bnr_ldy, bnr_sw, bnr_sh, bnr_sn;
+  int vW, vH;                // extent of the output (view) grid of the implicit-conv modes              // tile index runs over row tiles first (BN statistics: a CTA's column block changes rarely)
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
@@ -137,6 +148,24 @@ __device__ __forceinline__ void decode_tile(const GemmKParams& p, int t, int& ks
     mt = fdiv(rem, p.d_nt);
     nt = rem - mt * p.n_tiles;
   }
+}
+__device__ __forceinline__ void tma_prefetch_l2_2d(const void* tmap, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(tmap)),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_l2_4d(const void* tmap, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(
+                   reinterpret_cast<uint64_t>(tmap)),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ uint4 ldg128_nc(const void* ptr) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(ptr));
+  return v;
 }
 constexpr int kSched = 8;  // depth of the tile-index ring between the producer (who fetches) and the MMA / epilogue roles
 
@@ -256,10 +285,15 @@ __device__ __forceinline__ void epi_store_f32(const float* v, const GemmKParams&
   }
 }
 
+// kBnr (1: ReLU mask recomputed from y, 2: ReLU bit mask): the statistics pass over the staged output tile computes the BATCH-NORM BACKWARD sums instead of sum / sum of
+// squares: this GEMM's output is the gradient dA w.r.t. a BN(+ReLU) output, and  sum_m dz,  sum_m dz * xhat  with
+// dz = dA * [ReLU mask], xhat = (y - mean) * invstd  used to be a separate pass over dA and y (vtx_bn_bwd_reduce).  The
+// y tile is pulled into L2 by a TMA prefetch when the tile's epilogue starts and read with 16-byte loads in the pass.
+template <int kBnr>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR,
-               const GemmKParams p) {
+               const __grid_constant__ CUtensorMap tmY, const GemmKParams p) {
   VTX_PDL_TRIGGER();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -288,11 +322,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // need not wait for the previous kernel) and consumed after the prologue
   int t_first = (int)blockIdx.x;
   if (warp == 0 && lane == 0) {
-    if (p.sched != nullptr) t_first = (int)atomicAdd(p.sched, 1u);
+    if (p.sched != nullptr) t_first = (int)(atomicAdd(p.sched, 1u) - p.sched_base) * p.sched_chunk;
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (p.cbytes) tma_prefetch_desc(&tmD);
     if (p.res_tma) tma_prefetch_desc(&tmR);
+    if (kBnr) tma_prefetch_desc(&tmY);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < nstages; ++i) {
@@ -331,6 +366,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // modes 0-3: every tile index goes through the ring, whether it came from the counter or from the static schedule;
       // two end markers (>= total_tiles) close it, one per epilogue group
       int t = t_first, sit = 0, ends = 0;
+      // tile after `t_`: the next one of the current chunk, else the first one of a freshly fetched chunk (dynamic), or
+      // the CTA's next round-robin tile (static)
+      auto next_after = [&](int t_) -> int {
+        if (p.sched == nullptr) return t_ + (int)gridDim.x;
+        if ((t_ + 1) % p.sched_chunk != 0 && t_ + 1 < total_tiles) return t_ + 1;
+        return (int)(atomicAdd(p.sched, 1u) - p.sched_base) * p.sched_chunk;
+      };
       auto publish = [&]() {
         const int slot = sit & (kSched - 1);
         mbar_wait(&sch_empty[slot], ((sit / kSched) & 1) ^ 1);
@@ -351,7 +393,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             continue;
           }
           // the next index is requested now and needed only after this tile's loads are queued
-          const int t_next = p.sched != nullptr ? (int)atomicAdd(p.sched, 1u) : t + (int)gridDim.x;
+          const int t_next = next_after(t);
           const int tn = fdiv(t, p.d_twh);
           const int r_wh = t - tn * (p.tiles_w * p.tiles_h);
           const int th = fdiv(r_wh, p.d_tw);
@@ -386,7 +428,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (++ends == 2) break;
           continue;
         }
-        const int t_next = p.sched != nullptr ? (int)atomicAdd(p.sched, 1u) : t + (int)gridDim.x;
+        const int t_next = next_after(t);
         int ks, mt, nt;
         decode_tile(p, t, ks, mt, nt);
         const int kb0 = ks * p.kb_per_split;
@@ -624,6 +666,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           a += v.x;
           b += v.y;
         }
+        if (kBnr) b *= __ldg(p.bnr_bnp + p.N + st_nt * p.bn + et);  // sum dz * (y - mean)  ->  sum dz * xhat
         atomicAdd(p.stats + st_nt * p.bn + et, a);
         atomicAdd(p.stats + p.N + st_nt * p.bn + et, b);
       }
@@ -701,6 +744,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (p.nbuf > 1 && ngrp == 1) tma_store_wait_read<1>();
           else tma_store_wait_read<0>();
           if (p.res_tma) issue_residual(t, cbi);  // requested now that this (group's) buffer is free
+          if (kBnr) {
+            const int slabs = (min(p.bn, p.N - n_base) + 63) >> 6;
+            for (int sl = 0; sl < slabs; ++sl) {
+              if (p.mode & 1) tma_prefetch_l2_4d(&tmY, n_base + sl * 64, tw << p.lbw, th << p.lbh, tn << p.lbn);
+              else tma_prefetch_l2_2d(&tmY, n_base + sl * 64, mt * kBM);
+            }
+          }
         }
         epi_bar(bar_id, epi_threads);
         if (p.stats != nullptr && st_nt != nt) {
@@ -800,7 +850,81 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         // ---------------- BN statistics of the staged (bf16-rounded) tile, accumulated in registers.
         // Rows outside the problem are exact zeros (TMA zero fill; stats forbids bias/residual): no masking needed.
-        if (p.stats != nullptr && st_on) {
+        if (kBnr && st_on && n_base + scg * 8 < p.N) {
+          const int r0 = srg * st_rpt;  // first row of this thread (a multiple of 4)
+          const uint32_t cp = smem_u32(cbuf) + (scg >> 3) * 16384 + r0 * 128;
+          const int c8 = scg & 7;
+          const int col = n_base + scg * 8;
+          // per-column BN parameters of this thread's 8 columns, re-read per tile (L1 hits) so that they do not occupy
+          // registers during the accumulator phase
+          float mean[8], sc[8], sh[8];
+          {
+            const float4 m0 = __ldg(reinterpret_cast<const float4*>(p.bnr_bnp + col));
+            const float4 m1 = __ldg(reinterpret_cast<const float4*>(p.bnr_bnp + col + 4));
+            mean[0] = m0.x; mean[1] = m0.y; mean[2] = m0.z; mean[3] = m0.w;
+            mean[4] = m1.x; mean[5] = m1.y; mean[6] = m1.z; mean[7] = m1.w;
+            if (kBnr == 1) {
+              const float4 a0 = __ldg(reinterpret_cast<const float4*>(p.bnr_bnp + 2 * p.N + col));
+              const float4 a1 = __ldg(reinterpret_cast<const float4*>(p.bnr_bnp + 2 * p.N + col + 4));
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bnr_bnp + 3 * p.N + col));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bnr_bnp + 3 * p.N + col + 4));
+              sc[0] = a0.x; sc[1] = a0.y; sc[2] = a0.z; sc[3] = a0.w; sc[4] = a1.x; sc[5] = a1.y; sc[6] = a1.z; sc[7] = a1.w;
+              sh[0] = b0.x; sh[1] = b0.y; sh[2] = b0.z; sh[3] = b0.w; sh[4] = b1.x; sh[5] = b1.y; sh[6] = b1.z; sh[7] = b1.w;
+            }
+          }
+          for (int rb = 0; rb < st_rpt; rb += 4) {
+            uint4 yv[4];
+            uint32_t mbits[4];
+#pragma unroll
+            for (int r4 = 0; r4 < 4; ++r4) {
+              const int r = r0 + rb + r4;  // row of the tile
+              long long off;
+              bool ok;
+              long long lin = 0;
+              if (p.mode & 1) {
+                const int dw = r & ((1 << p.lbw) - 1);
+                const int dh = (r >> p.lbw) & ((1 << p.lbh) - 1);
+                const int dn = r >> (p.lbw + p.lbh);
+                const int w = (tw << p.lbw) + dw, h = (th << p.lbh) + dh, n = (tn << p.lbn) + dn;
+                ok = (w < p.vW) && (h < p.vH) && (n < p.cN);
+                off = (long long)n * p.bnr_sn + (long long)h * p.bnr_sh + (long long)w * p.bnr_sw;
+              } else {
+                lin = (long long)mt * kBM + r;
+                ok = lin < p.M;
+                off = lin * p.bnr_ldy;
+              }
+              yv[r4] = ok ? ldg128_nc(p.bnr_y + off + col) : make_uint4(0u, 0u, 0u, 0u);
+              // rows outside the output contribute nothing: their mask word is 0 (bit-mask form) or their staged value
+              // is an exact zero / forced to zero below (mask-from-y form)
+              mbits[r4] = ok ? (kBnr == 2 ? (uint32_t)__ldg(p.bnr_mask + (lin * p.N + col) / 8) : 0xffu) : 0u;
+            }
+#pragma unroll
+            for (int r4 = 0; r4 < 4; ++r4) {
+              const int r = rb + r4;
+              const uint4 raw = lds128(cp + r * 128 + ((c8 ^ ((r0 + r) & 7)) << 4));
+              float f[8], yy[8];
+              unpack8(*reinterpret_cast<const bf16x8*>(&raw), f);
+              unpack8(*reinterpret_cast<const bf16x8*>(&yv[r4]), yy);
+              if (kBnr == 1) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const bool on = (yy[i] * sc[i] + sh[i] > 0.f) && (mbits[r4] != 0u);
+                  const float dz = on ? f[i] : 0.f;
+                  st_s[i] += dz;
+                  st_q[i] += dz * (yy[i] - mean[i]);
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float dz = ((mbits[r4] >> i) & 1u) ? f[i] : 0.f;
+                  st_s[i] += dz;
+                  st_q[i] += dz * (yy[i] - mean[i]);
+                }
+              }
+            }
+          }
+        }
+        if (!kBnr && p.stats != nullptr && st_on) {
           const int r0 = srg * st_rpt;  // first row of this thread (a multiple of 4)
           const uint32_t cp = smem_u32(cbuf) + (scg >> 3) * 16384 + r0 * 128;
           const int c8 = scg & 7;
@@ -833,14 +957,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
-  }
-  if (threadIdx.x == 0 && p.sched != nullptr) {
-    // every fetch of this CTA has returned; the last CTA to get here re-arms the slot for the launch that reuses it
-    __threadfence();
-    if (atomicAdd(p.sched + 1, 1u) == gridDim.x - 1) {
-      p.sched[0] = 0u;
-      p.sched[1] = 0u;
-    }
   }
 }
 
@@ -888,26 +1004,39 @@ static int make_tmap(CUtensorMap* tm, const void* ptr, int rank, const uint64_t*
   return VTX_OK;
 }
 
-// Tile-counter slots of the dynamic scheduler: {next tile, finished CTAs} pairs, zero when idle.  Launch i of a device
-// uses slot i mod kSchedSlots; its last CTA zeroes the pair again, and the launch that reuses the slot is thousands of
-// launches later on the same stream order, so no host-side reset is ever needed (graph replays included).
+// Tile counters of the dynamic scheduler.  Launch i of a device uses counter i mod kSchedSlots (adjacent launches overlap
+// under programmatic dependent launch, launches thousands apart do not) and the host keeps the value every counter will
+// have reached when its users so far are done: a launch performs exactly `fetches` atomic increments (one per chunk of
+// tiles + one end marker per CTA), so its window starts at the running total.  Counters wrap modulo 2^32 with the
+// window arithmetic.  (A captured CUDA graph would replay stale windows: capture with the static schedule.)
 constexpr int kSchedSlots = 4096;
-static unsigned int* sched_slot() {
-  static unsigned int* ring[64] = {nullptr};
-  static unsigned int next[64] = {0};
-  static const bool off = getenv("VTX_GEMM_STATIC") != nullptr;  // debugging / A-B knob: the static round-robin schedule
-  if (off) return nullptr;
+static int g_sched_dynamic = 0;  // 0: static round-robin schedule (default), 1: dynamic
+static struct SchedRing {
+  unsigned int* ctr;
+  unsigned int base[kSchedSlots];
+  unsigned int next;
+} g_sched[64];
+static unsigned int* sched_slot(unsigned int fetches, unsigned int* base_out) {
+  static const char* env = getenv("VTX_GEMM_SCHEDULE");  // measurement knob: "static" / "dynamic" overrides the setter
+  const bool dyn = env != nullptr ? (env[0] == 'd') : (g_sched_dynamic != 0);
+  if (!dyn) return nullptr;
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64) return nullptr;
-  if (ring[dev] == nullptr) {
+  SchedRing& r = g_sched[dev];
+  if (r.ctr == nullptr) {
     unsigned int* ptr = nullptr;
-    if (cudaMalloc(&ptr, sizeof(unsigned int) * 2 * kSchedSlots) != cudaSuccess) return nullptr;
-    cudaMemset(ptr, 0, sizeof(unsigned int) * 2 * kSchedSlots);
+    if (cudaMalloc(&ptr, sizeof(unsigned int) * kSchedSlots) != cudaSuccess) return nullptr;
+    cudaMemset(ptr, 0, sizeof(unsigned int) * kSchedSlots);
     cudaDeviceSynchronize();
-    ring[dev] = ptr;
+    memset(r.base, 0, sizeof(r.base));
+    r.next = 0;
+    r.ctr = ptr;
   }
-  return ring[dev] + 2 * (next[dev]++ % kSchedSlots);
+  const unsigned int slot = r.next++ % kSchedSlots;
+  *base_out = r.base[slot];
+  r.base[slot] += fetches;
+  return r.ctr + slot;
 }
 
 static int ilog2(int x) {
@@ -935,6 +1064,11 @@ static void choose_box(int H, int W, int positions, int* bw, int* bh, int* bn) {
 }  // namespace vtx
 
 using namespace vtx;
+
+extern "C" int vtx_gemm_set_dynamic_schedule(int on) {
+  g_sched_dynamic = on ? 1 : 0;
+  return VTX_OK;
+}
 
 extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -1020,6 +1154,20 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
                                 (reinterpret_cast<uintptr_t>(g->residual_mask) & 3) != 0))
     return set_error(VTX_EINVAL, "vtx_gemm: residual_mask needs a residual, a plain bf16 GEMM and N %% 32 == 0");
   p.stats = g->stats;
+  const bool bnr = g->bnr_y != nullptr;
+  if (bnr) {
+    if (!g->bnr_bnp || !g->bnr_sums || g->stats || g->out_f32 || g->bias || g->act || (g->alpha != 0.f && g->alpha != 1.f) ||
+        g->N % 8 != 0 || g->bnr_ldy % 8 != 0 || (reinterpret_cast<uintptr_t>(g->bnr_y) & 15) != 0 ||
+        (reinterpret_cast<uintptr_t>(g->bnr_bnp) & 15) != 0 || (g->bnr_mask != nullptr && g->conv_mode != 0) ||
+        g->conv_mode == 2 || g->conv_mode >= 4 || split_k > 1)
+      return set_error(VTX_EINVAL, "vtx_gemm: bnr needs a plain bf16 output (no stats/bias/activation/alpha/split-K), "
+                                   "N %% 8 == 0, 16-byte aligned y / bnp; the bit-mask form needs conv_mode 0");
+    p.stats = g->bnr_sums;
+    p.bnr_y = reinterpret_cast<const __nv_bfloat16*>(g->bnr_y);
+    p.bnr_bnp = g->bnr_bnp;
+    p.bnr_mask = g->bnr_mask;
+    p.bnr_ldy = g->bnr_ldy;
+  }
 
   CUtensorMap tmA, tmB;
   int rc;
@@ -1150,7 +1298,8 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
     if (st < 2) return set_error(VTX_EUNSUPPORTED, "vtx_gemm: not enough shared memory for a 2-stage pipeline");
     p.stages = st;
   }
-  CUtensorMap tmD, tmR;
+  CUtensorMap tmD, tmR, tmY;
+  memset(&tmY, 0, sizeof(tmY));
   p.epi_warps = (bn >= 128 && p.mode != 4) ? kEpiWarps : 8;
   p.epi_groups = 1;
   memset(&tmD, 0, sizeof(tmD));
@@ -1180,6 +1329,14 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
       }
       uint32_t db[4] = {64, 1u << p.lbw, 1u << p.lbh, 1u << p.lbn};
       if ((rc = make_tmap(&tmD, g->D, 4, dd, ds, db)) != VTX_OK) return rc;
+      p.vW = (int)dd[1]; p.vH = (int)dd[2];
+      if (bnr) {
+        // y has D's geometry: the same strides for a view (y of the strided sub-grid), its own row stride otherwise
+        uint64_t ys[3] = {(uint64_t)g->bnr_ldy, (uint64_t)p.cW * g->bnr_ldy, (uint64_t)p.cH * p.cW * g->bnr_ldy};
+        if (g->conv_out_w > 0) { ys[0] = ds[0]; ys[1] = ds[1]; ys[2] = ds[2]; }
+        p.bnr_sw = (long long)ys[0]; p.bnr_sh = (long long)ys[1]; p.bnr_sn = (long long)ys[2];
+        if ((rc = make_tmap(&tmY, g->bnr_y, 4, dd, ys, db)) != VTX_OK) return rc;
+      }
       if (p.res_tma) {
         // a residual of a view GEMM is a view with the SAME strides (in-place accumulation into the strided sub-grid)
         uint64_t rs[3] = {(uint64_t)g->ldr, (uint64_t)p.cW * g->ldr, (uint64_t)p.cH * p.cW * g->ldr};
@@ -1191,6 +1348,10 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
       uint64_t ds[1] = {(uint64_t)g->ldd};
       uint32_t db[2] = {64, 128};
       if ((rc = make_tmap(&tmD, g->D, 2, dd, ds, db)) != VTX_OK) return rc;
+      if (bnr) {
+        uint64_t ys[1] = {(uint64_t)g->bnr_ldy};
+        if ((rc = make_tmap(&tmY, g->bnr_y, 2, dd, ys, db)) != VTX_OK) return rc;
+      }
       if (p.res_tma) {
         uint64_t rs[1] = {(uint64_t)g->ldr};
         if ((rc = make_tmap(&tmR, g->residual, 2, dd, rs, db)) != VTX_OK) return rc;
@@ -1203,7 +1364,11 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-      cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
+      cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
       if (e != cudaSuccess) return set_error(VTX_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
@@ -1215,14 +1380,20 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
   // changes at most n_tiles - 1 times whatever order the tiles are handed out in (the activation operand of every conv
   // with more than one column tile fits the L2, so the extra passes over it do not reach DRAM)
   p.nt_major = (p.stats != nullptr && p.n_tiles > 1 && p.mode < 3) ? 1 : 0;
-  p.sched = p.mode == 4 ? nullptr : sched_slot();
+  const long total = (long)p.m_tiles * p.n_tiles * p.k_splits;
+  const int sms = vtx_num_sms();
+  const int grid = (int)(total < sms ? total : sms);
+  // many short tiles per CTA (64-wide layer1 / stem convs: ~170): one fetch hands out a few consecutive tiles
+  p.sched_chunk = total >= 32L * grid ? 4 : total >= 12L * grid ? 2 : 1;
+  p.sched = nullptr;
+  if (p.mode != 4) {
+    const unsigned int fetches = (unsigned int)((total + p.sched_chunk - 1) / p.sched_chunk) + (unsigned int)grid;
+    p.sched = sched_slot(fetches, &p.sched_base);
+  }
   p.d_tw = make_fastdiv(p.tiles_w);
   p.d_twh = make_fastdiv(p.tiles_w * p.tiles_h);
   p.d_cpb = make_fastdiv(p.cpb);
   p.d_taps = make_fastdiv(p.taps_w);
-  const long total = (long)p.m_tiles * p.n_tiles * p.k_splits;
-  const int sms = vtx_num_sms();
-  const int grid = (int)(total < sms ? total : sms);
   {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -1235,7 +1406,9 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel, tmA, tmB, tmD, tmR, p);
+    cudaError_t le = !bnr ? cudaLaunchKernelEx(&cfg, gemm_tc_kernel<0>, tmA, tmB, tmD, tmR, tmY, p)
+                     : p.bnr_mask == nullptr ? cudaLaunchKernelEx(&cfg, gemm_tc_kernel<1>, tmA, tmB, tmD, tmR, tmY, p)
+                                             : cudaLaunchKernelEx(&cfg, gemm_tc_kernel<2>, tmA, tmB, tmD, tmR, tmY, p);
     if (le != cudaSuccess) return set_error(VTX_ECUDA, "gemm_tc_kernel PDL launch: %s", cudaGetErrorString(le));
   }
   cudaError_t e = cudaGetLastError();

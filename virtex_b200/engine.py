@@ -16,6 +16,7 @@ decoder residual stream fp32 with bf16 shadows feeding the GEMMs, logits bf16 (f
 from __future__ import annotations
 
 import math
+import os
 import struct
 from typing import Dict, List, Optional, Tuple
 
@@ -151,6 +152,10 @@ class Engine:
         self._tape = None
         self.generation = 0  # bumped by every forward(): a backward must match the forward that filled the tape
         self._weights_fresh = False
+        # BN-backward reductions (sum dz, sum dz * xhat) accumulated by the epilogue of the GEMM that produces the
+        # gradient (bn1 / bn2 of every block, bn3 of blocks followed by an identity block) instead of a separate pass;
+        # VTX_BNR_FUSE=0 is the measurement knob for the A/B against the standalone vtx_bn_bwd_reduce launches
+        self.fuse_bn_reduce = os.environ.get("VTX_BNR_FUSE", "1") != "0"
         self._build_backbone_plan()
 
     # ------------------------------------------------------------------------------------------------ parameters
@@ -410,14 +415,18 @@ class Engine:
         sk = ops.split_k_for(tiles, (m_rows + 63) // 64)
         gemm(dY, X, dW, n_out, k_in, m_rows, a_mn=1, b_mn=1, atomic=True, split_k=sk, ldd=k_in, out_f32=True)
 
-    def _bn_bwd(self, dA, a, y, bnp, bn_name, M, C, dy, two=None, dz_out=None, mask_from_y=0):
+    def _bn_bwd(self, dA, a, y, bnp, bn_name, M, C, dy, two=None, dz_out=None, mask_from_y=0, sums=None):
         """dA -> dy through (ReLU from the bit mask `a`, or recomputed from y when mask_from_y) + train-mode BN;
-        two = (y2, bnp2, bn2_name, dy2) shares dz."""
+        two = (y2, bnp2, bn2_name, dy2) shares dz.  `sums`: the [2, C] reduction already accumulated by the epilogue of
+        the GEMM that produced dA (VtxGemm.bnr_*), so only the apply pass is left."""
         s = _stream()
-        sums = self._slab_take(2 * C)
+        fused = sums is not None
+        if not fused:
+            sums = self._slab_take(2 * C)
         if two is None:
-            call("vtx_bn_bwd_reduce", dA.data_ptr(), _p(a), y.data_ptr(), bnp.data_ptr(), 0, 0, sums.data_ptr(), 0,
-                 M, C, mask_from_y, s)
+            if not fused:
+                call("vtx_bn_bwd_reduce", dA.data_ptr(), _p(a), y.data_ptr(), bnp.data_ptr(), 0, 0, sums.data_ptr(), 0,
+                     M, C, mask_from_y, s)
             call("vtx_bn_bwd_finalize_apply", sums.data_ptr(), 0, float(M), self.G(bn_name + ".weight").data_ptr(),
                  self.G(bn_name + ".bias").data_ptr(), 0, 0, dA.data_ptr(), _p(a), y.data_ptr(), bnp.data_ptr(),
                  dy.data_ptr(), 0, 0, 0, _p(dz_out), M, C, mask_from_y, s)
@@ -448,7 +457,11 @@ class Engine:
         prev_layer = None
         self._dwp_flat.zero_()
         stem_s2d = tape["stem"]["s2d"] is not None
-        for rec in reversed(tape["blocks"]):
+        blocks = tape["blocks"]
+        fuse = self.fuse_bn_reduce
+        sums3 = None  # bn3 sums of the current block when the GEMM that produced dOut already accumulated them
+        for bi in range(len(blocks) - 1, -1, -1):
+            rec = blocks[bi]
             name, planes, Cin, stride = rec["name"], rec["planes"], rec["Cin"], rec["stride"]
             layer = name.split(".")[2]
             if prev_layer is not None and layer != prev_layer:
@@ -469,17 +482,21 @@ class Engine:
                 # the shortcut gradient dz = dOut * [block output > 0] is never written: conv1's dgrad epilogue adds
                 # dOut under the same bit mask (VtxGemm.residual_mask)
                 dz = None
-                self._bn_bwd(dOut, rec["m3"], rec["y3"], rec["bnp3"], name + ".bn3", Mout, C4, dy3)
-            # ---- conv3 (1x1): wgrad + dgrad
+                self._bn_bwd(dOut, rec["m3"], rec["y3"], rec["bnp3"], name + ".bn3", Mout, C4, dy3, sums=sums3)
+            sums3 = None
+            # ---- conv3 (1x1): wgrad + dgrad; the dgrad epilogue accumulates bn2's backward sums (ReLU mask from y2)
             self._wgrad(dy3, rec["a2"], self.G(name + ".conv3.weight"), C4, planes, Mout)
             da2 = ws.get("bwd.da2", (Mout, planes), BF16)
-            gemm(dy3, self.W(name + ".conv3.weight").view(C4, planes), da2, Mout, planes, C4, b_mn=1)
+            sums2 = self._slab_take(2 * planes) if fuse else None
+            gemm(dy3, self.W(name + ".conv3.weight").view(C4, planes), da2, Mout, planes, C4, b_mn=1,
+                 bnr=(rec["y2"], rec["bnp2"], sums2, None) if fuse else None)
             # ---- bn2 + ReLU backward
             dy2 = ws.get("bwd.dy2", (Mout, planes), BF16)
-            self._bn_bwd(da2, None, rec["y2"], rec["bnp2"], name + ".bn2", Mout, planes, dy2, mask_from_y=1)
+            self._bn_bwd(da2, None, rec["y2"], rec["bnp2"], name + ".bn2", Mout, planes, dy2, mask_from_y=1, sums=sums2)
             # ---- conv2 (3x3): wgrad + dgrad
             dwp = self._dwp[name + ".conv2"].view(planes, 9 * planes)
             da1 = ws.get("bwd.da1", (Min, planes), BF16)
+            sums1 = None
             if rec["cols2"] is None:
                 if planes == 64 and stride == 1:
                     # halo-reuse wgrad: D[(tap, cin), cout], accumulated in TMEM over all spatial tiles of a CTA
@@ -490,9 +507,12 @@ class Engine:
                     sk = ops.split_k_for(tiles, (Mout + 63) // 64)
                     gemm(dy2, rec["a1"], dwp, planes, 9 * planes, Mout, atomic=True, split_k=sk, lda=planes,
                          ldb=planes, conv=(B, Hc, Wc, planes), conv_mode=2, out_f32=True, conv_stride=stride)
+                if fuse and stride in (1, 2):
+                    sums1 = self._slab_take(2 * planes)  # bn1's backward sums, accumulated by the conv2-dgrad epilogue(s)
                 if stride == 1:
                     gemm(dy2, self._packed[name + ".conv2.weight#dgrad"], da1, Min, planes, 9 * planes, lda=planes,
-                         conv=(B, Hc, Wc, planes), conv_mode=1)
+                         conv=(B, Hc, Wc, planes), conv_mode=1,
+                         bnr=(rec["y1"], rec["bnp1"], sums1, None) if fuse else None)
                 elif stride == 2:
                     # strided dgrad as four implicit GEMMs, one per parity class (ph, pw) of the input position: row
                     # 2i+ph of da1 gathers dy rows i+a, a < 1+ph, through kernel rows ph+1-2a (same along w); each class
@@ -504,10 +524,12 @@ class Engine:
                             Hs, Ws = (Hc - ph + 1) // 2, (Wc - pw + 1) // 2
                             if Hs <= 0 or Ws <= 0:
                                 continue
+                            voff = (ph * Wc + pw) * planes * 2
                             gemm(dy2, self._packed[f"{name}.conv2.weight#dgrad_s2_{ph}{pw}"], da1, Mout, planes,
                                  th * tw * planes, lda=planes, conv=(B, Hn, Wn, planes), conv_mode=1, tap_grid=(th, tw, 0),
-                                 d_ptr=da1.data_ptr() + (ph * Wc + pw) * planes * 2,
-                                 out_view=(Hs, Ws, 2 * planes, 2 * Wc * planes, Hc * Wc * planes))
+                                 d_ptr=da1.data_ptr() + voff,
+                                 out_view=(Hs, Ws, 2 * planes, 2 * Wc * planes, Hc * Wc * planes),
+                                 bnr=(rec["y1"], rec["bnp1"], sums1, None, rec["y1"].data_ptr() + voff) if fuse else None)
                 else:  # other strides: per-tap gradients by a plain GEMM, scattered back by col2im
                     dcols = ws.get("bwd.dcols", (Mout, 9 * planes), BF16)
                     gemm(dy2, self._packed[name + ".conv2.weight"], dcols, Mout, 9 * planes, planes, b_mn=1)
@@ -519,7 +541,7 @@ class Engine:
                 call("vtx_col2im3x3", dcols.data_ptr(), da1.data_ptr(), B, Hc, Wc, planes, stride, s)
             # ---- bn1 + ReLU backward
             dy1 = ws.get("bwd.dy1", (Min, planes), BF16)
-            self._bn_bwd(da1, None, rec["y1"], rec["bnp1"], name + ".bn1", Min, planes, dy1, mask_from_y=1)
+            self._bn_bwd(da1, None, rec["y1"], rec["bnp1"], name + ".bn1", Min, planes, dy1, mask_from_y=1, sums=sums1)
             # ---- conv1 (1x1): wgrad + dgrad (+ shortcut gradient)
             self._wgrad(dy1, rec["x"], self.G(name + ".conv1.weight"), planes, Cin, Min)
             dx = ws.get(f"bwd.dx{scratch_i & 1}", (Min, Cin), BF16)
@@ -548,7 +570,14 @@ class Engine:
                     gemm(dyd, wd, dxs, Mout, Cin, C4, b_mn=1)
                     call("vtx_upsample_add", dxs.data_ptr(), dx.data_ptr(), B, Hc, Wc, Cin, stride, s)
             else:
-                gemm(dy1, w1, dx, Min, Cin, planes, b_mn=1, residual=dOut, residual_mask=rec["m3"])
+                # dx is the output gradient of the previous block: when that block has a single-branch bn3, its backward
+                # sums (ReLU bit mask m3 of THAT block) are accumulated here, over the staged dx tiles
+                prev = blocks[bi - 1] if bi > 0 else None
+                bnr3 = None
+                if fuse and prev is not None and not prev["has_ds"] and Cin % 32 == 0:
+                    sums3 = self._slab_take(2 * Cin)
+                    bnr3 = (prev["y3"], prev["bnp3"], sums3, prev["m3"])
+                gemm(dy1, w1, dx, Min, Cin, planes, b_mn=1, residual=dOut, residual_mask=rec["m3"], bnr=bnr3)
             dOut = dx
         # ---- stem: maxpool bwd -> ReLU/BN bwd -> wgrad
         st = tape["stem"]

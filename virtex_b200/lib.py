@@ -35,6 +35,7 @@ class VtxGemm(ctypes.Structure):
         ("conv_out_h", c_i32), ("conv_out_w", c_i32),
         ("ldd_w", c_i64), ("ldd_h", c_i64), ("ldd_n", c_i64),
         ("residual_mask", c_void_p),
+        ("bnr_y", c_void_p), ("bnr_bnp", c_void_p), ("bnr_sums", c_void_p), ("bnr_mask", c_void_p), ("bnr_ldy", c_i64),
     ]
 
 

@@ -74,7 +74,8 @@ def _get(name):
 
 def exported_symbols():
     """All C-ABI entry points this module binds (used by the CPU test that checks the library exports them)."""
-    return sorted(_PROTOS) + ["vtx_last_error", "vtx_version", "vtx_num_sms", "vtx_weight_job_block_elems", "vtx_sizeof_gemm"]
+    return sorted(_PROTOS) + ["vtx_last_error", "vtx_version", "vtx_num_sms", "vtx_weight_job_block_elems", "vtx_sizeof_gemm",
+                              "vtx_gemm_set_dynamic_schedule"]
 
 
 def _stream():
@@ -116,14 +117,21 @@ def num_sms():
     return L.load().vtx_num_sms()
 
 
+def set_dynamic_gemm_schedule(on: bool):
+    """Tile schedule of the persistent GEMM (include/virtex_b200.h): dynamic when another stream's kernels (NCCL) share
+    the SMs with it, static otherwise."""
+    L.check(L.load().vtx_gemm_set_dynamic_schedule(int(bool(on))), "vtx_gemm_set_dynamic_schedule")
+
+
 # --------------------------------------------------------------------------------------------------------------- GEMM
 _gemm_struct = L.VtxGemm()
 
 
 def gemm(A, B, D, M, N, K, *, lda=None, ldb=None, ldd=None, a_mn=0, b_mn=0, bias=None, act=0, residual=None,
          ldr=0, stats=None, atomic=False, split_k=1, tile_n=0, conv=None, conv_mode=0, out_f32=None, residual_mask=None,
-         conv_stride=1, conv_taps=0, tap_grid=None, out_view=None, d_ptr=None):
-    """D[M,N] = epilogue(A . B^T) through the tcgen05 kernel; see include/virtex_b200.h (VtxGemm)."""
+         conv_stride=1, conv_taps=0, tap_grid=None, out_view=None, d_ptr=None, bnr=None):
+    """D[M,N] = epilogue(A . B^T) through the tcgen05 kernel; see include/virtex_b200.h (VtxGemm).
+    bnr = (y, bnp, sums, mask or None[, y_ptr]): BN-backward reduction of the output fused into the epilogue."""
     g = _gemm_struct
     g.A, g.B, g.D = A.data_ptr(), B.data_ptr(), (D.data_ptr() if d_ptr is None else d_ptr)
     g.bias, g.residual, g.stats = _p(bias), _p(residual), _p(stats)
@@ -146,6 +154,13 @@ def gemm(A, B, D, M, N, K, *, lda=None, ldb=None, ldd=None, a_mn=0, b_mn=0, bias
     g.conv_taps_h, g.conv_taps_w, g.conv_pad = tap_grid if tap_grid is not None else (0, 0, 0)
     # out_view = (out_h, out_w, ldd_w, ldd_h, ldd_n): D (at d_ptr) is a strided sub-grid of a larger NHWC tensor
     g.conv_out_h, g.conv_out_w, g.ldd_w, g.ldd_h, g.ldd_n = out_view if out_view is not None else (0, 0, 0, 0, 0)
+    if bnr is not None:
+        g.bnr_y = bnr[0].data_ptr() if len(bnr) < 5 else bnr[4]
+        g.bnr_bnp, g.bnr_sums, g.bnr_mask = bnr[1].data_ptr(), bnr[2].data_ptr(), _p(bnr[3])
+        g.bnr_ldy = bnr[0].stride(0)
+    else:
+        g.bnr_y = g.bnr_bnp = g.bnr_sums = g.bnr_mask = None
+        g.bnr_ldy = 0
     if _gemm_profile is None:
         call("vtx_gemm", ctypes.addressof(g), _stream())
     else:
@@ -154,6 +169,8 @@ def gemm(A, B, D, M, N, K, *, lda=None, ldb=None, ldd=None, a_mn=0, b_mn=0, bias
         call("vtx_gemm", ctypes.addressof(g), _stream())
         e1.record()
         extra = (2 * M * N if residual is not None else 0) + (M * N // 8 if residual_mask is not None else 0)
+        if bnr is not None:
+            extra += 2 * M * N + (M * N // 8 if bnr[3] is not None else 0)
         _gemm_profile.append((e0, e1, 2.0 * M * N * K, M, N, K, conv_mode, a_mn, b_mn, extra))
 
 

@@ -97,6 +97,9 @@ class Trainer:
         self._seed_base = (int(config.RANDOM_SEED) << 24) + rank * 1000003
         eng.seed.fill_(self._seed_base)
         self.comm_stream = torch.cuda.Stream(device=dev) if self.world > 1 else None
+        # NCCL's all-reduce CTAs take SMs away from the persistent GEMM while a bucket is in flight: hand its tiles out
+        # dynamically then (an SM that starts late finds nothing left instead of delaying its fixed share of every GEMM)
+        ops.set_dynamic_gemm_schedule(self.world > 1)
         self._pending = []
         self._ranges = self._bucket_ranges()
         if self.world > 1:  # DDP constructor semantics: rank 0's parameters and buffers everywhere
