@@ -579,6 +579,96 @@ def test_gemm_fused_bn_backward_reduce_strided_parity_classes(NI, H, W, C, Cout)
     _check_bnr(ops, D, y, bnp, outs[1][1], None, (y.float() * bnp[2] + bnp[3]) > 0)
 
 
+def _pair_env(on):
+    import os
+    if on:
+        os.environ.pop("VTX_GEMM_PAIR", None)
+    else:
+        os.environ["VTX_GEMM_PAIR"] = "0"
+
+
+@pytest.mark.parametrize("M,N,K", [(7680, 1024, 1024), (1000, 256, 512), (896, 10000, 256), (50176, 256, 1024), (641, 384, 320)])
+def test_gemm_cta_pairs_match_single_cta_and_torch(M, N, K):
+    """cta_group::2: a 2-CTA cluster runs one M = 256 MMA over two row tiles, each CTA staging half of the B tile.  Every
+    operand layout (K-major / MN-major A and B, split-K fp32 atomics), odd numbers of row tiles (the last pair's second CTA
+    is all padding), bias / activation / residual / statistics / fused BN-backward sums -- against the one-CTA-per-tile
+    path of the same library and torch."""
+    _need_cuda()
+    ops = _ops()
+    g = torch.Generator().manual_seed(M + N)
+    A = (torch.randn(M, K, generator=g) * 0.5).bfloat16().cuda()
+    B = (torch.randn(N, K, generator=g) * 0.1).bfloat16().cuda()
+    Bt = B.t().contiguous()                      # [K, N]: MN-major B
+    At = A.t().contiguous()                      # [K, M]: MN-major A
+    ref = A.float() @ B.float().t()
+    bias = torch.randn(N, generator=g).cuda()
+    R = torch.randn(M, N, generator=g).bfloat16().cuda()
+    y = (torch.randn(M, N, generator=g) * 1.5).bfloat16().cuda()
+    bnp = _bnp(N, g)
+    outs = {}
+    try:
+        for pair in (False, True):
+            _pair_env(pair)
+            D1 = torch.empty(M, N, dtype=BF16, device="cuda")
+            st = torch.zeros(2, N, device="cuda")
+            ops.gemm(A, B, D1, M, N, K, stats=st)
+            D2 = torch.empty(M, N, dtype=BF16, device="cuda")
+            ops.gemm(A, Bt, D2, M, N, K, b_mn=1, bias=bias, act=1)
+            D3 = torch.empty(M, N, dtype=BF16, device="cuda")
+            sums = torch.zeros(2, N, device="cuda")
+            if N % 32 == 0:
+                ops.gemm(A, Bt, D3, M, N, K, b_mn=1, residual=R, bnr=(y, bnp, sums, None))
+            D4 = torch.zeros(M, N, device="cuda")
+            if M % 8 == 0:
+                ops.gemm(At, Bt, D4, M, N, K, a_mn=1, b_mn=1, atomic=True, split_k=2, out_f32=True)
+            outs[pair] = (D1, st, D2, D3, sums, D4)
+    finally:
+        _pair_env(True)
+    D1, st, D2, D3, sums, D4 = outs[True]
+    assert rel(D1, ref) < 4e-3 and rel(D2, torch.relu(ref + bias)) < 4e-3
+    assert rel(st[0], D1.double().sum(0)) < 1e-4 and rel(st[1], (D1.double() ** 2).sum(0)) < 1e-4
+    if N % 32 == 0:
+        assert rel(D3, ref + R.float()) < 4e-3
+        _check_bnr(ops, D3, y, bnp, sums, None, (y.float() * bnp[2] + bnp[3]) > 0)
+    if M % 8 == 0:
+        assert rel(D4, ref) < 1e-4
+    for a, b in zip(outs[True], outs[False]):
+        assert rel(a, b) < (2e-3 if a.dtype == BF16 else 1e-4)   # (bf16: at most a few last-bit flips)
+
+
+@pytest.mark.parametrize("NI,H,W,C,Cout", [(16, 14, 14, 256, 256), (9, 7, 7, 512, 512), (5, 28, 28, 128, 128)])
+def test_gemm_cta_pairs_implicit_conv(NI, H, W, C, Cout):
+    """CTA pairs through the implicit 3x3 convolution modes: fprop (4-D activation boxes per CTA, half of the K-major
+    weight tile each) and wgrad (each CTA gathers the taps of its half of the (tap, cin) columns)."""
+    _need_cuda()
+    ops = _ops()
+    g = torch.Generator().manual_seed(H + C)
+    M = NI * H * W
+    x = (torch.randn(NI, H, W, C, generator=g) * 0.5).bfloat16().cuda()
+    w = (torch.randn(Cout, 3, 3, C, generator=g) * 0.03).bfloat16().cuda()
+    dy = (torch.randn(NI, H, W, Cout, generator=g) * 0.5).bfloat16().cuda()
+    outs = {}
+    try:
+        for pair in (False, True):
+            _pair_env(pair)
+            yo = torch.empty(M, Cout, dtype=BF16, device="cuda")
+            st = torch.zeros(2, Cout, device="cuda")
+            ops.gemm(x, w.view(Cout, 9 * C), yo, M, Cout, 9 * C, lda=C, stats=st, conv=(NI, H, W, C), conv_mode=1)
+            dw = torch.zeros(Cout, 9 * C, device="cuda")
+            ops.gemm(dy, x, dw, Cout, 9 * C, M, atomic=True, split_k=2, lda=Cout, ldb=C, conv=(NI, H, W, C), conv_mode=2,
+                     out_f32=True)
+            outs[pair] = (yo, st, dw)
+    finally:
+        _pair_env(True)
+    yo, st, dw = outs[True]
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), padding=1).permute(0, 2, 3, 1).reshape(M, Cout)
+    assert rel(yo, ref) < 4e-3
+    assert rel(st[0], yo.double().sum(0)) < 1e-4
+    dwr = torch.nn.grad.conv2d_weight(x.float().permute(0, 3, 1, 2), (Cout, C, 3, 3), dy.float().permute(0, 3, 1, 2), padding=1)
+    assert rel(dw.view(Cout, 3, 3, C), dwr.permute(0, 2, 3, 1)) < 2e-3
+    assert rel(outs[True][0], outs[False][0]) < 2e-3 and rel(outs[True][2], outs[False][2]) < 1e-4
+
+
 def test_gemm_tile_counter_windows_stay_in_step():
     """The dynamic tile scheduler takes its tiles from a ring of 4096 ever-growing counters whose per-launch windows the
     host keeps track of: more launches than counters (of alternating sizes and chunk widths, so that a window that is

@@ -125,7 +125,11 @@ struct GemmKParams {
   const float* bnr_bnp;      // [4, N]: mean, invstd, scale, shift of the BN whose output gradient D is
   const uint8_t* bnr_mask;   // optional ReLU bit mask [M, N/8] (plain GEMMs); nullptr: mask recomputed from y
   long long bnr_ldy, bnr_sw, bnr_sh, bnr_sn;
-  int vW, vH;                // extent of the output (view) grid of the implicit-conv modes              // tile index runs over row tiles first (BN statistics: a CTA's column block changes rarely)
+  int vW, vH;                // extent of the output (view) grid of the implicit-conv modes
+  // CTA pair (kPair kernel, cta_group::2): a 2-CTA cluster works on two vertically adjacent 128-row tiles with ONE
+  // M = 256 MMA per K step; each CTA stages its own A tile and half of the B tile, so every SM pulls 1.5x fewer operand
+  // bytes through L2 and shared memory per flop.  The schedule then runs over m_sched = ceil(m_tiles / 2) row-tile pairs.
+  int pair, m_sched;              // tile index runs over row tiles first (BN statistics: a CTA's column block changes rarely)
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
@@ -138,16 +142,18 @@ __device__ __forceinline__ void epi_bar(int id, int threads) {
 }
 
 // schedule index -> (split, row tile, column tile)
-__device__ __forceinline__ void decode_tile(const GemmKParams& p, int t, int& ks, int& mt, int& nt) {
+// (`rank`: this CTA's rank in its pair -- the pair shares the schedule index, rank r owns row tile 2 * index + r)
+__device__ __forceinline__ void decode_tile(const GemmKParams& p, int t, int& ks, int& mt, int& nt, int rank = 0) {
   ks = fdiv(t, p.d_mn);
-  const int rem = t - ks * (p.m_tiles * p.n_tiles);
+  const int rem = t - ks * (p.m_sched * p.n_tiles);
   if (p.nt_major) {
     nt = fdiv(rem, p.d_mt);
-    mt = rem - nt * p.m_tiles;
+    mt = rem - nt * p.m_sched;
   } else {
     mt = fdiv(rem, p.d_nt);
     nt = rem - mt * p.n_tiles;
   }
+  if (p.pair) mt = 2 * mt + rank;
 }
 __device__ __forceinline__ void tma_prefetch_l2_2d(const void* tmap, int c0, int c1) {
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(tmap)),
@@ -285,11 +291,13 @@ __device__ __forceinline__ void epi_store_f32(const float* v, const GemmKParams&
   }
 }
 
+#define LOAD2D(...) (kPair ? tma_load_2d_pair(__VA_ARGS__) : tma_load_2d(__VA_ARGS__))
+#define LOAD4D(...) (kPair ? tma_load_4d_pair(__VA_ARGS__) : tma_load_4d(__VA_ARGS__))
 // kBnr (1: ReLU mask recomputed from y, 2: ReLU bit mask): the statistics pass over the staged output tile computes the BATCH-NORM BACKWARD sums instead of sum / sum of
 // squares: this GEMM's output is the gradient dA w.r.t. a BN(+ReLU) output, and  sum_m dz,  sum_m dz * xhat  with
 // dz = dA * [ReLU mask], xhat = (y - mean) * invstd  used to be a separate pass over dA and y (vtx_bn_bwd_reduce).  The
 // y tile is pulled into L2 by a TMA prefetch when the tile's epilogue starts and read with 16-byte loads in the pass.
-template <int kBnr>
+template <int kBnr, int kPair>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR,
@@ -315,12 +323,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // broadcast from lane 0 so that the compiler sees the warp index (and every role branch on it) as warp-uniform
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
-  const int total_tiles = p.m_tiles * p.n_tiles * p.k_splits;
+  const int total_tiles = p.m_sched * p.n_tiles * p.k_splits;
+  // schedule identity: a CTA, or a CTA pair (the two CTAs of a pair walk the same static schedule)
+  const int rank = kPair ? (int)cluster_ctarank() : 0;
+  const int sched_id = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int sched_n = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int nstages = p.stages;
 
   // the producer thread's first tile: requested before anything else (the counter belongs to this launch alone, so it
   // need not wait for the previous kernel) and consumed after the prologue
-  int t_first = (int)blockIdx.x;
+  int t_first = sched_id;
   if (warp == 0 && lane == 0) {
     if (p.sched != nullptr) t_first = (int)(atomicAdd(p.sched, 1u) - p.sched_base) * p.sched_chunk;
     tma_prefetch_desc(&tmA);
@@ -336,7 +348,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], p.epi_warps * 32 / p.epi_groups);
+      mbar_init(&tempty_bar[i], (kPair ? 2 : 1) * (p.epi_warps * 32 / p.epi_groups));  // pair: both CTAs' epilogues
       mbar_init(&res_bar[i], 1);
     }
     mbar_init(bst_bar, 1);
@@ -347,16 +359,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
+    if (kPair) {
+      tmem_alloc_pair(tmem_slot, 512);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, 512);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  // pair: the peer's barriers must exist before the leader's MMA commits / this CTA's TMA loads signal across the pair
+  if (kPair) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   VTX_PDL_WAIT();  // everything above overlapped the previous kernel's tail; its results are visible from here
 
-  const uint32_t b_bytes = (uint32_t)p.bn * kBK * 2;
+  const int bn_cta = kPair ? (p.bn >> 1) : p.bn;  // B rows staged by this CTA
+  const uint32_t b_bytes = (uint32_t)bn_cta * kBK * 2;
 
   if (warp == 0) {
     // ===================================================== TMA producer
@@ -369,7 +389,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // tile after `t_`: the next one of the current chunk, else the first one of a freshly fetched chunk (dynamic), or
       // the CTA's next round-robin tile (static)
       auto next_after = [&](int t_) -> int {
-        if (p.sched == nullptr) return t_ + (int)gridDim.x;
+        if (p.sched == nullptr) return t_ + sched_n;
         if ((t_ + 1) % p.sched_chunk != 0 && t_ + 1 < total_tiles) return t_ + 1;
         return (int)(atomicAdd(p.sched, 1u) - p.sched_base) * p.sched_chunk;
       };
@@ -430,7 +450,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         const int t_next = next_after(t);
         int ks, mt, nt;
-        decode_tile(p, t, ks, mt, nt);
+        decode_tile(p, t, ks, mt, nt, rank);
         const int kb0 = ks * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         int w0 = 0, h0 = 0, n0 = 0;
@@ -447,27 +467,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint8_t* sB = sA + kABytes;
           // MN-major A tiles are loaded as two 64-row atoms; when the second lies entirely beyond M it is not fetched
           // (its accumulator rows are garbage, and masked by the epilogue)
-          const bool half_a = p.a_mn && (mt * kBM + 64 >= p.M);
-          mbar_arrive_expect_tx(&full_bar[stage], (half_a ? kABytes / 2 : kABytes) + b_bytes);
+          // pair: every load of both CTAs counts on the LEADER's barrier, which expects the bytes of both (fixed: the
+          // half-A shortcut is off); B rows / atoms of this CTA's half of the column tile
+          const bool half_a = !kPair && p.a_mn && (mt * kBM + 64 >= p.M);
+          if (!kPair) mbar_arrive_expect_tx(&full_bar[stage], (half_a ? kABytes / 2 : kABytes) + b_bytes);
+          else if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * (kABytes + b_bytes));
+          const int nb0 = nt * p.bn + rank * bn_cta;  // first B row (column of the output) staged by this CTA
           if (p.mode == 0) {
             if (!p.a_mn) {
-              tma_load_2d(sA, &tmA, &full_bar[stage], kb * kBK, mt * kBM);
+              LOAD2D(sA, &tmA, &full_bar[stage], kb * kBK, mt * kBM);
             } else {
-              tma_load_2d(sA, &tmA, &full_bar[stage], mt * kBM, kb * kBK);
-              if (!half_a) tma_load_2d(sA + 8192, &tmA, &full_bar[stage], mt * kBM + 64, kb * kBK);
+              LOAD2D(sA, &tmA, &full_bar[stage], mt * kBM, kb * kBK);
+              if (!half_a) LOAD2D(sA + 8192, &tmA, &full_bar[stage], mt * kBM + 64, kb * kBK);
             }
             if (!p.b_mn) {
-              tma_load_2d(sB, &tmB, &full_bar[stage], kb * kBK, nt * p.bn);
+              LOAD2D(sB, &tmB, &full_bar[stage], kb * kBK, nb0);
             } else {
-              for (int j = 0; j < (p.bn >> 6); ++j)
-                tma_load_2d(sB + j * 8192, &tmB, &full_bar[stage], nt * p.bn + 64 * j, kb * kBK);
+              for (int j = 0; j < (bn_cta >> 6); ++j)
+                LOAD2D(sB + j * 8192, &tmB, &full_bar[stage], nb0 + 64 * j, kb * kBK);
             }
           } else if (p.mode == 1) {
             const int tap = fdiv(kb, p.d_cpb);
             const int cb = kb - tap * p.cpb;
             const int kh = fdiv(tap, p.d_taps), kw = tap - kh * KP_TAPS_W;
-            tma_load_4d(sA, &tmA, &full_bar[stage], cb * 64, p.cstride * w0 + kw - KP_PAD, p.cstride * h0 + kh - KP_PAD, n0);
-            tma_load_2d(sB, &tmB, &full_bar[stage], kb * kBK, nt * p.bn);
+            LOAD4D(sA, &tmA, &full_bar[stage], cb * 64, p.cstride * w0 + kw - KP_PAD, p.cstride * h0 + kh - KP_PAD, n0);
+            LOAD2D(sB, &tmB, &full_bar[stage], kb * kBK, nb0);
           } else {
             // wgrad: reduction block kb is a spatial box of 64 output positions
             const int tn = fdiv(kb, p.d_twh);
@@ -475,17 +499,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int th = fdiv(r_wh, p.d_tw);
             const int tw = r_wh - th * p.tiles_w;
             const int bw0 = tw << p.lbw, bh0 = th << p.lbh, bn0 = tn << p.lbn;
-            tma_load_4d(sA, &tmA, &full_bar[stage], mt * kBM, bw0, bh0, bn0);
-            if (!half_a) tma_load_4d(sA + 8192, &tmA, &full_bar[stage], mt * kBM + 64, bw0, bh0, bn0);
-            for (int j = 0; j < (p.bn >> 6); ++j) {
-              const int atom = nt * (p.bn >> 6) + j;
+            LOAD4D(sA, &tmA, &full_bar[stage], mt * kBM, bw0, bh0, bn0);
+            if (!half_a) LOAD4D(sA + 8192, &tmA, &full_bar[stage], mt * kBM + 64, bw0, bh0, bn0);
+            for (int j = 0; j < (bn_cta >> 6); ++j) {
+              const int atom = (nb0 >> 6) + j;
               const int tap = fdiv(atom, p.d_cpb);
               const int cb = atom - tap * p.cpb;
               const int kh = fdiv(tap, p.d_taps), kw = tap - kh * KP_TAPS_W;
               // atoms past the 9 taps are loaded fully out of bounds (zero fill) to keep the tx count fixed
               const int nn = tap < KP_NTAPS ? bn0 : p.cN + 1;
-              tma_load_4d(sB + j * 8192, &tmB, &full_bar[stage], cb * 64, p.cstride * bw0 + kw - KP_PAD,
-                          p.cstride * bh0 + kh - KP_PAD, nn);
+              LOAD4D(sB + j * 8192, &tmB, &full_bar[stage], cb * 64, p.cstride * bw0 + kw - KP_PAD,
+                     p.cstride * bh0 + kh - KP_PAD, nn);
             }
           }
           if (++stage == nstages) { stage = 0; phase ^= 1; }
@@ -504,7 +528,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // can treat as warp-uniform and feed to tcgen05.mma without a per-instruction ELECT / R2UR.BROADCAST sequence
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     {
-      const uint32_t idesc = make_idesc_bf16(p.bn, p.a_mn, p.b_mn);
+      const uint32_t idesc = make_idesc_bf16(p.bn, p.a_mn, p.b_mn, kPair ? 256 : 128);
       const uint32_t a_step = p.a_mn ? 2048u : 32u;
       const uint32_t b_step = p.b_mn ? 2048u : 32u;
       const uint32_t a_lbo = p.a_mn ? 8192u : 16u;
@@ -590,6 +614,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (; p.mode < 3; ++it) {
         const int t = next_tile(it);
         if (t >= total_tiles) break;
+        if (kPair && rank != 0) continue;  // the leader issues the pair's MMAs; this warp only keeps the index ring moving
         const int ks = fdiv(t, p.d_mn);
         const int kb0 = ks * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
@@ -606,12 +631,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int k = 0; k < kBK / 16; ++k) {
             const uint64_t ad = make_smem_desc(sA + k * a_step, a_lbo, 1024);
             const uint64_t bd = make_smem_desc(sB + k * b_step, b_lbo, 1024);
-            umma_bf16_ws(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (kPair) umma_bf16_pair_ws(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else umma_bf16_ws(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit_ws(&empty_bar[stage]);
+          // pair: the commits arrive on the barrier of BOTH CTAs (each producer refills its own stage, each epilogue
+          // drains its own 128 accumulator lanes)
+          if (kPair) umma_commit_pair_ws(&empty_bar[stage]);
+          else umma_commit_ws(&empty_bar[stage]);
           if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
-        umma_commit_ws(&tfull_bar[as]);
+        if (kPair) umma_commit_pair_ws(&tfull_bar[as]);
+        else umma_commit_ws(&tfull_bar[as]);
       }
     }
     __syncwarp();
@@ -676,7 +706,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // (called by ONE thread, only once the TMA store that last read that buffer has finished reading it)
     auto issue_residual = [&](int t_, int bi_) {
       int ks_, mt_, nt_;
-      decode_tile(p, t_, ks_, mt_, nt_);
+      decode_tile(p, t_, ks_, mt_, nt_, rank);
       const int nb_ = nt_ * p.bn;
       uint8_t* buf_ = cstage0 + (size_t)bi_ * p.cbytes;
       const int slabs = (min(p.bn, p.N - nb_) + 63) >> 6;
@@ -722,7 +752,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_arrive(&sch_empty[slot]);
       if (t >= total_tiles) break;
       int ks, mt, nt;
-      decode_tile(p, t, ks, mt, nt);
+      decode_tile(p, t, ks, mt, nt, rank);
       const int as = it & 1;
       const int n_base = nt * p.bn;
       int tw = 0, th = 0, tn = 0;
@@ -735,6 +765,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int cbi = p.nbuf > 1 ? (it & 1) : 0;
       uint8_t* cbuf = cstage0 + (size_t)cbi * p.cbytes;
       if (staged) {
+        // (fused BN reduction over a TMA-loaded residual: every thread of the group must be done READING the previous
+        // tile in its statistics pass before the leader lets the next residual tile land in the same buffer)
+        if (kBnr && p.res_tma) epi_bar(bar_id, epi_threads);
         // the TMA store that last read this staging buffer must have finished reading it
         if (et == 0) {
           // (two groups: this leader's bulk groups are all stores from ITS buffer, so the latest one must be done.
@@ -832,7 +865,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(&tempty_bar[as]);  // accumulator stage is free for the MMA warp
+      // accumulator stage is free for the MMA warp (pair: the leader's, which waits for both CTAs' epilogues)
+      if (kPair) mbar_arrive_cluster(mapa_u32(&tempty_bar[as], 0));
+      else mbar_arrive(&tempty_bar[as]);
 
       if (staged) {
         fence_proxy_async();  // make this thread's staging writes visible to the TMA (async proxy)
@@ -953,12 +988,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 
   tc_fence_before();
-  __syncthreads();
+  // pair: neither CTA may leave (or free tensor memory) while the other can still signal one of its barriers
+  if (kPair) cluster_sync_all();
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (kPair) tmem_dealloc_pair(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
   }
 }
+#undef LOAD2D
+#undef LOAD4D
 
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -1016,10 +1056,12 @@ static struct SchedRing {
   unsigned int base[kSchedSlots];
   unsigned int next;
 } g_sched[64];
-static unsigned int* sched_slot(unsigned int fetches, unsigned int* base_out) {
+static bool sched_is_dynamic() {
   static const char* env = getenv("VTX_GEMM_SCHEDULE");  // measurement knob: "static" / "dynamic" overrides the setter
-  const bool dyn = env != nullptr ? (env[0] == 'd') : (g_sched_dynamic != 0);
-  if (!dyn) return nullptr;
+  return env != nullptr ? (env[0] == 'd') : (g_sched_dynamic != 0);
+}
+static unsigned int* sched_slot(unsigned int fetches, unsigned int* base_out) {
+  if (!sched_is_dynamic()) return nullptr;
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64) return nullptr;
@@ -1143,6 +1185,20 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
     return set_error(VTX_EINVAL, "vtx_gemm: bad tile_n %d", bn);
   p.bn = bn;
   p.n_tiles = (g->N + bn - 1) / bn;
+  // CTA pairs (cta_group::2) for the tensor-bound shapes: long K loops over 128- / 256-wide tiles.  Each CTA of a pair
+  // stages half of the B tile (whole 64-column atoms when B is MN-major), so the width must split accordingly; the
+  // short-K HBM-bound convs gain nothing from it and keep one CTA per tile.  (Static schedule only.)
+  {
+    const char* pair_env = getenv("VTX_GEMM_PAIR");  // measurement / test knob, read per call: "0" = one CTA per tile
+    const bool pair_off = pair_env != nullptr && pair_env[0] == '0';
+    const bool b_atoms = p.b_mn || p.mode == 2;
+    const long kblocks = p.mode == 2 ? 64 : (g->K + kBK - 1) / kBK;
+    const bool halo_shape = p.mode == 1 && g->conv_c == 64 && g->N == 64;
+    p.pair = (!pair_off && !sched_is_dynamic() && (g->conv_mode == 0 || g->conv_mode == 1 || g->conv_mode == 2) && !stem &&
+              !halo_shape && bn >= 128 && bn % (b_atoms ? 128 : 32) == 0 && kblocks >= 4 &&
+              (p.mode == 2 ? g->M >= 256 : g->M >= 4 * kBM)) ? 1 : 0;
+  }
+  const int bn_cta = p.pair ? bn / 2 : bn;  // B rows per CTA (box height of the K-major B maps)
   p.out_f32 = g->out_f32; p.atomic = g->atomic; p.act = g->act;
   p.alpha = g->alpha == 0.f ? 1.0f : g->alpha;
   p.D = g->D; p.ldd = g->ldd;
@@ -1185,7 +1241,7 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
     {
       uint64_t dims[2], str[1];
       uint32_t box[2];
-      if (!p.b_mn) { dims[0] = g->K; dims[1] = g->N; box[0] = 64; box[1] = (uint32_t)bn; }
+      if (!p.b_mn) { dims[0] = g->K; dims[1] = g->N; box[0] = 64; box[1] = (uint32_t)bn_cta; }
       else { dims[0] = g->N; dims[1] = g->K; box[0] = 64; box[1] = 64; }
       str[0] = g->ldb;
       if ((rc = make_tmap(&tmB, g->B, 2, dims, str, box)) != VTX_OK) return rc;
@@ -1248,7 +1304,7 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
       if ((rc = make_tmap(&tmA, g->A, 4, xdims, xstr, box, cstride > 1 ? es : nullptr)) != VTX_OK) return rc;
       uint64_t bd[2] = {(uint64_t)g->K, (uint64_t)g->N};
       uint64_t bs[1] = {(uint64_t)g->ldb};
-      uint32_t bb[2] = {64, (uint32_t)bn};
+      uint32_t bb[2] = {64, (uint32_t)bn_cta};
       if ((rc = make_tmap(&tmB, g->B, 2, bd, bs, bb)) != VTX_OK) return rc;
     } else {
       // wgrad: D[M = Cout, N = 9*C] += sum over positions dy[pos, Cout] * x_shift[pos, C]
@@ -1274,7 +1330,9 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
 
   // ---- shared-memory carve-up: [1 KB control][stages x (A 16 KB + B bn*128 B)][bf16 staging tile 128 x (bn*2+16) B]
   // mode 3 stages hold one halo tile, rounded up to whole 1024-byte swizzle atoms
-  p.stage_bytes = p.mode == 3 ? ((p.halo_w * kHaloH * 128 + 1023) / 1024) * 1024 : kABytes + bn * kBK * 2;
+  if (p.mode >= 3) p.pair = 0;
+  p.m_sched = p.pair ? (p.m_tiles + 1) / 2 : p.m_tiles;
+  p.stage_bytes = p.mode == 3 ? ((p.halo_w * kHaloH * 128 + 1023) / 1024) * 1024 : kABytes + bn_cta * kBK * 2;
   p.dy_off = 0;
   if (p.mode == 4) {
     p.dy_off = ((p.halo_w * kHaloH * 128 + 1023) / 1024) * 1024;
@@ -1364,29 +1422,31 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-      cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
-      if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
-      if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
+      cudaError_t e = cudaSuccess;
+      const void* kernels[6] = {(const void*)gemm_tc_kernel<0, 0>, (const void*)gemm_tc_kernel<1, 0>,
+                                (const void*)gemm_tc_kernel<2, 0>, (const void*)gemm_tc_kernel<0, 1>,
+                                (const void*)gemm_tc_kernel<1, 1>, (const void*)gemm_tc_kernel<2, 1>};
+      for (int i = 0; i < 6 && e == cudaSuccess; ++i)
+        e = cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
       if (e != cudaSuccess) return set_error(VTX_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
   }
-  p.d_mn = make_fastdiv(p.m_tiles * p.n_tiles);
+  p.d_mn = make_fastdiv(p.m_sched * p.n_tiles);
   p.d_nt = make_fastdiv(p.n_tiles);
-  p.d_mt = make_fastdiv(p.m_tiles);
+  p.d_mt = make_fastdiv(p.m_sched);
   // BN statistics are kept in registers per column block: run over the row tiles first, so that a CTA's column block
   // changes at most n_tiles - 1 times whatever order the tiles are handed out in (the activation operand of every conv
   // with more than one column tile fits the L2, so the extra passes over it do not reach DRAM)
   p.nt_major = (p.stats != nullptr && p.n_tiles > 1 && p.mode < 3) ? 1 : 0;
-  const long total = (long)p.m_tiles * p.n_tiles * p.k_splits;
+  const long total = (long)p.m_sched * p.n_tiles * p.k_splits;  // schedule slots: tiles, or pairs of row tiles
   const int sms = vtx_num_sms();
-  const int grid = (int)(total < sms ? total : sms);
+  const int workers = p.pair ? sms / 2 : sms;
+  const int grid = (int)(total < workers ? total : workers) * (p.pair ? 2 : 1);
   // many short tiles per CTA (64-wide layer1 / stem convs: ~170): one fetch hands out a few consecutive tiles
   p.sched_chunk = total >= 32L * grid ? 4 : total >= 12L * grid ? 2 : 1;
   p.sched = nullptr;
-  if (p.mode != 4) {
+  if (p.mode != 4 && !p.pair) {
     const unsigned int fetches = (unsigned int)((total + p.sched_chunk - 1) / p.sched_chunk) + (unsigned int)grid;
     p.sched = sched_slot(fetches, &p.sched_base);
   }
@@ -1401,14 +1461,28 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = kSmemTotal;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
+    attr[1].id = cudaLaunchAttributeClusterDimension;  // CTA pairs: 2-CTA clusters (the two SMs of one TPC)
+    attr[1].val.clusterDim.x = 2;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t le = !bnr ? cudaLaunchKernelEx(&cfg, gemm_tc_kernel<0>, tmA, tmB, tmD, tmR, tmY, p)
-                     : p.bnr_mask == nullptr ? cudaLaunchKernelEx(&cfg, gemm_tc_kernel<1>, tmA, tmB, tmD, tmR, tmY, p)
-                                             : cudaLaunchKernelEx(&cfg, gemm_tc_kernel<2>, tmA, tmB, tmD, tmR, tmY, p);
+    cfg.numAttrs = p.pair ? 2 : 1;
+    const int variant = !bnr ? 0 : (p.bnr_mask == nullptr ? 1 : 2);
+    cudaError_t le;
+#define VTX_LAUNCH(B_, P_) le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<B_, P_>, tmA, tmB, tmD, tmR, tmY, p)
+    if (p.pair) {
+      if (variant == 0) VTX_LAUNCH(0, 1);
+      else if (variant == 1) VTX_LAUNCH(1, 1);
+      else VTX_LAUNCH(2, 1);
+    } else {
+      if (variant == 0) VTX_LAUNCH(0, 0);
+      else if (variant == 1) VTX_LAUNCH(1, 0);
+      else VTX_LAUNCH(2, 0);
+    }
+#undef VTX_LAUNCH
     if (le != cudaSuccess) return set_error(VTX_ECUDA, "gemm_tc_kernel PDL launch: %s", cudaGetErrorString(le));
   }
   cudaError_t e = cudaGetLastError();
