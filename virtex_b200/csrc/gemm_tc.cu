@@ -126,6 +126,7 @@ struct GemmKParams {
   const uint8_t* bnr_mask;   // optional ReLU bit mask [M, N/8] (plain GEMMs); nullptr: mask recomputed from y
   long long bnr_ldy, bnr_sw, bnr_sh, bnr_sn;
   int vW, vH;                // extent of the output (view) grid of the implicit-conv modes
+  int bnr_prefetch;          // pull the y tile into L2 with a TMA prefetch when the tile's epilogue starts
   // CTA pair (kPair kernel, cta_group::2): a 2-CTA cluster works on two vertically adjacent 128-row tiles with ONE
   // M = 256 MMA per K step; each CTA stages its own A tile and half of the B tile, so every SM pulls 1.5x fewer operand
   // bytes through L2 and shared memory per flop.  The schedule then runs over m_sched = ceil(m_tiles / 2) row-tile pairs.
@@ -696,7 +697,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           a += v.x;
           b += v.y;
         }
-        if (kBnr) b *= __ldg(p.bnr_bnp + p.N + st_nt * p.bn + et);  // sum dz * (y - mean)  ->  sum dz * xhat
+        if (kBnr) {  // sum dz * y  ->  sum dz * xhat = (sum dz * y - mean * sum dz) * invstd
+          const int c = st_nt * p.bn + et;
+          b = (b - __ldg(p.bnr_bnp + c) * a) * __ldg(p.bnr_bnp + p.N + c);
+        }
         atomicAdd(p.stats + st_nt * p.bn + et, a);
         atomicAdd(p.stats + p.N + st_nt * p.bn + et, b);
       }
@@ -769,15 +773,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // tile in its statistics pass before the leader lets the next residual tile land in the same buffer)
         if (kBnr && p.res_tma) epi_bar(bar_id, epi_threads);
         // the TMA store that last read this staging buffer must have finished reading it
+        // (two groups: this leader's bulk groups are all stores from ITS buffer, so the latest one must be done.
+        // Round 2 also tried requesting the residual one full tile ahead -- it removed the wait for the residual,
+        // 25 % of the warp samples of the dgrad + shortcut GEMMs, but exposed the drain of the previous store -- and a
+        // third staging buffer, 305 vs 256 us; the two independent groups below made both moot.)
         if (et == 0) {
-          // (two groups: this leader's bulk groups are all stores from ITS buffer, so the latest one must be done.
-          // Round 2 also tried requesting the residual one full tile ahead -- it removed the wait for the residual,
-          // 25 % of the warp samples of the dgrad + shortcut GEMMs, but exposed the drain of the previous store -- and a
-          // third staging buffer, 305 vs 256 us; the two independent groups below made both moot.)
           if (p.nbuf > 1 && ngrp == 1) tma_store_wait_read<1>();
           else tma_store_wait_read<0>();
+        }
+        // the column block changed: the sums kept in registers go out through the (now idle) staging buffer -- with a
+        // TMA-loaded residual that has to happen BEFORE the residual tile is requested into the same buffer
+        const bool new_block = p.stats != nullptr && st_nt != nt;
+        if (new_block && st_nt >= 0 && p.res_tma) {
+          epi_bar(bar_id, epi_threads);
+          flush_stats(cbuf);
+        }
+        if (et == 0) {
           if (p.res_tma) issue_residual(t, cbi);  // requested now that this (group's) buffer is free
-          if (kBnr) {
+          if (kBnr && p.bnr_prefetch) {
             const int slabs = (min(p.bn, p.N - n_base) + 63) >> 6;
             for (int sl = 0; sl < slabs; ++sl) {
               if (p.mode & 1) tma_prefetch_l2_4d(&tmY, n_base + sl * 64, tw << p.lbw, th << p.lbh, tn << p.lbn);
@@ -786,8 +799,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         epi_bar(bar_id, epi_threads);
-        if (p.stats != nullptr && st_nt != nt) {
-          if (st_nt >= 0) flush_stats(cbuf);
+        if (new_block) {
+          if (st_nt >= 0 && !p.res_tma) flush_stats(cbuf);
           st_nt = nt;
         }
       }
@@ -869,6 +882,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (kPair) mbar_arrive_cluster(mapa_u32(&tempty_bar[as], 0));
       else mbar_arrive(&tempty_bar[as]);
 
+      // fused BN reduction: this thread's rows / columns of the staged tile, and the loader of one batch of four rows of
+      // y (16 bytes each) and of the ReLU mask words; rows outside the output contribute nothing -- their mask word is 0
+      const int bnr_r0 = srg * st_rpt;           // first row of this thread (a multiple of 4)
+      const int bnr_col = n_base + scg * 8;
+      const bool bnr_on = kBnr && st_on && bnr_col < p.N;
+      // (element offsets fit 32 bits: the host checks M * ldy < 2^31; the four mask bytes of a batch share one register)
+      auto bnr_load = [&](int rb, uint4* yv, uint32_t& mbits) {
+        mbits = 0u;
+#pragma unroll
+        for (int r4 = 0; r4 < 4; ++r4) {
+          const int r = bnr_r0 + rb + r4;  // row of the tile
+          uint32_t off, lin = 0;
+          bool ok;
+          if (p.mode & 1) {
+            const int dw = r & ((1 << p.lbw) - 1);
+            const int dh = (r >> p.lbw) & ((1 << p.lbh) - 1);
+            const int dn = r >> (p.lbw + p.lbh);
+            const int w = (tw << p.lbw) + dw, h = (th << p.lbh) + dh, n = (tn << p.lbn) + dn;
+            ok = (w < p.vW) && (h < p.vH) && (n < p.cN);
+            off = (uint32_t)n * (uint32_t)p.bnr_sn + (uint32_t)h * (uint32_t)p.bnr_sh + (uint32_t)w * (uint32_t)p.bnr_sw;
+          } else {
+            lin = (uint32_t)(mt * kBM + r);
+            ok = lin < (uint32_t)p.M;
+            off = lin * (uint32_t)p.bnr_ldy;
+          }
+          yv[r4] = ok ? ldg128_nc(p.bnr_y + off + bnr_col) : make_uint4(0u, 0u, 0u, 0u);
+          const uint32_t mw = ok ? (kBnr == 2 ? (uint32_t)__ldg(p.bnr_mask + ((lin * (uint32_t)p.N + bnr_col) >> 3)) : 0xffu) : 0u;
+          mbits |= mw << (8 * r4);
+        }
+      };
+      uint4 ya[4];
+      uint32_t ma = 0u;
+      if (kBnr && bnr_on) bnr_load(0, ya, ma);  // in flight across the fence, the barrier and the store issue below
+
       if (staged) {
         fence_proxy_async();  // make this thread's staging writes visible to the TMA (async proxy)
         epi_bar(bar_id, epi_threads);
@@ -885,78 +932,59 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         // ---------------- BN statistics of the staged (bf16-rounded) tile, accumulated in registers.
         // Rows outside the problem are exact zeros (TMA zero fill; stats forbids bias/residual): no masking needed.
-        if (kBnr && st_on && n_base + scg * 8 < p.N) {
-          const int r0 = srg * st_rpt;  // first row of this thread (a multiple of 4)
-          const uint32_t cp = smem_u32(cbuf) + (scg >> 3) * 16384 + r0 * 128;
+        if (kBnr && bnr_on) {
+          const uint32_t cp = smem_u32(cbuf) + (scg >> 3) * 16384 + bnr_r0 * 128;
           const int c8 = scg & 7;
-          const int col = n_base + scg * 8;
           // per-column BN parameters of this thread's 8 columns, re-read per tile (L1 hits) so that they do not occupy
           // registers during the accumulator phase
-          float mean[8], sc[8], sh[8];
+          // (the mean is taken out of the loop: the pass accumulates sum dz * y, flush_stats subtracts mean * sum dz)
+          float sc[8], sh[8];
           {
-            const float4 m0 = __ldg(reinterpret_cast<const float4*>(p.bnr_bnp + col));
-            const float4 m1 = __ldg(reinterpret_cast<const float4*>(p.bnr_bnp + col + 4));
-            mean[0] = m0.x; mean[1] = m0.y; mean[2] = m0.z; mean[3] = m0.w;
-            mean[4] = m1.x; mean[5] = m1.y; mean[6] = m1.z; mean[7] = m1.w;
             if (kBnr == 1) {
-              const float4 a0 = __ldg(reinterpret_cast<const float4*>(p.bnr_bnp + 2 * p.N + col));
-              const float4 a1 = __ldg(reinterpret_cast<const float4*>(p.bnr_bnp + 2 * p.N + col + 4));
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bnr_bnp + 3 * p.N + col));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bnr_bnp + 3 * p.N + col + 4));
+              const float4 a0 = __ldg(reinterpret_cast<const float4*>(p.bnr_bnp + 2 * p.N + bnr_col));
+              const float4 a1 = __ldg(reinterpret_cast<const float4*>(p.bnr_bnp + 2 * p.N + bnr_col + 4));
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bnr_bnp + 3 * p.N + bnr_col));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bnr_bnp + 3 * p.N + bnr_col + 4));
               sc[0] = a0.x; sc[1] = a0.y; sc[2] = a0.z; sc[3] = a0.w; sc[4] = a1.x; sc[5] = a1.y; sc[6] = a1.z; sc[7] = a1.w;
               sh[0] = b0.x; sh[1] = b0.y; sh[2] = b0.z; sh[3] = b0.w; sh[4] = b1.x; sh[5] = b1.y; sh[6] = b1.z; sh[7] = b1.w;
             }
           }
-          for (int rb = 0; rb < st_rpt; rb += 4) {
-            uint4 yv[4];
-            uint32_t mbits[4];
-#pragma unroll
-            for (int r4 = 0; r4 < 4; ++r4) {
-              const int r = r0 + rb + r4;  // row of the tile
-              long long off;
-              bool ok;
-              long long lin = 0;
-              if (p.mode & 1) {
-                const int dw = r & ((1 << p.lbw) - 1);
-                const int dh = (r >> p.lbw) & ((1 << p.lbh) - 1);
-                const int dn = r >> (p.lbw + p.lbh);
-                const int w = (tw << p.lbw) + dw, h = (th << p.lbh) + dh, n = (tn << p.lbn) + dn;
-                ok = (w < p.vW) && (h < p.vH) && (n < p.cN);
-                off = (long long)n * p.bnr_sn + (long long)h * p.bnr_sh + (long long)w * p.bnr_sw;
-              } else {
-                lin = (long long)mt * kBM + r;
-                ok = lin < p.M;
-                off = lin * p.bnr_ldy;
-              }
-              yv[r4] = ok ? ldg128_nc(p.bnr_y + off + col) : make_uint4(0u, 0u, 0u, 0u);
-              // rows outside the output contribute nothing: their mask word is 0 (bit-mask form) or their staged value
-              // is an exact zero / forced to zero below (mask-from-y form)
-              mbits[r4] = ok ? (kBnr == 2 ? (uint32_t)__ldg(p.bnr_mask + (lin * p.N + col) / 8) : 0xffu) : 0u;
-            }
+          // one batch of four rows: staged gradient x mask -> the two running sums
+          auto bnr_compute = [&](int rb, const uint4* yv, const uint32_t mbits) {
 #pragma unroll
             for (int r4 = 0; r4 < 4; ++r4) {
               const int r = rb + r4;
-              const uint4 raw = lds128(cp + r * 128 + ((c8 ^ ((r0 + r) & 7)) << 4));
+              const uint4 raw = lds128(cp + r * 128 + ((c8 ^ ((bnr_r0 + r) & 7)) << 4));
               float f[8], yy[8];
               unpack8(*reinterpret_cast<const bf16x8*>(&raw), f);
               unpack8(*reinterpret_cast<const bf16x8*>(&yv[r4]), yy);
               if (kBnr == 1) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                  const bool on = (yy[i] * sc[i] + sh[i] > 0.f) && (mbits[r4] != 0u);
+                  const bool on = (yy[i] * sc[i] + sh[i] > 0.f) && ((mbits >> (8 * r4)) & 0xffu) != 0u;
                   const float dz = on ? f[i] : 0.f;
                   st_s[i] += dz;
-                  st_q[i] += dz * (yy[i] - mean[i]);
+                  st_q[i] += dz * yy[i];
                 }
               } else {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                  const float dz = ((mbits[r4] >> i) & 1u) ? f[i] : 0.f;
+                  const float dz = ((mbits >> (8 * r4 + i)) & 1u) ? f[i] : 0.f;
                   st_s[i] += dz;
-                  st_q[i] += dz * (yy[i] - mean[i]);
+                  st_q[i] += dz * yy[i];
                 }
               }
             }
+          };
+          // software pipeline over the row batches: the loads of batch b + 1 are in flight while batch b is reduced (the
+          // first batch was requested before the barrier / TMA store above)
+          uint4 yb[4];
+          uint32_t mb = 0u;
+          for (int rb = 0; rb < st_rpt; rb += 8) {
+            if (rb + 4 < st_rpt) bnr_load(rb + 4, yb, mb);
+            bnr_compute(rb, ya, ma);
+            if (rb + 8 < st_rpt) bnr_load(rb + 8, ya, ma);
+            if (rb + 4 < st_rpt) bnr_compute(rb + 4, yb, mb);
           }
         }
         if (!kBnr && p.stats != nullptr && st_on) {
@@ -1186,17 +1214,24 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
   p.bn = bn;
   p.n_tiles = (g->N + bn - 1) / bn;
   // CTA pairs (cta_group::2) for the tensor-bound shapes: long K loops over 128- / 256-wide tiles.  Each CTA of a pair
-  // stages half of the B tile (whole 64-column atoms when B is MN-major), so the width must split accordingly; the
-  // short-K HBM-bound convs gain nothing from it and keep one CTA per tile.  (Static schedule only.)
+  // stages half of the B tile (whole 64-column atoms when B is MN-major), so the width must split accordingly.  Measured
+  // per shape class on B200 (profiles/r02o_gemm_launches_{pair,nopair}.json): K >= 1024 gains 10-19 %, the implicit 3x3
+  // weight gradients 17 %, plain weight gradients with both extents >= 1024 8-14 %; K = 256 / 512 convs over many rows
+  // (HBM-bound) LOSE 8-29 % and small-output weight gradients 7 %, so those keep one CTA per tile.  (Static schedule only.)
   {
-    const char* pair_env = getenv("VTX_GEMM_PAIR");  // measurement / test knob, read per call: "0" = one CTA per tile
-    const bool pair_off = pair_env != nullptr && pair_env[0] == '0';
+    const char* pair_env = getenv("VTX_GEMM_PAIR");  // measurement / test knob, read per call: "0" = one CTA per tile,
+    const bool pair_off = pair_env != nullptr && pair_env[0] == '0';       // "2" = every eligible shape (tests)
+    const bool pair_all = pair_env != nullptr && pair_env[0] == '2';
     const bool b_atoms = p.b_mn || p.mode == 2;
-    const long kblocks = p.mode == 2 ? 64 : (g->K + kBK - 1) / kBK;
     const bool halo_shape = p.mode == 1 && g->conv_c == 64 && g->N == 64;
-    p.pair = (!pair_off && !sched_is_dynamic() && (g->conv_mode == 0 || g->conv_mode == 1 || g->conv_mode == 2) && !stem &&
-              !halo_shape && bn >= 128 && bn % (b_atoms ? 128 : 32) == 0 && kblocks >= 4 &&
-              (p.mode == 2 ? g->M >= 256 : g->M >= 4 * kBM)) ? 1 : 0;
+    const bool eligible = !pair_off && !sched_is_dynamic() && (g->conv_mode == 0 || g->conv_mode == 1 || g->conv_mode == 2) &&
+                          !stem && !halo_shape && bn >= 128 && bn % (b_atoms ? 128 : 32) == 0 &&
+                          (p.mode == 2 ? g->M >= 256 : (g->M >= 4 * kBM && g->K >= 4 * kBK));
+    bool wanted;
+    if (p.mode == 2) wanted = true;
+    else if (p.a_mn && p.b_mn) wanted = g->M >= 1024 && g->N >= 1024;
+    else wanted = g->K >= 1024;
+    p.pair = (eligible && (wanted || pair_all)) ? 1 : 0;
   }
   const int bn_cta = p.pair ? bn / 2 : bn;  // B rows per CTA (box height of the K-major B maps)
   p.out_f32 = g->out_f32; p.atomic = g->atomic; p.act = g->act;
@@ -1218,11 +1253,15 @@ extern "C" int vtx_gemm(const VtxGemm* g, void* stream_) {
         g->conv_mode == 2 || g->conv_mode >= 4 || split_k > 1)
       return set_error(VTX_EINVAL, "vtx_gemm: bnr needs a plain bf16 output (no stats/bias/activation/alpha/split-K), "
                                    "N %% 8 == 0, 16-byte aligned y / bnp; the bit-mask form needs conv_mode 0");
+    if ((long long)g->M * (g->bnr_ldy > g->N ? g->bnr_ldy : g->N) >= (1ll << 31))
+      return set_error(VTX_EUNSUPPORTED, "vtx_gemm: bnr needs M * ld(y) < 2^31");
     p.stats = g->bnr_sums;
     p.bnr_y = reinterpret_cast<const __nv_bfloat16*>(g->bnr_y);
     p.bnr_bnp = g->bnr_bnp;
     p.bnr_mask = g->bnr_mask;
     p.bnr_ldy = g->bnr_ldy;
+    const char* pf = getenv("VTX_BNR_PREFETCH");  // measurement knob, read per call
+    p.bnr_prefetch = (pf != nullptr && pf[0] == '0') ? 0 : 1;
   }
 
   CUtensorMap tmA, tmB;
