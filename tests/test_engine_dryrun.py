@@ -156,9 +156,10 @@ def test_training_step_schedule(dry, spec_kw, batch_kw):
     # BN-backward reductions: bn1 / bn2 of every block and bn3 of every block that is followed by an identity block and
     # has no downsample branch are accumulated by GEMM epilogues (a stride-2 conv2 dgrad is four GEMMs); stand-alone
     # reduce launches remain for the stem BN, the four two-branch blocks, the last block of every layer
-    fused_bn3 = n_blocks - 4 - 4
+    # ... and of those bn3 only at large tensor sizes (Engine.fuse_bn3_min_rows; none at the batch sizes of this test)
+    fused_bn3 = 0
     assert len([g for g in gemms if g[5]]) == 2 * n_blocks + 3 * 3 + fused_bn3
-    assert names.count("vtx_bn_bwd_reduce") == 1 + 4 + 4
+    assert names.count("vtx_bn_bwd_reduce") == 1 + n_blocks - fused_bn3
     assert names.count("vtx_bn_bwd_finalize_apply") == 1 + 3 * n_blocks
 
 

@@ -579,6 +579,38 @@ def test_gemm_fused_bn_backward_reduce_strided_parity_classes(NI, H, W, C, Cout)
     _check_bnr(ops, D, y, bnp, outs[1][1], None, (y.float() * bnp[2] + bnp[3]) > 0)
 
 
+@pytest.mark.parametrize("N", [256, 512, 1024])
+def test_gemm_fused_bn_backward_reduce_over_residual_is_exact_for_every_tile_count(N):
+    """The fused reduction over the TMA-staged residual tile (conv1 dgrad + shortcut gradient -> the previous block's bn3)
+    across launches with 1, 1-2, 2-3 ... tiles per CTA and one to four column blocks: the bf16 output must equal the
+    plain epilogue's bit for bit (the statistics pass only READS the staged tile; the register sums leave through the
+    staging buffer BEFORE the next residual tile is requested into it), and the sums must match the stand-alone pass."""
+    _need_cuda()
+    ops = _ops()
+    g = torch.Generator().manual_seed(N)
+    K = 64
+    sms = ops.num_sms()
+    for tiles in (sms - 9, sms + 1, sms + 9, 2 * sms - 3, 2 * sms + 20, 3 * sms + 5):
+        M = tiles * 128 - 37
+        A = (torch.randn(M, K, generator=g) * 0.5).bfloat16().cuda()
+        B = (torch.randn(K, N, generator=g) * 0.2).bfloat16().cuda()
+        y = (torch.randn(M, N, generator=g) * 1.5).bfloat16().cuda()
+        bnp = _bnp(N, g)
+        R = torch.randn(M, N, generator=g).bfloat16().cuda()
+        rbits = _pack_mask((torch.rand(M, N, generator=g) > 0.5).cuda())
+        bkeep = (torch.rand(M, N, generator=g) > 0.45).cuda()
+        bbits = _pack_mask(bkeep)
+        for kw in (dict(residual=R, residual_mask=rbits), dict(residual=R)):
+            D0 = torch.full((M, N), 7.0, dtype=BF16, device="cuda")
+            ops.gemm(A, B, D0, M, N, K, b_mn=1, **kw)
+            for mask in (bbits, None):
+                D = torch.full((M, N), 7.0, dtype=BF16, device="cuda")
+                sums = torch.zeros(2, N, device="cuda")
+                ops.gemm(A, B, D, M, N, K, b_mn=1, bnr=(y, bnp, sums, mask), **kw)
+                assert torch.equal(D, D0), (tiles, N, mask is None)
+                _check_bnr(ops, D, y, bnp, sums, mask, bkeep if mask is not None else (y.float() * bnp[2] + bnp[3]) > 0)
+
+
 def _pair_env(on):
     import os
     os.environ["VTX_GEMM_PAIR"] = "2" if on else "0"   # "2": pairs for every eligible shape, not only where they pay
@@ -611,7 +643,7 @@ def test_gemm_cta_pairs_match_single_cta_and_torch(M, N, K):
             ops.gemm(A, B, D1, M, N, K, stats=st)
             D2 = torch.empty(M, N, dtype=BF16, device="cuda")
             ops.gemm(A, Bt, D2, M, N, K, b_mn=1, bias=bias, act=1)
-            D3 = torch.empty(M, N, dtype=BF16, device="cuda")
+            D3 = torch.zeros(M, N, dtype=BF16, device="cuda")
             sums = torch.zeros(2, N, device="cuda")
             if N % 32 == 0:
                 ops.gemm(A, Bt, D3, M, N, K, b_mn=1, residual=R, bnr=(y, bnp, sums, None))

@@ -259,6 +259,33 @@ def test_backbone_forward_backward_vs_oracle():
     assert int(eng.buffers["visual.cnn.bn1.num_batches_tracked"]) == 1
 
 
+def test_backbone_backward_fused_bn_reductions_match_standalone_passes():
+    """The BN-backward sums accumulated by the dgrad epilogues (bn1 / bn2 everywhere; bn3 of identity-followed blocks,
+    forced on at this small size) against the same backward with the stand-alone vtx_bn_bwd_reduce launches: identical
+    arithmetic up to the fp32 summation order, so every backbone gradient agrees far below the bf16 noise floor."""
+    _need_cuda()
+    spec = O.Spec(hidden=128, layers=1, heads=2, ffn=256)
+    state = O.synth_state(spec, 5, bn3_gain=0.25)
+    model = build_model(spec, state)
+    B = 6
+    batch = O.synth_batch(B, seed=3)
+    eng = model.engine
+    model.train()
+    g = torch.Generator().manual_seed(0)
+    grads = {}
+    for fused in (True, False):
+        eng.fuse_bn_reduce, eng.fuse_bn3_min_rows = fused, 0
+        feat, h, w = eng.backbone_forward(batch["image"].cuda(), training=True)
+        if fused:
+            dfeat = (torch.randn(feat.shape, generator=g) * 0.01).bfloat16().cuda()
+        eng.arena.grads.zero_()
+        eng.backbone_backward(dfeat)
+        torch.cuda.synchronize()
+        grads[fused] = {n: eng.G(n).clone() for n in eng.arena.names if n.startswith("visual.")}
+    worst = max((rel(grads[True][n], grads[False][n]), n) for n in grads[True])
+    assert worst[0] < 2e-3, worst
+
+
 def test_backbone_backward_relu_open_vs_fp32_oracle():
     """Same backbone test with BN beta shifted by +3 so that ReLUs are (almost) always open: no mask flips, hence the
     conv / BN / pooling / strided / downsample backward arithmetic can be checked against the plain fp32 oracle."""

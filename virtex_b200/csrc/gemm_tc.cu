@@ -912,9 +912,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbits |= mw << (8 * r4);
         }
       };
-      uint4 ya[4];
-      uint32_t ma = 0u;
-      if (kBnr && bnr_on) bnr_load(0, ya, ma);  // in flight across the fence, the barrier and the store issue below
 
       if (staged) {
         fence_proxy_async();  // make this thread's staging writes visible to the TMA (async proxy)
@@ -976,15 +973,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
             }
           };
-          // software pipeline over the row batches: the loads of batch b + 1 are in flight while batch b is reduced (the
-          // first batch was requested before the barrier / TMA store above)
-          uint4 yb[4];
-          uint32_t mb = 0u;
-          for (int rb = 0; rb < st_rpt; rb += 8) {
-            if (rb + 4 < st_rpt) bnr_load(rb + 4, yb, mb);
+          // (A software pipeline over the row batches -- loads of batch b + 1 in flight while batch b is reduced, first
+          // batch requested before the barrier -- spilled ~60 registers at the kernel's 96-register budget and measured
+          // 0.6 ms/step SLOWER than this plain loop: profiles/r02p_*.)
+          uint4 ya[4];
+          uint32_t ma = 0u;
+          for (int rb = 0; rb < st_rpt; rb += 4) {
+            bnr_load(rb, ya, ma);
             bnr_compute(rb, ya, ma);
-            if (rb + 8 < st_rpt) bnr_load(rb + 8, ya, ma);
-            if (rb + 4 < st_rpt) bnr_compute(rb + 4, yb, mb);
           }
         }
         if (!kBnr && p.stats != nullptr && st_on) {

@@ -156,6 +156,7 @@ class Engine:
         # gradient (bn1 / bn2 of every block, bn3 of blocks followed by an identity block) instead of a separate pass;
         # VTX_BNR_FUSE=0 is the measurement knob for the A/B against the standalone vtx_bn_bwd_reduce launches
         self.fuse_bn_reduce = os.environ.get("VTX_BNR_FUSE", "1") != "0"
+        self.fuse_bn3_min_rows = 100000
         self._build_backbone_plan()
 
     # ------------------------------------------------------------------------------------------------ parameters
@@ -574,7 +575,9 @@ class Engine:
                 # sums (ReLU bit mask m3 of THAT block) are accumulated here, over the staged dx tiles
                 prev = blocks[bi - 1] if bi > 0 else None
                 bnr3 = None
-                if fuse and prev is not None and not prev["has_ds"] and Cin % 32 == 0:
+                # (only for the large early-layer tensors: at layer3 / layer4 sizes the longer epilogue costs what the
+                # stand-alone pass costs -- +42 us vs 44 us per launch at 50176 x 1024, profiles/r02n_*)
+                if fuse and prev is not None and not prev["has_ds"] and Cin % 32 == 0 and Min >= self.fuse_bn3_min_rows:
                     sums3 = self._slab_take(2 * Cin)
                     bnr3 = (prev["y3"], prev["bnp3"], sums3, prev["m3"])
                 gemm(dy1, w1, dx, Min, Cin, planes, b_mn=1, residual=dOut, residual_mask=rec["m3"], bnr=bnr3)
