@@ -5,6 +5,7 @@ through the C ABI (virtex_b200.ops.call).  Tolerances: bf16 outputs -> 1 bf16 ul
 tensor norm, and max-abs 2^-7 relative to the largest magnitude); fp32 reductions -> 1e-4 relative.
 """
 import math
+import os
 
 import pytest
 import torch
@@ -612,7 +613,6 @@ def test_gemm_fused_bn_backward_reduce_over_residual_is_exact_for_every_tile_cou
 
 
 def _pair_env(on):
-    import os
     os.environ["VTX_GEMM_PAIR"] = "2" if on else "0"   # "2": pairs for every eligible shape, not only where they pay
 
 

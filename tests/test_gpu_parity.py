@@ -261,8 +261,10 @@ def test_backbone_forward_backward_vs_oracle():
 
 def test_backbone_backward_fused_bn_reductions_match_standalone_passes():
     """The BN-backward sums accumulated by the dgrad epilogues (bn1 / bn2 everywhere; bn3 of identity-followed blocks,
-    forced on at this small size) against the same backward with the stand-alone vtx_bn_bwd_reduce launches: identical
-    arithmetic up to the fp32 summation order, so every backbone gradient agrees far below the bf16 noise floor."""
+    forced on at this small size) against the same backward with the stand-alone vtx_bn_bwd_reduce launches -- over ONE
+    forward tape (two forward passes of this random network already differ by tens of percent in their gradients: the
+    fp32 atomics of the BN statistics reorder, a few bf16 roundings flip ReLU masks, and the random residual stack
+    amplifies that).  Given the tape the backward is linear, so the two agree to the fp32 summation order."""
     _need_cuda()
     spec = O.Spec(hidden=128, layers=1, heads=2, ffn=256)
     state = O.synth_state(spec, 5, bn3_gain=0.25)
@@ -271,19 +273,21 @@ def test_backbone_backward_fused_bn_reductions_match_standalone_passes():
     batch = O.synth_batch(B, seed=3)
     eng = model.engine
     model.train()
-    g = torch.Generator().manual_seed(0)
+    feat, h, w = eng.backbone_forward(batch["image"].cuda(), training=True)
+    slab_off = eng._slab_off
+    dfeat = (torch.randn(feat.shape, generator=torch.Generator().manual_seed(0)) * 0.01).bfloat16().cuda()
     grads = {}
-    for fused in (True, False):
-        eng.fuse_bn_reduce, eng.fuse_bn3_min_rows = fused, 0
-        feat, h, w = eng.backbone_forward(batch["image"].cuda(), training=True)
-        if fused:
-            dfeat = (torch.randn(feat.shape, generator=g) * 0.01).bfloat16().cuda()
+    for tag, fused, min_rows in (("standalone", False, 0), ("fused", True, 0), ("fused_bn12", True, 10 ** 9)):
+        eng.fuse_bn_reduce, eng.fuse_bn3_min_rows = fused, min_rows
+        eng._slab_off = slab_off            # the backward's sums live behind the forward's statistics in the slab
+        eng._slab[slab_off:].zero_()
         eng.arena.grads.zero_()
         eng.backbone_backward(dfeat)
         torch.cuda.synchronize()
-        grads[fused] = {n: eng.G(n).clone() for n in eng.arena.names if n.startswith("visual.")}
-    worst = max((rel(grads[True][n], grads[False][n]), n) for n in grads[True])
-    assert worst[0] < 2e-3, worst
+        grads[tag] = {n: eng.G(n).clone() for n in eng.arena.names if n.startswith("visual.")}
+    for tag in ("fused", "fused_bn12"):
+        worst = sorted(((rel(grads[tag][n], grads["standalone"][n]), n) for n in grads[tag]), reverse=True)
+        assert worst[0][0] < 1e-3, (tag, worst[:8])
 
 
 def test_backbone_backward_relu_open_vs_fp32_oracle():

@@ -697,10 +697,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           a += v.x;
           b += v.y;
         }
-        if (kBnr) {  // sum dz * y  ->  sum dz * xhat = (sum dz * y - mean * sum dz) * invstd
-          const int c = st_nt * p.bn + et;
-          b = (b - __ldg(p.bnr_bnp + c) * a) * __ldg(p.bnr_bnp + p.N + c);
-        }
+        if (kBnr) b *= __ldg(p.bnr_bnp + p.N + st_nt * p.bn + et);  // sum dz * (y - mean)  ->  sum dz * xhat
         atomicAdd(p.stats + st_nt * p.bn + et, a);
         atomicAdd(p.stats + p.N + st_nt * p.bn + et, b);
       }
@@ -934,9 +931,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int c8 = scg & 7;
           // per-column BN parameters of this thread's 8 columns, re-read per tile (L1 hits) so that they do not occupy
           // registers during the accumulator phase
-          // (the mean is taken out of the loop: the pass accumulates sum dz * y, flush_stats subtracts mean * sum dz)
-          float sc[8], sh[8];
+          // (y - mean per element, like the stand-alone pass: taking the mean out of the loop -- sum dz * y - mean * sum dz
+          // -- cancels catastrophically when |mean| >> std, which post-ReLU inputs with a common mode do produce)
+          float mean[8], sc[8], sh[8];
           {
+            const float4 m0 = __ldg(reinterpret_cast<const float4*>(p.bnr_bnp + bnr_col));
+            const float4 m1 = __ldg(reinterpret_cast<const float4*>(p.bnr_bnp + bnr_col + 4));
+            mean[0] = m0.x; mean[1] = m0.y; mean[2] = m0.z; mean[3] = m0.w;
+            mean[4] = m1.x; mean[5] = m1.y; mean[6] = m1.z; mean[7] = m1.w;
             if (kBnr == 1) {
               const float4 a0 = __ldg(reinterpret_cast<const float4*>(p.bnr_bnp + 2 * p.N + bnr_col));
               const float4 a1 = __ldg(reinterpret_cast<const float4*>(p.bnr_bnp + 2 * p.N + bnr_col + 4));
@@ -961,14 +963,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   const bool on = (yy[i] * sc[i] + sh[i] > 0.f) && ((mbits >> (8 * r4)) & 0xffu) != 0u;
                   const float dz = on ? f[i] : 0.f;
                   st_s[i] += dz;
-                  st_q[i] += dz * yy[i];
+                  st_q[i] += dz * (yy[i] - mean[i]);
                 }
               } else {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                   const float dz = ((mbits >> (8 * r4 + i)) & 1u) ? f[i] : 0.f;
                   st_s[i] += dz;
-                  st_q[i] += dz * yy[i];
+                  st_q[i] += dz * (yy[i] - mean[i]);
                 }
               }
             }
