@@ -2,21 +2,27 @@
 // VirTex bicaptioning step (1x1 convs, implicit 3x3 convs, im2col'd strided convs, all nn.Linear fwd/dgrad/wgrad,
 // vocabulary projection).  See include/virtex_b200.h (VtxGemm) for the contract.
 //
-// Structure (persistent, warp specialised, one CTA per SM, 384 threads):
+// Structure (persistent, warp specialised, one CTA per SM, 640 threads):
 //   warp 0 : TMA producer   (one elected lane)  global -> 128B-swizzled smem ring of (A 16 KB, B = tile_n*128 B) stages;
-//                           the ring depth is whatever fits next to the output staging tile (3..8 stages)
-//   warp 1 : MMA issuer     tcgen05.mma.cta_group::1.kind::f16, M=128, N=tile_n, K=16 per issue; the whole warp walks
-//                           the schedule (uniform-datapath descriptors), one elect.sync lane issues
+//                           the ring depth is whatever fits next to the output staging tile (2..8 stages); it also owns
+//                           the tile schedule: every tile index (static round robin, or fetched from a per-launch atomic
+//                           counter) is published to the other roles through a small index ring in shared memory
+//   warp 1 : MMA issuer     tcgen05.mma.kind::f16, M=128, N=tile_n, K=16 per issue; the whole warp walks the schedule
+//                           (uniform-datapath descriptors), one elect.sync lane issues
 //   warp 2 : TMEM allocator (512 columns = 2 accumulator stages of up to 256 fp32 columns)
-//   warps 4-11 : epilogue   tcgen05.ld (double buffered) -> bias / residual / activation in fp32 -> bf16 tile in
-//                           128B-swizzled smem (TMEM is released to the MMA warp here) -> one elected thread issues
-//                           TMA stores (cp.async.bulk.tensor, out-of-bounds rows/columns clipped by the hardware);
-//                           per-column BN statistics are read from the staged tile and accumulated in registers across
-//                           the CTA's tiles.  Two staging buffers when the K loop is short (HBM-bound convs) so the
-//                           store of tile i overlaps the epilogue of tile i+1.  (fp32 / split-K outputs skip staging:
-//                           vector stores or red.global.add.v4.f32 straight from registers.)
-// Three mbarrier pipelines: smem full/empty (TMA <-> MMA), tmem full/empty (MMA <-> epilogue), and a static
-// round-robin tile schedule shared by the three roles.
+//   warps 4-19 : epilogue   tcgen05.ld -> bias / residual / activation -> bf16 tile in 128B-swizzled smem (TMEM is
+//                           released to the MMA warp here) -> one elected thread issues TMA stores (cp.async.bulk.tensor,
+//                           out-of-bounds rows/columns clipped by the hardware); a statistics pass over the staged tile
+//                           accumulates, in registers across the CTA's tiles, either the BN batch statistics of a conv
+//                           output or (kBnr) the BN-BACKWARD sums of a gradient.  With two staging buffers (short K
+//                           loops) the warps form two independent groups working on alternate tiles.  (fp32 / split-K
+//                           outputs skip staging: red.global.add.v4.f32 straight from registers.)
+// CTA pairs (kPair, cta_group::2): for long K loops the kernel is launched in 2-CTA clusters; one M = 256 MMA per K step
+// is issued by the leader CTA over the two CTAs' shared memories (own 128 rows of A and HALF of the B tile each, loaded
+// with the .cta_group::2 TMA form that signals the leader's barrier), commits are multicast to both CTAs' barriers, each
+// CTA's epilogue drains its own 128 accumulator lanes and releases them on the leader's barrier (remote mbarrier arrive).
+// Four mbarrier pipelines: smem full/empty (TMA <-> MMA), tmem full/empty (MMA <-> epilogue), residual landed, and the
+// tile-index ring (producer <-> MMA warp and epilogue groups).
 //
 // Operand "major-ness" is a runtime property (instruction-descriptor bits + smem descriptor strides), so the same
 // kernel serves fprop (A,B K-major), dgrad (B MN-major) and wgrad (A,B MN-major) without transposing activations.
