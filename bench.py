@@ -339,7 +339,9 @@ def main_ours(args, rank, world, local):
         # DRAM bytes cannot be counted without ncu: `traffic` is the per-launch average of the committed ncu capture of
         # this same command (profiles/, newest round first); traffic_source says which capture and at which commit
         traffic = traffic_src = None
-        for tname in ("r02_gemm_dram_traffic.json", "r01_gemm_dram_traffic.json"):
+        tnames = sorted((n for n in os.listdir(os.path.join(ROOT, "profiles")) if n.endswith("_gemm_dram_traffic.json")),
+                        reverse=True)  # newest capture first (r02s_ > r02_ > r01_)
+        for tname in tnames:
             tpath = os.path.join(ROOT, "profiles", tname)
             if os.path.exists(tpath):
                 with open(tpath) as f:

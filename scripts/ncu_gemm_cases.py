@@ -49,5 +49,26 @@ for _ in range(2):
         D = torch.empty(256 * 196, 256, device=dev, dtype=torch.bfloat16)
         st = torch.zeros(2, 256, device=dev)
         ops.gemm(x, w, D, 256 * 196, 256, 2304, lda=256, stats=st, conv=(256, 14, 14, 256), conv_mode=1)
+    if "l1dgrad_bnr" in cases:  # layer1 conv1 dgrad + masked shortcut gradient + fused bn3-backward sums (kBnr = 2)
+        M, N, K = 802816, 256, 64
+        A, B, D = bf(M, K), bf(K, N), torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        R, y = bf(M, N), bf(M, N)
+        bits = torch.randint(0, 256, (M, N // 8), device=dev, dtype=torch.uint8)
+        bnp = torch.rand(4, N, device=dev) + 0.5
+        sums = torch.zeros(2, N, device=dev)
+        ops.gemm(A, B, D, M, N, K, b_mn=1, residual=R, residual_mask=bits, bnr=(y, bnp, sums, bits))
+    if "l1conv3_dgrad_bnr" in cases:  # layer1 conv3 dgrad 256 -> 64 + fused bn2-backward sums (kBnr = 1, mask from y)
+        M, N, K = 802816, 64, 256
+        A, B, D = bf(M, K), bf(K, N), torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        y, bnp, sums = bf(M, N), torch.rand(4, N, device=dev) + 0.5, torch.zeros(2, N, device=dev)
+        ops.gemm(A, B, D, M, N, K, b_mn=1, bnr=(y, bnp, sums, None))
+    if "vocab_pair" in cases:  # vocabulary projection dgrad 7680 x 1024 x 10000: CTA pairs (cta_group::2)
+        M, N, K = 7680, 1024, 10000
+        A, B, D = bf(M, K), bf(K, N), torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        ops.gemm(A, B, D, M, N, K, b_mn=1)
+    if "ffn2_pair" in cases:  # FFN linear2 7680 x 1024 x 4096 with bias: CTA pairs
+        M, N, K = 7680, 1024, 4096
+        A, B, D = bf(M, K), bf(N, K), torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        ops.gemm(A, B, D, M, N, K, bias=torch.randn(N, device=dev))
     torch.cuda.synchronize()
 print("done")

@@ -71,7 +71,8 @@ def launches(src, dst):
         out = {"commit": commit(), "launches": len(g),
                "dram_bytes_per_launch": sum(d.get("dram__bytes_read.sum", 0) + d.get("dram__bytes_write.sum", 0) for d in g) / len(g),
                "source": os.path.basename(src)}
-        with open(os.path.join(os.path.dirname(dst), "r02_gemm_dram_traffic.json"), "w") as f:
+        tag = os.path.basename(dst).split("_")[0]  # r02s_launches_step_summary.md -> r02s_gemm_dram_traffic.json
+        with open(os.path.join(os.path.dirname(dst), f"{tag}_gemm_dram_traffic.json"), "w") as f:
             json.dump(out, f, indent=1)
     print(f"{len(rows)} launches, {tot_ns / 1e6:.2f} ms, {tot_b / 1e9:.1f} GB -> {dst}")
 

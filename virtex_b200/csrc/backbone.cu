@@ -339,7 +339,6 @@ __global__ void __launch_bounds__(256, 2) bn_act_kernel(const __nv_bfloat16* __r
                               __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ relu_mask, long long M, int C,
                               int relu, const BnFwdFold f) {
   VTX_PDL_TRIGGER();
-  VTX_PDL_WAIT();  // launched with programmatic serialisation: the launch latency overlaps the predecessor's tail
   const int cg = C / 8;
   const long long total = M * cg;
   // blockDim.x (256) is a multiple of cg, so a thread's 8-channel group never changes across the grid-stride loop:
@@ -655,7 +654,6 @@ __global__ void __launch_bounds__(256, kTwo ? 1 : 2) bn_bwd_reduce_kernel(const 
                                      float* __restrict__ sums, float* __restrict__ sums2, long long M, int C,
                                      int mask_from_y) {
   VTX_PDL_TRIGGER();
-  VTX_PDL_WAIT();  // launched with programmatic serialisation: the launch latency overlaps the predecessor's tail
   extern __shared__ float red[];  // [rows_par][C][2 or 4]
   const int cg = C / 8;
   const int rows_par = blockDim.x / cg;  // rows handled in parallel by one CTA
@@ -787,7 +785,6 @@ __global__ void __launch_bounds__(256, kTwo ? 1 : 2) bn_bwd_apply_kernel(const _
                                     __nv_bfloat16* __restrict__ dz_out, long long M, int C, int mask_from_y,
                                     const BnBwdFold f) {
   VTX_PDL_TRIGGER();
-  VTX_PDL_WAIT();  // launched with programmatic serialisation: the launch latency overlaps the predecessor's tail
   const int cg = C / 8;
   const long long total = M * cg;
   const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -1126,10 +1123,10 @@ extern "C" int vtx_bn_act(const void* y, const float* bnp, const void* res, cons
   BnFwdFold f;
   memset(&f, 0, sizeof(f));
   if (res == nullptr)
-    launch_pdl(bn_act_kernel<false, 8>, dim3(grid_for((M * (C / 8) + 7) / 8, 256, 2)), dim3(256), 0, STREAM, 
+    bn_act_kernel<false, 8><<<grid_for((M * (C / 8) + 7) / 8, 256, 2), 256, 0, STREAM>>>(
         (const __nv_bfloat16*)y, const_cast<float*>(bnp), nullptr, bnp_res, (__nv_bfloat16*)out, relu_mask, M, C, relu, f);
   else
-    launch_pdl(bn_act_kernel<false, kU>, dim3(grid_for((M * (C / 8) + kU - 1) / kU, 256, 2)), dim3(256), 0, STREAM, 
+    bn_act_kernel<false, kU><<<grid_for((M * (C / 8) + kU - 1) / kU, 256, 2), 256, 0, STREAM>>>(
         (const __nv_bfloat16*)y, const_cast<float*>(bnp), (const __nv_bfloat16*)res, bnp_res, (__nv_bfloat16*)out,
         relu_mask, M, C, relu, f);
   return check_launch("bn_act");
@@ -1145,10 +1142,10 @@ extern "C" int vtx_bn_finalize_act(const float* stats, float count, const float*
   f.stats = stats; f.gamma = gamma; f.beta = beta; f.rmean = rmean; f.rvar = rvar; f.nbt = (long long*)nbt;
   f.count = count; f.momentum = momentum; f.eps = eps; f.training = training;
   if (res == nullptr)
-    launch_pdl(bn_act_kernel<true, 8>, dim3(grid_for((M * (C / 8) + 7) / 8, 256, 2)), dim3(256), 0, STREAM, 
+    bn_act_kernel<true, 8><<<grid_for((M * (C / 8) + 7) / 8, 256, 2), 256, 0, STREAM>>>(
         (const __nv_bfloat16*)y, bnp, nullptr, bnp_res, (__nv_bfloat16*)out, relu_mask, M, C, relu, f);
   else
-    launch_pdl(bn_act_kernel<true, kU>, dim3(grid_for((M * (C / 8) + kU - 1) / kU, 256, 2)), dim3(256), 0, STREAM, 
+    bn_act_kernel<true, kU><<<grid_for((M * (C / 8) + kU - 1) / kU, 256, 2), 256, 0, STREAM>>>(
         (const __nv_bfloat16*)y, bnp, (const __nv_bfloat16*)res, bnp_res, (__nv_bfloat16*)out, relu_mask, M, C, relu, f);
   return check_launch("bn_finalize_act");
 }
@@ -1204,12 +1201,12 @@ extern "C" int vtx_bn_bwd_reduce(const void* dA, const uint8_t* a, const void* y
   if (blocks > cap) blocks = cap;
   if (two) {
     REQ(bnp2 && sums2, "second BN needs bnp2/sums2");
-    launch_pdl(bn_bwd_reduce_kernel<1, kU>, dim3((int)blocks), dim3(threads), smem, STREAM, (const __nv_bfloat16*)dA, (const uint8_t*)a,
+    bn_bwd_reduce_kernel<1, kU><<<(int)blocks, threads, smem, STREAM>>>((const __nv_bfloat16*)dA, (const uint8_t*)a,
                                                                     (const __nv_bfloat16*)y, bnp,
                                                                     (const __nv_bfloat16*)y2, bnp2, sums, sums2, M, C,
                                                                     mask_from_y);
   } else {
-    launch_pdl(bn_bwd_reduce_kernel<0, kUred>, dim3((int)blocks), dim3(threads), smem, STREAM, (const __nv_bfloat16*)dA, (const uint8_t*)a,
+    bn_bwd_reduce_kernel<0, kUred><<<(int)blocks, threads, smem, STREAM>>>((const __nv_bfloat16*)dA, (const uint8_t*)a,
                                                                     (const __nv_bfloat16*)y, bnp, nullptr, nullptr,
                                                                     sums, nullptr, M, C, mask_from_y);
   }
@@ -1231,11 +1228,11 @@ static int launch_bn_bwd_apply(bool fold, const BnBwdFold& f, const void* dA, co
                        (__nv_bfloat16*)dy, (const __nv_bfloat16*)y2, bnp2, coef2, (__nv_bfloat16*)dy2,                  \
                        (__nv_bfloat16*)dz_out, M, C, mask_from_y, f
   if (y2 != nullptr) {
-    if (fold) launch_pdl(bn_bwd_apply_kernel<1, true, kU>, dim3(grid), dim3(256), 0, st, VTX_APPLY_ARGS);
-    else launch_pdl(bn_bwd_apply_kernel<1, false, kU>, dim3(grid), dim3(256), 0, st, VTX_APPLY_ARGS);
+    if (fold) bn_bwd_apply_kernel<1, true, kU><<<grid, 256, 0, st>>>(VTX_APPLY_ARGS);
+    else bn_bwd_apply_kernel<1, false, kU><<<grid, 256, 0, st>>>(VTX_APPLY_ARGS);
   } else {
-    if (fold) launch_pdl(bn_bwd_apply_kernel<0, true, kUbwd>, dim3(grid), dim3(256), 0, st, VTX_APPLY_ARGS);
-    else launch_pdl(bn_bwd_apply_kernel<0, false, kU>, dim3(grid), dim3(256), 0, st, VTX_APPLY_ARGS);
+    if (fold) bn_bwd_apply_kernel<0, true, kUbwd><<<grid, 256, 0, st>>>(VTX_APPLY_ARGS);
+    else bn_bwd_apply_kernel<0, false, kU><<<grid, 256, 0, st>>>(VTX_APPLY_ARGS);
   }
 #undef VTX_APPLY_ARGS
   return check_launch("bn_bwd_apply");

@@ -3,7 +3,6 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
-#include <stdlib.h>
 #include <string.h>
 
 // Programmatic dependent launch (validated on B200 in round 2: -0.4 ms/step).  Every kernel of the library signals at
@@ -15,26 +14,6 @@
 #define VTX_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
 
 namespace vtx {
-// Launch with the programmatic-stream-serialisation attribute: the kernel may be scheduled while its predecessor drains
-// and MUST execute VTX_PDL_WAIT() before its first global access (a no-op when launched without the attribute).
-template <typename... KArgs, typename... Args>
-static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
-                                     Args&&... args) {
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = grid;
-  cfg.blockDim = block;
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  static const bool off = getenv("VTX_PDL_AUX") != nullptr && getenv("VTX_PDL_AUX")[0] == '0';  // measurement knob
-  cfg.numAttrs = off ? 0 : 1;
-  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
-}
-
 // printf-style error recording; returns `code` so call sites can `return set_error(...)`.
 int set_error(int code, const char* fmt, ...);
 int check_launch(const char* what);
