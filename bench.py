@@ -359,9 +359,11 @@ def main_ours(args, rank, world, local):
                 "hbm_view": {"achieved_gbs": round(g_by / (g_ms * 1e-3) / 1e9, 1), "peak_gbs": peak_bw,
                              "frac": round(g_by / (g_ms * 1e-3) / 1e9 / peak_bw, 4)},
                 "per_launch_roofline_frac": round(t_min / g_ms, 4),
-                "note": "209 launches of mixed shapes: 'frac' is sum(2MNK)/sum(time) against the bf16 peak; about half of the "
+                "note": "launches of mixed shapes: 'frac' is sum(2MNK)/sum(time) against the bf16 peak; about half of the "
                         "launches (layer1-2 convs, all wgrads) are HBM-bound, so per_launch_roofline_frac = "
-                        "sum(max(flops/peak_tf, min_bytes/peak_bw))/sum(time) is the tighter figure"}
+                        "sum(max(flops/peak_tf, min_bytes/peak_bw))/sum(time) is the tighter figure; the kernel's time "
+                        "includes the BN statistics / BN-backward reductions fused into its epilogues (their y / residual / "
+                        "mask reads are counted in min_bytes)"}
     barrier()
     dp = dp_gradient_check(trainer, dev_batch, world) if world > 1 else None
     name = f"{cfg.MODEL.VISUAL.NAME.split('::')[-1]} + {cfg.MODEL.TEXTUAL.NAME}"
