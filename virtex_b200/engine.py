@@ -7,7 +7,8 @@ This replaces, for the hot path, what autograd + cuDNN + cuBLASLt + ATen do for 
     of identical layout (what the data-parallel all-reduce and the fused optimiser consume), and a flat bf16 mirror of
     the parameters (the GEMM B operands) plus packed bf16 layouts for the 3x3 / 7x7 convolution weights;
   * every activation / workspace buffer, allocated once per (batch, caption length) shape -- no allocation, no host
-    synchronisation and no Python-side tensor math inside a step, so a whole step can be captured in a CUDA graph.
+    synchronisation and no Python-side tensor math inside a step (the step is launch-ahead of the GPU by design; it is
+    NOT captured in a CUDA graph today -- the GPU is 99 % busy without one, and the tensor maps are re-encoded per launch).
 
 Data layout in HBM: backbone activations NHWC bf16 (a conv output is a row-major [N*H*W, C] matrix: 1x1 convs are
 GEMMs as-is, 3x3/stride-1 convs are implicit GEMMs through 4-D TMA boxes), BN statistics / affine parameters fp32,
