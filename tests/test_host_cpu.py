@@ -69,6 +69,34 @@ def test_library_exports_every_declared_symbol():
     assert so.vtx_version() >= 100
 
 
+def test_ctypes_gemm_struct_mirrors_the_header_field_for_field():
+    """`virtex_b200.lib.VtxGemm` (what every GEMM call marshals) against `typedef struct VtxGemm` of
+    include/virtex_b200.h: same field names in the same order, C types of the same width, and the size the built
+    library reports -- so an edit of either side that forgets the other fails here, not as a corrupted launch."""
+    from virtex_b200 import lib as L
+    header = open(os.path.join(ROOT, "include", "virtex_b200.h")).read()
+    body = header[header.index("typedef struct VtxGemm {"):header.index("} VtxGemm;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S).split("{", 1)[1]
+    fields = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        ctype, names = decl.rsplit(" ", 1)[0], decl
+        # "int64_t lda, ldb, ldd, ldr" / "const void* A" / "float* stats"
+        m = re.match(r"(const\s+)?(\w+)\s*(\*?)\s*(.*)", decl)
+        base, ptr, rest = m.group(2), m.group(3), m.group(4)
+        for name in rest.split(","):
+            name = name.strip()
+            is_ptr = bool(ptr) or name.startswith("*")
+            fields.append((name.lstrip("* "), "ptr" if is_ptr else base))
+    width = {"ptr": 8, "int64_t": 8, "int32_t": 4, "float": 4}
+    mirror = [(n, ctypes.sizeof(t)) for n, t in L.VtxGemm._fields_]
+    assert [n for n, _ in fields] == [n for n, _ in mirror]
+    assert [width[t] for _, t in fields] == [w for _, w in mirror]
+    assert ctypes.CDLL(L.LIB_PATH).vtx_sizeof_gemm() == ctypes.sizeof(L.VtxGemm)
+
+
 def test_virtex_alias_package_and_hubconf():
     """`import virtex.*` paths of the reference resolve to this implementation; hubconf exposes resnet50()."""
     import importlib
