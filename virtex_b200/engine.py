@@ -157,7 +157,7 @@ class Engine:
         # gradient (bn1 / bn2 of every block, bn3 of blocks followed by an identity block) instead of a separate pass;
         # VTX_BNR_FUSE=0 is the measurement knob for the A/B against the standalone vtx_bn_bwd_reduce launches
         self.fuse_bn_reduce = os.environ.get("VTX_BNR_FUSE", "1") != "0"
-        self.fuse_bn3_min_rows = 100000
+        self.fuse_bn3_min_rows = int(os.environ.get("VTX_BNR_BN3_MIN_ROWS", "100000"))  # (env: measurement knob)
         self._build_backbone_plan()
 
     # ------------------------------------------------------------------------------------------------ parameters
