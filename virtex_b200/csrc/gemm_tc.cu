@@ -76,7 +76,7 @@ static FastDiv make_fastdiv(int d) {
     int l = 0;
     while ((1u << l) < (uint32_t)d) ++l;  // ceil(log2 d)
     const int pw = 31 + l;
-    const unsigned long long m = ((1ull << pw) + (uint32_t)d - 1) / (uint32_t)d;  // 2^31 < m < 2^32: never 0
+    const unsigned long long m = ((1ull << pw) + (uint32_t)d - 1) / (uint32_t)d;  // 2^31 <= m < 2^32: never 0
     f.mul = (uint32_t)m;
     f.shr = (uint32_t)(pw - 32);
   }
